@@ -1,0 +1,596 @@
+// fs_api.cu -- the extern "C" boundary (include/frequensee.h).  No CPU fallback anywhere: every
+// entry point either runs the CUDA path or returns an error.
+#include "fs_internal.h"
+
+#include <stdio.h>
+#include <new>
+#include <vector>
+
+static thread_local std::string g_create_err;
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call);                            \
+    } while (0)
+
+static int fail(fs_ctx* ctx, int code, const char* msg)
+{
+    if (ctx) ctx->err = msg; else g_create_err = msg;
+    return code;
+}
+static int fail_cuda(fs_ctx* ctx, cudaError_t e, const char* what)
+{
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    if (ctx) ctx->err = buf; else g_create_err = buf;
+    return e == cudaErrorMemoryAllocation ? FS_ERR_NOMEM : FS_ERR_CUDA;
+}
+
+struct dev_guard {
+    int prev; bool ok;
+    explicit dev_guard(int dev) : prev(-1), ok(false) { if (cudaGetDevice(&prev) == cudaSuccess) ok = (cudaSetDevice(dev) == cudaSuccess); }
+    ~dev_guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+extern "C" {
+
+void fs_default_config(fs_config* c)
+{
+    memset(c, 0, sizeof(*c));
+    c->n_bands = 8; c->n_bins = 1000; c->bin_ms = 1.0f; c->rr_prob = 0.9f;
+    c->eps_offset = 1e-3f; c->eps_connect = 1e-3f; c->min_seg = 1e-2f; c->sound_speed = 343.0f;
+    c->pdf_exponent = 0.1f; c->energy_clamp = 1.0f; c->energy_gain = 10.0f;
+    static const float air[FS_MAX_BANDS] = {0.0001f, 0.0003f, 0.0006f, 0.0010f, 0.0017f, 0.0035f, 0.0050f, 0.0120f};
+    for (int b = 0; b < FS_MAX_BANDS; ++b) c->air_absorption[b] = air[b];
+    c->sample_rate = 48000; c->n_channels = 2; c->ir_threshold = 1e-6f; c->ir_lowpass = 0.25f;
+    c->conv_block = 1024; c->conv_clamp = 1; c->conv_wet = 1.0f;
+    c->max_batch_paths = 0; c->flags = 0; c->device = -1;
+}
+
+const char* fs_last_error(const fs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int fs_create(const fs_config* cfg, fs_ctx** out)
+{
+    if (!cfg || !out) return fail(nullptr, FS_ERR_INVALID, "fs_create: null argument");
+    *out = nullptr;
+    if (cfg->n_bands < 1 || cfg->n_bands > FS_MAX_BANDS) return fail(nullptr, FS_ERR_INVALID, "n_bands must be 1..8");
+    if (cfg->n_bins < 1 || cfg->n_bins > (1u << 20)) return fail(nullptr, FS_ERR_INVALID, "n_bins out of range");
+    if (!(cfg->bin_ms > 0.f) || !(cfg->sound_speed > 0.f)) return fail(nullptr, FS_ERR_INVALID, "bin_ms/sound_speed must be > 0");
+    if (!(cfg->rr_prob > 0.f) || cfg->rr_prob > 1.0f) return fail(nullptr, FS_ERR_INVALID, "rr_prob must be in (0,1]");
+    if (cfg->n_channels < 1 || cfg->n_channels > 8) return fail(nullptr, FS_ERR_INVALID, "n_channels must be 1..8");
+    if (cfg->conv_block < 32 || cfg->conv_block > 2048 || (cfg->conv_block & (cfg->conv_block - 1)))
+        return fail(nullptr, FS_ERR_INVALID, "conv_block must be a power of two in 32..2048");
+    if (cfg->sample_rate < cfg->conv_block) return fail(nullptr, FS_ERR_INVALID, "sample_rate < conv_block");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "no usable CUDA device (%s); this library has no CPU fallback",
+                 e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return fail(nullptr, FS_ERR_CUDA, buf);
+    }
+    int dev = cfg->device;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+    if (dev >= ndev) return fail(nullptr, FS_ERR_INVALID, "device ordinal out of range");
+    fs_ctx* ctx = new (std::nothrow) fs_ctx();
+    if (!ctx) return fail(nullptr, FS_ERR_NOMEM, "out of host memory");
+    ctx->cfg = *cfg;
+    if (ctx->cfg.max_batch_paths == 0) ctx->cfg.max_batch_paths = 1u << 20;
+    ctx->device = dev;
+    dev_guard g(dev);
+    int rc = FS_OK;
+    do {
+        cudaDeviceProp prop;
+        if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaGetDeviceProperties"); break; }
+        if (prop.major < 10) {
+            char buf[256];
+            snprintf(buf, sizeof(buf), "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+            rc = fail(nullptr, FS_ERR_CUDA, buf); break;
+        }
+        ctx->sm_count = prop.multiProcessorCount;
+        if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaStreamCreate"); break; }
+        ctx->stream = ctx->own_stream;
+        if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaEventCreate"); break; }
+        if ((e = cudaMalloc(&ctx->d_counters, sizeof(fs_dev_counters))) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaMalloc counters"); break; }
+        if ((e = cudaMemset(ctx->d_counters, 0, sizeof(fs_dev_counters))) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaMemset"); break; }
+        if ((e = cudaMalloc(&ctx->d_amp, sizeof(float) * cfg->n_bins)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaMalloc amp"); break; }
+        if ((e = cudaMalloc(&ctx->d_energy, sizeof(float) * cfg->n_bins)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaMalloc energy"); break; }
+        if ((e = fs_conv_setup(ctx)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "fs_conv_setup"); break; }
+    } while (0);
+    if (rc != FS_OK) { fs_destroy(ctx); return rc; }
+    *out = ctx;
+    return FS_OK;
+}
+
+void fs_destroy(fs_ctx* ctx)
+{
+    if (!ctx) return;
+    dev_guard g(ctx->device);
+    cudaDeviceSynchronize();
+    fs_conv_teardown(ctx);
+    fs_wave_free(&ctx->wb);
+    fs_bvh_free(&ctx->bvh);
+    cudaFree(ctx->d_verts); cudaFree(ctx->d_tri_mat); cudaFree(ctx->d_refl_over_pi);
+    cudaFree(ctx->d_hist); cudaFree(ctx->d_counters); cudaFree(ctx->d_src_pos); cudaFree(ctx->d_dbg);
+    cudaFree(ctx->d_amp); cudaFree(ctx->d_energy);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int fs_set_stream(fs_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return FS_OK;
+}
+
+int fs_synchronize(fs_ctx* ctx)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    dev_guard g(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FS_OK;
+}
+
+// ---- scene -----------------------------------------------------------------------------------
+int fs_scene_set_triangles(fs_ctx* ctx, const float* verts, const uint32_t* tri_material, uint64_t n_tris)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    if (n_tris && (!verts || !tri_material)) return fail(ctx, FS_ERR_INVALID, "fs_scene_set_triangles: null array");
+    if (n_tris >= (1ull << 28)) return fail(ctx, FS_ERR_INVALID, "too many triangles (< 2^28 supported)");
+    dev_guard g(ctx->device);
+    for (uint64_t i = 0; i < n_tris * 9; ++i)
+        if (!(verts[i] == verts[i]) || fabsf(verts[i]) > 1e18f) return fail(ctx, FS_ERR_INVALID, "non-finite vertex");
+    cudaFree(ctx->d_verts); cudaFree(ctx->d_tri_mat);
+    ctx->d_verts = nullptr; ctx->d_tri_mat = nullptr;
+    ctx->n_tris = n_tris; ctx->committed = false; ctx->tris_set = false;
+    if (n_tris) {
+        CK(cudaMalloc(&ctx->d_verts, sizeof(float) * 9 * n_tris));
+        CK(cudaMalloc(&ctx->d_tri_mat, sizeof(uint32_t) * n_tris));
+        CK(cudaMemcpyAsync(ctx->d_verts, verts, sizeof(float) * 9 * n_tris, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_tri_mat, tri_material, sizeof(uint32_t) * n_tris, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    // material ids are validated against the table at commit time
+    ctx->tris_set = true;
+    return FS_OK;
+}
+
+int fs_scene_set_materials(fs_ctx* ctx, const float* absorption, uint32_t n_materials, uint32_t n_bands)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    if (!absorption || n_materials == 0) return fail(ctx, FS_ERR_INVALID, "fs_scene_set_materials: empty table");
+    if (n_bands != ctx->cfg.n_bands) return fail(ctx, FS_ERR_INVALID, "n_bands differs from fs_config.n_bands");
+    dev_guard g(ctx->device);
+    std::vector<float> r((size_t)n_materials * n_bands);
+    for (size_t i = 0; i < r.size(); ++i) {
+        float a = absorption[i];
+        if (!(a >= 0.0f && a <= 1.0f)) return fail(ctx, FS_ERR_INVALID, "absorption must be in [0,1]");
+        // reflectivity / PI (SUB.cpp:381-386); the reference's "Absorption" asset field is used as
+        // reflectivity there -- here absorption alpha means rho = 1 - alpha
+        r[i] = (1.0f - a) / FS_PI;
+    }
+    cudaFree(ctx->d_refl_over_pi); ctx->d_refl_over_pi = nullptr;
+    CK(cudaMalloc(&ctx->d_refl_over_pi, sizeof(float) * r.size()));
+    CK(cudaMemcpy(ctx->d_refl_over_pi, r.data(), sizeof(float) * r.size(), cudaMemcpyHostToDevice));
+    ctx->n_mats = n_materials; ctx->mats_set = true; ctx->committed = false;
+    return FS_OK;
+}
+
+int fs_scene_commit(fs_ctx* ctx)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    if (!ctx->tris_set || !ctx->mats_set) return fail(ctx, FS_ERR_STATE, "fs_scene_commit: set triangles and materials first");
+    dev_guard g(ctx->device);
+    if (ctx->n_tris) {
+        // validate material ids on the host copy-back of the id array (one-time, commit only)
+        std::vector<uint32_t> m(ctx->n_tris);
+        CK(cudaMemcpy(m.data(), ctx->d_tri_mat, sizeof(uint32_t) * ctx->n_tris, cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < ctx->n_tris; ++i)
+            if (m[i] >= ctx->n_mats) return fail(ctx, FS_ERR_INVALID, "triangle material id out of range");
+    }
+    CK(fs_bvh_build(ctx->stream, ctx->d_verts, ctx->d_tri_mat, ctx->n_tris, &ctx->bvh, &ctx->stats.kernel_launches));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.bvh_nodes = ctx->bvh.n_inner;
+    ctx->stats.bvh_max_leaf = ctx->bvh.max_leaf;
+    ctx->committed = true;
+    return FS_OK;
+}
+
+// ---- trace -----------------------------------------------------------------------------------
+static void fill_params(fs_ctx* ctx, fs_trace_params* tp, const float lis[3], uint64_t n_paths, uint32_t max_depth,
+                        uint64_t seed)
+{
+    const fs_config& c = ctx->cfg;
+    memset(tp, 0, sizeof(*tp));
+    tp->bv.nodes = ctx->bvh.nodes; tp->bv.tris = ctx->bvh.tris; tp->bv.tri_orig = ctx->bvh.tri_orig;
+    tp->bv.tri_mat = ctx->bvh.tri_mat; tp->bv.n_tris = ctx->bvh.n_tris; tp->bv.n_inner = ctx->bvh.n_inner;
+    tp->top = ctx->bvh.top_nodes; tp->n_top = ctx->bvh.n_top;
+    tp->refl_over_pi = ctx->d_refl_over_pi; tp->n_mats = ctx->n_mats;
+    tp->ep.min_seg = c.min_seg; tp->ep.pdf_exponent = c.pdf_exponent; tp->ep.n_bands = c.n_bands;
+    for (int b = 0; b < FS_MAX_BANDS; ++b) tp->ep.air[b] = c.air_absorption[b];
+    tp->n_bins = c.n_bins; tp->bin_ms = c.bin_ms; tp->rr_prob = c.rr_prob; tp->eps_offset = c.eps_offset;
+    tp->eps_connect = c.eps_connect; tp->sound_speed = c.sound_speed; tp->energy_clamp = c.energy_clamp;
+    tp->energy_gain = c.energy_gain; tp->max_depth = max_depth;
+    tp->seed_lo = (uint32_t)seed; tp->seed_hi = (uint32_t)(seed >> 32);
+    tp->n_paths = n_paths;
+    tp->src_pos = ctx->d_src_pos;
+    if (lis) { tp->lis[0] = lis[0]; tp->lis[1] = lis[1]; tp->lis[2] = lis[2]; }
+    tp->flags = c.flags;
+    tp->cap = ctx->wb.cap;
+}
+
+static int ensure_hist(fs_ctx* ctx, uint32_t n_sources)
+{
+    if (ctx->d_hist && ctx->hist_sources >= n_sources) return FS_OK;
+    cudaFree(ctx->d_hist); ctx->d_hist = nullptr;
+    const size_t n = (size_t)n_sources * ctx->cfg.n_bands * ctx->cfg.n_bins;
+    CK(cudaMalloc(&ctx->d_hist, 8 * n));
+    ctx->hist_sources = n_sources;
+    return FS_OK;
+}
+
+static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, const float lis_pos[3],
+                        uint64_t n_paths, uint64_t g_first, uint64_t g_count, uint32_t max_depth, uint64_t seed,
+                        unsigned long long* d_hist, fs_path_dbg* d_dbg)
+{
+    if (!ctx->committed) return fail(ctx, FS_ERR_STATE, "fs_trace: call fs_scene_commit first");
+    if (!src_pos || !lis_pos || n_sources == 0) return fail(ctx, FS_ERR_INVALID, "fs_trace: null positions / no source");
+    if (n_paths == 0) return fail(ctx, FS_ERR_INVALID, "fs_trace: n_paths must be > 0");
+    if (max_depth > 1024) return fail(ctx, FS_ERR_INVALID, "fs_trace: max_depth > 1024");
+    if (g_first + g_count > (uint64_t)n_sources * n_paths) return fail(ctx, FS_ERR_INVALID, "fs_trace: work range exceeds n_sources * n_paths");
+    if ((uint64_t)n_sources * ctx->cfg.n_bins >= 0xffffffffull) return fail(ctx, FS_ERR_INVALID, "fs_trace: n_sources * n_bins too large");
+    if (ctx->src_cap < n_sources) {
+        cudaFree(ctx->d_src_pos); ctx->d_src_pos = nullptr;
+        CK(cudaMalloc(&ctx->d_src_pos, sizeof(float) * 3 * n_sources));
+        ctx->src_cap = n_sources;
+    }
+    CK(cudaMemcpyAsync(ctx->d_src_pos, src_pos, sizeof(float) * 3 * n_sources, cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t cap_cfg = ctx->cfg.max_batch_paths;
+    uint32_t cap = (uint32_t)(g_count < cap_cfg ? (g_count ? g_count : 1) : cap_cfg);
+    CK(fs_wave_alloc(ctx, cap, max_depth));
+    fs_trace_params tp;
+    fill_params(ctx, &tp, lis_pos, n_paths, max_depth, seed);
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(fs_wave_reset_counters(ctx));
+    for (uint64_t done = 0; done < g_count;) {
+        uint64_t nb = g_count - done;
+        if (nb > ctx->wb.cap) nb = ctx->wb.cap;
+        tp.g_first = g_first + done;
+        tp.batch = (uint32_t)nb;
+        CK(fs_wave_trace_batch(ctx, tp, d_hist, d_dbg ? d_dbg + done : nullptr));
+        done += nb;
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->timed = true;
+    ctx->stats.paths = g_count;
+    return FS_OK;
+}
+
+static int finish_stats(fs_ctx* ctx)
+{
+    fs_dev_counters h;
+    CK(cudaMemcpyAsync(&h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.ext_rays = h.ext_rays; ctx->stats.shadow_rays = h.shadow_rays; ctx->stats.connected = h.connected;
+    ctx->stats.node_visits = h.node_visits; ctx->stats.tri_tests = h.tri_tests;
+    if (ctx->timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.last_trace_ms = ms;
+        else (void)cudaGetLastError();
+    }
+    if (h.overflow) return fail(ctx, FS_ERR_OVERFLOW, "BVH traversal stack overflow (tree deeper than FS_STACK_SIZE)");
+    return FS_OK;
+}
+
+int fs_trace(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, const float lis_pos[3], uint64_t n_paths,
+             uint32_t max_depth, uint64_t seed, uint64_t* hist_out)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    dev_guard g(ctx->device);
+    if (n_sources == 0) return fail(ctx, FS_ERR_INVALID, "fs_trace: no source");
+    int rc = ensure_hist(ctx, n_sources);
+    if (rc) return rc;
+    const size_t hn = (size_t)n_sources * ctx->cfg.n_bands * ctx->cfg.n_bins;
+    CK(cudaMemsetAsync(ctx->d_hist, 0, 8 * hn, ctx->stream));            // FlushEnergyBuffer, COMP.h:76-79
+    rc = trace_common(ctx, src_pos, n_sources, lis_pos, n_paths, 0, (uint64_t)n_sources * n_paths, max_depth, seed,
+                      ctx->d_hist, nullptr);
+    if (rc) return rc;
+    ctx->hist_n_paths = n_paths;
+    if (hist_out) {
+        CK(cudaMemcpyAsync(hist_out, ctx->d_hist, 8 * hn, cudaMemcpyDeviceToHost, ctx->stream));
+        return finish_stats(ctx);
+    }
+    return FS_OK;
+}
+
+int fs_trace_range_device(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, const float lis_pos[3],
+                          uint64_t n_paths, uint64_t g_first, uint64_t g_count, uint32_t max_depth, uint64_t seed,
+                          void* d_hist, int zero_first)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    if (!d_hist) return fail(ctx, FS_ERR_INVALID, "fs_trace_range_device: null histogram");
+    dev_guard g(ctx->device);
+    const size_t hn = (size_t)n_sources * ctx->cfg.n_bands * ctx->cfg.n_bins;
+    if (zero_first) CK(cudaMemsetAsync(d_hist, 0, 8 * hn, ctx->stream));
+    return trace_common(ctx, src_pos, n_sources, lis_pos, n_paths, g_first, g_count, max_depth, seed,
+                        (unsigned long long*)d_hist, nullptr);
+}
+
+int fs_trace_range(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, const float lis_pos[3], uint64_t n_paths,
+                   uint64_t g_first, uint64_t g_count, uint32_t max_depth, uint64_t seed, uint64_t* hist_inout)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    if (!hist_inout) return fail(ctx, FS_ERR_INVALID, "fs_trace_range: null histogram");
+    dev_guard g(ctx->device);
+    int rc = ensure_hist(ctx, n_sources);
+    if (rc) return rc;
+    const size_t hn = (size_t)n_sources * ctx->cfg.n_bands * ctx->cfg.n_bins;
+    CK(cudaMemcpyAsync(ctx->d_hist, hist_inout, 8 * hn, cudaMemcpyHostToDevice, ctx->stream));
+    rc = trace_common(ctx, src_pos, n_sources, lis_pos, n_paths, g_first, g_count, max_depth, seed, ctx->d_hist, nullptr);
+    if (rc) return rc;
+    ctx->hist_n_paths = n_paths;
+    CK(cudaMemcpyAsync(hist_inout, ctx->d_hist, 8 * hn, cudaMemcpyDeviceToHost, ctx->stream));
+    return finish_stats(ctx);
+}
+
+int fs_trace_debug(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, const float lis_pos[3], uint64_t n_paths,
+                   uint64_t g_first, uint64_t g_count, uint32_t max_depth, uint64_t seed, fs_path_dbg* dbg_out)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    if (!dbg_out) return fail(ctx, FS_ERR_INVALID, "fs_trace_debug: null output");
+    dev_guard g(ctx->device);
+    int rc = ensure_hist(ctx, n_sources);
+    if (rc) return rc;
+    if (ctx->dbg_cap < g_count) {
+        cudaFree(ctx->d_dbg); ctx->d_dbg = nullptr;
+        CK(cudaMalloc(&ctx->d_dbg, sizeof(fs_path_dbg) * g_count));
+        ctx->dbg_cap = g_count;
+    }
+    const size_t hn = (size_t)n_sources * ctx->cfg.n_bands * ctx->cfg.n_bins;
+    CK(cudaMemsetAsync(ctx->d_hist, 0, 8 * hn, ctx->stream));
+    rc = trace_common(ctx, src_pos, n_sources, lis_pos, n_paths, g_first, g_count, max_depth, seed, ctx->d_hist, ctx->d_dbg);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(dbg_out, ctx->d_dbg, sizeof(fs_path_dbg) * g_count, cudaMemcpyDeviceToHost, ctx->stream));
+    return finish_stats(ctx);
+}
+
+static int debug_rays(fs_ctx* ctx, const float* rays, const float* tmax, uint64_t n, float* out_t, uint32_t* out_tri,
+                      uint8_t* out_hit)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    if (!ctx->committed) return fail(ctx, FS_ERR_STATE, "commit the scene first");
+    if (n == 0) return FS_OK;
+    dev_guard g(ctx->device);
+    float *d_rays = nullptr, *d_tmax = nullptr, *d_t = nullptr; uint32_t* d_tri = nullptr; uint8_t* d_hit = nullptr;
+    int rc = FS_OK;
+    cudaError_t e = cudaSuccess;
+    fs_trace_params tp;
+    fill_params(ctx, &tp, nullptr, 1, 1, 0);
+    do {
+        if ((e = cudaMalloc(&d_rays, sizeof(float) * 6 * n)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(d_rays, rays, sizeof(float) * 6 * n, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if (out_hit) {
+            if ((e = cudaMalloc(&d_tmax, sizeof(float) * n)) != cudaSuccess) break;
+            if ((e = cudaMemcpy(d_tmax, tmax, sizeof(float) * n, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+            if ((e = cudaMalloc(&d_hit, n)) != cudaSuccess) break;
+        } else {
+            if ((e = cudaMalloc(&d_t, sizeof(float) * n)) != cudaSuccess) break;
+            if ((e = cudaMalloc(&d_tri, sizeof(uint32_t) * n)) != cudaSuccess) break;
+        }
+        if ((e = fs_wave_reset_counters(ctx)) != cudaSuccess) break;
+        if ((e = fs_wave_debug_rays(ctx, tp, d_rays, d_tmax, n, d_t, d_tri, d_hit)) != cudaSuccess) break;
+        if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) break;
+        if (out_hit) { if ((e = cudaMemcpy(out_hit, d_hit, n, cudaMemcpyDeviceToHost)) != cudaSuccess) break; }
+        else {
+            if ((e = cudaMemcpy(out_t, d_t, sizeof(float) * n, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+            if ((e = cudaMemcpy(out_tri, d_tri, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        }
+    } while (0);
+    cudaFree(d_rays); cudaFree(d_tmax); cudaFree(d_t); cudaFree(d_tri); cudaFree(d_hit);
+    if (e != cudaSuccess) rc = fail_cuda(ctx, e, "fs_debug rays");
+    return rc;
+}
+
+int fs_debug_closest_hits(fs_ctx* ctx, const float* rays, uint64_t n, float* out_t, uint32_t* out_tri)
+{
+    if (!rays || !out_t || !out_tri) return ctx ? fail(ctx, FS_ERR_INVALID, "null argument") : FS_ERR_INVALID;
+    return debug_rays(ctx, rays, nullptr, n, out_t, out_tri, nullptr);
+}
+int fs_debug_any_hits(fs_ctx* ctx, const float* rays, const float* tmax, uint64_t n, uint8_t* out_hit)
+{
+    if (!rays || !tmax || !out_hit) return ctx ? fail(ctx, FS_ERR_INVALID, "null argument") : FS_ERR_INVALID;
+    return debug_rays(ctx, rays, tmax, n, nullptr, nullptr, out_hit);
+}
+
+// ---- histogram / IR ---------------------------------------------------------------------------
+int fs_set_histogram(fs_ctx* ctx, const uint64_t* hist, uint32_t n_sources, uint64_t n_paths)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    if (!hist || n_sources == 0 || n_paths == 0) return fail(ctx, FS_ERR_INVALID, "fs_set_histogram: bad argument");
+    dev_guard g(ctx->device);
+    int rc = ensure_hist(ctx, n_sources);
+    if (rc) return rc;
+    const size_t hn = (size_t)n_sources * ctx->cfg.n_bands * ctx->cfg.n_bins;
+    CK(cudaMemcpyAsync(ctx->d_hist, hist, 8 * hn, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->hist_n_paths = n_paths;
+    return FS_OK;
+}
+
+int fs_set_histogram_device(fs_ctx* ctx, const void* d_hist, uint32_t n_sources, uint64_t n_paths)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    if (!d_hist || n_sources == 0 || n_paths == 0) return fail(ctx, FS_ERR_INVALID, "fs_set_histogram_device: bad argument");
+    dev_guard g(ctx->device);
+    int rc = ensure_hist(ctx, n_sources);
+    if (rc) return rc;
+    const size_t hn = (size_t)n_sources * ctx->cfg.n_bands * ctx->cfg.n_bins;
+    CK(cudaMemcpyAsync(ctx->d_hist, d_hist, 8 * hn, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->hist_n_paths = n_paths;
+    return FS_OK;
+}
+
+int fs_get_histogram(fs_ctx* ctx, uint64_t* hist_out)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    if (!hist_out || !ctx->d_hist) return fail(ctx, FS_ERR_STATE, "fs_get_histogram: no histogram");
+    dev_guard g(ctx->device);
+    const size_t hn = (size_t)ctx->hist_sources * ctx->cfg.n_bands * ctx->cfg.n_bins;
+    CK(cudaMemcpyAsync(hist_out, ctx->d_hist, 8 * hn, cudaMemcpyDeviceToHost, ctx->stream));
+    return finish_stats(ctx);
+}
+
+static int ir_common(fs_ctx* ctx, uint32_t source, const float* energy, float* ir_out)
+{
+    const fs_config& c = ctx->cfg;
+    if (source >= ctx->conv_cap || !ctx->conv[source].ir) {
+        // the IR lives in the convolver's per-source state; create it on first use
+        cudaError_t e = fs_conv_source_alloc(ctx, source);
+        if (e != cudaSuccess) return fail_cuda(ctx, e, "fs_conv_source_alloc");
+    }
+    fs_conv_source& s = ctx->conv[source];
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    CK(cudaEventRecord(a, ctx->stream));
+    const float* d_energy = nullptr;
+    if (energy) {
+        CK(cudaMemcpyAsync(ctx->d_energy, energy, sizeof(float) * c.n_bins, cudaMemcpyHostToDevice, ctx->stream));
+        d_energy = ctx->d_energy;
+    }
+    const unsigned long long* hsrc = ctx->d_hist ? ctx->d_hist + (size_t)source * c.n_bands * c.n_bins : nullptr;
+    CK(fs_ir_build(ctx, hsrc, ctx->hist_n_paths, d_energy, s.ir));
+    { std::lock_guard<std::mutex> lk(ctx->conv_mu); CK(fs_conv_update_ir(ctx, source, ctx->stream)); }
+    CK(cudaEventRecord(b, ctx->stream));
+    if (ir_out) {
+        CK(cudaMemcpyAsync(ir_out, s.ir, sizeof(float) * c.n_channels * c.sample_rate, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) ctx->stats.last_ir_ms = ms;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return FS_OK;
+}
+
+int fs_build_ir(fs_ctx* ctx, uint32_t source, float* ir_out)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    if (!ctx->d_hist || source >= ctx->hist_sources || ctx->hist_n_paths == 0)
+        return fail(ctx, FS_ERR_STATE, "fs_build_ir: no histogram for this source (call fs_trace or fs_set_histogram)");
+    dev_guard g(ctx->device);
+    return ir_common(ctx, source, nullptr, ir_out);
+}
+
+int fs_build_ir_from_energy(fs_ctx* ctx, uint32_t source, const float* energy, float* ir_out)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    if (!energy) return fail(ctx, FS_ERR_INVALID, "fs_build_ir_from_energy: null energy");
+    dev_guard g(ctx->device);
+    return ir_common(ctx, source, energy, ir_out);
+}
+
+int fs_set_ir(fs_ctx* ctx, uint32_t source, const float* ir)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    if (!ir) return fail(ctx, FS_ERR_INVALID, "fs_set_ir: null ir");
+    dev_guard g(ctx->device);
+    if (source >= ctx->conv_cap || !ctx->conv[source].ir) {
+        cudaError_t e = fs_conv_source_alloc(ctx, source);
+        if (e != cudaSuccess) return fail_cuda(ctx, e, "fs_conv_source_alloc");
+    }
+    fs_conv_source& s = ctx->conv[source];
+    const fs_config& c = ctx->cfg;
+    CK(cudaMemcpyAsync(s.ir, ir, sizeof(float) * c.n_channels * c.sample_rate, cudaMemcpyHostToDevice, ctx->stream));
+    { std::lock_guard<std::mutex> lk(ctx->conv_mu); CK(fs_conv_update_ir(ctx, source, ctx->stream)); }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FS_OK;
+}
+
+// ---- convolution --------------------------------------------------------------------------------
+int fs_conv_init_source(fs_ctx* ctx, uint32_t source)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    if (source >= 4096) return fail(ctx, FS_ERR_INVALID, "source id too large");
+    dev_guard g(ctx->device);
+    std::lock_guard<std::mutex> lk(ctx->conv_mu);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(fs_conv_source_alloc(ctx, source));
+    return FS_OK;
+}
+
+int fs_conv_release_source(fs_ctx* ctx, uint32_t source)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    dev_guard g(ctx->device);
+    std::lock_guard<std::mutex> lk(ctx->conv_mu);
+    CK(cudaStreamSynchronize(ctx->stream));
+    fs_conv_source_free(ctx, source);            // Source.ClearBuffers(), REV.cpp:112-116
+    return FS_OK;
+}
+
+int fs_conv_process_many(fs_ctx* ctx, uint32_t source, const float* in, float* out, uint32_t frames, uint32_t n_blocks)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    if (!in || !out) return fail(ctx, FS_ERR_INVALID, "fs_conv_process: null buffer");
+    if (frames != ctx->cfg.conv_block) return fail(ctx, FS_ERR_INVALID, "fs_conv_process: frames must equal conv_block");
+    if (n_blocks == 0) return FS_OK;
+    dev_guard g(ctx->device);
+    std::lock_guard<std::mutex> lk(ctx->conv_mu);
+    if (source >= ctx->conv_cap || !ctx->conv[source].active)
+        return fail(ctx, FS_ERR_STATE, "fs_conv_process: source not initialised (fs_conv_init_source)");
+    const fs_config& c = ctx->cfg;
+    const size_t n = (size_t)n_blocks * frames * c.n_channels;
+    if (ctx->conv_io_cap < n) {
+        cudaFree(ctx->d_conv_in); cudaFree(ctx->d_conv_out); ctx->d_conv_in = ctx->d_conv_out = nullptr;
+        if (ctx->h_pin_in) cudaFreeHost(ctx->h_pin_in);
+        if (ctx->h_pin_out) cudaFreeHost(ctx->h_pin_out);
+        ctx->h_pin_in = ctx->h_pin_out = nullptr; ctx->conv_io_cap = 0;
+        CK(cudaMalloc(&ctx->d_conv_in, sizeof(float) * n));
+        CK(cudaMalloc(&ctx->d_conv_out, sizeof(float) * n));
+        CK(cudaMallocHost(&ctx->h_pin_in, sizeof(float) * n));
+        CK(cudaMallocHost(&ctx->h_pin_out, sizeof(float) * n));
+        ctx->conv_io_cap = (uint32_t)n;
+    }
+    memcpy(ctx->h_pin_in, in, sizeof(float) * n);
+    CK(cudaMemcpyAsync(ctx->d_conv_in, ctx->h_pin_in, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(fs_conv_run(ctx, source, ctx->d_conv_in, ctx->d_conv_out, n_blocks, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_pin_out, ctx->d_conv_out, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(out, ctx->h_pin_out, sizeof(float) * n);
+    return FS_OK;
+}
+
+int fs_conv_process(fs_ctx* ctx, uint32_t source, const float* in, float* out, uint32_t frames)
+{
+    return fs_conv_process_many(ctx, source, in, out, frames, 1);
+}
+
+int fs_debug_rfft(fs_ctx* ctx, const float* in, uint32_t n, float* out_ri)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    if (!in || !out_ri || n < 64 || n > 4096 || (n & (n - 1))) return fail(ctx, FS_ERR_INVALID, "fs_debug_rfft: n must be a power of two in 64..4096");
+    dev_guard g(ctx->device);
+    float* d_in = nullptr; float2* d_out = nullptr;
+    CK(cudaMalloc(&d_in, sizeof(float) * n));
+    CK(cudaMalloc(&d_out, sizeof(float2) * (n / 2 + 1)));
+    CK(cudaMemcpy(d_in, in, sizeof(float) * n, cudaMemcpyHostToDevice));
+    CK(fs_conv_rfft(ctx, d_in, n, d_out, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(out_ri, d_out, sizeof(float2) * (n / 2 + 1), cudaMemcpyDeviceToHost));
+    cudaFree(d_in); cudaFree(d_out);
+    return FS_OK;
+}
+
+int fs_get_stats(fs_ctx* ctx, fs_stats* out)
+{
+    if (!ctx || !out) return FS_ERR_INVALID;
+    dev_guard g(ctx->device);
+    int rc = finish_stats(ctx);
+    *out = ctx->stats;
+    return rc;
+}
+
+}  // extern "C"

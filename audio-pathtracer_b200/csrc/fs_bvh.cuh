@@ -1,0 +1,216 @@
+// fs_bvh.cuh -- device BVH layout and stack-based traversal (closest hit / any hit).
+//
+// Layout in HBM (all 16-byte aligned, fetched as float4 through the read-only path):
+//   nodes : float4[n_inner][4]   64 B per BVH2 inner node, holding BOTH children's boxes:
+//             n0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)
+//             n1 = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
+//             n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
+//             n3 = (child0, child1, -, -) as int bits.  child >= 0: inner node index;
+//                  child < 0: leaf, payload = ~child = (first_tri << 3) | (count - 1)
+//   tris  : float4[T][3]         48 B per triangle in leaf (Morton) order:
+//             (v0.xyz, n.x) (e1.xyz, n.y) (e2.xyz, n.z), n = unit geometric normal
+//   tri_orig : uint32[T]  original triangle id (tie-break key; closest hit = min (t, orig id))
+//   tri_mat  : uint32[T]  material id
+// Boxes are padded at build time so that the slab test (FMA form, not bit-reproducible against
+// the oracle and not required to be) is conservative: any triangle whose exact-arithmetic
+// fs_intersect_tri() succeeds is reached.  The hit itself comes from fs_intersect_tri() only.
+#pragma once
+
+#include "fs_math.cuh"
+
+#define FS_STACK_SIZE 64
+#define FS_LEAF_MAX 4
+#define FS_TOP_FLAG 0x40000000     // node index refers to the shared-memory treelet copy
+
+// Optional bring-up guard: bounds the number of inner-node visits per ray so that a malformed
+// tree can never hang the GPU (sets the overflow flag instead).  Off in release builds.
+#if defined(FS_TRAVERSAL_GUARD)
+#define FS_GUARD_DECL uint32_t guard_ = 0;
+#define FS_GUARD_STEP if (++guard_ > 4000000u) { *overflow = 2u; node = SENTINEL; sp = 0; break; }
+#else
+#define FS_GUARD_DECL
+#define FS_GUARD_STEP
+#endif
+
+struct fs_bvh_view {
+    const float4* nodes;
+    const float4* tris;
+    const uint32_t* tri_orig;
+    const uint32_t* tri_mat;
+    uint32_t n_tris;
+    uint32_t n_inner;
+};
+
+struct fs_visit_counters { uint32_t nodes, tris; };
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ float4 fs_ldg4(const float4* p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+struct fs_ray_prep {
+    fs_vec3 o, d;
+    float idx, idy, idz, oodx, oody, oodz;
+};
+
+__device__ __forceinline__ fs_ray_prep fs_prep_ray(fs_vec3 o, fs_vec3 d)
+{
+    fs_ray_prep r;
+    r.o = o; r.d = d;
+    float dx = (fabsf(d.x) > 1e-30f) ? d.x : ((d.x < 0.0f) ? -1e-30f : 1e-30f);
+    float dy = (fabsf(d.y) > 1e-30f) ? d.y : ((d.y < 0.0f) ? -1e-30f : 1e-30f);
+    float dz = (fabsf(d.z) > 1e-30f) ? d.z : ((d.z < 0.0f) ? -1e-30f : 1e-30f);
+    r.idx = 1.0f / dx; r.idy = 1.0f / dy; r.idz = 1.0f / dz;
+    r.oodx = o.x * r.idx; r.oody = o.y * r.idy; r.oodz = o.z * r.idz;
+    return r;
+}
+
+// Both children of one node against the ray interval [0, tmax].
+__device__ __forceinline__ void fs_slab2(const fs_ray_prep& r, float4 n0, float4 n1, float4 n2,
+                                         float tmax, bool& h0, bool& h1, float& t0n, float& t1n)
+{
+    float c0lox = fmaf(n0.x, r.idx, -r.oodx), c0hix = fmaf(n0.y, r.idx, -r.oodx);
+    float c0loy = fmaf(n0.z, r.idy, -r.oody), c0hiy = fmaf(n0.w, r.idy, -r.oody);
+    float c0loz = fmaf(n2.x, r.idz, -r.oodz), c0hiz = fmaf(n2.y, r.idz, -r.oodz);
+    float c1lox = fmaf(n1.x, r.idx, -r.oodx), c1hix = fmaf(n1.y, r.idx, -r.oodx);
+    float c1loy = fmaf(n1.z, r.idy, -r.oody), c1hiy = fmaf(n1.w, r.idy, -r.oody);
+    float c1loz = fmaf(n2.z, r.idz, -r.oodz), c1hiz = fmaf(n2.w, r.idz, -r.oodz);
+    float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.0f));
+    float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tmax));
+    float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.0f));
+    float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tmax));
+    h0 = c0min <= c0max;
+    h1 = c1min <= c1max;
+    t0n = c0min; t1n = c1min;
+}
+
+// Closest hit.  Returns sorted triangle index (>= 0) or -1; best_t receives t.
+// `top`/`n_top`: optional shared-memory copy of the top treelet (node indices with FS_TOP_FLAG).
+template <bool COUNT, bool USE_TOP>
+__device__ __forceinline__ int fs_closest_hit(const fs_bvh_view& bv, const float4* __restrict__ top,
+                                              fs_vec3 o, fs_vec3 d, float& best_t,
+                                              fs_visit_counters* cnt, uint32_t* overflow)
+{
+    int best = -1;
+    uint32_t best_orig = 0xffffffffu;
+    float bt = __int_as_float(0x7f800000);
+    if (bv.n_tris == 0) { best_t = bt; return -1; }
+    const fs_ray_prep r = fs_prep_ray(o, d);
+    int stack[FS_STACK_SIZE];
+    int sp = 0;
+    const int SENTINEL = 0x7fffffff;
+    int node = USE_TOP ? FS_TOP_FLAG : 0;
+    FS_GUARD_DECL
+    while (node != SENTINEL) {
+        while (node >= 0 && node != SENTINEL) {
+            FS_GUARD_STEP
+            float4 n0, n1, n2, n3;
+            if (USE_TOP && (node & FS_TOP_FLAG)) {
+                const float4* p = top + (size_t)(node & ~FS_TOP_FLAG) * 4;
+                n0 = p[0]; n1 = p[1]; n2 = p[2]; n3 = p[3];
+            } else {
+                const float4* p = bv.nodes + (size_t)node * 4;
+                n0 = fs_ldg4(p); n1 = fs_ldg4(p + 1); n2 = fs_ldg4(p + 2); n3 = fs_ldg4(p + 3);
+            }
+            if (COUNT) cnt->nodes++;
+            bool h0, h1; float t0, t1;
+            fs_slab2(r, n0, n1, n2, bt, h0, h1, t0, t1);
+            int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+            if (!h0 && !h1) {
+                node = sp ? stack[--sp] : SENTINEL;
+            } else {
+                node = h0 ? c0 : c1;
+                if (h0 && h1) {
+                    int far_ = c1;
+                    if (t1 < t0) { far_ = c0; node = c1; }
+                    if (sp < FS_STACK_SIZE) stack[sp++] = far_; else *overflow = 1u;
+                }
+            }
+        }
+        while (node < 0) {
+            uint32_t payload = (uint32_t)(~node);
+            uint32_t first = payload >> 3, count = (payload & 7u) + 1u;
+            for (uint32_t i = 0; i < count; ++i) {
+                const float4* tp = bv.tris + (size_t)(first + i) * 3;
+                float4 a = fs_ldg4(tp), b = fs_ldg4(tp + 1), c = fs_ldg4(tp + 2);
+                if (COUNT) cnt->tris++;
+                float t;
+                if (fs_intersect_tri(o, d, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z), fs_mk(c.x, c.y, c.z), t)) {
+                    if (t < bt) {
+                        bt = t; best = (int)(first + i); best_orig = 0xffffffffu;
+                    } else if (t == bt) {
+                        // tie: lower ORIGINAL id wins (acceleration-structure independent)
+                        if (best_orig == 0xffffffffu) best_orig = __ldg(bv.tri_orig + best);
+                        uint32_t oi = __ldg(bv.tri_orig + first + i);
+                        if (oi < best_orig) { best = (int)(first + i); best_orig = oi; }
+                    }
+                }
+            }
+            node = sp ? stack[--sp] : SENTINEL;
+        }
+    }
+    best_t = bt;
+    return best;
+}
+
+// Any hit with 0 < t < tmax.
+template <bool COUNT, bool USE_TOP>
+__device__ __forceinline__ bool fs_any_hit(const fs_bvh_view& bv, const float4* __restrict__ top,
+                                           fs_vec3 o, fs_vec3 d, float tmax,
+                                           fs_visit_counters* cnt, uint32_t* overflow)
+{
+    if (bv.n_tris == 0) return false;
+    const fs_ray_prep r = fs_prep_ray(o, d);
+    int stack[FS_STACK_SIZE];
+    int sp = 0;
+    const int SENTINEL = 0x7fffffff;
+    int node = USE_TOP ? FS_TOP_FLAG : 0;
+    FS_GUARD_DECL
+    while (node != SENTINEL) {
+        while (node >= 0 && node != SENTINEL) {
+            FS_GUARD_STEP
+            float4 n0, n1, n2, n3;
+            if (USE_TOP && (node & FS_TOP_FLAG)) {
+                const float4* p = top + (size_t)(node & ~FS_TOP_FLAG) * 4;
+                n0 = p[0]; n1 = p[1]; n2 = p[2]; n3 = p[3];
+            } else {
+                const float4* p = bv.nodes + (size_t)node * 4;
+                n0 = fs_ldg4(p); n1 = fs_ldg4(p + 1); n2 = fs_ldg4(p + 2); n3 = fs_ldg4(p + 3);
+            }
+            if (COUNT) cnt->nodes++;
+            bool h0, h1; float t0, t1;
+            fs_slab2(r, n0, n1, n2, tmax, h0, h1, t0, t1);
+            int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+            if (!h0 && !h1) {
+                node = sp ? stack[--sp] : SENTINEL;
+            } else {
+                node = h0 ? c0 : c1;
+                if (h0 && h1) {
+                    if (sp < FS_STACK_SIZE) stack[sp++] = c1; else *overflow = 1u;
+                }
+            }
+        }
+        while (node < 0) {
+            uint32_t payload = (uint32_t)(~node);
+            uint32_t first = payload >> 3, count = (payload & 7u) + 1u;
+            for (uint32_t i = 0; i < count; ++i) {
+                const float4* tp = bv.tris + (size_t)(first + i) * 3;
+                float4 a = fs_ldg4(tp), b = fs_ldg4(tp + 1), c = fs_ldg4(tp + 2);
+                if (COUNT) cnt->tris++;
+                float t;
+                if (fs_intersect_tri(o, d, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z), fs_mk(c.x, c.y, c.z), t)
+                    && t < tmax)
+                    return true;
+            }
+            node = sp ? stack[--sp] : SENTINEL;
+        }
+    }
+    return false;
+}
+
+#endif  // __CUDACC__

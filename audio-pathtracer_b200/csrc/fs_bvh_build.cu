@@ -1,0 +1,472 @@
+// fs_bvh_build.cu -- LBVH build on the device (one-time per fs_scene_commit).
+//
+// Pipeline (all kernels hand-written, no CUB/thrust):
+//   k_tri_bounds   per-triangle AABB + centroid-bounds reduction (ordered-uint atomics)
+//   k_morton       63-bit Morton code of the normalised AABB centre (21 bits per axis)
+//   radix sort     8 LSD passes of 8 bits over (u64 key, u32 triangle id): k_sort_hist,
+//                  k_sort_scan, k_sort_scatter (stable: warp match + ordered warp hand-over)
+//   k_pack         triangle records (v0,e1,e2,n) / original id / material in sorted order,
+//                  leaf boxes
+//   k_karras       binary radix tree topology (Karras 2012), ties broken by sorted index
+//   k_refit        bottom-up box fit with one atomic arrival counter per inner node
+//   k_emit         64 B traversal nodes holding both children's padded boxes; subtrees of
+//                  <= FS_LEAF_MAX triangles collapse into one leaf (ranges are contiguous)
+//   k_top_treelet  BFS copy of the top levels for shared-memory staging
+//
+// Replaces UAudioRayTracingSubsystem::RegisterGeometry (SUB.h:99-100) + the Chaos scene query
+// acceleration behind UWorld::LineTraceSingleByObjectType (SUB.cpp:252, 340).
+#include "fs_internal.h"
+
+namespace {
+
+__device__ __forceinline__ uint32_t f2ord(float f)
+{
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(uint32_t u)
+{
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
+// bounds[0..2] = min (ordered uint), bounds[3..5] = max of AABB centres
+__global__ void k_init_bounds(uint32_t* bounds)
+{
+    if (threadIdx.x < 3) bounds[threadIdx.x] = 0xffffffffu;
+    else if (threadIdx.x < 6) bounds[threadIdx.x] = 0u;
+}
+
+__global__ void k_tri_bounds(const float* __restrict__ verts, uint32_t n, float4* __restrict__ tlo,
+                             float4* __restrict__ thi, uint32_t* __restrict__ bounds,
+                             uint32_t* __restrict__ extent_ord)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float cx = 0, cy = 0, cz = 0, ext = 0;
+    bool valid = i < n;
+    if (valid) {
+        const float* p = verts + (size_t)i * 9;
+        float x0 = p[0], y0 = p[1], z0 = p[2], x1 = p[3], y1 = p[4], z1 = p[5], x2 = p[6], y2 = p[7], z2 = p[8];
+        float lx = fminf(x0, fminf(x1, x2)), ly = fminf(y0, fminf(y1, y2)), lz = fminf(z0, fminf(z1, z2));
+        float hx = fmaxf(x0, fmaxf(x1, x2)), hy = fmaxf(y0, fmaxf(y1, y2)), hz = fmaxf(z0, fmaxf(z1, z2));
+        tlo[i] = make_float4(lx, ly, lz, 0.f);
+        thi[i] = make_float4(hx, hy, hz, 0.f);
+        cx = 0.5f * lx + 0.5f * hx; cy = 0.5f * ly + 0.5f * hy; cz = 0.5f * lz + 0.5f * hz;
+        ext = fmaxf(fmaxf(fmaxf(fabsf(lx), fabsf(hx)), fmaxf(fabsf(ly), fabsf(hy))), fmaxf(fabsf(lz), fabsf(hz)));
+    }
+    // warp reduce then one atomic per warp
+    uint32_t m = __ballot_sync(0xffffffffu, valid);
+    if (!m) return;
+    float mnx = valid ? cx : INFINITY, mny = valid ? cy : INFINITY, mnz = valid ? cz : INFINITY;
+    float mxx = valid ? cx : -INFINITY, mxy = valid ? cy : -INFINITY, mxz = valid ? cz : -INFINITY;
+    for (int o = 16; o; o >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, o));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, o));
+        ext = fmaxf(ext, __shfl_xor_sync(0xffffffffu, ext, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(bounds + 0, f2ord(mnx)); atomicMin(bounds + 1, f2ord(mny)); atomicMin(bounds + 2, f2ord(mnz));
+        atomicMax(bounds + 3, f2ord(mxx)); atomicMax(bounds + 4, f2ord(mxy)); atomicMax(bounds + 5, f2ord(mxz));
+        atomicMax(extent_ord, f2ord(ext));
+    }
+}
+
+__device__ __forceinline__ uint64_t expand21(uint32_t v)
+{
+    uint64_t x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void k_morton(const float4* __restrict__ tlo, const float4* __restrict__ thi, uint32_t n,
+                         const uint32_t* __restrict__ bounds, uint64_t* __restrict__ keys,
+                         uint32_t* __restrict__ vals)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float bx = ord2f(bounds[0]), by = ord2f(bounds[1]), bz = ord2f(bounds[2]);
+    float ex = ord2f(bounds[3]) - bx, ey = ord2f(bounds[4]) - by, ez = ord2f(bounds[5]) - bz;
+    float4 lo = tlo[i], hi = thi[i];
+    float cx = 0.5f * lo.x + 0.5f * hi.x, cy = 0.5f * lo.y + 0.5f * hi.y, cz = 0.5f * lo.z + 0.5f * hi.z;
+    const float S = 2097151.0f;   // 2^21 - 1
+    float fx = ex > 0.f ? (cx - bx) / ex : 0.f, fy = ey > 0.f ? (cy - by) / ey : 0.f, fz = ez > 0.f ? (cz - bz) / ez : 0.f;
+    uint32_t qx = (uint32_t)fminf(fmaxf(fx * S, 0.f), S);
+    uint32_t qy = (uint32_t)fminf(fmaxf(fy * S, 0.f), S);
+    uint32_t qz = (uint32_t)fminf(fmaxf(fz * S, 0.f), S);
+    keys[i] = (expand21(qx) << 2) | (expand21(qy) << 1) | expand21(qz);
+    vals[i] = i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LSD radix sort, 8 bits per pass
+// ---------------------------------------------------------------------------------------------
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 8;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+
+__global__ void __launch_bounds__(SORT_THREADS)
+k_sort_hist(const uint64_t* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__ block_hist,
+            uint32_t n_blocks)
+{
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t base = blockIdx.x * SORT_TILE;
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; ++r) {
+        uint32_t i = base + r * SORT_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    block_hist[(size_t)threadIdx.x * n_blocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan of `total` counters, one CTA, chunked with a running carry
+__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t* __restrict__ data, uint32_t total)
+{
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < total; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = (i < total) ? data[i] : 0u;
+        uint32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((int)lane >= o) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_sums[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if ((int)lane >= o) w += y;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        uint32_t carry = carry_s;
+        uint32_t incl = x + (warp ? warp_sums[warp - 1] : 0u) + carry;
+        if (i < total) data[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = incl;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+k_sort_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+               uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
+               const uint32_t* __restrict__ block_hist, uint32_t n_blocks)
+{
+    __shared__ uint32_t base_s[256];
+    base_s[threadIdx.x] = block_hist[(size_t)threadIdx.x * n_blocks + blockIdx.x];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t tile = blockIdx.x * SORT_TILE;
+    for (int r = 0; r < SORT_ITEMS; ++r) {
+        uint32_t i = tile + r * SORT_THREADS + threadIdx.x;
+        bool valid = i < n;
+        uint64_t k = valid ? keys_in[i] : 0ull;
+        uint32_t v = valid ? vals_in[i] : 0u;
+        uint32_t digit = valid ? ((uint32_t)(k >> shift) & 255u) : 256u;
+        uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        uint32_t rank = __popc(peers & lt);
+        // warps take turns in index order so that equal digits keep their input order (stable)
+        for (uint32_t w = 0; w < SORT_THREADS / 32; ++w) {
+            if (warp == w) {
+                uint32_t pos = 0;
+                if (valid) pos = base_s[digit] + rank;
+                __syncwarp();
+                if (valid && rank == 0) base_s[digit] += __popc(peers);
+                if (valid) { keys_out[pos] = k; vals_out[pos] = v; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tree
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pack(const float* __restrict__ verts, const uint32_t* __restrict__ mats,
+                       const uint32_t* __restrict__ sorted_ids, uint32_t n,
+                       const float4* __restrict__ tlo, const float4* __restrict__ thi,
+                       float4* __restrict__ tris, uint32_t* __restrict__ tri_orig,
+                       uint32_t* __restrict__ tri_mat, float4* __restrict__ bb_lo, float4* __restrict__ bb_hi)
+{
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t id = sorted_ids[j];
+    const float* p = verts + (size_t)id * 9;
+    fs_vec3 v0 = fs_mk(p[0], p[1], p[2]);
+    fs_vec3 e1 = fs_mk(p[3] - p[0], p[4] - p[1], p[5] - p[2]);
+    fs_vec3 e2 = fs_mk(p[6] - p[0], p[7] - p[1], p[8] - p[2]);
+    fs_vec3 nn = fs_tri_normal(e1, e2);
+    tris[(size_t)j * 3 + 0] = make_float4(v0.x, v0.y, v0.z, nn.x);
+    tris[(size_t)j * 3 + 1] = make_float4(e1.x, e1.y, e1.z, nn.y);
+    tris[(size_t)j * 3 + 2] = make_float4(e2.x, e2.y, e2.z, nn.z);
+    tri_orig[j] = id;
+    tri_mat[j] = mats[id];
+    bb_lo[(n - 1) + j] = tlo[id];
+    bb_hi[(n - 1) + j] = thi[id];
+}
+
+__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, int i, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    uint64_t a = keys[i], b = keys[j];
+    if (a != b) return __clzll((long long)(a ^ b));
+    return 64 + __clz(i ^ j);
+}
+
+// node ids: inner i in [0, n-1), leaf j -> (n-1)+j
+__global__ void k_karras(const uint64_t* __restrict__ keys, int n, int2* __restrict__ children,
+                         int2* __restrict__ ranges, int* __restrict__ parent)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(keys, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    int left = (lo == gamma) ? (n - 1) + gamma : gamma;
+    int right = (hi == gamma + 1) ? (n - 1) + gamma + 1 : gamma + 1;
+    children[i] = make_int2(left, right);
+    ranges[i] = make_int2(lo, hi);
+    parent[left] = i;
+    parent[right] = i;
+    if (i == 0) parent[0] = -1;
+}
+
+__global__ void k_refit(int n, const int2* __restrict__ children, const int* __restrict__ parent,
+                        float4* bb_lo, float4* bb_hi, uint32_t* __restrict__ arrive)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int cur = parent[(n - 1) + j];
+    for (int guard = 0; cur >= 0 && guard < 4096; ++guard) {     // bounded: a tree is never this deep
+        __threadfence();
+        if (atomicAdd(&arrive[cur], 1u) == 0u) return;      // first arrival stops
+        __threadfence();
+        int2 c = children[cur];
+        float4 l0 = __ldcg(bb_lo + c.x), h0 = __ldcg(bb_hi + c.x);
+        float4 l1 = __ldcg(bb_lo + c.y), h1 = __ldcg(bb_hi + c.y);
+        __stcg(bb_lo + cur, make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.f));
+        __stcg(bb_hi + cur, make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f));
+        cur = parent[cur];
+    }
+}
+
+__device__ __forceinline__ int encode_child(int c, int n, const int2* __restrict__ ranges)
+{
+    if (c >= n - 1) {                       // leaf j, one triangle
+        uint32_t j = (uint32_t)(c - (n - 1));
+        return ~(int)((j << 3) | 0u);
+    }
+    int2 r = ranges[c];
+    int cnt = r.y - r.x + 1;
+    if (cnt <= FS_LEAF_MAX) return ~(int)(((uint32_t)r.x << 3) | (uint32_t)(cnt - 1));
+    return c;
+}
+
+// Conservative padding of a child box: 2^-15 of its largest |coordinate| (~512 float ulps at
+// that magnitude) + 1e-5 m.  It must cover (a) the rounding of the FMA slab test (~3 ulps of
+// max(|o|, |plane|)), (b) v0+e1 / v0+e2 differing from v1 / v2 by an ulp, (c) the rounding of
+// fs_intersect_tri's barycentrics, so that every triangle the exact-sequence test accepts is
+// reached.  tests/test_gpu_intersect.py checks BVH == brute force on the device.
+__device__ __forceinline__ float box_pad(float4 lo, float4 hi)
+{
+    float m = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))),
+                    fmaxf(fabsf(lo.z), fabsf(hi.z)));
+    return fmaf(m, 1.0f / 32768.0f, 1e-5f);
+}
+
+__global__ void k_emit(int n, const int2* __restrict__ children, const int2* __restrict__ ranges,
+                       const float4* __restrict__ bb_lo, const float4* __restrict__ bb_hi,
+                       float4* __restrict__ nodes)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int2 c = children[i];
+    float4 l0 = bb_lo[c.x], h0 = bb_hi[c.x], l1 = bb_lo[c.y], h1 = bb_hi[c.y];
+    float p0 = box_pad(l0, h0), p1 = box_pad(l1, h1);
+    int e0 = encode_child(c.x, n, ranges), e1 = encode_child(c.y, n, ranges);
+    nodes[(size_t)i * 4 + 0] = make_float4(l0.x - p0, h0.x + p0, l0.y - p0, h0.y + p0);
+    nodes[(size_t)i * 4 + 1] = make_float4(l1.x - p1, h1.x + p1, l1.y - p1, h1.y + p1);
+    nodes[(size_t)i * 4 + 2] = make_float4(l0.z - p0, h0.z + p0, l1.z - p1, h1.z + p1);
+    nodes[(size_t)i * 4 + 3] = make_float4(__int_as_float(e0), __int_as_float(e1), 0.f, 0.f);
+}
+
+// single-triangle scene: root whose second child is a far-away point box (never entered in practice)
+__global__ void k_emit_single(const float4* __restrict__ bb_lo, const float4* __restrict__ bb_hi,
+                              float4* __restrict__ nodes)
+{
+    float4 l0 = bb_lo[0], h0 = bb_hi[0];
+    float pad = box_pad(l0, h0);
+    const float F = 1e30f;
+    nodes[0] = make_float4(l0.x - pad, h0.x + pad, l0.y - pad, h0.y + pad);
+    nodes[1] = make_float4(F, F, F, F);
+    nodes[2] = make_float4(l0.z - pad, h0.z + pad, F, F);
+    nodes[3] = make_float4(__int_as_float(~0), __int_as_float(~0), 0.f, 0.f);
+}
+
+// BFS copy of the top of the tree; children inside the copy get FS_TOP_FLAG | local index.
+// One thread: the order of local-index assignment is sequential by construction (<= 2048 nodes).
+__global__ void k_top_treelet(const float4* __restrict__ nodes, uint32_t n_inner, uint32_t cap,
+                              float4* __restrict__ top, uint32_t* __restrict__ n_top_out, int* __restrict__ queue)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t qn = 0;
+    queue[qn++] = 0;
+    for (uint32_t p = 0; p < qn; ++p) {
+        const float4* src = nodes + (size_t)queue[p] * 4;
+        float4 n3 = src[3];
+        int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+        if (c0 >= 0 && qn < cap) { queue[qn] = c0; c0 = FS_TOP_FLAG | (int)qn; ++qn; }
+        if (c1 >= 0 && qn < cap) { queue[qn] = c1; c1 = FS_TOP_FLAG | (int)qn; ++qn; }
+        top[(size_t)p * 4 + 0] = src[0];
+        top[(size_t)p * 4 + 1] = src[1];
+        top[(size_t)p * 4 + 2] = src[2];
+        top[(size_t)p * 4 + 3] = make_float4(__int_as_float(c0), __int_as_float(c1), 0.f, 0.f);
+    }
+    *n_top_out = qn;
+    (void)n_inner;
+}
+
+// largest leaf / reachable inner-node statistics are cheap enough on one pass over ranges
+__global__ void k_leaf_stats(int n, const int2* __restrict__ ranges, uint32_t* __restrict__ max_leaf)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int cnt = ranges[i].y - ranges[i].x + 1;
+    if (cnt <= FS_LEAF_MAX) atomicMax(max_leaf, (uint32_t)cnt);
+}
+
+}  // namespace
+
+#define BCHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = e_; goto fail; } } while (0)
+
+cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* d_mats, uint64_t T64,
+                         fs_bvh_device* out, uint64_t* launches)
+{
+    cudaError_t err = cudaSuccess;
+    const uint32_t n = (uint32_t)T64;
+    fs_bvh_free(out);
+    out->n_tris = n;
+    if (n == 0) return cudaSuccess;
+    const uint32_t n_inner = n > 1 ? n - 1 : 1;
+    const uint32_t n_blocks_sort = (n + SORT_TILE - 1) / SORT_TILE;
+    float4 *tlo = nullptr, *thi = nullptr, *bb_lo = nullptr, *bb_hi = nullptr;
+    uint64_t *keys0 = nullptr, *keys1 = nullptr;
+    uint32_t *vals0 = nullptr, *vals1 = nullptr, *block_hist = nullptr, *misc = nullptr, *arrive = nullptr;
+    int2 *children = nullptr, *ranges = nullptr;
+    int *parent = nullptr, *queue = nullptr;
+    const int TPB = 256;
+    const uint32_t gb = (n + TPB - 1) / TPB;
+
+    BCHECK(cudaMalloc(&tlo, sizeof(float4) * n));
+    BCHECK(cudaMalloc(&thi, sizeof(float4) * n));
+    BCHECK(cudaMalloc(&bb_lo, sizeof(float4) * (2ull * n)));
+    BCHECK(cudaMalloc(&bb_hi, sizeof(float4) * (2ull * n)));
+    BCHECK(cudaMalloc(&keys0, 8ull * n));
+    BCHECK(cudaMalloc(&keys1, 8ull * n));
+    BCHECK(cudaMalloc(&vals0, 4ull * n));
+    BCHECK(cudaMalloc(&vals1, 4ull * n));
+    BCHECK(cudaMalloc(&block_hist, 4ull * 256 * n_blocks_sort));
+    BCHECK(cudaMalloc(&misc, 4 * 16));
+    BCHECK(cudaMalloc(&arrive, 4ull * n_inner));
+    BCHECK(cudaMalloc(&children, sizeof(int2) * n_inner));
+    BCHECK(cudaMalloc(&ranges, sizeof(int2) * n_inner));
+    BCHECK(cudaMalloc(&parent, 4ull * 2 * n));
+    BCHECK(cudaMalloc(&queue, 4ull * FS_TOP_CAP));
+    BCHECK(cudaMalloc(&out->nodes, sizeof(float4) * 4ull * n_inner));
+    BCHECK(cudaMalloc(&out->tris, sizeof(float4) * 3ull * n));
+    BCHECK(cudaMalloc(&out->tri_orig, 4ull * n));
+    BCHECK(cudaMalloc(&out->tri_mat, 4ull * n));
+    BCHECK(cudaMalloc(&out->top_nodes, sizeof(float4) * 4ull * FS_TOP_CAP));
+    out->n_inner = n_inner;
+
+    BCHECK(cudaMemsetAsync(misc, 0, 4 * 16, st));
+    BCHECK(cudaMemsetAsync(arrive, 0, 4ull * n_inner, st));
+    // misc[0..5] centre bounds, misc[6] extent (ordered), misc[7] n_top, misc[8] max_leaf
+    k_init_bounds<<<1, 32, 0, st>>>(misc); ++*launches;
+    k_tri_bounds<<<gb, TPB, 0, st>>>(d_verts, n, tlo, thi, misc, misc + 6); ++*launches;
+    k_morton<<<gb, TPB, 0, st>>>(tlo, thi, n, misc, keys0, vals0); ++*launches;
+    {
+        uint64_t *ki = keys0, *ko = keys1;
+        uint32_t *vi = vals0, *vo = vals1;
+        for (int pass = 0; pass < 8; ++pass) {
+            int shift = pass * 8;
+            k_sort_hist<<<n_blocks_sort, SORT_THREADS, 0, st>>>(ki, n, shift, block_hist, n_blocks_sort);
+            k_sort_scan<<<1, 1024, 0, st>>>(block_hist, 256u * n_blocks_sort);
+            k_sort_scatter<<<n_blocks_sort, SORT_THREADS, 0, st>>>(ki, vi, ko, vo, n, shift, block_hist, n_blocks_sort);
+            *launches += 3;
+            uint64_t* tk = ki; ki = ko; ko = tk;
+            uint32_t* tv = vi; vi = vo; vo = tv;
+        }
+        // 8 passes: result is back in keys0/vals0
+    }
+    k_pack<<<gb, TPB, 0, st>>>(d_verts, d_mats, vals0, n, tlo, thi, out->tris, out->tri_orig, out->tri_mat, bb_lo, bb_hi);
+    ++*launches;
+    if (n == 1) {
+        k_emit_single<<<1, 1, 0, st>>>(bb_lo, bb_hi, out->nodes); ++*launches;
+        out->max_leaf = 1;
+    } else {
+        k_karras<<<gb, TPB, 0, st>>>(keys0, (int)n, children, ranges, parent); ++*launches;
+        k_refit<<<gb, TPB, 0, st>>>((int)n, children, parent, bb_lo, bb_hi, arrive); ++*launches;
+        k_emit<<<gb, TPB, 0, st>>>((int)n, children, ranges, bb_lo, bb_hi, out->nodes); ++*launches;
+        k_leaf_stats<<<gb, TPB, 0, st>>>((int)n, ranges, misc + 8); ++*launches;
+    }
+    k_top_treelet<<<1, 32, 0, st>>>(out->nodes, n_inner, FS_TOP_CAP, out->top_nodes, misc + 7, queue); ++*launches;
+    BCHECK(cudaGetLastError());
+    {
+        uint32_t h[16];
+        BCHECK(cudaMemcpyAsync(h, misc, sizeof(h), cudaMemcpyDeviceToHost, st));
+        BCHECK(cudaStreamSynchronize(st));
+        out->n_top = h[7];
+        if (n > 1) out->max_leaf = h[8] ? h[8] : 1;
+        out->extent = ord2f(h[6]);
+    }
+fail:
+    cudaFree(tlo); cudaFree(thi); cudaFree(bb_lo); cudaFree(bb_hi); cudaFree(keys0); cudaFree(keys1);
+    cudaFree(vals0); cudaFree(vals1); cudaFree(block_hist); cudaFree(misc); cudaFree(arrive);
+    cudaFree(children); cudaFree(ranges); cudaFree(parent); cudaFree(queue);
+    if (err != cudaSuccess) fs_bvh_free(out);
+    return err;
+}
+
+void fs_bvh_free(fs_bvh_device* b)
+{
+    cudaFree(b->nodes); cudaFree(b->tris); cudaFree(b->tri_orig); cudaFree(b->tri_mat); cudaFree(b->top_nodes);
+    memset(b, 0, sizeof(*b));
+}

@@ -1,0 +1,134 @@
+// fs_internal.h -- context and cross-translation-unit declarations (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+#include <string>
+#include <atomic>
+#include <mutex>
+
+#include "../../include/frequensee.h"
+#include "fs_math.cuh"
+#include "fs_bvh.cuh"
+
+#define FS_TOP_CAP 1024          // nodes of the shared-memory treelet (64 KB)
+
+struct fs_bvh_device {
+    float4* nodes;
+    float4* tris;
+    uint32_t* tri_orig;
+    uint32_t* tri_mat;
+    float4* top_nodes;
+    uint32_t n_tris, n_inner, n_top, max_leaf;
+    float extent;
+};
+
+cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* d_mats, uint64_t n_tris,
+                         fs_bvh_device* out, uint64_t* launches);
+void fs_bvh_free(fs_bvh_device* b);
+
+// device-side counters of one trace call
+struct fs_dev_counters {
+    unsigned long long ext_rays, shadow_rays, connected, node_visits, tri_tests;
+    uint32_t overflow, pad;
+};
+
+// constant-ish parameters every wavefront kernel needs
+struct fs_trace_params {
+    fs_bvh_view bv;
+    const float4* top;          // global copy of the treelet (staged to smem by each CTA)
+    uint32_t n_top;
+    const float* refl_over_pi;  // [M][B]
+    uint32_t n_mats;
+    fs_eval_params ep;
+    uint32_t n_bins;
+    float bin_ms, rr_prob, eps_offset, eps_connect, sound_speed, energy_clamp, energy_gain;
+    uint32_t max_depth;
+    uint32_t seed_lo, seed_hi;
+    uint64_t n_paths;           // per source
+    uint64_t g_first;           // first global work index of this batch
+    uint32_t batch;             // path pairs in this batch
+    uint32_t cap;               // allocated path pairs (stride of per-node records = 2 * cap)
+    const float* src_pos;       // device [S][3]
+    float lis[3];
+    uint32_t flags;
+};
+
+struct fs_wave_buffers {
+    float4* st_pos[2];          // ping-pong subpath state: (pos.xyz, bits(sp_id))
+    float4* st_nrm[2];          //                          (nrm.xyz, bits(depth))
+    float4* rec;                // [max_depth+1][2*cap]: (d, bits(mat), prob, -)
+    float4* end_pos;            // [2*cap]: (end.xyz, bits(n_nodes))
+    uint32_t* conn_queue;       // [cap] path ids whose connection is unoccluded
+    float* conn_len;            // [cap] connection segment length
+    uint32_t* q_count;          // [max_depth+2] live subpaths per bounce, [max_depth+1] = connected
+    uint32_t* q_cursor;         // [max_depth+2] work cursors
+    uint32_t cap, depth_cap;
+};
+
+struct fs_conv_source {
+    bool active;
+    float2* fdl;                // [P][C][NF] input spectra ring
+    float2* H[2];               // double-buffered IR partition spectra [P][C][NF]
+    float* prev;                // [C][Bk] previous input block
+    float* ir;                  // [C][sample_rate] device IR of this source
+    std::atomic<int> h_published;   // which H buffer the audio thread uses
+    int h_valid;
+    uint32_t head;              // FDL head slot
+};
+
+struct fs_ctx {
+    fs_config cfg;
+    int device;
+    cudaStream_t own_stream, stream;
+    cudaStream_t conv_stream;
+    std::string err;
+    // scene
+    float* d_verts; uint32_t* d_tri_mat; uint64_t n_tris;
+    float* d_refl_over_pi; uint32_t n_mats;
+    bool mats_set, tris_set, committed;
+    fs_bvh_device bvh;
+    // trace
+    fs_wave_buffers wb;
+    unsigned long long* d_hist; uint32_t hist_sources;   // [S][B][K]
+    uint64_t hist_n_paths;
+    fs_dev_counters* d_counters;
+    float* d_src_pos; uint32_t src_cap;
+    fs_path_dbg* d_dbg; uint64_t dbg_cap;
+    fs_stats stats;
+    cudaEvent_t ev0, ev1; bool timed;
+    int sm_count;
+    // IR / conv
+    float* d_energy;            // [K] scratch
+    float* d_amp;               // [K]
+    float2* d_twiddle;          // [conv fft size / 2]
+    uint32_t fft_n, n_part, n_freq;
+    fs_conv_source* conv; uint32_t conv_cap;
+    float *d_conv_in, *d_conv_out; uint32_t conv_io_cap;   // device staging [blocks][frames][C]
+    float *h_pin_in, *h_pin_out;
+    std::mutex conv_mu;
+};
+
+// fs_wavefront.cu
+cudaError_t fs_wave_alloc(fs_ctx* ctx, uint32_t cap, uint32_t max_depth);
+void fs_wave_free(fs_wave_buffers* wb);
+cudaError_t fs_wave_trace_batch(fs_ctx* ctx, const fs_trace_params& tp, unsigned long long* d_hist,
+                                fs_path_dbg* d_dbg);
+cudaError_t fs_wave_reset_counters(fs_ctx* ctx);
+cudaError_t fs_wave_debug_rays(fs_ctx* ctx, const fs_trace_params& tp, const float* d_rays, const float* d_tmax,
+                               uint64_t n, float* d_t, uint32_t* d_tri, uint8_t* d_hit);
+
+// fs_ir.cu
+cudaError_t fs_ir_build(fs_ctx* ctx, const unsigned long long* d_hist_src, uint64_t n_paths,
+                        const float* d_energy_in, float* d_ir_out);
+
+// fs_conv.cu
+cudaError_t fs_conv_setup(fs_ctx* ctx);
+void fs_conv_teardown(fs_ctx* ctx);
+cudaError_t fs_conv_source_alloc(fs_ctx* ctx, uint32_t source);
+void fs_conv_source_free(fs_ctx* ctx, uint32_t source);
+cudaError_t fs_conv_update_ir(fs_ctx* ctx, uint32_t source, cudaStream_t st);
+cudaError_t fs_conv_run(fs_ctx* ctx, uint32_t source, const float* d_in, float* d_out, uint32_t n_blocks,
+                        cudaStream_t st);
+cudaError_t fs_conv_rfft(fs_ctx* ctx, const float* d_in, uint32_t n, float2* d_out, cudaStream_t st);

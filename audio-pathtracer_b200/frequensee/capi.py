@@ -1,0 +1,308 @@
+"""ctypes binding of the C-ABI in include/frequensee.h (libfrequensee.so, CUDA sm_100a).
+
+This is the only way Python reaches the product: there is no CPU fallback.  Loading fails loudly
+if the shared library is missing (run `python -c "import __graft_entry__ as g; g.build()"` or
+`make -C audio-pathtracer_b200/csrc`), and fs_create fails loudly if no B200-class GPU is usable.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(HERE), "lib", "libfrequensee.so")
+MAX_BANDS = 8
+
+FS_OK = 0
+FS_ERR_INVALID, FS_ERR_CUDA, FS_ERR_NOMEM, FS_ERR_STATE, FS_ERR_OVERFLOW = -1, -2, -3, -4, -5
+FLAG_COUNT_VISITS, FLAG_NO_SPLAT_AGG, FLAG_NO_TREELET, FLAG_BRUTE_FORCE = 1, 2, 4, 8
+
+# every symbol include/frequensee.h declares (tests/test_abi.py checks the library exports them all)
+ABI_SYMBOLS = [
+    "fs_default_config", "fs_create", "fs_destroy", "fs_last_error", "fs_set_stream", "fs_synchronize",
+    "fs_scene_set_triangles", "fs_scene_set_materials", "fs_scene_commit",
+    "fs_trace", "fs_trace_range_device", "fs_trace_range", "fs_trace_debug",
+    "fs_debug_closest_hits", "fs_debug_any_hits",
+    "fs_build_ir", "fs_build_ir_from_energy", "fs_set_histogram", "fs_set_histogram_device",
+    "fs_get_histogram", "fs_set_ir",
+    "fs_conv_init_source", "fs_conv_release_source", "fs_conv_process", "fs_conv_process_many",
+    "fs_debug_rfft", "fs_get_stats",
+]
+
+
+class Config(C.Structure):
+    """fs_config"""
+    _fields_ = [
+        ("n_bands", C.c_uint32), ("n_bins", C.c_uint32), ("bin_ms", C.c_float),
+        ("rr_prob", C.c_float), ("eps_offset", C.c_float), ("eps_connect", C.c_float),
+        ("min_seg", C.c_float), ("sound_speed", C.c_float), ("pdf_exponent", C.c_float),
+        ("energy_clamp", C.c_float), ("energy_gain", C.c_float),
+        ("air_absorption", C.c_float * MAX_BANDS),
+        ("sample_rate", C.c_uint32), ("n_channels", C.c_uint32),
+        ("ir_threshold", C.c_float), ("ir_lowpass", C.c_float),
+        ("conv_block", C.c_uint32), ("conv_clamp", C.c_uint32), ("conv_wet", C.c_float),
+        ("max_batch_paths", C.c_uint32), ("flags", C.c_uint32), ("device", C.c_int32),
+    ]
+
+
+class Stats(C.Structure):
+    """fs_stats"""
+    _fields_ = [("paths", C.c_uint64), ("ext_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
+                ("connected", C.c_uint64), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("bvh_nodes", C.c_uint64), ("bvh_max_leaf", C.c_uint64),
+                ("last_trace_ms", C.c_float), ("last_ir_ms", C.c_float)]
+
+    def as_dict(self):
+        return {k: (float(getattr(self, k)) if t is C.c_float else int(getattr(self, k)))
+                for k, t in self._fields_}
+
+
+PATH_DBG_DTYPE = np.dtype([
+    ("n_src_nodes", np.uint32), ("n_lis_nodes", np.uint32), ("connected", np.uint32),
+    ("bin", np.int32), ("delay_s", np.float32), ("total_dist", np.float32),
+    ("energy", np.float32, (MAX_BANDS,)), ("src_end", np.float32, (3,)), ("lis_end", np.float32, (3,)),
+])
+
+
+class FrequenSeeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("frequensee error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """dlopen libfrequensee.so and declare prototypes; raises if the library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libfrequensee.so not built at %s -- the product has no CPU fallback; "
+                          "run __graft_entry__.build()" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    L.fs_default_config.argtypes = [C.POINTER(Config)]
+    L.fs_default_config.restype = None
+    L.fs_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.fs_destroy.argtypes = [vp]
+    L.fs_destroy.restype = None
+    L.fs_last_error.argtypes = [vp]
+    L.fs_last_error.restype = C.c_char_p
+    L.fs_set_stream.argtypes = [vp, vp]
+    L.fs_synchronize.argtypes = [vp]
+    L.fs_scene_set_triangles.argtypes = [vp, vp, vp, u64]
+    L.fs_scene_set_materials.argtypes = [vp, vp, u32, u32]
+    L.fs_scene_commit.argtypes = [vp]
+    L.fs_trace.argtypes = [vp, vp, u32, vp, u64, u32, u64, vp]
+    L.fs_trace_range_device.argtypes = [vp, vp, u32, vp, u64, u64, u64, u32, u64, vp, i32]
+    L.fs_trace_range.argtypes = [vp, vp, u32, vp, u64, u64, u64, u32, u64, vp]
+    L.fs_trace_debug.argtypes = [vp, vp, u32, vp, u64, u64, u64, u32, u64, vp]
+    L.fs_debug_closest_hits.argtypes = [vp, vp, u64, vp, vp]
+    L.fs_debug_any_hits.argtypes = [vp, vp, vp, u64, vp]
+    L.fs_build_ir.argtypes = [vp, u32, vp]
+    L.fs_build_ir_from_energy.argtypes = [vp, u32, vp, vp]
+    L.fs_set_histogram.argtypes = [vp, vp, u32, u64]
+    L.fs_set_histogram_device.argtypes = [vp, vp, u32, u64]
+    L.fs_get_histogram.argtypes = [vp, vp]
+    L.fs_set_ir.argtypes = [vp, u32, vp]
+    L.fs_conv_init_source.argtypes = [vp, u32]
+    L.fs_conv_release_source.argtypes = [vp, u32]
+    L.fs_conv_process.argtypes = [vp, u32, vp, vp, u32]
+    L.fs_conv_process_many.argtypes = [vp, u32, vp, vp, u32, u32]
+    L.fs_debug_rfft.argtypes = [vp, vp, u32, vp]
+    L.fs_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    for n in ABI_SYMBOLS:
+        if n not in ("fs_default_config", "fs_destroy", "fs_last_error"):
+            getattr(L, n).restype = C.c_int
+    _lib = L
+    return L
+
+
+def default_config(**over):
+    cfg = Config()
+    load().fs_default_config(C.byref(cfg))
+    for k, v in over.items():
+        if k == "air_absorption":
+            for i, a in enumerate(v):
+                cfg.air_absorption[i] = a
+        else:
+            setattr(cfg, k, v)
+    return cfg
+
+
+class Context:
+    """Owns one fs_ctx.  Thin: argument marshalling + error codes -> exceptions."""
+
+    def __init__(self, cfg=None, **over):
+        self.L = load()
+        self.cfg = cfg if cfg is not None else default_config(**over)
+        h = C.c_void_p()
+        rc = self.L.fs_create(C.byref(self.cfg), C.byref(h))
+        if rc != FS_OK:
+            raise FrequenSeeError(rc, (self.L.fs_last_error(None) or b"").decode())
+        self.h = h
+        self.n_sources = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.fs_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != FS_OK:
+            raise FrequenSeeError(rc, (self.L.fs_last_error(self.h) or b"").decode())
+
+    # -- scene --
+    def set_scene(self, verts, tri_mat, absorption):
+        verts = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3, 3)
+        tri_mat = np.ascontiguousarray(tri_mat, dtype=np.uint32)
+        absorption = np.ascontiguousarray(absorption, dtype=np.float32)
+        if len(verts) != len(tri_mat):
+            raise ValueError("verts / tri_mat length mismatch")
+        self._ck(self.L.fs_scene_set_triangles(self.h, verts.ctypes.data, tri_mat.ctypes.data, len(verts)))
+        self._ck(self.L.fs_scene_set_materials(self.h, absorption.ctypes.data, absorption.shape[0],
+                                                absorption.shape[1]))
+        self._ck(self.L.fs_scene_commit(self.h))
+
+    def set_stream(self, stream_ptr):
+        self._ck(self.L.fs_set_stream(self.h, C.c_void_p(stream_ptr)))
+
+    def synchronize(self):
+        self._ck(self.L.fs_synchronize(self.h))
+
+    # -- trace --
+    @staticmethod
+    def _pos(src_pos, lis_pos):
+        src = np.ascontiguousarray(src_pos, dtype=np.float32).reshape(-1, 3)
+        lis = np.ascontiguousarray(lis_pos, dtype=np.float32).reshape(3)
+        return src, lis
+
+    def trace(self, src_pos, lis_pos, n_paths, max_depth, seed, want_hist=True):
+        src, lis = self._pos(src_pos, lis_pos)
+        S = len(src)
+        self.n_sources = S
+        hist = np.zeros((S, self.cfg.n_bands, self.cfg.n_bins), dtype=np.uint64) if want_hist else None
+        self._ck(self.L.fs_trace(self.h, src.ctypes.data, S, lis.ctypes.data, n_paths, max_depth, seed,
+                                 hist.ctypes.data if want_hist else None))
+        return hist
+
+    def trace_range(self, src_pos, lis_pos, n_paths, g_first, g_count, max_depth, seed, hist=None):
+        src, lis = self._pos(src_pos, lis_pos)
+        S = len(src)
+        self.n_sources = S
+        if hist is None:
+            hist = np.zeros((S, self.cfg.n_bands, self.cfg.n_bins), dtype=np.uint64)
+        self._ck(self.L.fs_trace_range(self.h, src.ctypes.data, S, lis.ctypes.data, n_paths, g_first, g_count,
+                                       max_depth, seed, hist.ctypes.data))
+        return hist
+
+    def trace_range_device(self, src_pos, lis_pos, n_paths, g_first, g_count, max_depth, seed, d_hist_ptr,
+                           zero_first=True):
+        src, lis = self._pos(src_pos, lis_pos)
+        self.n_sources = len(src)
+        self._ck(self.L.fs_trace_range_device(self.h, src.ctypes.data, len(src), lis.ctypes.data, n_paths,
+                                              g_first, g_count, max_depth, seed, C.c_void_p(d_hist_ptr),
+                                              int(zero_first)))
+
+    def trace_debug(self, src_pos, lis_pos, n_paths, g_first, g_count, max_depth, seed):
+        src, lis = self._pos(src_pos, lis_pos)
+        dbg = np.zeros(g_count, dtype=PATH_DBG_DTYPE)
+        self._ck(self.L.fs_trace_debug(self.h, src.ctypes.data, len(src), lis.ctypes.data, n_paths, g_first,
+                                       g_count, max_depth, seed, dbg.ctypes.data))
+        return dbg
+
+    def closest_hits(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 6)
+        t = np.zeros(len(rays), dtype=np.float32)
+        tri = np.zeros(len(rays), dtype=np.uint32)
+        self._ck(self.L.fs_debug_closest_hits(self.h, rays.ctypes.data, len(rays), t.ctypes.data, tri.ctypes.data))
+        return t, tri
+
+    def any_hits(self, rays, tmax):
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 6)
+        tmax = np.ascontiguousarray(tmax, dtype=np.float32)
+        out = np.zeros(len(rays), dtype=np.uint8)
+        self._ck(self.L.fs_debug_any_hits(self.h, rays.ctypes.data, tmax.ctypes.data, len(rays), out.ctypes.data))
+        return out.astype(bool)
+
+    # -- histogram / IR --
+    def set_histogram(self, hist, n_paths):
+        hist = np.ascontiguousarray(hist, dtype=np.uint64)
+        if hist.ndim == 2:
+            hist = hist[None]
+        self.n_sources = hist.shape[0]
+        self._ck(self.L.fs_set_histogram(self.h, hist.ctypes.data, hist.shape[0], n_paths))
+
+    def set_histogram_device(self, d_ptr, n_sources, n_paths):
+        self.n_sources = n_sources
+        self._ck(self.L.fs_set_histogram_device(self.h, C.c_void_p(d_ptr), n_sources, n_paths))
+
+    def get_histogram(self):
+        hist = np.zeros((self.n_sources, self.cfg.n_bands, self.cfg.n_bins), dtype=np.uint64)
+        self._ck(self.L.fs_get_histogram(self.h, hist.ctypes.data))
+        return hist
+
+    def build_ir(self, source=0, want_ir=True):
+        ir = np.zeros((self.cfg.n_channels, self.cfg.sample_rate), dtype=np.float32) if want_ir else None
+        self._ck(self.L.fs_build_ir(self.h, source, ir.ctypes.data if want_ir else None))
+        return ir
+
+    def build_ir_from_energy(self, energy, source=0):
+        energy = np.ascontiguousarray(energy, dtype=np.float32)
+        if energy.shape != (self.cfg.n_bins,):
+            raise ValueError("energy must have n_bins entries")
+        ir = np.zeros((self.cfg.n_channels, self.cfg.sample_rate), dtype=np.float32)
+        self._ck(self.L.fs_build_ir_from_energy(self.h, source, energy.ctypes.data, ir.ctypes.data))
+        return ir
+
+    def set_ir(self, ir, source=0):
+        ir = np.ascontiguousarray(ir, dtype=np.float32)
+        if ir.shape != (self.cfg.n_channels, self.cfg.sample_rate):
+            raise ValueError("ir must be [n_channels][sample_rate]")
+        self._ck(self.L.fs_set_ir(self.h, source, ir.ctypes.data))
+
+    # -- convolution --
+    def conv_init_source(self, source=0):
+        self._ck(self.L.fs_conv_init_source(self.h, source))
+
+    def conv_release_source(self, source=0):
+        self._ck(self.L.fs_conv_release_source(self.h, source))
+
+    def conv_process(self, block, source=0):
+        block = np.ascontiguousarray(block, dtype=np.float32)
+        out = np.zeros_like(block)
+        self._ck(self.L.fs_conv_process(self.h, source, block.ctypes.data, out.ctypes.data, block.shape[0]))
+        return out
+
+    def conv_process_many(self, blocks, source=0):
+        """blocks: [n_blocks][frames][C]"""
+        blocks = np.ascontiguousarray(blocks, dtype=np.float32)
+        out = np.zeros_like(blocks)
+        self._ck(self.L.fs_conv_process_many(self.h, source, blocks.ctypes.data, out.ctypes.data,
+                                             blocks.shape[1], blocks.shape[0]))
+        return out
+
+    def rfft(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.zeros((len(x) // 2 + 1, 2), dtype=np.float32)
+        self._ck(self.L.fs_debug_rfft(self.h, x.ctypes.data, len(x), out.ctypes.data))
+        return out[:, 0] + 1j * out[:, 1]
+
+    def stats(self):
+        st = Stats()
+        self._ck(self.L.fs_get_stats(self.h, C.byref(st)))
+        return st.as_dict()

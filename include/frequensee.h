@@ -1,0 +1,200 @@
+/*
+ * frequensee.h -- C-ABI of the B200-native FrequenSee propagation core.
+ *
+ * Drop-in boundary for ONE path of henreedev/audio-pathtracer: the per-frame BDPT sound
+ * propagation update, its impulse-response stage and the FFT convolution.  Plain pointers and
+ * sizes only: no Unreal types, no torch types.  Every entry point cites the reference
+ * interface it replaces (paths relative to Plugins/FrequenSee/Source/FrequenSee/):
+ *
+ *   SUB.h/.cpp = Public/AudioRayTracingSubsystem.h, Private/AudioRayTracingSubsystem.cpp
+ *   COMP.h/.cpp = Public/FrequenSeeAudioComponent.h, Private/FrequenSeeAudioComponent.cpp
+ *   REV.h/.cpp  = Private/FrequenSeeAudioReverbPlugin.{h,cpp}
+ *   GEO.h, MAT.h = Public/AcousticGeometryComponent.h, Public/AcousticMaterial.h
+ *
+ * Error convention: every function returns fs_status (0 = OK, negative = error);
+ * fs_last_error(ctx) returns a human-readable message for the last failure on that context.
+ * Nothing throws across this boundary.  There is NO CPU fallback: if no CUDA device is usable
+ * fs_create fails with FS_ERR_CUDA.
+ *
+ * Threading: fs_scene_*, fs_trace*, fs_build_ir* from one thread at a time per context (the
+ * reference's game thread, SUB.cpp:55); fs_conv_process may be called from another thread (the
+ * reference's audio render thread, REV.cpp:118); the IR hand-off between them is a
+ * double-buffered set of partition spectra published with an atomic index swap at a block
+ * boundary (the reference shares ImpulseBuffer with no synchronisation, COMP.cpp:378 vs
+ * REV.cpp:136).
+ *
+ * Ownership: the caller owns every host buffer passed in or out; the library copies at call
+ * time and retains nothing.  Device memory is owned by the context.
+ */
+#ifndef FREQUENSEE_H
+#define FREQUENSEE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FS_MAX_BANDS 8
+
+typedef enum fs_status {
+    FS_OK = 0,
+    FS_ERR_INVALID = -1,      /* bad argument / bad call order */
+    FS_ERR_CUDA = -2,         /* CUDA runtime failure (message has the CUDA error string) */
+    FS_ERR_NOMEM = -3,
+    FS_ERR_STATE = -4,        /* e.g. fs_trace before fs_scene_commit */
+    FS_ERR_OVERFLOW = -5      /* traversal stack overflow (BVH deeper than the kernel supports) */
+} fs_status;
+
+/* flags for fs_config.flags */
+#define FS_FLAG_COUNT_VISITS   1u   /* instrumented traversal: count BVH nodes popped / triangles tested */
+#define FS_FLAG_NO_SPLAT_AGG   2u   /* plain one-atomic-per-lane splat instead of warp-aggregated */
+#define FS_FLAG_NO_TREELET     4u   /* do not stage the top treelet in shared memory */
+#define FS_FLAG_BRUTE_FORCE    8u   /* test every triangle (debug/parity only, tiny scenes) */
+
+/* All tunables of the path in one POD: tier (i) UPROPERTYs (COMP.h:35-66) + tier (ii)
+ * compile-time constants of the reference, reference values as defaults
+ * (fs_default_config), units converted from UE centimetres to metres. */
+typedef struct fs_config {
+    uint32_t n_bands;          /* B, 1..8.  Reference reads one band, Absorption[2] (SUB.cpp:385) */
+    uint32_t n_bins;           /* K = NumBins = 1000 (COMP.h:137-138) */
+    float    bin_ms;           /* BinSizeMs = 1 (COMP.h:72) */
+    float    rr_prob;          /* RUSSIAN_ROULETTE_PROB = 0.9 (SUB.cpp:282); 1.0 disables */
+    float    eps_offset;       /* ImpactPoint + 0.1 * ImpactNormal (SUB.cpp:345): 1e-3 m */
+    float    eps_connect;      /* connection ray stops 0.1 short (SUB.cpp:253): 1e-3 m */
+    float    min_seg;          /* "NodeDistance < 1.0 -> continue" glitch guard (SUB.cpp:375): 1e-2 m */
+    float    sound_speed;      /* SoundSpeed = 343 (SUB.cpp:362) */
+    float    pdf_exponent;     /* powf(Node.Probability, 0.1) (SUB.cpp:398) */
+    float    energy_clamp;     /* FMath::Min(Energy, 1) (SUB.cpp:410) */
+    float    energy_gain;      /* Energy *= 10 (SUB.cpp:413) */
+    float    air_absorption[FS_MAX_BANDS]; /* per metre per band (AIR_ABSORPTION_FACTOR, SUB.cpp:395) */
+    uint32_t sample_rate;      /* SampleRate = 48000 (COMP.h:133) */
+    uint32_t n_channels;       /* NumChannels = 2 (COMP.h:135) */
+    float    ir_threshold;     /* kEnergyThreshold = 1e-6 (COMP.cpp:322) */
+    float    ir_lowpass;       /* FilterCoefficient = 0.25 (COMP.cpp:366) */
+    uint32_t conv_block;       /* AudioCallbackBufferFrameSize = 1024 (Config/DefaultEngine.ini:15) */
+    uint32_t conv_clamp;       /* clamp to +-1 (REV.cpp:162-168) */
+    float    conv_wet;         /* MixAlpha = 1 (REV.cpp:161) */
+    uint32_t max_batch_paths;  /* path pairs in flight per wavefront batch; 0 = default (1<<20) */
+    uint32_t flags;            /* FS_FLAG_* */
+    int32_t  device;           /* CUDA device ordinal; -1 = current device */
+} fs_config;
+
+/* counters of the last fs_trace* call; replaces the UE_LOG at SUB.cpp:232
+ * ("%d paths connected out of %d") */
+typedef struct fs_stats {
+    uint64_t paths;
+    uint64_t ext_rays;         /* extension rays traced (closest hit) */
+    uint64_t shadow_rays;      /* connection rays traced (any hit) */
+    uint64_t connected;
+    uint64_t node_visits;      /* only with FS_FLAG_COUNT_VISITS */
+    uint64_t tri_tests;        /* only with FS_FLAG_COUNT_VISITS */
+    uint64_t kernel_launches;  /* CUDA kernels launched by this context since fs_create */
+    uint64_t bvh_nodes;        /* inner nodes of the committed BVH */
+    uint64_t bvh_max_leaf;     /* triangles in the largest leaf */
+    float    last_trace_ms;    /* device time of the last fs_trace*, CUDA events on the context stream */
+    float    last_ir_ms;
+} fs_stats;
+
+/* per-path debug record, same layout as fso_path_dbg in oracle/fs_oracle.h */
+typedef struct fs_path_dbg {
+    uint32_t n_src_nodes, n_lis_nodes, connected;
+    int32_t  bin;
+    float    delay_s, total_dist;
+    float    energy[FS_MAX_BANDS];
+    float    src_end[3], lis_end[3];
+} fs_path_dbg;
+
+typedef struct fs_ctx fs_ctx;
+
+/* ---- lifetime ---------------------------------------------------------------------------
+ * replaces: UAudioRayTracingSubsystem construction + FFrequenSeeAudioReverbPlugin::Initialize
+ * (REV.cpp:74-102) + plugin registration in StartupModule (MOD.cpp:12-23) */
+void        fs_default_config(fs_config* cfg);
+int         fs_create(const fs_config* cfg, fs_ctx** out);
+void        fs_destroy(fs_ctx* ctx);
+const char* fs_last_error(const fs_ctx* ctx);      /* ctx may be NULL: last fs_create failure */
+/* run this context's work on an existing CUDA stream (cudaStream_t as void*), e.g. torch's
+ * current stream; NULL restores the context's own stream */
+int         fs_set_stream(fs_ctx* ctx, void* cuda_stream);
+int         fs_synchronize(fs_ctx* ctx);
+
+/* ---- scene -------------------------------------------------------------------------------
+ * replaces: UAudioRayTracingSubsystem::RegisterGeometry (SUB.h:99-100), the per-hit
+ * H.GetActor()->FindComponentByClass<UAcousticGeometryComponent>() (SUB.cpp:347) and
+ * UAcousticMaterial::Absorption (MAT.h:22-24).
+ * verts: [T][3][3] float32 metres; tri_material: [T]; absorption: [M][B] in [0,1]. */
+int fs_scene_set_triangles(fs_ctx* ctx, const float* verts, const uint32_t* tri_material, uint64_t n_tris);
+int fs_scene_set_materials(fs_ctx* ctx, const float* absorption, uint32_t n_materials, uint32_t n_bands);
+/* builds the BVH on the device (LBVH: Morton codes, radix sort, Karras topology, bottom-up fit) */
+int fs_scene_commit(fs_ctx* ctx);
+
+/* ---- BDPT update ---------------------------------------------------------------------------
+ * replaces: UAudioRayTracingSubsystem::UpdateSource (SUB.cpp:128-195) = GenerateFullPaths
+ * (:201-233) + ConnectSubpaths (:235-277) + EvaluatePath (:360-420) +
+ * UFrequenSeeAudioComponent::FlushEnergyBuffer / AddEnergyAtDelay (COMP.h:76-79, 87-91).
+ *
+ * Traces n_paths path pairs per source (global work index g = source * n_paths + i, Philox
+ * stream keyed by (seed, g)) and accumulates Q32.32 fixed-point energy into the context's
+ * device histogram [S][B][K], which is zeroed first ("Flush").  hist_out (host, [S][B][K]
+ * uint64) may be NULL to keep the result on the device only. */
+int fs_trace(fs_ctx* ctx, const float* src_pos /*[S][3]*/, uint32_t n_sources, const float lis_pos[3],
+             uint64_t n_paths, uint32_t max_depth, uint64_t seed, uint64_t* hist_out);
+
+/* Shard form for multi-GPU: traces only g in [g_first, g_first + g_count) and ACCUMULATES into
+ * a caller-provided DEVICE histogram d_hist [S][B][K] (uint64; e.g. a torch int64 tensor that
+ * is then summed over ranks with one NCCL reduce).  zero_first != 0 clears it before. */
+int fs_trace_range_device(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, const float lis_pos[3],
+                          uint64_t n_paths, uint64_t g_first, uint64_t g_count, uint32_t max_depth,
+                          uint64_t seed, void* d_hist, int zero_first);
+/* host-buffer shard form (accumulates into hist_inout) */
+int fs_trace_range(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, const float lis_pos[3],
+                   uint64_t n_paths, uint64_t g_first, uint64_t g_count, uint32_t max_depth,
+                   uint64_t seed, uint64_t* hist_inout);
+/* debug: one record per path pair of the range (slow; parity localisation only) */
+int fs_trace_debug(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, const float lis_pos[3],
+                   uint64_t n_paths, uint64_t g_first, uint64_t g_count, uint32_t max_depth,
+                   uint64_t seed, fs_path_dbg* dbg_out);
+/* single rays through the device BVH (parity tests of the intersector):
+ * rays: [n][6] (origin, direction); out_t [n] (inf on miss), out_tri [n] (0xffffffff on miss) */
+int fs_debug_closest_hits(fs_ctx* ctx, const float* rays, uint64_t n, float* out_t, uint32_t* out_tri);
+int fs_debug_any_hits(fs_ctx* ctx, const float* rays, const float* tmax, uint64_t n, uint8_t* out_hit);
+
+/* ---- impulse response -----------------------------------------------------------------------
+ * replaces: UFrequenSeeAudioComponent::ReconstructImpulseResponse (COMP.cpp:320-380) and
+ * GetImpulseResponse (COMP.h:113).  Uses the histogram of `source` left by the last fs_trace
+ * (or set by fs_set_histogram), normalised by 1/n_paths (SUB.cpp:164).  Also refreshes that
+ * source's convolver partition spectra.  ir_out: host [C][sample_rate] float, may be NULL. */
+int fs_build_ir(fs_ctx* ctx, uint32_t source, float* ir_out);
+/* seam 1 of the reference taken literally: EnergyBuffer float[K] -> IR (AddEnergyAtDelay users) */
+int fs_build_ir_from_energy(fs_ctx* ctx, uint32_t source, const float* energy /*[K]*/, float* ir_out);
+/* install an already reduced histogram (host [S][B][K]) and its path count, e.g. after an NCCL reduce */
+int fs_set_histogram(fs_ctx* ctx, const uint64_t* hist, uint32_t n_sources, uint64_t n_paths);
+int fs_set_histogram_device(fs_ctx* ctx, const void* d_hist, uint32_t n_sources, uint64_t n_paths);
+int fs_get_histogram(fs_ctx* ctx, uint64_t* hist_out /*[S][B][K]*/);
+/* install an external IR (host [C][sample_rate]) for `source`, e.g. a loaded saved_ir.txt
+ * (COMP.cpp:454-490) */
+int fs_set_ir(fs_ctx* ctx, uint32_t source, const float* ir);
+
+/* ---- convolution ----------------------------------------------------------------------------
+ * replaces: IAudioReverb::OnInitSource / OnReleaseSource / ProcessSourceAudio (REV.h:39-47,
+ * REV.cpp:104-170) and ConvolveFFT (REV.cpp:172-213), FCircularAudioBuffer (CIRC.cpp:43-75).
+ * Uniformly partitioned overlap-save: output block = history (*) current IR, history initially
+ * zero.  in/out: interleaved host [frames][C] float; frames must equal cfg.conv_block. */
+int fs_conv_init_source(fs_ctx* ctx, uint32_t source);
+int fs_conv_release_source(fs_ctx* ctx, uint32_t source);
+int fs_conv_process(fs_ctx* ctx, uint32_t source, const float* in_interleaved, float* out_interleaved,
+                    uint32_t frames);
+/* offline form: n_blocks consecutive callbacks in one call (config 3 bench); host buffers */
+int fs_conv_process_many(fs_ctx* ctx, uint32_t source, const float* in_interleaved,
+                         float* out_interleaved, uint32_t frames_per_block, uint32_t n_blocks);
+/* real FFT of n samples on the device FFT kernel (n power of two, 64..4096); out [n/2+1][2] */
+int fs_debug_rfft(fs_ctx* ctx, const float* in, uint32_t n, float* out_ri);
+
+/* ---- stats ------------------------------------------------------------------------------- */
+int fs_get_stats(fs_ctx* ctx, fs_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

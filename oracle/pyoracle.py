@@ -1,0 +1,301 @@
+"""ctypes binding of the CPU oracle (oracle/fs_oracle.c) and of oracle/_ref (the reference's
+vendored KissFFT compiled in place).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product (audio-pathtracer_b200/) never imports it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MAX_BANDS = 8
+
+
+class Config(C.Structure):
+    """fso_config (oracle/fs_oracle.h) -- layout-compatible with fs_config (include/frequensee.h)"""
+    _fields_ = [
+        ("n_bands", C.c_uint32), ("n_bins", C.c_uint32), ("bin_ms", C.c_float),
+        ("rr_prob", C.c_float), ("eps_offset", C.c_float), ("eps_connect", C.c_float),
+        ("min_seg", C.c_float), ("sound_speed", C.c_float), ("pdf_exponent", C.c_float),
+        ("energy_clamp", C.c_float), ("energy_gain", C.c_float),
+        ("air_absorption", C.c_float * MAX_BANDS),
+        ("sample_rate", C.c_uint32), ("n_channels", C.c_uint32),
+        ("ir_threshold", C.c_float), ("ir_lowpass", C.c_float),
+        ("conv_block", C.c_uint32), ("conv_clamp", C.c_uint32), ("conv_wet", C.c_float),
+        ("reserved", C.c_uint32 * 3),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [("paths", C.c_uint64), ("ext_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
+                ("connected", C.c_uint64), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+PATH_DBG_DTYPE = np.dtype([
+    ("n_src_nodes", np.uint32), ("n_lis_nodes", np.uint32), ("connected", np.uint32),
+    ("bin", np.int32), ("delay_s", np.float32), ("total_dist", np.float32),
+    ("energy", np.float32, (MAX_BANDS,)), ("src_end", np.float32, (3,)), ("lis_end", np.float32, (3,)),
+])
+
+
+def _has_fma():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return " fma " in (line + " ")
+    except OSError:
+        pass
+    return False
+
+
+def _build_if_needed():
+    libs = [os.path.join(HERE, n) for n in ("liboracle_fma.so", "liboracle_generic.so")]
+    src = os.path.join(HERE, "fs_oracle.c")
+    stale = any((not os.path.exists(p)) or os.path.getmtime(p) < os.path.getmtime(src) for p in libs)
+    if stale:
+        subprocess.check_call(["make", "-C", HERE, "-s"], stdout=subprocess.DEVNULL)
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _build_if_needed()
+        name = "liboracle_fma.so" if _has_fma() else "liboracle_generic.so"
+        L = C.CDLL(os.path.join(HERE, name))
+        fp = C.POINTER(C.c_float)
+        L.fso_default_config.argtypes = [C.POINTER(Config)]
+        L.fso_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
+        for n in ("fso_expf", "fso_logf", "fso_u01"):
+            getattr(L, n).restype = C.c_float
+        L.fso_expf.argtypes = [C.c_float]
+        L.fso_logf.argtypes = [C.c_float]
+        L.fso_u01.argtypes = [C.c_uint32]
+        L.fso_powf.restype = C.c_float
+        L.fso_powf.argtypes = [C.c_float, C.c_float]
+        L.fso_sincos_2pi.argtypes = [C.c_float, fp, fp]
+        L.fso_sample_sphere.argtypes = [C.c_float, C.c_float, fp]
+        L.fso_sample_cos_hemisphere.argtypes = [fp, C.c_float, C.c_float, fp, fp]
+        L.fso_intersect_tri.argtypes = [fp] * 6
+        L.fso_intersect_tri.restype = C.c_int
+        L.fso_scene_create.restype = C.c_void_p
+        L.fso_scene_create.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32,
+                                       C.c_uint32, C.c_int]
+        L.fso_scene_destroy.argtypes = [C.c_void_p]
+        L.fso_closest_hit.argtypes = [C.c_void_p, fp, fp, fp, C.POINTER(C.c_uint32)]
+        L.fso_closest_hit.restype = C.c_int
+        L.fso_any_hit.argtypes = [C.c_void_p, fp, fp, C.c_float]
+        L.fso_any_hit.restype = C.c_int
+        L.fso_trace.restype = C.c_int
+        L.fso_trace.argtypes = [C.c_void_p, C.POINTER(Config), C.c_void_p, C.c_uint32, C.c_void_p,
+                                C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64,
+                                C.c_void_p, C.POINTER(Stats), C.c_void_p, C.c_int]
+        L.fso_build_ir.argtypes = [C.POINTER(Config), C.c_void_p, C.c_uint64, C.c_void_p]
+        L.fso_build_ir_from_energy.argtypes = [C.POINTER(Config), C.c_void_p, C.c_void_p]
+        L.fso_conv_create.restype = C.c_void_p
+        L.fso_conv_create.argtypes = [C.POINTER(Config)]
+        L.fso_conv_destroy.argtypes = [C.c_void_p]
+        L.fso_conv_set_ir.argtypes = [C.c_void_p, C.c_void_p]
+        L.fso_conv_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.fso_conv_process.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def ref_lib():
+    """oracle/_ref/libref_kissfft.so, or None when it was never built (reference tree absent)."""
+    global _ref
+    if _ref is None:
+        p = os.path.join(HERE, "_ref", "libref_kissfft.so")
+        if not os.path.exists(p):
+            if os.path.isdir("/root/reference"):
+                subprocess.check_call(["make", "-C", HERE, "-s", "ref"], stdout=subprocess.DEVNULL)
+            if not os.path.exists(p):
+                return None
+        R = C.CDLL(p)
+        R.ref_conv_create.restype = C.c_void_p
+        R.ref_conv_create.argtypes = [C.c_int, C.c_int, C.c_int]
+        R.ref_conv_destroy.argtypes = [C.c_void_p]
+        R.ref_conv_fft_size.argtypes = [C.c_void_p]
+        R.ref_conv_fft_size.restype = C.c_int
+        R.ref_conv_set_ir.argtypes = [C.c_void_p, C.c_void_p]
+        R.ref_conv_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        R.ref_kiss_fftr.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        R.ref_kiss_fftri.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        _ref = R
+    return _ref
+
+
+def default_config(**over):
+    cfg = Config()
+    lib().fso_default_config(C.byref(cfg))
+    for k, v in over.items():
+        if k == "air_absorption":
+            for i, a in enumerate(v):
+                cfg.air_absorption[i] = a
+        else:
+            setattr(cfg, k, v)
+    return cfg
+
+
+def _f3(a):
+    return (C.c_float * 3)(*[float(x) for x in a])
+
+
+def philox(ctr, key):
+    out = (C.c_uint32 * 4)()
+    lib().fso_philox4x32_10((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out)
+    return [int(x) for x in out]
+
+
+def sincos_2pi(u):
+    c, s = C.c_float(), C.c_float()
+    lib().fso_sincos_2pi(u, C.byref(c), C.byref(s))
+    return c.value, s.value
+
+
+def sample_sphere(u1, u2):
+    d = (C.c_float * 3)()
+    lib().fso_sample_sphere(u1, u2, d)
+    return np.array(d[:], dtype=np.float32)
+
+
+def sample_cos_hemisphere(n, u1, u2):
+    d = (C.c_float * 3)()
+    ct = C.c_float()
+    lib().fso_sample_cos_hemisphere(_f3(n), u1, u2, d, C.byref(ct))
+    return np.array(d[:], dtype=np.float32), ct.value
+
+
+class Scene:
+    def __init__(self, verts, tri_mat, absorption, use_bvh=True):
+        self.verts = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3, 3)
+        self.tri_mat = np.ascontiguousarray(tri_mat, dtype=np.uint32)
+        self.absorption = np.ascontiguousarray(absorption, dtype=np.float32)
+        assert self.absorption.ndim == 2
+        self.n_mats, self.n_bands = self.absorption.shape
+        self.h = lib().fso_scene_create(self.verts.ctypes.data, self.tri_mat.ctypes.data,
+                                        len(self.verts), self.absorption.ctypes.data,
+                                        self.n_mats, self.n_bands, int(use_bvh))
+        assert self.h
+
+    def close(self):
+        if self.h:
+            lib().fso_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def closest_hit(self, o, d):
+        t = C.c_float()
+        tri = C.c_uint32()
+        hit = lib().fso_closest_hit(self.h, _f3(o), _f3(d), C.byref(t), C.byref(tri))
+        return (bool(hit), t.value, tri.value)
+
+    def any_hit(self, o, d, tmax):
+        return bool(lib().fso_any_hit(self.h, _f3(o), _f3(d), float(tmax)))
+
+    def trace(self, cfg, src_pos, lis_pos, n_paths, max_depth, seed, g_first=0, g_count=None,
+              n_threads=1, debug=False):
+        src = np.ascontiguousarray(src_pos, dtype=np.float32).reshape(-1, 3)
+        lis = np.ascontiguousarray(lis_pos, dtype=np.float32).reshape(3)
+        S = len(src)
+        if g_count is None:
+            g_count = S * n_paths - g_first
+        hist = np.zeros((S, cfg.n_bands, cfg.n_bins), dtype=np.uint64)
+        st = Stats()
+        dbg = np.zeros(g_count, dtype=PATH_DBG_DTYPE) if debug else None
+        rc = lib().fso_trace(self.h, C.byref(cfg), src.ctypes.data, S, lis.ctypes.data, n_paths,
+                             g_first, g_count, max_depth, seed, hist.ctypes.data, C.byref(st),
+                             dbg.ctypes.data if debug else None, n_threads)
+        if rc != 0:
+            raise RuntimeError("fso_trace failed: %d" % rc)
+        return (hist, st.as_dict(), dbg) if debug else (hist, st.as_dict())
+
+
+def build_ir(cfg, hist, n_paths):
+    hist = np.ascontiguousarray(hist, dtype=np.uint64)
+    out = np.zeros((cfg.n_channels, cfg.sample_rate), dtype=np.float32)
+    lib().fso_build_ir(C.byref(cfg), hist.ctypes.data, n_paths, out.ctypes.data)
+    return out
+
+
+def build_ir_from_energy(cfg, energy):
+    energy = np.ascontiguousarray(energy, dtype=np.float32)
+    out = np.zeros((cfg.n_channels, cfg.sample_rate), dtype=np.float32)
+    lib().fso_build_ir_from_energy(C.byref(cfg), energy.ctypes.data, out.ctypes.data)
+    return out
+
+
+class Conv:
+    """streaming direct-form double-precision convolver (semantics of REV.cpp:118-213)"""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.h = lib().fso_conv_create(C.byref(cfg))
+
+    def set_ir(self, ir):
+        ir = np.ascontiguousarray(ir, dtype=np.float32)
+        assert ir.shape == (self.cfg.n_channels, self.cfg.sample_rate)
+        lib().fso_conv_set_ir(self.h, ir.ctypes.data)
+
+    def process(self, block):
+        block = np.ascontiguousarray(block, dtype=np.float32)
+        out = np.zeros_like(block)
+        rc = lib().fso_conv_process(self.h, block.ctypes.data, out.ctypes.data, block.shape[0])
+        assert rc == 0
+        return out
+
+    def __del__(self):
+        if self.h:
+            lib().fso_conv_destroy(self.h)
+            self.h = None
+
+
+class RefKissConv:
+    """the reference's own convolution scheme on its own KissFFT (oracle/_ref)"""
+
+    def __init__(self, sample_rate=48000, frame=1024, channels=2):
+        self.R = ref_lib()
+        if self.R is None:
+            raise RuntimeError("oracle/_ref not built")
+        self.frame, self.channels, self.sample_rate = frame, channels, sample_rate
+        self.h = self.R.ref_conv_create(sample_rate, frame, channels)
+
+    @property
+    def fft_size(self):
+        return self.R.ref_conv_fft_size(self.h)
+
+    def set_ir(self, ir):
+        ir = np.ascontiguousarray(ir, dtype=np.float32)
+        self.R.ref_conv_set_ir(self.h, ir.ctypes.data)
+
+    def process(self, block, clamp=True):
+        block = np.ascontiguousarray(block, dtype=np.float32)
+        out = np.zeros_like(block)
+        self.R.ref_conv_process(self.h, block.ctypes.data, out.ctypes.data, int(clamp))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.R.ref_conv_destroy(self.h)
+            self.h = None
+
+
+def kiss_fftr(x):
+    R = ref_lib()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.zeros((len(x) // 2 + 1, 2), dtype=np.float32)
+    R.ref_kiss_fftr(len(x), x.ctypes.data, out.ctypes.data)
+    return out[:, 0] + 1j * out[:, 1]
