@@ -114,6 +114,7 @@ void fs_destroy(fs_ctx* ctx)
     cudaFree(ctx->d_verts); cudaFree(ctx->d_tri_mat); cudaFree(ctx->d_refl_over_pi);
     cudaFree(ctx->d_hist); cudaFree(ctx->d_counters); cudaFree(ctx->d_src_pos); cudaFree(ctx->d_dbg);
     cudaFree(ctx->d_amp); cudaFree(ctx->d_energy);
+    for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -255,6 +256,7 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
     fs_trace_params tp;
     fill_params(ctx, &tp, lis_pos, n_paths, max_depth, seed);
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    ctx->kev_used = 0; ctx->stats.extend_launches = 0;
     CK(fs_wave_reset_counters(ctx));
     for (uint64_t done = 0; done < g_count;) {
         uint64_t nb = g_count - done;
@@ -277,6 +279,17 @@ static int finish_stats(fs_ctx* ctx)
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stats.ext_rays = h.ext_rays; ctx->stats.shadow_rays = h.shadow_rays; ctx->stats.connected = h.connected;
     ctx->stats.node_visits = h.node_visits; ctx->stats.tri_tests = h.tri_tests;
+    ctx->stats.shadow_node_visits = h.shadow_node_visits; ctx->stats.shadow_tri_tests = h.shadow_tri_tests;
+    if (ctx->kev_used) {
+        float ext = 0.f, con = 0.f, evl = 0.f, ms;
+        for (size_t i = 0; i + 3 < ctx->kev_used; i += 4) {
+            if (cudaEventElapsedTime(&ms, ctx->kev[i], ctx->kev[i + 1]) == cudaSuccess) ext += ms;
+            if (cudaEventElapsedTime(&ms, ctx->kev[i + 1], ctx->kev[i + 2]) == cudaSuccess) con += ms;
+            if (cudaEventElapsedTime(&ms, ctx->kev[i + 2], ctx->kev[i + 3]) == cudaSuccess) evl += ms;
+        }
+        (void)cudaGetLastError();
+        ctx->stats.extend_ms = ext; ctx->stats.connect_ms = con; ctx->stats.eval_ms = evl;
+    }
     if (ctx->timed) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.last_trace_ms = ms;

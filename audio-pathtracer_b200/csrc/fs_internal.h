@@ -7,6 +7,7 @@
 #include <string>
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "../../include/frequensee.h"
 #include "fs_math.cuh"
@@ -31,6 +32,7 @@ void fs_bvh_free(fs_bvh_device* b);
 // device-side counters of one trace call
 struct fs_dev_counters {
     unsigned long long ext_rays, shadow_rays, connected, node_visits, tri_tests;
+    unsigned long long shadow_node_visits, shadow_tri_tests;
     uint32_t overflow, pad;
 };
 
@@ -98,6 +100,7 @@ struct fs_ctx {
     fs_path_dbg* d_dbg; uint64_t dbg_cap;
     fs_stats stats;
     cudaEvent_t ev0, ev1; bool timed;
+    std::vector<cudaEvent_t> kev; size_t kev_used;   // FS_FLAG_TIME_KERNELS: 4 events per batch
     int sm_count;
     // IR / conv
     float* d_energy;            // [K] scratch

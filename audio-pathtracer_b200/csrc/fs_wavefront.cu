@@ -78,7 +78,7 @@ __device__ __forceinline__ void stage_top(const fs_trace_params& tp, float4* sme
     __syncthreads();
 }
 
-__device__ __forceinline__ void flush_counters(fs_dev_counters* dc, fs_visit_counters vc)
+__device__ __forceinline__ void flush_counters(fs_dev_counters* dc, fs_visit_counters vc, bool shadow = false)
 {
     uint32_t n = vc.nodes, t = vc.tris;
     for (int o = 16; o; o >>= 1) {
@@ -88,6 +88,10 @@ __device__ __forceinline__ void flush_counters(fs_dev_counters* dc, fs_visit_cou
     if (lane_id() == 0) {
         atomicAdd(&dc->node_visits, (unsigned long long)n);
         atomicAdd(&dc->tri_tests, (unsigned long long)t);
+        if (shadow) {
+            atomicAdd(&dc->shadow_node_visits, (unsigned long long)n);
+            atomicAdd(&dc->shadow_tri_tests, (unsigned long long)t);
+        }
     }
 }
 
@@ -259,7 +263,7 @@ k_connect(const fs_trace_params tp, const fs_wave_buffers wb, fs_dev_counters* _
     }
     for (int o = 16; o; o >>= 1) rays_local += __shfl_xor_sync(0xffffffffu, rays_local, o);
     if (lane == 0 && rays_local) atomicAdd(&dc->shadow_rays, (unsigned long long)rays_local);
-    if (COUNT) flush_counters(dc, vc);
+    if (COUNT) flush_counters(dc, vc, true);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -387,6 +391,7 @@ __global__ void k_reset_queues(uint32_t* q_count, uint32_t* q_cursor, uint32_t n
     if (i < n) { q_count[i] = 0u; q_cursor[i] = 0u; }
     if (reset_dc && i == 0) {
         dc->ext_rays = 0; dc->shadow_rays = 0; dc->connected = 0; dc->node_visits = 0; dc->tri_tests = 0;
+        dc->shadow_node_visits = 0; dc->shadow_tri_tests = 0;
         dc->overflow = 0;
     }
 }
@@ -480,6 +485,17 @@ static cudaError_t launch_batch(fs_ctx* ctx, const fs_trace_params& tp, unsigned
         cudaFuncSetAttribute(k_extend<COUNT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_connect<COUNT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
+    const bool timing = (tp.flags & FS_FLAG_TIME_KERNELS) != 0;
+    cudaEvent_t* ev = nullptr;
+    if (timing) {
+        if (ctx->kev.size() < ctx->kev_used + 4) {
+            size_t old = ctx->kev.size();
+            ctx->kev.resize(ctx->kev_used + 4);
+            for (size_t i = old; i < ctx->kev.size(); ++i) cudaEventCreate(&ctx->kev[i]);
+        }
+        ev = &ctx->kev[ctx->kev_used];
+        ctx->kev_used += 4;
+    }
     const uint32_t nq = tp.max_depth + 2;
     k_reset_queues<<<(nq + 63) / 64, 64, 0, st>>>(wb.q_count, wb.q_cursor, nq, ctx->d_counters, 0);
     ++ctx->stats.kernel_launches;
@@ -488,6 +504,7 @@ static cudaError_t launch_batch(fs_ctx* ctx, const fs_trace_params& tp, unsigned
     uint32_t grid_ext = (uint32_t)(ctx->sm_count * occ_ext);
     uint32_t ctas_needed = (warps_needed + WF_THREADS / 32 - 1) / (WF_THREADS / 32);
     if (grid_ext > ctas_needed) grid_ext = ctas_needed ? ctas_needed : 1;
+    if (timing) cudaEventRecord(ev[0], st);
     if (tp.max_depth == 0) {
         k_init_ends<<<(2u * tp.batch + 255u) / 256u, 256, 0, st>>>(tp, wb);
         ++ctx->stats.kernel_launches;
@@ -495,16 +512,20 @@ static cudaError_t launch_batch(fs_ctx* ctx, const fs_trace_params& tp, unsigned
     for (uint32_t k = 0; k < tp.max_depth; ++k) {
         k_extend<COUNT, MODE><<<grid_ext, WF_THREADS, smem, st>>>(tp, wb, k, (int)(k & 1u), ctx->d_counters);
         ++ctx->stats.kernel_launches;
+        ++ctx->stats.extend_launches;
     }
+    if (timing) cudaEventRecord(ev[1], st);
     uint32_t grid_con = (uint32_t)(ctx->sm_count * occ_con);
     uint32_t ctas_con = ((tp.batch + 31u) / 32u + WF_THREADS / 32 - 1) / (WF_THREADS / 32);
     if (grid_con > ctas_con) grid_con = ctas_con ? ctas_con : 1;
     k_connect<COUNT, MODE><<<grid_con, WF_THREADS, smem, st>>>(tp, wb, ctx->d_counters, d_dbg);
     ++ctx->stats.kernel_launches;
+    if (timing) cudaEventRecord(ev[2], st);
     uint32_t grid_ev = (uint32_t)ctx->sm_count * 4u;
     if (grid_ev > ctas_con) grid_ev = ctas_con ? ctas_con : 1;
     k_eval<<<grid_ev, WF_THREADS, 0, st>>>(tp, wb, d_hist, ctx->d_counters, d_dbg);
     ++ctx->stats.kernel_launches;
+    if (timing) cudaEventRecord(ev[3], st);
     return cudaGetLastError();
 }
 

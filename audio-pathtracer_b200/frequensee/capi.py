@@ -15,7 +15,7 @@ MAX_BANDS = 8
 
 FS_OK = 0
 FS_ERR_INVALID, FS_ERR_CUDA, FS_ERR_NOMEM, FS_ERR_STATE, FS_ERR_OVERFLOW = -1, -2, -3, -4, -5
-FLAG_COUNT_VISITS, FLAG_NO_SPLAT_AGG, FLAG_NO_TREELET, FLAG_BRUTE_FORCE = 1, 2, 4, 8
+FLAG_COUNT_VISITS, FLAG_NO_SPLAT_AGG, FLAG_NO_TREELET, FLAG_BRUTE_FORCE, FLAG_TIME_KERNELS = 1, 2, 4, 8, 16
 
 # every symbol include/frequensee.h declares (tests/test_abi.py checks the library exports them all)
 ABI_SYMBOLS = [
@@ -49,8 +49,11 @@ class Stats(C.Structure):
     """fs_stats"""
     _fields_ = [("paths", C.c_uint64), ("ext_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("connected", C.c_uint64), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64),
+                ("shadow_node_visits", C.c_uint64), ("shadow_tri_tests", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("bvh_nodes", C.c_uint64), ("bvh_max_leaf", C.c_uint64),
-                ("last_trace_ms", C.c_float), ("last_ir_ms", C.c_float)]
+                ("last_trace_ms", C.c_float), ("last_ir_ms", C.c_float),
+                ("extend_ms", C.c_float), ("connect_ms", C.c_float), ("eval_ms", C.c_float),
+                ("extend_launches", C.c_uint32)]
 
     def as_dict(self):
         return {k: (float(getattr(self, k)) if t is C.c_float else int(getattr(self, k)))

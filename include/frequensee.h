@@ -51,6 +51,7 @@ typedef enum fs_status {
 #define FS_FLAG_NO_SPLAT_AGG   2u   /* plain one-atomic-per-lane splat instead of warp-aggregated */
 #define FS_FLAG_NO_TREELET     4u   /* do not stage the top treelet in shared memory */
 #define FS_FLAG_BRUTE_FORCE    8u   /* test every triangle (debug/parity only, tiny scenes) */
+#define FS_FLAG_TIME_KERNELS  16u   /* CUDA events around each kernel class -> fs_stats.*_ms */
 
 /* All tunables of the path in one POD: tier (i) UPROPERTYs (COMP.h:35-66) + tier (ii)
  * compile-time constants of the reference, reference values as defaults
@@ -87,13 +88,19 @@ typedef struct fs_stats {
     uint64_t ext_rays;         /* extension rays traced (closest hit) */
     uint64_t shadow_rays;      /* connection rays traced (any hit) */
     uint64_t connected;
-    uint64_t node_visits;      /* only with FS_FLAG_COUNT_VISITS */
-    uint64_t tri_tests;        /* only with FS_FLAG_COUNT_VISITS */
+    uint64_t node_visits;      /* only with FS_FLAG_COUNT_VISITS: BVH nodes popped, all rays */
+    uint64_t tri_tests;        /* only with FS_FLAG_COUNT_VISITS: triangles tested, all rays */
+    uint64_t shadow_node_visits; /* the part of node_visits spent on connection rays */
+    uint64_t shadow_tri_tests;
     uint64_t kernel_launches;  /* CUDA kernels launched by this context since fs_create */
     uint64_t bvh_nodes;        /* inner nodes of the committed BVH */
     uint64_t bvh_max_leaf;     /* triangles in the largest leaf */
     float    last_trace_ms;    /* device time of the last fs_trace*, CUDA events on the context stream */
     float    last_ir_ms;
+    float    extend_ms;        /* only with FS_FLAG_TIME_KERNELS: sum over the k_extend launches of the last trace */
+    float    connect_ms;       /*   "   k_connect */
+    float    eval_ms;          /*   "   k_eval (evaluate + splat) */
+    uint32_t extend_launches;  /* k_extend launches in the last trace */
 } fs_stats;
 
 /* per-path debug record, same layout as fso_path_dbg in oracle/fs_oracle.h */

@@ -1,0 +1,108 @@
+"""IR reconstruction and partitioned FFT convolution on the device vs the oracle.
+Floating point: tolerance is BASELINE.json's 1e-5 relative L2."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(np.asarray(a, np.float64) - np.asarray(b, np.float64)) /
+                 max(np.linalg.norm(np.asarray(b, np.float64)), 1e-30))
+
+
+def test_ir_from_trace_matches_oracle(fs, oracle):
+    from frequensee import scenes
+    sc = scenes.shoebox()
+    with fs.Context() as ctx:
+        ctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
+        h = ctx.trace(sc.sources, sc.listener, 16384, 8, 0x5EED)
+        ir = ctx.build_ir(0)
+    iro = oracle.build_ir(oracle.default_config(), h[0], 16384)
+    assert ir.shape == (2, 48000) and np.array_equal(ir[0], ir[1])
+    assert np.abs(iro).max() > 0 and _rel(ir, iro) < TOL
+
+
+def test_ir_from_energy_seam_and_edge_histograms(fs, oracle):
+    """seam 1 of the reference taken literally: EnergyBuffer float[1000] -> ReconstructImpulseResponse"""
+    rng = np.random.default_rng(2)
+    cfg = oracle.default_config()
+    with fs.Context() as ctx:
+        for e in (np.zeros(1000, np.float32),
+                  (rng.uniform(0, 0.05, 1000) * (rng.uniform(size=1000) < 0.3)).astype(np.float32),
+                  np.where(np.arange(1000) == 999, 0.02, 0).astype(np.float32),
+                  np.full(1000, 5e-7, np.float32)):
+            ir = ctx.build_ir_from_energy(e)
+            iro = oracle.build_ir_from_energy(cfg, e)
+            if not iro.any():
+                assert not ir.any()
+            else:
+                assert _rel(ir, iro) < TOL
+        h = np.zeros((2, 8, 1000), np.uint64)                      # set_histogram path, 2 sources
+        h[1, :, 100:400] = rng.integers(0, 2 ** 30, size=(8, 300)).astype(np.uint64)
+        ctx.set_histogram(h, 1000)
+        assert not ctx.build_ir(0).any()
+        assert _rel(ctx.build_ir(1), oracle.build_ir(cfg, h[1], 1000)) < TOL
+        assert np.array_equal(ctx.get_histogram(), h)
+
+
+def test_device_fft_vs_reference_kissfft_and_numpy(fs, oracle):
+    rng = np.random.default_rng(0)
+    with fs.Context() as ctx:
+        for n in (64, 256, 2048, 4096):
+            x = rng.uniform(-1, 1, n).astype(np.float32)
+            X = ctx.rfft(x)
+            assert _rel(X, np.fft.rfft(x.astype(np.float64))) < 1e-6
+            if oracle.ref_lib() is not None:                        # the reference's own kiss_fftr
+                assert _rel(X, oracle.kiss_fftr(x)) < TOL
+
+
+def test_convolution_matches_direct_form(fs, oracle):
+    """config 3 semantics: y_block = history (*) current IR (REV.cpp:172-213); unit impulse at frame 0
+    plus white noise; IR refreshed mid-stream takes effect at the next block boundary."""
+    rng = np.random.default_rng(3)
+    cfg = oracle.default_config()
+    def mk_ir(seed):
+        r = np.random.default_rng(seed)
+        ir = np.zeros((2, 48000), np.float32)
+        ir[:, :30000] = (r.normal(size=(2, 30000)) * np.exp(-np.arange(30000) / 6000.0) * 0.01).astype(np.float32)
+        ir[0, 47999] = 0.02
+        return ir
+    ir_a, ir_b = mk_ir(1), mk_ir(2)
+    x = rng.uniform(-0.5, 0.5, size=(60, 1024, 2)).astype(np.float32)
+    x[0, 0] = 1.0
+    cv = oracle.Conv(cfg); cv.set_ir(ir_a)
+    with fs.Context() as ctx:
+        ctx.conv_init_source(0); ctx.set_ir(ir_a, 0)
+        num = den = 0.0
+        ys = []
+        for b in range(60):
+            if b == 52:
+                cv.set_ir(ir_b); ctx.set_ir(ir_b, 0)
+            y = ctx.conv_process(x[b], 0); yo = cv.process(x[b])
+            ys.append(y)
+            num += float(((y - yo) ** 2).sum()); den += float((yo ** 2).sum())
+        assert den > 0 and (num / den) ** 0.5 < TOL
+        # offline form == streaming form
+        ctx.conv_init_source(1); ctx.set_ir(ir_a, 1)
+        many = ctx.conv_process_many(x[:52], 1)
+        assert np.array_equal(many, np.stack(ys[:52]))
+        # release + re-init clears the history
+        ctx.conv_release_source(1)
+        with pytest.raises(fs.FrequenSeeError):
+            ctx.conv_process(x[0], 1)
+        with pytest.raises(fs.FrequenSeeError):
+            ctx.conv_process(x[0, :512], 0)                          # wrong frame count
+
+
+def test_clamp_and_wet_mix(fs, oracle):
+    rng = np.random.default_rng(4)
+    ir = np.zeros((2, 48000), np.float32); ir[:, 0] = 3.0           # gain 3 -> clamps
+    x = rng.uniform(-0.9, 0.9, size=(2, 1024, 2)).astype(np.float32)
+    for over in (dict(), dict(conv_clamp=0), dict(conv_wet=0.25)):
+        cv = oracle.Conv(oracle.default_config(**over)); cv.set_ir(ir)
+        with fs.Context(**over) as ctx:
+            ctx.conv_init_source(0); ctx.set_ir(ir, 0)
+            for b in range(2):
+                assert np.allclose(ctx.conv_process(x[b], 0), cv.process(x[b]), rtol=1e-5, atol=2e-6)
