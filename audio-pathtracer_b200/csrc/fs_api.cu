@@ -3,6 +3,7 @@
 #include "fs_internal.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <new>
 #include <vector>
 
@@ -78,6 +79,10 @@ int fs_create(const fs_config* cfg, fs_ctx** out)
     ctx->cfg = *cfg;
     if (ctx->cfg.max_batch_paths == 0) ctx->cfg.max_batch_paths = 1u << 20;
     ctx->device = dev;
+    ctx->tune_refill = 8; ctx->tune_leaf_max = FS_LEAF_MAX; ctx->tune_tex = 0;
+    if (const char* e3 = getenv("FS_TUNE_TEX")) ctx->tune_tex = (uint32_t)atoi(e3);
+    if (const char* e1 = getenv("FS_TUNE_REFILL")) { int v = atoi(e1); if (v >= 1 && v <= 32) ctx->tune_refill = (uint32_t)v; }
+    if (const char* e2 = getenv("FS_TUNE_LEAF_MAX")) { int v = atoi(e2); if (v >= 1 && v <= 8) ctx->tune_leaf_max = (uint32_t)v; }
     dev_guard g(dev);
     int rc = FS_OK;
     do {
@@ -193,7 +198,8 @@ int fs_scene_commit(fs_ctx* ctx)
         for (uint64_t i = 0; i < ctx->n_tris; ++i)
             if (m[i] >= ctx->n_mats) return fail(ctx, FS_ERR_INVALID, "triangle material id out of range");
     }
-    CK(fs_bvh_build(ctx->stream, ctx->d_verts, ctx->d_tri_mat, ctx->n_tris, &ctx->bvh, &ctx->stats.kernel_launches));
+    CK(fs_bvh_build(ctx->stream, ctx->d_verts, ctx->d_tri_mat, ctx->n_tris, &ctx->bvh, &ctx->stats.kernel_launches,
+                    ctx->tune_leaf_max));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stats.bvh_nodes = ctx->bvh.n_inner;
     ctx->stats.bvh_max_leaf = ctx->bvh.max_leaf;
@@ -207,6 +213,9 @@ static void fill_params(fs_ctx* ctx, fs_trace_params* tp, const float lis[3], ui
 {
     const fs_config& c = ctx->cfg;
     memset(tp, 0, sizeof(*tp));
+    tp->bv.nodes_tex = (ctx->tune_tex && ctx->bvh.nodes_tex) ? (unsigned long long)ctx->bvh.nodes_tex : 0ull;
+    tp->bv.qnodes = ctx->bvh.qnodes;
+    for (int a = 0; a < 3; ++a) { tp->bv.qbase[a] = ctx->bvh.qbase[a]; tp->bv.qscale[a] = ctx->bvh.qscale[a]; }
     tp->bv.nodes = ctx->bvh.nodes; tp->bv.tris = ctx->bvh.tris; tp->bv.tri_orig = ctx->bvh.tri_orig;
     tp->bv.tri_mat = ctx->bvh.tri_mat; tp->bv.n_tris = ctx->bvh.n_tris; tp->bv.n_inner = ctx->bvh.n_inner;
     tp->top = ctx->bvh.top_nodes; tp->n_top = ctx->bvh.n_top;

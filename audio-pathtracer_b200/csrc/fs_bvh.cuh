@@ -7,10 +7,22 @@
 //             n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
 //             n3 = (child0, child1, -, -) as int bits.  child >= 0: inner node index;
 //                  child < 0: leaf, payload = ~child = (first_tri << 3) | (count - 1)
-//   tris  : float4[T][3]         48 B per triangle in leaf (Morton) order:
-//             (v0.xyz, n.x) (e1.xyz, n.y) (e2.xyz, n.z), n = unit geometric normal
-//   tri_orig : uint32[T]  original triangle id (tie-break key; closest hit = min (t, orig id))
-//   tri_mat  : uint32[T]  material id
+//   tris  : float4[T][4]         64 B per triangle in leaf (Morton) order, fetched as two 256-bit
+//             loads: (v0.xyz, n.x) (e1.xyz, n.y) | (e2.xyz, n.z) (bits(orig id), bits(material), -, -)
+//             n = unit geometric normal; orig id = tie-break key (closest hit = min (t, orig id))
+//   tri_orig : uint32[T]  original triangle id (copy, for the debug entry points)
+//   tri_mat  : uint32[T]  material id (copy)
+// Fetches are 128-bit ld.global.nc.  ncu shows the traversal bound by the L1TEX LSU data pipe
+// (l1tex__data_pipe_lsu_wavefronts ~ 88 %): a divergent warp load costs one wavefront per lane,
+// whatever its width -- 256-bit loads (LDG.E.ENL2.256) were measured and are not cheaper.
+//   qnodes : uint4[n_inner][2]   32 B per node, the production traversal format: child boxes
+//             quantised to 16 bits per coordinate on a scene-wide grid, rounded outward by one
+//             extra quantum:  u0 = (c0.lox | c0.hix << 16, c0.loy | c0.hiy << 16, c0.loz | c0.hiz << 16, child0)
+//                             u1 = (same for child 1, child1)
+//             A divergent warp load costs one L1TEX wavefront per lane per 16 B, and the traversal
+//             is bound by exactly that (ncu: l1tex__data_pipe_lsu_wavefronts ~ 88 %), so halving
+//             the node size halves the dominant cost.  Dequantisation is folded into the slab
+//             FMA: t = fma(2^23 + q, s, b') with s = qscale * idir, b' = (qbase - o) * idir - 2^23 s.
 // Boxes are padded at build time so that the slab test (FMA form, not bit-reproducible against
 // the oracle and not required to be) is conservative: any triangle whose exact-arithmetic
 // fs_intersect_tri() succeeds is reached.  The hit itself comes from fs_intersect_tri() only.
@@ -33,6 +45,9 @@
 #endif
 
 struct fs_bvh_view {
+    unsigned long long nodes_tex;   // cudaTextureObject_t over `nodes` (float4 texels), 0 if absent
+    const uint4* qnodes;            // 32 B quantised nodes (see below), same indexing as `nodes`
+    float qbase[3], qscale[3];      // world = qbase + q * qscale, q in [0, 65535]
     const float4* nodes;
     const float4* tris;
     const uint32_t* tri_orig;
@@ -51,6 +66,14 @@ __device__ __forceinline__ float4 fs_ldg4(const float4* p)
     asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
+}
+
+// 256-bit read-only load (LDG.E.256 on sm_100a); p must be 32-byte aligned
+__device__ __forceinline__ void fs_ldg8(const float4* p, float4& a, float4& b)
+{
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
 }
 
 struct fs_ray_prep {
@@ -136,19 +159,14 @@ __device__ __forceinline__ int fs_closest_hit(const fs_bvh_view& bv, const float
             uint32_t payload = (uint32_t)(~node);
             uint32_t first = payload >> 3, count = (payload & 7u) + 1u;
             for (uint32_t i = 0; i < count; ++i) {
-                const float4* tp = bv.tris + (size_t)(first + i) * 3;
-                float4 a = fs_ldg4(tp), b = fs_ldg4(tp + 1), c = fs_ldg4(tp + 2);
+                const float4* tp = bv.tris + (size_t)(first + i) * 4;
+                const float4 a = fs_ldg4(tp), b = fs_ldg4(tp + 1), c = fs_ldg4(tp + 2);
                 if (COUNT) cnt->tris++;
                 float t;
-                if (fs_intersect_tri(o, d, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z), fs_mk(c.x, c.y, c.z), t)) {
-                    if (t < bt) {
-                        bt = t; best = (int)(first + i); best_orig = 0xffffffffu;
-                    } else if (t == bt) {
-                        // tie: lower ORIGINAL id wins (acceleration-structure independent)
-                        if (best_orig == 0xffffffffu) best_orig = __ldg(bv.tri_orig + best);
-                        uint32_t oi = __ldg(bv.tri_orig + first + i);
-                        if (oi < best_orig) { best = (int)(first + i); best_orig = oi; }
-                    }
+                if (fs_intersect_tri(o, d, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z), fs_mk(c.x, c.y, c.z), t) && t <= bt) {
+                    // tie: lower ORIGINAL id wins (acceleration-structure independent)
+                    const uint32_t oi = __float_as_uint(fs_ldg4(tp + 3).x);
+                    if (t < bt || (t == bt && oi < best_orig)) { bt = t; best = (int)(first + i); best_orig = oi; }
                 }
             }
             node = sp ? stack[--sp] : SENTINEL;
@@ -199,8 +217,8 @@ __device__ __forceinline__ bool fs_any_hit(const fs_bvh_view& bv, const float4* 
             uint32_t payload = (uint32_t)(~node);
             uint32_t first = payload >> 3, count = (payload & 7u) + 1u;
             for (uint32_t i = 0; i < count; ++i) {
-                const float4* tp = bv.tris + (size_t)(first + i) * 3;
-                float4 a = fs_ldg4(tp), b = fs_ldg4(tp + 1), c = fs_ldg4(tp + 2);
+                const float4* tp = bv.tris + (size_t)(first + i) * 4;
+                const float4 a = fs_ldg4(tp), b = fs_ldg4(tp + 1), c = fs_ldg4(tp + 2);
                 if (COUNT) cnt->tris++;
                 float t;
                 if (fs_intersect_tri(o, d, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z), fs_mk(c.x, c.y, c.z), t)

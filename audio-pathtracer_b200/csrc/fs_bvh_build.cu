@@ -5,7 +5,7 @@
 //   k_morton       63-bit Morton code of the normalised AABB centre (21 bits per axis)
 //   radix sort     8 LSD passes of 8 bits over (u64 key, u32 triangle id): k_sort_hist,
 //                  k_sort_scan, k_sort_scatter (stable: warp match + ordered warp hand-over)
-//   k_pack         triangle records (v0,e1,e2,n) / original id / material in sorted order,
+//   k_pack         64 B triangle records (v0,e1,e2,n,orig id,material) in sorted order,
 //                  leaf boxes
 //   k_karras       binary radix tree topology (Karras 2012), ties broken by sorted index
 //   k_refit        bottom-up box fit with one atomic arrival counter per inner node
@@ -39,6 +39,8 @@ __global__ void k_init_bounds(uint32_t* bounds)
 {
     if (threadIdx.x < 3) bounds[threadIdx.x] = 0xffffffffu;
     else if (threadIdx.x < 6) bounds[threadIdx.x] = 0u;
+    if (threadIdx.x >= 9 && threadIdx.x < 12) bounds[threadIdx.x] = 0xffffffffu;   // scene box min
+    else if (threadIdx.x >= 12 && threadIdx.x < 15) bounds[threadIdx.x] = 0u;      // scene box max
 }
 
 __global__ void k_tri_bounds(const float* __restrict__ verts, uint32_t n, float4* __restrict__ tlo,
@@ -47,6 +49,7 @@ __global__ void k_tri_bounds(const float* __restrict__ verts, uint32_t n, float4
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float cx = 0, cy = 0, cz = 0, ext = 0;
+    float blx = INFINITY, bly = INFINITY, blz = INFINITY, bhx = -INFINITY, bhy = -INFINITY, bhz = -INFINITY;
     bool valid = i < n;
     if (valid) {
         const float* p = verts + (size_t)i * 9;
@@ -55,6 +58,7 @@ __global__ void k_tri_bounds(const float* __restrict__ verts, uint32_t n, float4
         float hx = fmaxf(x0, fmaxf(x1, x2)), hy = fmaxf(y0, fmaxf(y1, y2)), hz = fmaxf(z0, fmaxf(z1, z2));
         tlo[i] = make_float4(lx, ly, lz, 0.f);
         thi[i] = make_float4(hx, hy, hz, 0.f);
+        blx = lx; bly = ly; blz = lz; bhx = hx; bhy = hy; bhz = hz;
         cx = 0.5f * lx + 0.5f * hx; cy = 0.5f * ly + 0.5f * hy; cz = 0.5f * lz + 0.5f * hz;
         ext = fmaxf(fmaxf(fmaxf(fabsf(lx), fabsf(hx)), fmaxf(fabsf(ly), fabsf(hy))), fmaxf(fabsf(lz), fabsf(hz)));
     }
@@ -71,11 +75,16 @@ __global__ void k_tri_bounds(const float* __restrict__ verts, uint32_t n, float4
         mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
         mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, o));
         ext = fmaxf(ext, __shfl_xor_sync(0xffffffffu, ext, o));
+        blx = fminf(blx, __shfl_xor_sync(0xffffffffu, blx, o)); bly = fminf(bly, __shfl_xor_sync(0xffffffffu, bly, o));
+        blz = fminf(blz, __shfl_xor_sync(0xffffffffu, blz, o)); bhx = fmaxf(bhx, __shfl_xor_sync(0xffffffffu, bhx, o));
+        bhy = fmaxf(bhy, __shfl_xor_sync(0xffffffffu, bhy, o)); bhz = fmaxf(bhz, __shfl_xor_sync(0xffffffffu, bhz, o));
     }
     if ((threadIdx.x & 31) == 0) {
         atomicMin(bounds + 0, f2ord(mnx)); atomicMin(bounds + 1, f2ord(mny)); atomicMin(bounds + 2, f2ord(mnz));
         atomicMax(bounds + 3, f2ord(mxx)); atomicMax(bounds + 4, f2ord(mxy)); atomicMax(bounds + 5, f2ord(mxz));
         atomicMax(extent_ord, f2ord(ext));
+        atomicMin(bounds + 9, f2ord(blx)); atomicMin(bounds + 10, f2ord(bly)); atomicMin(bounds + 11, f2ord(blz));
+        atomicMax(bounds + 12, f2ord(bhx)); atomicMax(bounds + 13, f2ord(bhy)); atomicMax(bounds + 14, f2ord(bhz));
     }
 }
 
@@ -219,11 +228,13 @@ __global__ void k_pack(const float* __restrict__ verts, const uint32_t* __restri
     fs_vec3 e1 = fs_mk(p[3] - p[0], p[4] - p[1], p[5] - p[2]);
     fs_vec3 e2 = fs_mk(p[6] - p[0], p[7] - p[1], p[8] - p[2]);
     fs_vec3 nn = fs_tri_normal(e1, e2);
-    tris[(size_t)j * 3 + 0] = make_float4(v0.x, v0.y, v0.z, nn.x);
-    tris[(size_t)j * 3 + 1] = make_float4(e1.x, e1.y, e1.z, nn.y);
-    tris[(size_t)j * 3 + 2] = make_float4(e2.x, e2.y, e2.z, nn.z);
+    const uint32_t mat = mats[id];
+    tris[(size_t)j * 4 + 0] = make_float4(v0.x, v0.y, v0.z, nn.x);
+    tris[(size_t)j * 4 + 1] = make_float4(e1.x, e1.y, e1.z, nn.y);
+    tris[(size_t)j * 4 + 2] = make_float4(e2.x, e2.y, e2.z, nn.z);
+    tris[(size_t)j * 4 + 3] = make_float4(__uint_as_float(id), __uint_as_float(mat), 0.f, 0.f);
     tri_orig[j] = id;
-    tri_mat[j] = mats[id];
+    tri_mat[j] = mat;
     bb_lo[(n - 1) + j] = tlo[id];
     bb_hi[(n - 1) + j] = thi[id];
 }
@@ -287,7 +298,7 @@ __global__ void k_refit(int n, const int2* __restrict__ children, const int* __r
     }
 }
 
-__device__ __forceinline__ int encode_child(int c, int n, const int2* __restrict__ ranges)
+__device__ __forceinline__ int encode_child(int c, int n, const int2* __restrict__ ranges, int leaf_max)
 {
     if (c >= n - 1) {                       // leaf j, one triangle
         uint32_t j = (uint32_t)(c - (n - 1));
@@ -295,7 +306,7 @@ __device__ __forceinline__ int encode_child(int c, int n, const int2* __restrict
     }
     int2 r = ranges[c];
     int cnt = r.y - r.x + 1;
-    if (cnt <= FS_LEAF_MAX) return ~(int)(((uint32_t)r.x << 3) | (uint32_t)(cnt - 1));
+    if (cnt <= leaf_max) return ~(int)(((uint32_t)r.x << 3) | (uint32_t)(cnt - 1));
     return c;
 }
 
@@ -311,25 +322,66 @@ __device__ __forceinline__ float box_pad(float4 lo, float4 hi)
     return fmaf(m, 1.0f / 32768.0f, 1e-5f);
 }
 
+// Scene-wide 16-bit grid.  misc[9..14] = box of all triangle boxes; grid[0..2] = qbase, grid[3..5] = qscale.
+// The grid covers the (padded) scene box with 4 spare quanta on each side so that the outward
+// rounding below never clamps.
+__global__ void k_quant_grid(const uint32_t* __restrict__ bounds, float* __restrict__ grid)
+{
+    int a = threadIdx.x;
+    if (a >= 3) return;
+    float lo = ord2f(bounds[9 + a]), hi = ord2f(bounds[12 + a]);
+    float m = fmaxf(fabsf(lo), fabsf(hi));
+    float pad = fmaf(m, 1.0f / 32768.0f, 1e-5f) * 2.0f;
+    lo -= pad; hi += pad;
+    float scale = (hi - lo) / 65520.0f;
+    if (!(scale > 0.f)) scale = 1e-6f;
+    grid[a] = lo - 8.0f * scale;
+    grid[3 + a] = scale;
+}
+
+__device__ __forceinline__ uint32_t quant_lo(float v, float base, float scale)
+{
+    float q = floorf((v - base) / scale) - 1.0f;         // outward + one spare quantum
+    return (uint32_t)fminf(fmaxf(q, 0.0f), 65535.0f);
+}
+__device__ __forceinline__ uint32_t quant_hi(float v, float base, float scale)
+{
+    float q = ceilf((v - base) / scale) + 1.0f;
+    return (uint32_t)fminf(fmaxf(q, 0.0f), 65535.0f);
+}
+
 __global__ void k_emit(int n, const int2* __restrict__ children, const int2* __restrict__ ranges,
                        const float4* __restrict__ bb_lo, const float4* __restrict__ bb_hi,
-                       float4* __restrict__ nodes)
+                       float4* __restrict__ nodes, int leaf_max, const float* __restrict__ grid,
+                       uint4* __restrict__ qnodes)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     int2 c = children[i];
     float4 l0 = bb_lo[c.x], h0 = bb_hi[c.x], l1 = bb_lo[c.y], h1 = bb_hi[c.y];
     float p0 = box_pad(l0, h0), p1 = box_pad(l1, h1);
-    int e0 = encode_child(c.x, n, ranges), e1 = encode_child(c.y, n, ranges);
+    int e0 = encode_child(c.x, n, ranges, leaf_max), e1 = encode_child(c.y, n, ranges, leaf_max);
     nodes[(size_t)i * 4 + 0] = make_float4(l0.x - p0, h0.x + p0, l0.y - p0, h0.y + p0);
     nodes[(size_t)i * 4 + 1] = make_float4(l1.x - p1, h1.x + p1, l1.y - p1, h1.y + p1);
     nodes[(size_t)i * 4 + 2] = make_float4(l0.z - p0, h0.z + p0, l1.z - p1, h1.z + p1);
     nodes[(size_t)i * 4 + 3] = make_float4(__int_as_float(e0), __int_as_float(e1), 0.f, 0.f);
+    const float gx = grid[0], gy = grid[1], gz = grid[2], sx = grid[3], sy = grid[4], sz = grid[5];
+    uint4 q0, q1;
+    q0.x = quant_lo(l0.x - p0, gx, sx) | (quant_hi(h0.x + p0, gx, sx) << 16);
+    q0.y = quant_lo(l0.y - p0, gy, sy) | (quant_hi(h0.y + p0, gy, sy) << 16);
+    q0.z = quant_lo(l0.z - p0, gz, sz) | (quant_hi(h0.z + p0, gz, sz) << 16);
+    q0.w = (uint32_t)e0;
+    q1.x = quant_lo(l1.x - p1, gx, sx) | (quant_hi(h1.x + p1, gx, sx) << 16);
+    q1.y = quant_lo(l1.y - p1, gy, sy) | (quant_hi(h1.y + p1, gy, sy) << 16);
+    q1.z = quant_lo(l1.z - p1, gz, sz) | (quant_hi(h1.z + p1, gz, sz) << 16);
+    q1.w = (uint32_t)e1;
+    qnodes[(size_t)i * 2] = q0;
+    qnodes[(size_t)i * 2 + 1] = q1;
 }
 
 // single-triangle scene: root whose second child is a far-away point box (never entered in practice)
 __global__ void k_emit_single(const float4* __restrict__ bb_lo, const float4* __restrict__ bb_hi,
-                              float4* __restrict__ nodes)
+                              float4* __restrict__ nodes, const float* __restrict__ grid, uint4* __restrict__ qnodes)
 {
     float4 l0 = bb_lo[0], h0 = bb_hi[0];
     float pad = box_pad(l0, h0);
@@ -338,6 +390,15 @@ __global__ void k_emit_single(const float4* __restrict__ bb_lo, const float4* __
     nodes[1] = make_float4(F, F, F, F);
     nodes[2] = make_float4(l0.z - pad, h0.z + pad, F, F);
     nodes[3] = make_float4(__int_as_float(~0), __int_as_float(~0), 0.f, 0.f);
+    const float gx = grid[0], gy = grid[1], gz = grid[2], sx = grid[3], sy = grid[4], sz = grid[5];
+    uint4 q0, q1;
+    q0.x = quant_lo(l0.x - pad, gx, sx) | (quant_hi(h0.x + pad, gx, sx) << 16);
+    q0.y = quant_lo(l0.y - pad, gy, sy) | (quant_hi(h0.y + pad, gy, sy) << 16);
+    q0.z = quant_lo(l0.z - pad, gz, sz) | (quant_hi(h0.z + pad, gz, sz) << 16);
+    q0.w = (uint32_t)(~0);
+    q1.x = q1.y = q1.z = 0x0000ffffu;     // lo = 65535 > hi = 0: inverted box, never entered
+    q1.w = (uint32_t)(~0);
+    qnodes[0] = q0; qnodes[1] = q1;
 }
 
 // BFS copy of the top of the tree; children inside the copy get FS_TOP_FLAG | local index.
@@ -364,12 +425,12 @@ __global__ void k_top_treelet(const float4* __restrict__ nodes, uint32_t n_inner
 }
 
 // largest leaf / reachable inner-node statistics are cheap enough on one pass over ranges
-__global__ void k_leaf_stats(int n, const int2* __restrict__ ranges, uint32_t* __restrict__ max_leaf)
+__global__ void k_leaf_stats(int n, const int2* __restrict__ ranges, uint32_t* __restrict__ max_leaf, int leaf_max)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     int cnt = ranges[i].y - ranges[i].x + 1;
-    if (cnt <= FS_LEAF_MAX) atomicMax(max_leaf, (uint32_t)cnt);
+    if (cnt <= leaf_max) atomicMax(max_leaf, (uint32_t)cnt);
 }
 
 }  // namespace
@@ -377,8 +438,9 @@ __global__ void k_leaf_stats(int n, const int2* __restrict__ ranges, uint32_t* _
 #define BCHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = e_; goto fail; } } while (0)
 
 cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* d_mats, uint64_t T64,
-                         fs_bvh_device* out, uint64_t* launches)
+                         fs_bvh_device* out, uint64_t* launches, uint32_t leaf_max_u)
 {
+    const int leaf_max = (int)(leaf_max_u < 1 ? 1 : (leaf_max_u > 8 ? 8 : leaf_max_u));
     cudaError_t err = cudaSuccess;
     const uint32_t n = (uint32_t)T64;
     fs_bvh_free(out);
@@ -389,6 +451,7 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
     float4 *tlo = nullptr, *thi = nullptr, *bb_lo = nullptr, *bb_hi = nullptr;
     uint64_t *keys0 = nullptr, *keys1 = nullptr;
     uint32_t *vals0 = nullptr, *vals1 = nullptr, *block_hist = nullptr, *misc = nullptr, *arrive = nullptr;
+    float* grid = nullptr;
     int2 *children = nullptr, *ranges = nullptr;
     int *parent = nullptr, *queue = nullptr;
     const int TPB = 256;
@@ -403,14 +466,16 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
     BCHECK(cudaMalloc(&vals0, 4ull * n));
     BCHECK(cudaMalloc(&vals1, 4ull * n));
     BCHECK(cudaMalloc(&block_hist, 4ull * 256 * n_blocks_sort));
-    BCHECK(cudaMalloc(&misc, 4 * 16));
+    BCHECK(cudaMalloc(&misc, 4 * 16));   // [0..5] centre bounds [6] extent [7] n_top [8] max_leaf [9..14] scene box
     BCHECK(cudaMalloc(&arrive, 4ull * n_inner));
     BCHECK(cudaMalloc(&children, sizeof(int2) * n_inner));
     BCHECK(cudaMalloc(&ranges, sizeof(int2) * n_inner));
     BCHECK(cudaMalloc(&parent, 4ull * 2 * n));
     BCHECK(cudaMalloc(&queue, 4ull * FS_TOP_CAP));
+    BCHECK(cudaMalloc(&grid, sizeof(float) * 8));
     BCHECK(cudaMalloc(&out->nodes, sizeof(float4) * 4ull * n_inner));
-    BCHECK(cudaMalloc(&out->tris, sizeof(float4) * 3ull * n));
+    BCHECK(cudaMalloc(&out->qnodes, sizeof(uint4) * 2ull * n_inner));
+    BCHECK(cudaMalloc(&out->tris, sizeof(float4) * 4ull * n));
     BCHECK(cudaMalloc(&out->tri_orig, 4ull * n));
     BCHECK(cudaMalloc(&out->tri_mat, 4ull * n));
     BCHECK(cudaMalloc(&out->top_nodes, sizeof(float4) * 4ull * FS_TOP_CAP));
@@ -422,6 +487,7 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
     k_init_bounds<<<1, 32, 0, st>>>(misc); ++*launches;
     k_tri_bounds<<<gb, TPB, 0, st>>>(d_verts, n, tlo, thi, misc, misc + 6); ++*launches;
     k_morton<<<gb, TPB, 0, st>>>(tlo, thi, n, misc, keys0, vals0); ++*launches;
+    k_quant_grid<<<1, 32, 0, st>>>(misc, grid); ++*launches;
     {
         uint64_t *ki = keys0, *ko = keys1;
         uint32_t *vi = vals0, *vo = vals1;
@@ -439,34 +505,48 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
     k_pack<<<gb, TPB, 0, st>>>(d_verts, d_mats, vals0, n, tlo, thi, out->tris, out->tri_orig, out->tri_mat, bb_lo, bb_hi);
     ++*launches;
     if (n == 1) {
-        k_emit_single<<<1, 1, 0, st>>>(bb_lo, bb_hi, out->nodes); ++*launches;
+        k_emit_single<<<1, 1, 0, st>>>(bb_lo, bb_hi, out->nodes, grid, out->qnodes); ++*launches;
         out->max_leaf = 1;
     } else {
         k_karras<<<gb, TPB, 0, st>>>(keys0, (int)n, children, ranges, parent); ++*launches;
         k_refit<<<gb, TPB, 0, st>>>((int)n, children, parent, bb_lo, bb_hi, arrive); ++*launches;
-        k_emit<<<gb, TPB, 0, st>>>((int)n, children, ranges, bb_lo, bb_hi, out->nodes); ++*launches;
-        k_leaf_stats<<<gb, TPB, 0, st>>>((int)n, ranges, misc + 8); ++*launches;
+        k_emit<<<gb, TPB, 0, st>>>((int)n, children, ranges, bb_lo, bb_hi, out->nodes, leaf_max, grid, out->qnodes); ++*launches;
+        k_leaf_stats<<<gb, TPB, 0, st>>>((int)n, ranges, misc + 8, leaf_max); ++*launches;
+    }
+    {
+        cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = out->nodes;
+        rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+        rd.res.linear.sizeInBytes = sizeof(float4) * 4ull * n_inner;
+        cudaTextureDesc td; memset(&td, 0, sizeof(td));
+        td.readMode = cudaReadModeElementType;
+        if (cudaCreateTextureObject(&out->nodes_tex, &rd, &td, nullptr) != cudaSuccess) { out->nodes_tex = 0; (void)cudaGetLastError(); }
     }
     k_top_treelet<<<1, 32, 0, st>>>(out->nodes, n_inner, FS_TOP_CAP, out->top_nodes, misc + 7, queue); ++*launches;
     BCHECK(cudaGetLastError());
     {
-        uint32_t h[16];
+        uint32_t h[16];   // misc[0..15]
         BCHECK(cudaMemcpyAsync(h, misc, sizeof(h), cudaMemcpyDeviceToHost, st));
         BCHECK(cudaStreamSynchronize(st));
         out->n_top = h[7];
         if (n > 1) out->max_leaf = h[8] ? h[8] : 1;
         out->extent = ord2f(h[6]);
+        float hg[6];
+        BCHECK(cudaMemcpy(hg, grid, sizeof(hg), cudaMemcpyDeviceToHost));
+        for (int a = 0; a < 3; ++a) { out->qbase[a] = hg[a]; out->qscale[a] = hg[3 + a]; }
     }
 fail:
     cudaFree(tlo); cudaFree(thi); cudaFree(bb_lo); cudaFree(bb_hi); cudaFree(keys0); cudaFree(keys1);
     cudaFree(vals0); cudaFree(vals1); cudaFree(block_hist); cudaFree(misc); cudaFree(arrive);
-    cudaFree(children); cudaFree(ranges); cudaFree(parent); cudaFree(queue);
+    cudaFree(children); cudaFree(ranges); cudaFree(parent); cudaFree(queue); cudaFree(grid);
     if (err != cudaSuccess) fs_bvh_free(out);
     return err;
 }
 
 void fs_bvh_free(fs_bvh_device* b)
 {
-    cudaFree(b->nodes); cudaFree(b->tris); cudaFree(b->tri_orig); cudaFree(b->tri_mat); cudaFree(b->top_nodes);
+    if (b->nodes_tex) cudaDestroyTextureObject(b->nodes_tex);
+    cudaFree(b->nodes); cudaFree(b->qnodes); cudaFree(b->tris); cudaFree(b->tri_orig); cudaFree(b->tri_mat); cudaFree(b->top_nodes);
     memset(b, 0, sizeof(*b));
 }

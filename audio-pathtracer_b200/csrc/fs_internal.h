@@ -17,16 +17,19 @@
 
 struct fs_bvh_device {
     float4* nodes;
+    uint4* qnodes;
+    float qbase[3], qscale[3];
     float4* tris;
     uint32_t* tri_orig;
     uint32_t* tri_mat;
     float4* top_nodes;
+    cudaTextureObject_t nodes_tex;
     uint32_t n_tris, n_inner, n_top, max_leaf;
     float extent;
 };
 
 cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* d_mats, uint64_t n_tris,
-                         fs_bvh_device* out, uint64_t* launches);
+                         fs_bvh_device* out, uint64_t* launches, uint32_t leaf_max);
 void fs_bvh_free(fs_bvh_device* b);
 
 // device-side counters of one trace call
@@ -62,10 +65,11 @@ struct fs_wave_buffers {
     float4* st_nrm[2];          //                          (nrm.xyz, bits(depth))
     float4* rec;                // [max_depth+1][2*cap]: (d, bits(mat), prob, -)
     float4* end_pos;            // [2*cap]: (end.xyz, bits(n_nodes))
+    float2* hit;                // [2*cap]: closest-hit records (t, bits(sorted triangle index or -1))
     uint32_t* conn_queue;       // [cap] path ids whose connection is unoccluded
-    float* conn_len;            // [cap] connection segment length
-    uint32_t* q_count;          // [max_depth+2] live subpaths per bounce, [max_depth+1] = connected
-    uint32_t* q_cursor;         // [max_depth+2] work cursors
+    float* conn_len;            // [cap] connection segment length, indexed by path
+    uint32_t* q_count;          // [max_depth+4]: [k] rays of bounce k, [D+1] connected pairs, [D+2] shadow rays
+    uint32_t* q_cursor;         // [max_depth+4] work cursors of the persistent kernels
     uint32_t cap, depth_cap;
 };
 
@@ -102,6 +106,7 @@ struct fs_ctx {
     cudaEvent_t ev0, ev1; bool timed;
     std::vector<cudaEvent_t> kev; size_t kev_used;   // FS_FLAG_TIME_KERNELS: 4 events per batch
     int sm_count;
+    uint32_t tune_refill, tune_leaf_max, tune_tex;      // experiment knobs (env FS_TUNE_REFILL / FS_TUNE_LEAF_MAX)
     // IR / conv
     float* d_energy;            // [K] scratch
     float* d_amp;               // [K]

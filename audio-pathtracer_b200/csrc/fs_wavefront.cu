@@ -34,7 +34,7 @@ __device__ __forceinline__ int closest_brute(const fs_bvh_view& bv, fs_vec3 o, f
     int best = -1; uint32_t best_orig = 0xffffffffu;
     float bt = __int_as_float(0x7f800000);
     for (uint32_t i = 0; i < bv.n_tris; ++i) {
-        const float4* tp = bv.tris + (size_t)i * 3;
+        const float4* tp = bv.tris + (size_t)i * 4;
         float4 a = fs_ldg4(tp), b = fs_ldg4(tp + 1), c = fs_ldg4(tp + 2);
         float t;
         if (fs_intersect_tri(o, d, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z), fs_mk(c.x, c.y, c.z), t)) {
@@ -48,7 +48,7 @@ __device__ __forceinline__ int closest_brute(const fs_bvh_view& bv, fs_vec3 o, f
 __device__ __forceinline__ bool any_brute(const fs_bvh_view& bv, fs_vec3 o, fs_vec3 d, float tmax)
 {
     for (uint32_t i = 0; i < bv.n_tris; ++i) {
-        const float4* tp = bv.tris + (size_t)i * 3;
+        const float4* tp = bv.tris + (size_t)i * 4;
         float4 a = fs_ldg4(tp), b = fs_ldg4(tp + 1), c = fs_ldg4(tp + 2);
         float t;
         if (fs_intersect_tri(o, d, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z), fs_mk(c.x, c.y, c.z), t) && t < tmax)
@@ -162,7 +162,7 @@ k_extend(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, int in_
                 int tri = trace_closest<COUNT, MODE>(tp, smem_top, pos, dir, t, &vc, &ovf_dummy);
                 if (ovf_dummy) dc->overflow = 1u;
                 if (tri >= 0) {                          // SUB.cpp:343-348
-                    const float4* tq = tp.bv.tris + (size_t)tri * 3;
+                    const float4* tq = tp.bv.tris + (size_t)tri * 4;
                     fs_vec3 fn = fs_mk(fs_ldg4(tq).w, fs_ldg4(tq + 1).w, fs_ldg4(tq + 2).w);
                     if (fs_dot(fn, dir) > 0.0f) { fn.x = -fn.x; fn.y = -fn.y; fn.z = -fn.z; }
                     fs_vec3 np;
@@ -257,7 +257,7 @@ k_connect(const fs_trace_params tp, const fs_wave_buffers wb, fs_dev_counters* _
             if (connected) {
                 const uint32_t o = slot + __popc(m & ((1u << lane) - 1u));
                 wb.conn_queue[o] = p;
-                wb.conn_len[o] = len;
+                wb.conn_len[p] = len;
             }
         }
     }
@@ -312,7 +312,7 @@ k_eval(const fs_trace_params tp, const fs_wave_buffers wb, unsigned long long* _
         uint32_t s = 0, bin = 0;
         if (valid) {
             const uint32_t p = wb.conn_queue[j];
-            const float len = wb.conn_len[j];
+            const float len = wb.conn_len[p];
             const uint32_t sf = 2u * p, sb = 2u * p + 1u;
             const uint32_t nf = __float_as_uint(wb.end_pos[sf].w);
             const uint32_t nb = __float_as_uint(wb.end_pos[sb].w);
@@ -367,6 +367,443 @@ k_eval(const fs_trace_params tp, const fs_wave_buffers wb, unsigned long long* _
                     for (uint32_t b = 0; b < NBr; ++b) atomicAdd(h + (size_t)b * tp.n_bins, q[b]);
             }
         }
+    }
+}
+
+
+// =============================================================================================
+// Split wavefront (default path): shading/generation kernels with every lane busy, and PURE
+// traversal kernels with per-lane ray replacement.
+//
+// ncu on the fused k_extend showed smsp__thread_inst_executed_per_inst_executed = 7.5..8.9 of 32
+// (profiles/r1a_ncu_k_extend_summary.txt): lanes whose ray ended early idle until the slowest
+// lane of the warp finishes, and lanes at a leaf idle while others walk inner nodes.  Here
+//   k_shade_gen(k)    consumes the hits of bounce k-1 (node record, offset, termination) and
+//                     generates the rays of bounce k (Philox, Russian roulette, sampling) into a
+//                     ballot-compacted ray queue: coherent, all 32 lanes busy;
+//   k_trace_closest   persistent warps; a lane that retires its ray immediately pulls the next
+//                     one from the queue (one atomicAdd per warp refill), so a warp always walks
+//                     ~32 rays; "while-while" traversal with one postponed leaf per lane
+//                     (speculative traversal) and one triangle test per lane per leaf-phase step;
+//   k_connect_gen / k_trace_any  the same for the connection (shadow) rays.
+// Ray record (32 B): (origin.xyz, sp_id | tmax) (dir.xyz, pdf | path id); hit record 8 B (t, tri).
+// =============================================================================================
+constexpr int TR_THREADS = 256;
+#ifndef FS_TR_MINBLOCKS
+#define FS_TR_MINBLOCKS 1
+#endif
+// refill a warp once this many lanes are idle (kernel argument, default FS_REFILL_DEFAULT)
+#define FS_REFILL_DEFAULT 8u
+constexpr uint32_t FULLM = 0xffffffffu;
+#define TR_SENT 0x7fffffff
+
+__device__ __forceinline__ void leaf_range(int leafnode, uint32_t& tc, uint32_t& te)
+{
+    const uint32_t payload = (uint32_t)(~leafnode);
+    tc = payload >> 3;
+    te = tc + (payload & 7u) + 1u;
+}
+
+__global__ void __launch_bounds__(WF_THREADS)
+k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_dev_counters* __restrict__ dc)
+{
+    const uint32_t lane = lane_id();
+    const uint32_t count_in = (k == 0) ? 2u * tp.batch : wb.q_count[k - 1];
+    const int in = (int)((k + 1u) & 1u), out = (int)(k & 1u);
+    const float4* __restrict__ in_o = wb.st_pos[in];
+    const float4* __restrict__ in_d = wb.st_nrm[in];
+    float4* __restrict__ out_o = wb.st_pos[out];
+    float4* __restrict__ out_d = wb.st_nrm[out];
+    const uint32_t stride = 2u * wb.cap;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < count_in;
+         base += gridDim.x * blockDim.x) {
+        const uint32_t j = base + lane;
+        bool emit = false;
+        fs_vec3 pos = fs_mk(0.f, 0.f, 0.f), dir = fs_mk(0.f, 0.f, 0.f);
+        uint32_t sp_id = 0; float prob = 1.0f;
+        if (j < count_in) {
+            fs_vec3 nrm = fs_mk(0.f, 0.f, 0.f);
+            bool cont = true;
+            uint32_t nodes = 1;
+            if (k == 0) {                         // node 0 (SUB.cpp:287-291)
+                sp_id = j;
+                if (sp_id & 1u) pos = fs_mk(tp.lis[0], tp.lis[1], tp.lis[2]);
+                else {
+                    const uint64_t g0 = tp.g_first + (sp_id >> 1);
+                    const uint32_t s = (uint32_t)(g0 / tp.n_paths);
+                    pos = fs_mk(__ldg(tp.src_pos + 3 * s), __ldg(tp.src_pos + 3 * s + 1), __ldg(tp.src_pos + 3 * s + 2));
+                }
+            } else {
+                const float4 a = in_o[j], b = in_d[j];
+                const float2 h = wb.hit[j];
+                sp_id = __float_as_uint(a.w);
+                const fs_vec3 o = fs_mk(a.x, a.y, a.z), d = fs_mk(b.x, b.y, b.z);
+                const int tri = __float_as_int(h.y);
+                if (tri < 0) {                    // miss: FIX -> the subpath ends at its current node
+                    wb.end_pos[sp_id] = make_float4(o.x, o.y, o.z, __uint_as_float(k));
+                    cont = false;
+                } else {                          // SUB.cpp:343-348
+                    const float t = h.x;
+                    const float4* tq = tp.bv.tris + (size_t)tri * 4;
+                    fs_vec3 fn = fs_mk(fs_ldg4(tq).w, fs_ldg4(tq + 1).w, fs_ldg4(tq + 2).w);
+                    if (fs_dot(fn, d) > 0.0f) { fn.x = -fn.x; fn.y = -fn.y; fn.z = -fn.z; }
+                    pos.x = fmaf(tp.eps_offset, fn.x, fmaf(t, d.x, o.x));
+                    pos.y = fmaf(tp.eps_offset, fn.y, fmaf(t, d.y, o.y));
+                    pos.z = fmaf(tp.eps_offset, fn.z, fmaf(t, d.z, o.z));
+                    const fs_vec3 dl = fs_sub(pos, o);
+                    const float seg = sqrtf(fs_dot(dl, dl));
+                    const uint32_t mat = __ldg(tp.bv.tri_mat + tri);
+                    wb.rec[(size_t)k * stride + sp_id] = make_float4(seg, __uint_as_float(mat), b.w, 0.f);
+                    nrm = fn;
+                    nodes = k + 1;
+                    if (k >= tp.max_depth) {      // PARAM: ray budget per subpath exhausted
+                        wb.end_pos[sp_id] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(nodes));
+                        cont = false;
+                    }
+                }
+            }
+            if (cont) {
+                const uint64_t g = tp.g_first + (sp_id >> 1);
+                uint32_t r[4];
+                fs_philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), k, sp_id & 1u, tp.seed_lo, tp.seed_hi, r);
+                const float u0 = fs_u01(r[0]), u1 = fs_u01(r[1]), u2 = fs_u01(r[2]);
+                if (u0 < tp.rr_prob) {            // SUB.cpp:301-302
+                    if (k == 0) { dir = fs_sample_sphere(u1, u2); prob = FS_INV_4PI * tp.rr_prob; }
+                    else { float ct; dir = fs_sample_cos_hemisphere(nrm, u1, u2, ct); prob = (ct * FS_INV_PI) * tp.rr_prob; }
+                    emit = true;
+                } else {
+                    wb.end_pos[sp_id] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(nodes));
+                }
+            }
+        }
+        const uint32_t m = __ballot_sync(FULLM, emit);
+        if (m) {
+            uint32_t slot = 0;
+            if (lane == 0) { slot = atomicAdd(&wb.q_count[k], (uint32_t)__popc(m)); atomicAdd(&dc->ext_rays, (unsigned long long)__popc(m)); }
+            slot = __shfl_sync(FULLM, slot, 0);
+            if (emit) {
+                const uint32_t o = slot + __popc(m & ((1u << lane) - 1u));
+                out_o[o] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(sp_id));
+                out_d[o] = make_float4(dir.x, dir.y, dir.z, prob);
+            }
+        }
+    }
+}
+
+// per-lane traversal state shared by the two trace kernels
+struct tr_state {
+    fs_vec3 o, d;
+    float sx, sy, sz, bx, by, bz;       // t(q) = fma(2^23 + q, s, b): dequantisation folded into the slab test
+    int node, leaf, sp;
+    uint32_t tc, te;
+};
+
+__device__ __forceinline__ void tr_init(tr_state& s, const fs_bvh_view& bv, fs_vec3 o, fs_vec3 d)
+{
+    const fs_ray_prep r = fs_prep_ray(o, d);
+    s.o = o; s.d = d;
+    s.sx = bv.qscale[0] * r.idx; s.sy = bv.qscale[1] * r.idy; s.sz = bv.qscale[2] * r.idz;
+    // b' = (qbase - o) * idir - 2^23 * s; its rounding error is <= half a quantum, which the
+    // extra quantum of outward rounding at build time covers
+    s.bx = fmaf(-8388608.0f, s.sx, (bv.qbase[0] - o.x) * r.idx);
+    s.by = fmaf(-8388608.0f, s.sy, (bv.qbase[1] - o.y) * r.idy);
+    s.bz = fmaf(-8388608.0f, s.sz, (bv.qbase[2] - o.z) * r.idz);
+    s.node = bv.n_tris ? 0 : TR_SENT; s.leaf = 0; s.sp = 0; s.tc = 0; s.te = 0;
+}
+
+// 2^23 + (16 bits of w chosen by the selector) as a float: one PRMT.  0x7410 = low half, 0x7432 = high half
+__device__ __forceinline__ float q_sel(uint32_t w, uint32_t sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)); }
+// 2^23 + (low / high 16 bits of w) as a float: one PRMT
+__device__ __forceinline__ float q_lo16(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7410)); }
+__device__ __forceinline__ float q_hi16(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7432)); }
+
+__device__ __forceinline__ uint4 ldg_u4(const uint4* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// one inner-node step; tlimit = current closest t (or tmax for shadow rays)
+// Speculative traversal (Aila & Laine): the first leaf a lane reaches is POSTPONED and the lane
+// keeps walking; a second leaf makes it wait (node stays < 0) for the warp's triangle phase.
+__device__ __forceinline__ void tr_settle(tr_state& s, const int* stack)
+{
+    if (s.node < 0 && s.leaf == 0) {            // one postponed leaf; a second one makes the lane wait
+        s.leaf = s.node;
+        s.node = s.sp ? stack[--s.sp] : TR_SENT;
+    }
+}
+
+template <bool ORDERED, int TEX>
+__device__ __forceinline__ void tr_node_step(const fs_bvh_view& bv, tr_state& s, int* stack, float tlimit,
+                                             uint32_t* overflow)
+{
+    const uint4* p = bv.qnodes + (size_t)s.node * 2;
+    const uint4 u0 = ldg_u4(p), u1 = ldg_u4(p + 1);
+    // near/far planes picked by the ray octant: no per-axis min/max, 4 FMNMX(3) per child
+    // ray octant (sign of s = sign of the direction): with a negative direction the HIGH plane is entered first
+    const uint32_t nx = (s.sx < 0.0f) ? 0x7432u : 0x7410u, ny = (s.sy < 0.0f) ? 0x7432u : 0x7410u,
+                   nz = (s.sz < 0.0f) ? 0x7432u : 0x7410u;
+    const uint32_t fx = nx ^ 0x0022u, fy = ny ^ 0x0022u, fz = nz ^ 0x0022u;
+    const float t0 = fmaxf(fmaxf(fmaxf(fmaf(q_sel(u0.x, nx), s.sx, s.bx), fmaf(q_sel(u0.y, ny), s.sy, s.by)),
+                                 fmaf(q_sel(u0.z, nz), s.sz, s.bz)), 0.0f);
+    const float e0 = fminf(fminf(fminf(fmaf(q_sel(u0.x, fx), s.sx, s.bx), fmaf(q_sel(u0.y, fy), s.sy, s.by)),
+                                 fmaf(q_sel(u0.z, fz), s.sz, s.bz)), tlimit);
+    const float t1 = fmaxf(fmaxf(fmaxf(fmaf(q_sel(u1.x, nx), s.sx, s.bx), fmaf(q_sel(u1.y, ny), s.sy, s.by)),
+                                 fmaf(q_sel(u1.z, nz), s.sz, s.bz)), 0.0f);
+    const float e1 = fminf(fminf(fminf(fmaf(q_sel(u1.x, fx), s.sx, s.bx), fmaf(q_sel(u1.y, fy), s.sy, s.by)),
+                                 fmaf(q_sel(u1.z, fz), s.sz, s.bz)), tlimit);
+    const bool h0 = t0 <= e0, h1 = t1 <= e1;
+    const int c0 = (int)u0.w, c1 = (int)u1.w;
+    if (!h0 && !h1) {
+        s.node = s.sp ? stack[--s.sp] : TR_SENT;
+    } else {
+        s.node = h0 ? c0 : c1;
+        if (h0 && h1) {
+            int far_ = c1;
+            if (ORDERED && t1 < t0) { far_ = c0; s.node = c1; }
+            if (s.sp < FS_STACK_SIZE) stack[s.sp++] = far_; else *overflow = 1u;
+#if defined(FS_PREFETCH_FAR)
+            // the pushed subtree is visited later: pull its first record towards L1 now
+            const void* pf = far_ >= 0 ? (const void*)(bv.qnodes + (size_t)far_ * 2)
+                                       : (const void*)(bv.tris + (size_t)(((uint32_t)(~far_)) >> 3) * 4);
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(pf));
+#endif
+        }
+    }
+    tr_settle(s, stack);
+}
+
+// after a triangle step that exhausted the open range: open the postponed leaf, then re-settle
+__device__ __forceinline__ void tr_next_leaf(tr_state& s, const int* stack)
+{
+    if (s.tc == s.te) {
+        if (s.leaf != 0) { leaf_range(s.leaf, s.tc, s.te); s.leaf = 0; tr_settle(s, stack); }
+    }
+}
+
+template <bool COUNT, int TEX>
+__global__ void __launch_bounds__(TR_THREADS, FS_TR_MINBLOCKS)
+k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+                const uint32_t* __restrict__ count_ptr, uint32_t* __restrict__ cursor,
+                float2* __restrict__ hits, fs_dev_counters* __restrict__ dc, const uint32_t REFILL_MIN)
+{
+    const uint32_t lane = lane_id();
+    const uint32_t count = *count_ptr;
+    int stack[FS_STACK_SIZE];
+    tr_state s;
+    s.node = TR_SENT; s.leaf = 0; s.sp = 0; s.tc = 0; s.te = 0;
+    s.o = fs_mk(0.f, 0.f, 0.f); s.d = s.o; s.sx = s.sy = s.sz = s.bx = s.by = s.bz = 0.f;
+    bool running = false, exhausted = false;
+    uint32_t j = 0, ovf = 0, guard = 0;
+    float bt = 0.f; int best = -1;
+    fs_visit_counters vc; vc.nodes = 0; vc.tris = 0;
+    for (;;) {
+        // ---- refill idle lanes from the ray queue: one atomic per warp
+        const uint32_t m_idle = __ballot_sync(FULLM, !running);
+        if (!exhausted && ((uint32_t)__popc(m_idle) >= REFILL_MIN)) {
+            const uint32_t n = (uint32_t)__popc(m_idle);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(cursor, n);
+            base = __shfl_sync(FULLM, base, 0);
+            if (base + n >= count) exhausted = true;
+            if (!running) {
+                const uint32_t jj = base + (uint32_t)__popc(m_idle & ((1u << lane) - 1u));
+                if (jj < count) {
+                    const float4 a = ray_o[jj], b = ray_d[jj];
+                    tr_init(s, bv, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z));
+                    bt = __int_as_float(0x7f800000); best = -1;
+                    j = jj; running = true;
+                }
+            }
+        }
+        if (!__any_sync(FULLM, running)) break;
+        // ---- walk until enough lanes have retired their ray ("while-while" with postponed leaves)
+        for (;;) {
+#if defined(FS_TRAVERSAL_GUARD)
+            if (++guard > (1u << 22)) { ovf = 2u; running = false; exhausted = true; break; }   // bring-up guard
+#endif
+            // inner nodes, until every lane that can still walk has triangle work pending
+            for (;;) {
+                const bool can = running && s.node >= 0 && s.node != TR_SENT;
+                if (!__any_sync(FULLM, can && s.leaf == 0)) break;
+                if (can) {
+                    if (COUNT) vc.nodes++;
+                    tr_node_step<true, TEX>(bv, s, stack, bt, &ovf);
+                }
+            }
+            // triangles: one test per lane per step until every pending leaf of the warp is done
+            tr_next_leaf(s, stack);
+            for (;;) {
+                const bool has = s.tc < s.te;
+                if (!__any_sync(FULLM, has)) break;
+                if (has) {
+                    const float4* tq = bv.tris + (size_t)s.tc * 4;
+                    const float4 a = fs_ldg4(tq), b = fs_ldg4(tq + 1), c = fs_ldg4(tq + 2);
+                    if (COUNT) vc.tris++;
+                    float t;
+                    if (fs_intersect_tri(s.o, s.d, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z), fs_mk(c.x, c.y, c.z), t) && t <= bt) {
+                        // tie: lower ORIGINAL triangle id wins (rare: ids are fetched only then)
+                        if (t < bt || __float_as_uint(fs_ldg4(tq + 3).x) < __float_as_uint(fs_ldg4(bv.tris + (size_t)best * 4 + 3).x)) {
+                            bt = t; best = (int)s.tc;
+                        }
+                    }
+                    ++s.tc;
+                    tr_next_leaf(s, stack);
+                }
+            }
+            // retire finished rays (8 B hit record), then decide whether to refill
+            if (running && s.node == TR_SENT && s.leaf == 0) {
+                hits[j] = make_float2(bt, __int_as_float(best));
+                running = false;
+            }
+            const uint32_t m_run = __ballot_sync(FULLM, running);
+            if (m_run == 0u) break;
+            if (!exhausted && 32u - (uint32_t)__popc(m_run) >= REFILL_MIN) break;
+        }
+    }
+    if (ovf) dc->overflow = ovf;
+    (void)guard;
+    if (COUNT) flush_counters(dc, vc);
+}
+
+// connection rays: (F.xyz, tmax) (dir.xyz, path id); unoccluded paths are appended to conn_queue
+template <bool COUNT>
+__global__ void __launch_bounds__(TR_THREADS)
+k_trace_any(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+            const uint32_t* __restrict__ count_ptr, uint32_t* __restrict__ cursor,
+            uint32_t* __restrict__ conn_queue, uint32_t* __restrict__ conn_count,
+            fs_dev_counters* __restrict__ dc, fs_path_dbg* __restrict__ dbg, const uint32_t REFILL_MIN)
+{
+    const uint32_t lane = lane_id();
+    const uint32_t count = *count_ptr;
+    int stack[FS_STACK_SIZE];
+    tr_state s;
+    s.node = TR_SENT; s.leaf = 0; s.sp = 0; s.tc = 0; s.te = 0;
+    s.o = fs_mk(0.f, 0.f, 0.f); s.d = s.o; s.sx = s.sy = s.sz = s.bx = s.by = s.bz = 0.f;
+    bool running = false, exhausted = false, occluded = false;
+    uint32_t path = 0, ovf = 0, guard = 0;
+    float tmax = 0.f;
+    fs_visit_counters vc; vc.nodes = 0; vc.tris = 0;
+    for (;;) {
+        const uint32_t m_idle = __ballot_sync(FULLM, !running);
+        if (!exhausted && ((uint32_t)__popc(m_idle) >= REFILL_MIN)) {
+            const uint32_t n = (uint32_t)__popc(m_idle);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(cursor, n);
+            base = __shfl_sync(FULLM, base, 0);
+            if (base + n >= count) exhausted = true;
+            if (!running) {
+                const uint32_t jj = base + (uint32_t)__popc(m_idle & ((1u << lane) - 1u));
+                if (jj < count) {
+                    const float4 a = ray_o[jj], b = ray_d[jj];
+                    tr_init(s, bv, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z));
+                    tmax = a.w; path = __float_as_uint(b.w); occluded = false; running = true;
+                }
+            }
+        }
+        if (!__any_sync(FULLM, running)) break;
+        for (;;) {
+#if defined(FS_TRAVERSAL_GUARD)
+            if (++guard > (1u << 22)) { ovf = 2u; running = false; exhausted = true; break; }   // bring-up guard
+#endif
+            for (;;) {
+                const bool can = running && s.node >= 0 && s.node != TR_SENT;
+                if (!__any_sync(FULLM, can && s.leaf == 0)) break;
+                if (can) {
+                    if (COUNT) vc.nodes++;
+                    tr_node_step<false, 0>(bv, s, stack, tmax, &ovf);
+                }
+            }
+            tr_next_leaf(s, stack);
+            for (;;) {
+                const bool has = s.tc < s.te;
+                if (!__any_sync(FULLM, has)) break;
+                if (has) {
+                    const float4* tq = bv.tris + (size_t)s.tc * 4;
+                    const float4 a = fs_ldg4(tq), b = fs_ldg4(tq + 1), c = fs_ldg4(tq + 2);
+                    if (COUNT) vc.tris++;
+                    float t;
+                    ++s.tc;
+                    if (fs_intersect_tri(s.o, s.d, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z), fs_mk(c.x, c.y, c.z), t)
+                        && t < tmax) {           // any hit ends the ray
+                        occluded = true; s.tc = s.te; s.node = TR_SENT; s.leaf = 0; s.sp = 0;
+                    } else tr_next_leaf(s, stack);
+                }
+            }
+            const bool done = running && s.node == TR_SENT && s.leaf == 0;
+            const bool conn = done && !occluded;
+            const uint32_t mc = __ballot_sync(FULLM, conn);
+            if (mc) {                             // ballot-compacted append of the visible pairs
+                uint32_t slot = 0;
+                if (lane == 0) slot = atomicAdd(conn_count, (uint32_t)__popc(mc));
+                slot = __shfl_sync(FULLM, slot, 0);
+                if (conn) {
+                    conn_queue[slot + (uint32_t)__popc(mc & ((1u << lane) - 1u))] = path;
+                    if (dbg) dbg[path].connected = 1u;
+                }
+            }
+            if (done) running = false;
+            const uint32_t m_run = __ballot_sync(FULLM, running);
+            if (m_run == 0u) break;
+            if (!exhausted && 32u - (uint32_t)__popc(m_run) >= REFILL_MIN) break;
+        }
+    }
+    if (ovf) dc->overflow = ovf;
+    (void)guard;
+    if (COUNT) flush_counters(dc, vc, true);
+}
+
+// builds the connection ray of every pair; pairs closer than eps_connect are visible by definition
+__global__ void __launch_bounds__(WF_THREADS)
+k_connect_gen(const fs_trace_params tp, const fs_wave_buffers wb, fs_dev_counters* __restrict__ dc,
+              fs_path_dbg* __restrict__ dbg)
+{
+    const uint32_t lane = lane_id();
+    const uint32_t qc = tp.max_depth + 1, qs = tp.max_depth + 2;
+    float4* __restrict__ sh_o = wb.st_pos[0];
+    float4* __restrict__ sh_d = wb.st_nrm[0];
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < tp.batch;
+         base += gridDim.x * blockDim.x) {
+        const uint32_t p = base + lane;
+        bool shadow = false, direct = false;
+        fs_vec3 F = fs_mk(0.f, 0.f, 0.f), dir = F;
+        float tmax = 0.f;
+        if (p < tp.batch) {
+            const float4 fe = wb.end_pos[2u * p], be = wb.end_pos[2u * p + 1u];
+            F = fs_mk(fe.x, fe.y, fe.z);
+            const fs_vec3 dl = fs_sub(fs_mk(be.x, be.y, be.z), F);
+            const float len = sqrtf(fs_dot(dl, dl));
+            wb.conn_len[p] = len;
+            tmax = len - tp.eps_connect;                    // SUB.cpp:253
+            if (tmax > 0.0f) {
+                const float inv = 1.0f / len;
+                dir = fs_mk(dl.x * inv, dl.y * inv, dl.z * inv);
+                shadow = true;
+            } else direct = true;
+            if (dbg) {
+                fs_path_dbg* q = dbg + p;
+                q->n_src_nodes = __float_as_uint(fe.w); q->n_lis_nodes = __float_as_uint(be.w);
+                q->connected = direct ? 1u : 0u; q->bin = -1; q->delay_s = 0.f; q->total_dist = 0.f;
+                for (int b = 0; b < FS_MAX_BANDS; ++b) q->energy[b] = 0.f;
+                q->src_end[0] = fe.x; q->src_end[1] = fe.y; q->src_end[2] = fe.z;
+                q->lis_end[0] = be.x; q->lis_end[1] = be.y; q->lis_end[2] = be.z;
+            }
+        }
+        const uint32_t ms = __ballot_sync(FULLM, shadow), md = __ballot_sync(FULLM, direct);
+        uint32_t slot_s = 0, slot_d = 0;
+        if (lane == 0) {
+            if (ms) { slot_s = atomicAdd(&wb.q_count[qs], (uint32_t)__popc(ms)); atomicAdd(&dc->shadow_rays, (unsigned long long)__popc(ms)); }
+            if (md) slot_d = atomicAdd(&wb.q_count[qc], (uint32_t)__popc(md));
+        }
+        slot_s = __shfl_sync(FULLM, slot_s, 0); slot_d = __shfl_sync(FULLM, slot_d, 0);
+        if (shadow) {
+            const uint32_t o = slot_s + (uint32_t)__popc(ms & ((1u << lane) - 1u));
+            sh_o[o] = make_float4(F.x, F.y, F.z, tmax);
+            sh_d[o] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(p));
+        }
+        if (direct) wb.conn_queue[slot_d + (uint32_t)__popc(md & ((1u << lane) - 1u))] = p;
     }
 }
 
@@ -434,8 +871,8 @@ int resident_ctas(K kernel, int threads, size_t smem)
 int pick_mode(const fs_trace_params& tp)
 {
     if (tp.flags & FS_FLAG_BRUTE_FORCE) return MODE_BRUTE;
-    if ((tp.flags & FS_FLAG_NO_TREELET) || tp.n_top < 2) return MODE_BVH;
-    return MODE_TOP;
+    if ((tp.flags & FS_FLAG_SMEM_TREELET) && tp.n_top >= 2) return MODE_TOP;
+    return MODE_BVH;
 }
 
 }  // namespace
@@ -457,8 +894,9 @@ cudaError_t fs_wave_alloc(fs_ctx* ctx, uint32_t cap, uint32_t max_depth)
     if ((e = cudaMalloc(&wb->end_pos, sizeof(float4) * n2)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&wb->conn_queue, 4ull * cap)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&wb->conn_len, 4ull * cap)) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&wb->q_count, 4ull * (max_depth + 2))) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&wb->q_cursor, 4ull * (max_depth + 2))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&wb->hit, sizeof(float2) * n2)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&wb->q_count, 4ull * (max_depth + 4))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&wb->q_cursor, 4ull * (max_depth + 4))) != cudaSuccess) return e;
     wb->cap = cap; wb->depth_cap = max_depth;
     return cudaSuccess;
 }
@@ -467,7 +905,7 @@ void fs_wave_free(fs_wave_buffers* wb)
 {
     for (int i = 0; i < 2; ++i) { cudaFree(wb->st_pos[i]); cudaFree(wb->st_nrm[i]); }
     cudaFree(wb->rec); cudaFree(wb->end_pos); cudaFree(wb->conn_queue); cudaFree(wb->conn_len);
-    cudaFree(wb->q_count); cudaFree(wb->q_cursor);
+    cudaFree(wb->q_count); cudaFree(wb->q_cursor); cudaFree(wb->hit);
     memset(wb, 0, sizeof(*wb));
 }
 
@@ -496,7 +934,7 @@ static cudaError_t launch_batch(fs_ctx* ctx, const fs_trace_params& tp, unsigned
         ev = &ctx->kev[ctx->kev_used];
         ctx->kev_used += 4;
     }
-    const uint32_t nq = tp.max_depth + 2;
+    const uint32_t nq = tp.max_depth + 4;
     k_reset_queues<<<(nq + 63) / 64, 64, 0, st>>>(wb.q_count, wb.q_cursor, nq, ctx->d_counters, 0);
     ++ctx->stats.kernel_launches;
     // persistent grids: SMs x resident CTAs, capped by the work available
@@ -529,10 +967,91 @@ static cudaError_t launch_batch(fs_ctx* ctx, const fs_trace_params& tp, unsigned
     return cudaGetLastError();
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// split wavefront: shade_gen(0) trace(0) shade_gen(1) ... trace(D-1) shade_gen(D) connect_gen
+// trace_any eval
+// ---------------------------------------------------------------------------------------------
+template <bool COUNT>
+static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, unsigned long long* d_hist,
+                                      fs_path_dbg* d_dbg)
+{
+    cudaStream_t st = ctx->stream;
+    const fs_wave_buffers& wb = ctx->wb;
+    static int occ_tr = 0, occ_any = 0;
+    if (!occ_tr) occ_tr = resident_ctas(k_trace_closest<COUNT, 0>, TR_THREADS, 0);
+    if (!occ_any) occ_any = resident_ctas(k_trace_any<COUNT>, TR_THREADS, 0);
+    const bool timing = (tp.flags & FS_FLAG_TIME_KERNELS) != 0;
+    cudaEvent_t* ev = nullptr;
+    if (timing) {
+        if (ctx->kev.size() < ctx->kev_used + 4) {
+            size_t old = ctx->kev.size();
+            ctx->kev.resize(ctx->kev_used + 4);
+            for (size_t i = old; i < ctx->kev.size(); ++i) cudaEventCreate(&ctx->kev[i]);
+        }
+        ev = &ctx->kev[ctx->kev_used];
+        ctx->kev_used += 4;
+    }
+    const uint32_t nq = tp.max_depth + 4;
+    k_reset_queues<<<(nq + 63) / 64, 64, 0, st>>>(wb.q_count, wb.q_cursor, nq, ctx->d_counters, 0);
+    ++ctx->stats.kernel_launches;
+    const uint32_t D = tp.max_depth;
+    const uint32_t n_sub = 2u * tp.batch;
+    uint32_t grid_sh = (n_sub + WF_THREADS - 1) / WF_THREADS;
+    if (grid_sh > (uint32_t)ctx->sm_count * 8u) grid_sh = (uint32_t)ctx->sm_count * 8u;
+    uint32_t grid_tr = (uint32_t)(ctx->sm_count * occ_tr);
+    const uint32_t ctas_needed = (n_sub + TR_THREADS - 1) / TR_THREADS;
+    if (grid_tr > ctas_needed) grid_tr = ctas_needed ? ctas_needed : 1;
+    if (timing) cudaEventRecord(ev[0], st);
+    if (D == 0) {
+        k_init_ends<<<(n_sub + 255u) / 256u, 256, 0, st>>>(tp, wb);
+        ++ctx->stats.kernel_launches;
+    } else {
+        for (uint32_t k = 0; k <= D; ++k) {
+            k_shade_gen<<<grid_sh, WF_THREADS, 0, st>>>(tp, wb, k, ctx->d_counters);
+            ++ctx->stats.kernel_launches;
+            if (k == D) break;
+            const int texm = tp.bv.nodes_tex ? (int)ctx->tune_tex : 0;
+            if (texm == 1)
+                k_trace_closest<COUNT, 1><<<grid_tr, TR_THREADS, 0, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u],
+                    wb.q_count + k, wb.q_cursor + k, wb.hit, ctx->d_counters, ctx->tune_refill);
+            else if (texm == 2)
+                k_trace_closest<COUNT, 2><<<grid_tr, TR_THREADS, 0, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u],
+                    wb.q_count + k, wb.q_cursor + k, wb.hit, ctx->d_counters, ctx->tune_refill);
+            else
+                k_trace_closest<COUNT, 0><<<grid_tr, TR_THREADS, 0, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u],
+                    wb.q_count + k, wb.q_cursor + k, wb.hit, ctx->d_counters, ctx->tune_refill);
+            ++ctx->stats.kernel_launches;
+            ++ctx->stats.extend_launches;
+        }
+    }
+    if (timing) cudaEventRecord(ev[1], st);
+    uint32_t grid_cg = (tp.batch + WF_THREADS - 1) / WF_THREADS;
+    if (grid_cg > (uint32_t)ctx->sm_count * 8u) grid_cg = (uint32_t)ctx->sm_count * 8u;
+    if (!grid_cg) grid_cg = 1;
+    k_connect_gen<<<grid_cg, WF_THREADS, 0, st>>>(tp, wb, ctx->d_counters, d_dbg);
+    uint32_t grid_any = (uint32_t)(ctx->sm_count * occ_any);
+    const uint32_t ctas_any = (tp.batch + TR_THREADS - 1) / TR_THREADS;
+    if (grid_any > ctas_any) grid_any = ctas_any ? ctas_any : 1;
+    k_trace_any<COUNT><<<grid_any, TR_THREADS, 0, st>>>(tp.bv, wb.st_pos[0], wb.st_nrm[0], wb.q_count + (D + 2),
+                                                     wb.q_cursor + (D + 2), wb.conn_queue, wb.q_count + (D + 1),
+                                                     ctx->d_counters, d_dbg, ctx->tune_refill);
+    ctx->stats.kernel_launches += 2;
+    if (timing) cudaEventRecord(ev[2], st);
+    uint32_t grid_ev = (uint32_t)ctx->sm_count * 4u;
+    if (grid_ev > ctas_any) grid_ev = ctas_any ? ctas_any : 1;
+    k_eval<<<grid_ev, WF_THREADS, 0, st>>>(tp, wb, d_hist, ctx->d_counters, d_dbg);
+    ++ctx->stats.kernel_launches;
+    if (timing) cudaEventRecord(ev[3], st);
+    return cudaGetLastError();
+}
+
 cudaError_t fs_wave_trace_batch(fs_ctx* ctx, const fs_trace_params& tp, unsigned long long* d_hist,
                                 fs_path_dbg* d_dbg)
 {
     const bool count = (tp.flags & FS_FLAG_COUNT_VISITS) != 0;
+    if (!(tp.flags & (FS_FLAG_FUSED_EXTEND | FS_FLAG_BRUTE_FORCE)))
+        return count ? launch_batch_split<true>(ctx, tp, d_hist, d_dbg) : launch_batch_split<false>(ctx, tp, d_hist, d_dbg);
     switch (pick_mode(tp)) {
     case MODE_BRUTE: return launch_batch<false, MODE_BRUTE>(ctx, tp, d_hist, d_dbg);
     case MODE_TOP:

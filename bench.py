@@ -175,7 +175,9 @@ def run_b200(args):
     sc = scenes.furnished_room()
     ctx = fs.Context(device=local, flags=capi.FLAG_TIME_KERNELS)
     ctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()                            # a real (non-NULL) stream: the C-ABI treats NULL as "own stream"
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     B, Kb = ctx.cfg.n_bands, ctx.cfg.n_bins
     d_hist = torch.zeros((1, B, Kb), dtype=torch.int64, device="cuda")

@@ -49,9 +49,11 @@ typedef enum fs_status {
 /* flags for fs_config.flags */
 #define FS_FLAG_COUNT_VISITS   1u   /* instrumented traversal: count BVH nodes popped / triangles tested */
 #define FS_FLAG_NO_SPLAT_AGG   2u   /* plain one-atomic-per-lane splat instead of warp-aggregated */
-#define FS_FLAG_NO_TREELET     4u   /* do not stage the top treelet in shared memory */
+#define FS_FLAG_SMEM_TREELET   4u   /* fused path only: stage the top BVH treelet in shared memory */
 #define FS_FLAG_BRUTE_FORCE    8u   /* test every triangle (debug/parity only, tiny scenes) */
 #define FS_FLAG_TIME_KERNELS  16u   /* CUDA events around each kernel class -> fs_stats.*_ms */
+#define FS_FLAG_FUSED_EXTEND  32u   /* A/B: fused RR+sample+traverse+shade kernel per bounce instead of the
+                                       split shade/trace wavefront with per-lane ray replacement */
 
 /* All tunables of the path in one POD: tier (i) UPROPERTYs (COMP.h:35-66) + tier (ii)
  * compile-time constants of the reference, reference values as defaults

@@ -31,7 +31,7 @@ def test_bvh_equals_brute_force_and_oracle(fs, oracle, scene_name, kw, lo, hi):
     else:
         rays = _rays(rng, lo, hi, n)
     rays[:64, 3:] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 64)] * rng.choice([-1, 1], (64, 1))  # axis-parallel
-    with fs.Context() as a, fs.Context(flags=capi.FLAG_BRUTE_FORCE) as b, fs.Context(flags=capi.FLAG_NO_TREELET) as c:
+    with fs.Context() as a, fs.Context(flags=capi.FLAG_BRUTE_FORCE) as b, fs.Context(flags=capi.FLAG_SMEM_TREELET) as c:
         for ctx in (a, b, c):
             ctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
         ta, ia = a.closest_hits(rays)

@@ -67,8 +67,8 @@ def test_every_traversal_mode_gives_the_same_histogram(fs, oracle, room):
     ho, so = S.trace(oracle.default_config(), room.sources, room.listener, 8192, 16, 1, n_threads=16)
     g = _golden()
     assert np.array_equal(ho, _dense(g["room_idx"], g["room_val"], ho.shape))
-    for flags in (0, capi.FLAG_NO_TREELET, capi.FLAG_NO_SPLAT_AGG, capi.FLAG_COUNT_VISITS,
-                  capi.FLAG_COUNT_VISITS | capi.FLAG_NO_TREELET):
+    for flags in (0, capi.FLAG_FUSED_EXTEND, capi.FLAG_FUSED_EXTEND | capi.FLAG_SMEM_TREELET, capi.FLAG_NO_SPLAT_AGG,
+                  capi.FLAG_COUNT_VISITS, capi.FLAG_COUNT_VISITS | capi.FLAG_FUSED_EXTEND, capi.FLAG_TIME_KERNELS):
         with _ctx(fs, room, flags=flags) as ctx:
             h = ctx.trace(room.sources, room.listener, 8192, 16, 1)
             st = ctx.stats()

@@ -33,7 +33,7 @@ def main():
     sc = scenes.shoebox()
     cfgo = po.default_config()
     S = po.Scene(sc.verts, sc.tri_mat, sc.absorption, use_bvh=False)
-    for flags, tag in ((0, "shoebox/bvh+top"), (capi.FLAG_NO_TREELET, "shoebox/bvh"), (capi.FLAG_BRUTE_FORCE, "shoebox/brute"),
+    for flags, tag in ((0, "shoebox/split"), (capi.FLAG_FUSED_EXTEND, "shoebox/fused"), (capi.FLAG_BRUTE_FORCE, "shoebox/brute"),
                        (capi.FLAG_NO_SPLAT_AGG, "shoebox/noagg"), (capi.FLAG_COUNT_VISITS, "shoebox/count")):
         ctx = fs.Context(flags=flags)
         ctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
@@ -81,15 +81,15 @@ def main():
     print("IR rel-L2", rel, flush=True); out["fr/ir_rel"] = float(rel)
     ctx.close(); ctxb.close()
     # 3. timing, 1M paths
-    for flags, tag in ((0, "top"), (capi.FLAG_NO_TREELET, "notop"), (capi.FLAG_NO_SPLAT_AGG, "top/noagg")):
-        ctx = fs.Context(flags=flags)
+    for flags, tag in ((0, "split"), (capi.FLAG_FUSED_EXTEND, "fused"), (capi.FLAG_FUSED_EXTEND | capi.FLAG_SMEM_TREELET, "fused+top"), (capi.FLAG_NO_SPLAT_AGG, "split/noagg")):
+        ctx = fs.Context(flags=flags | capi.FLAG_TIME_KERNELS)
         ctx.set_scene(fr.verts, fr.tri_mat, fr.absorption)
         N = 1 << 20
         for it in range(3):
             ctx.trace(fr.sources, fr.listener, N, 16, 100 + it, want_hist=False); ctx.build_ir(0, want_ir=False)
             st = ctx.stats()
         rays = st["ext_rays"] + st["shadow_rays"]
-        print(f"[time {tag}] 1M paths: trace {st['last_trace_ms']:.3f} ms  paths/s {N / st['last_trace_ms'] * 1e3:.3e}  Mrays/s {rays / st['last_trace_ms'] / 1e3:.1f}  connected {st['connected']}", flush=True)
+        print(f"[time {tag}] ext {st['extend_ms']:.3f} con {st['connect_ms']:.3f} eval {st['eval_ms']:.3f} | 1M paths: trace {st['last_trace_ms']:.3f} ms  paths/s {N / st['last_trace_ms'] * 1e3:.3e}  Mrays/s {rays / st['last_trace_ms'] / 1e3:.1f}  connected {st['connected']}", flush=True)
         out["time/" + tag] = st["last_trace_ms"]
         ctx.close()
     # 4. conv + fft

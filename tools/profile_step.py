@@ -1,0 +1,17 @@
+"""Minimal driver for ncu: furnished room, W warm-up + S steps of the device-resident IR update."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "audio-pathtracer_b200"))
+import frequensee as fs
+from frequensee import scenes, capi
+flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+sc = scenes.by_name(sys.argv[3]) if len(sys.argv) > 3 else scenes.furnished_room()
+ctx = fs.Context(flags=flags | capi.FLAG_TIME_KERNELS)
+ctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
+for i in range(steps):
+    ctx.trace(sc.sources[:1], sc.listener, 1 << 20, 16, 1000 + i, want_hist=False)
+    ctx.build_ir(0, want_ir=False)
+    st = ctx.stats()
+    print("step", i, {k: st[k] for k in ("last_trace_ms", "extend_ms", "connect_ms", "eval_ms", "ext_rays", "shadow_rays", "connected")})
+ctx.close()
