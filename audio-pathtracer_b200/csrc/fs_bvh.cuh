@@ -15,14 +15,9 @@
 // Fetches are 128-bit ld.global.nc.  ncu shows the traversal bound by the L1TEX LSU data pipe
 // (l1tex__data_pipe_lsu_wavefronts ~ 88 %): a divergent warp load costs one wavefront per lane,
 // whatever its width -- 256-bit loads (LDG.E.ENL2.256) were measured and are not cheaper.
-//   qnodes : uint4[n_inner][2]   32 B per node, the production traversal format: child boxes
-//             quantised to 16 bits per coordinate on a scene-wide grid, rounded outward by one
-//             extra quantum:  u0 = (c0.lox | c0.hix << 16, c0.loy | c0.hiy << 16, c0.loz | c0.hiz << 16, child0)
-//                             u1 = (same for child 1, child1)
-//             A divergent warp load costs one L1TEX wavefront per lane per 16 B, and the traversal
-//             is bound by exactly that (ncu: l1tex__data_pipe_lsu_wavefronts ~ 88 %), so halving
-//             the node size halves the dominant cost.  Dequantisation is folded into the slab
-//             FMA: t = fma(2^23 + q, s, b') with s = qscale * idir, b' = (qbase - o) * idir - 2^23 s.
+// A 32 B node format (16-bit quantised boxes, octant plane selection by PRMT) halves those
+// wavefronts (48 %) but was measured no faster: the kernel then waits on load latency with the
+// ALU pipe as the busiest unit (profiles/r1_experiments.md); it is not kept in the tree.
 // Boxes are padded at build time so that the slab test (FMA form, not bit-reproducible against
 // the oracle and not required to be) is conservative: any triangle whose exact-arithmetic
 // fs_intersect_tri() succeeds is reached.  The hit itself comes from fs_intersect_tri() only.
@@ -46,8 +41,7 @@
 
 struct fs_bvh_view {
     unsigned long long nodes_tex;   // cudaTextureObject_t over `nodes` (float4 texels), 0 if absent
-    const uint4* qnodes;            // 32 B quantised nodes (see below), same indexing as `nodes`
-    float qbase[3], qscale[3];      // world = qbase + q * qscale, q in [0, 65535]
+    unsigned long long tris_tex;    // same over `tris`
     const float4* nodes;
     const float4* tris;
     const uint32_t* tri_orig;

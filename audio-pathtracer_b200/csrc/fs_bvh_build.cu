@@ -322,38 +322,9 @@ __device__ __forceinline__ float box_pad(float4 lo, float4 hi)
     return fmaf(m, 1.0f / 32768.0f, 1e-5f);
 }
 
-// Scene-wide 16-bit grid.  misc[9..14] = box of all triangle boxes; grid[0..2] = qbase, grid[3..5] = qscale.
-// The grid covers the (padded) scene box with 4 spare quanta on each side so that the outward
-// rounding below never clamps.
-__global__ void k_quant_grid(const uint32_t* __restrict__ bounds, float* __restrict__ grid)
-{
-    int a = threadIdx.x;
-    if (a >= 3) return;
-    float lo = ord2f(bounds[9 + a]), hi = ord2f(bounds[12 + a]);
-    float m = fmaxf(fabsf(lo), fabsf(hi));
-    float pad = fmaf(m, 1.0f / 32768.0f, 1e-5f) * 2.0f;
-    lo -= pad; hi += pad;
-    float scale = (hi - lo) / 65520.0f;
-    if (!(scale > 0.f)) scale = 1e-6f;
-    grid[a] = lo - 8.0f * scale;
-    grid[3 + a] = scale;
-}
-
-__device__ __forceinline__ uint32_t quant_lo(float v, float base, float scale)
-{
-    float q = floorf((v - base) / scale) - 1.0f;         // outward + one spare quantum
-    return (uint32_t)fminf(fmaxf(q, 0.0f), 65535.0f);
-}
-__device__ __forceinline__ uint32_t quant_hi(float v, float base, float scale)
-{
-    float q = ceilf((v - base) / scale) + 1.0f;
-    return (uint32_t)fminf(fmaxf(q, 0.0f), 65535.0f);
-}
-
 __global__ void k_emit(int n, const int2* __restrict__ children, const int2* __restrict__ ranges,
                        const float4* __restrict__ bb_lo, const float4* __restrict__ bb_hi,
-                       float4* __restrict__ nodes, int leaf_max, const float* __restrict__ grid,
-                       uint4* __restrict__ qnodes)
+                       float4* __restrict__ nodes, int leaf_max)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
@@ -365,23 +336,11 @@ __global__ void k_emit(int n, const int2* __restrict__ children, const int2* __r
     nodes[(size_t)i * 4 + 1] = make_float4(l1.x - p1, h1.x + p1, l1.y - p1, h1.y + p1);
     nodes[(size_t)i * 4 + 2] = make_float4(l0.z - p0, h0.z + p0, l1.z - p1, h1.z + p1);
     nodes[(size_t)i * 4 + 3] = make_float4(__int_as_float(e0), __int_as_float(e1), 0.f, 0.f);
-    const float gx = grid[0], gy = grid[1], gz = grid[2], sx = grid[3], sy = grid[4], sz = grid[5];
-    uint4 q0, q1;
-    q0.x = quant_lo(l0.x - p0, gx, sx) | (quant_hi(h0.x + p0, gx, sx) << 16);
-    q0.y = quant_lo(l0.y - p0, gy, sy) | (quant_hi(h0.y + p0, gy, sy) << 16);
-    q0.z = quant_lo(l0.z - p0, gz, sz) | (quant_hi(h0.z + p0, gz, sz) << 16);
-    q0.w = (uint32_t)e0;
-    q1.x = quant_lo(l1.x - p1, gx, sx) | (quant_hi(h1.x + p1, gx, sx) << 16);
-    q1.y = quant_lo(l1.y - p1, gy, sy) | (quant_hi(h1.y + p1, gy, sy) << 16);
-    q1.z = quant_lo(l1.z - p1, gz, sz) | (quant_hi(h1.z + p1, gz, sz) << 16);
-    q1.w = (uint32_t)e1;
-    qnodes[(size_t)i * 2] = q0;
-    qnodes[(size_t)i * 2 + 1] = q1;
 }
 
 // single-triangle scene: root whose second child is a far-away point box (never entered in practice)
 __global__ void k_emit_single(const float4* __restrict__ bb_lo, const float4* __restrict__ bb_hi,
-                              float4* __restrict__ nodes, const float* __restrict__ grid, uint4* __restrict__ qnodes)
+                              float4* __restrict__ nodes)
 {
     float4 l0 = bb_lo[0], h0 = bb_hi[0];
     float pad = box_pad(l0, h0);
@@ -390,15 +349,6 @@ __global__ void k_emit_single(const float4* __restrict__ bb_lo, const float4* __
     nodes[1] = make_float4(F, F, F, F);
     nodes[2] = make_float4(l0.z - pad, h0.z + pad, F, F);
     nodes[3] = make_float4(__int_as_float(~0), __int_as_float(~0), 0.f, 0.f);
-    const float gx = grid[0], gy = grid[1], gz = grid[2], sx = grid[3], sy = grid[4], sz = grid[5];
-    uint4 q0, q1;
-    q0.x = quant_lo(l0.x - pad, gx, sx) | (quant_hi(h0.x + pad, gx, sx) << 16);
-    q0.y = quant_lo(l0.y - pad, gy, sy) | (quant_hi(h0.y + pad, gy, sy) << 16);
-    q0.z = quant_lo(l0.z - pad, gz, sz) | (quant_hi(h0.z + pad, gz, sz) << 16);
-    q0.w = (uint32_t)(~0);
-    q1.x = q1.y = q1.z = 0x0000ffffu;     // lo = 65535 > hi = 0: inverted box, never entered
-    q1.w = (uint32_t)(~0);
-    qnodes[0] = q0; qnodes[1] = q1;
 }
 
 // BFS copy of the top of the tree; children inside the copy get FS_TOP_FLAG | local index.
@@ -451,7 +401,6 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
     float4 *tlo = nullptr, *thi = nullptr, *bb_lo = nullptr, *bb_hi = nullptr;
     uint64_t *keys0 = nullptr, *keys1 = nullptr;
     uint32_t *vals0 = nullptr, *vals1 = nullptr, *block_hist = nullptr, *misc = nullptr, *arrive = nullptr;
-    float* grid = nullptr;
     int2 *children = nullptr, *ranges = nullptr;
     int *parent = nullptr, *queue = nullptr;
     const int TPB = 256;
@@ -472,9 +421,7 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
     BCHECK(cudaMalloc(&ranges, sizeof(int2) * n_inner));
     BCHECK(cudaMalloc(&parent, 4ull * 2 * n));
     BCHECK(cudaMalloc(&queue, 4ull * FS_TOP_CAP));
-    BCHECK(cudaMalloc(&grid, sizeof(float) * 8));
     BCHECK(cudaMalloc(&out->nodes, sizeof(float4) * 4ull * n_inner));
-    BCHECK(cudaMalloc(&out->qnodes, sizeof(uint4) * 2ull * n_inner));
     BCHECK(cudaMalloc(&out->tris, sizeof(float4) * 4ull * n));
     BCHECK(cudaMalloc(&out->tri_orig, 4ull * n));
     BCHECK(cudaMalloc(&out->tri_mat, 4ull * n));
@@ -487,7 +434,6 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
     k_init_bounds<<<1, 32, 0, st>>>(misc); ++*launches;
     k_tri_bounds<<<gb, TPB, 0, st>>>(d_verts, n, tlo, thi, misc, misc + 6); ++*launches;
     k_morton<<<gb, TPB, 0, st>>>(tlo, thi, n, misc, keys0, vals0); ++*launches;
-    k_quant_grid<<<1, 32, 0, st>>>(misc, grid); ++*launches;
     {
         uint64_t *ki = keys0, *ko = keys1;
         uint32_t *vi = vals0, *vo = vals1;
@@ -505,12 +451,12 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
     k_pack<<<gb, TPB, 0, st>>>(d_verts, d_mats, vals0, n, tlo, thi, out->tris, out->tri_orig, out->tri_mat, bb_lo, bb_hi);
     ++*launches;
     if (n == 1) {
-        k_emit_single<<<1, 1, 0, st>>>(bb_lo, bb_hi, out->nodes, grid, out->qnodes); ++*launches;
+        k_emit_single<<<1, 1, 0, st>>>(bb_lo, bb_hi, out->nodes); ++*launches;
         out->max_leaf = 1;
     } else {
         k_karras<<<gb, TPB, 0, st>>>(keys0, (int)n, children, ranges, parent); ++*launches;
         k_refit<<<gb, TPB, 0, st>>>((int)n, children, parent, bb_lo, bb_hi, arrive); ++*launches;
-        k_emit<<<gb, TPB, 0, st>>>((int)n, children, ranges, bb_lo, bb_hi, out->nodes, leaf_max, grid, out->qnodes); ++*launches;
+        k_emit<<<gb, TPB, 0, st>>>((int)n, children, ranges, bb_lo, bb_hi, out->nodes, leaf_max); ++*launches;
         k_leaf_stats<<<gb, TPB, 0, st>>>((int)n, ranges, misc + 8, leaf_max); ++*launches;
     }
     {
@@ -522,6 +468,9 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
         cudaTextureDesc td; memset(&td, 0, sizeof(td));
         td.readMode = cudaReadModeElementType;
         if (cudaCreateTextureObject(&out->nodes_tex, &rd, &td, nullptr) != cudaSuccess) { out->nodes_tex = 0; (void)cudaGetLastError(); }
+        rd.res.linear.devPtr = out->tris;
+        rd.res.linear.sizeInBytes = sizeof(float4) * 4ull * n;
+        if (cudaCreateTextureObject(&out->tris_tex, &rd, &td, nullptr) != cudaSuccess) { out->tris_tex = 0; (void)cudaGetLastError(); }
     }
     k_top_treelet<<<1, 32, 0, st>>>(out->nodes, n_inner, FS_TOP_CAP, out->top_nodes, misc + 7, queue); ++*launches;
     BCHECK(cudaGetLastError());
@@ -532,14 +481,11 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
         out->n_top = h[7];
         if (n > 1) out->max_leaf = h[8] ? h[8] : 1;
         out->extent = ord2f(h[6]);
-        float hg[6];
-        BCHECK(cudaMemcpy(hg, grid, sizeof(hg), cudaMemcpyDeviceToHost));
-        for (int a = 0; a < 3; ++a) { out->qbase[a] = hg[a]; out->qscale[a] = hg[3 + a]; }
     }
 fail:
     cudaFree(tlo); cudaFree(thi); cudaFree(bb_lo); cudaFree(bb_hi); cudaFree(keys0); cudaFree(keys1);
     cudaFree(vals0); cudaFree(vals1); cudaFree(block_hist); cudaFree(misc); cudaFree(arrive);
-    cudaFree(children); cudaFree(ranges); cudaFree(parent); cudaFree(queue); cudaFree(grid);
+    cudaFree(children); cudaFree(ranges); cudaFree(parent); cudaFree(queue);
     if (err != cudaSuccess) fs_bvh_free(out);
     return err;
 }
@@ -547,6 +493,7 @@ fail:
 void fs_bvh_free(fs_bvh_device* b)
 {
     if (b->nodes_tex) cudaDestroyTextureObject(b->nodes_tex);
-    cudaFree(b->nodes); cudaFree(b->qnodes); cudaFree(b->tris); cudaFree(b->tri_orig); cudaFree(b->tri_mat); cudaFree(b->top_nodes);
+    if (b->tris_tex) cudaDestroyTextureObject(b->tris_tex);
+    cudaFree(b->nodes); cudaFree(b->tris); cudaFree(b->tri_orig); cudaFree(b->tri_mat); cudaFree(b->top_nodes);
     memset(b, 0, sizeof(*b));
 }

@@ -17,13 +17,11 @@
 
 struct fs_bvh_device {
     float4* nodes;
-    uint4* qnodes;
-    float qbase[3], qscale[3];
     float4* tris;
     uint32_t* tri_orig;
     uint32_t* tri_mat;
     float4* top_nodes;
-    cudaTextureObject_t nodes_tex;
+    cudaTextureObject_t nodes_tex, tris_tex;
     uint32_t n_tris, n_inner, n_top, max_leaf;
     float extent;
 };

@@ -390,7 +390,7 @@ k_eval(const fs_trace_params tp, const fs_wave_buffers wb, unsigned long long* _
 // =============================================================================================
 constexpr int TR_THREADS = 256;
 #ifndef FS_TR_MINBLOCKS
-#define FS_TR_MINBLOCKS 1
+#define FS_TR_MINBLOCKS 5      // <= 51 registers: 5 CTAs (40 warps) per SM
 #endif
 // refill a warp once this many lanes are idle (kernel argument, default FS_REFILL_DEFAULT)
 #define FS_REFILL_DEFAULT 8u
@@ -493,7 +493,7 @@ k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_d
 // per-lane traversal state shared by the two trace kernels
 struct tr_state {
     fs_vec3 o, d;
-    float sx, sy, sz, bx, by, bz;       // t(q) = fma(2^23 + q, s, b): dequantisation folded into the slab test
+    float idx, idy, idz, oodx, oody, oodz;
     int node, leaf, sp;
     uint32_t tc, te;
 };
@@ -502,29 +502,10 @@ __device__ __forceinline__ void tr_init(tr_state& s, const fs_bvh_view& bv, fs_v
 {
     const fs_ray_prep r = fs_prep_ray(o, d);
     s.o = o; s.d = d;
-    s.sx = bv.qscale[0] * r.idx; s.sy = bv.qscale[1] * r.idy; s.sz = bv.qscale[2] * r.idz;
-    // b' = (qbase - o) * idir - 2^23 * s; its rounding error is <= half a quantum, which the
-    // extra quantum of outward rounding at build time covers
-    s.bx = fmaf(-8388608.0f, s.sx, (bv.qbase[0] - o.x) * r.idx);
-    s.by = fmaf(-8388608.0f, s.sy, (bv.qbase[1] - o.y) * r.idy);
-    s.bz = fmaf(-8388608.0f, s.sz, (bv.qbase[2] - o.z) * r.idz);
+    s.idx = r.idx; s.idy = r.idy; s.idz = r.idz; s.oodx = r.oodx; s.oody = r.oody; s.oodz = r.oodz;
     s.node = bv.n_tris ? 0 : TR_SENT; s.leaf = 0; s.sp = 0; s.tc = 0; s.te = 0;
 }
 
-// 2^23 + (16 bits of w chosen by the selector) as a float: one PRMT.  0x7410 = low half, 0x7432 = high half
-__device__ __forceinline__ float q_sel(uint32_t w, uint32_t sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)); }
-// 2^23 + (low / high 16 bits of w) as a float: one PRMT
-__device__ __forceinline__ float q_lo16(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7410)); }
-__device__ __forceinline__ float q_hi16(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7432)); }
-
-__device__ __forceinline__ uint4 ldg_u4(const uint4* p)
-{
-    uint4 r;
-    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-
-// one inner-node step; tlimit = current closest t (or tmax for shadow rays)
 // Speculative traversal (Aila & Laine): the first leaf a lane reaches is POSTPONED and the lane
 // keeps walking; a second leaf makes it wait (node stays < 0) for the warp's triangle phase.
 __device__ __forceinline__ void tr_settle(tr_state& s, const int* stack)
@@ -539,23 +520,25 @@ template <bool ORDERED, int TEX>
 __device__ __forceinline__ void tr_node_step(const fs_bvh_view& bv, tr_state& s, int* stack, float tlimit,
                                              uint32_t* overflow)
 {
-    const uint4* p = bv.qnodes + (size_t)s.node * 2;
-    const uint4 u0 = ldg_u4(p), u1 = ldg_u4(p + 1);
-    // near/far planes picked by the ray octant: no per-axis min/max, 4 FMNMX(3) per child
-    // ray octant (sign of s = sign of the direction): with a negative direction the HIGH plane is entered first
-    const uint32_t nx = (s.sx < 0.0f) ? 0x7432u : 0x7410u, ny = (s.sy < 0.0f) ? 0x7432u : 0x7410u,
-                   nz = (s.sz < 0.0f) ? 0x7432u : 0x7410u;
-    const uint32_t fx = nx ^ 0x0022u, fy = ny ^ 0x0022u, fz = nz ^ 0x0022u;
-    const float t0 = fmaxf(fmaxf(fmaxf(fmaf(q_sel(u0.x, nx), s.sx, s.bx), fmaf(q_sel(u0.y, ny), s.sy, s.by)),
-                                 fmaf(q_sel(u0.z, nz), s.sz, s.bz)), 0.0f);
-    const float e0 = fminf(fminf(fminf(fmaf(q_sel(u0.x, fx), s.sx, s.bx), fmaf(q_sel(u0.y, fy), s.sy, s.by)),
-                                 fmaf(q_sel(u0.z, fz), s.sz, s.bz)), tlimit);
-    const float t1 = fmaxf(fmaxf(fmaxf(fmaf(q_sel(u1.x, nx), s.sx, s.bx), fmaf(q_sel(u1.y, ny), s.sy, s.by)),
-                                 fmaf(q_sel(u1.z, nz), s.sz, s.bz)), 0.0f);
-    const float e1 = fminf(fminf(fminf(fmaf(q_sel(u1.x, fx), s.sx, s.bx), fmaf(q_sel(u1.y, fy), s.sy, s.by)),
-                                 fmaf(q_sel(u1.z, fz), s.sz, s.bz)), tlimit);
-    const bool h0 = t0 <= e0, h1 = t1 <= e1;
-    const int c0 = (int)u0.w, c1 = (int)u1.w;
+    const float4* p = bv.nodes + (size_t)s.node * 4;
+    float4 n0, n1, n2, n3;
+    if (TEX >= 2) {
+        // The traversal is bound by the L1TEX LSU data pipe (one wavefront per lane per divergent
+        // 16 B load).  Two of the four quarters of a node go through the texture data pipe instead,
+        // which ncu/CUDA-event A/B measured ~8 % faster than four LSU loads; all four through TEX
+        // is slower.
+        const int b = s.node * 4;
+        n0 = tex1Dfetch<float4>((cudaTextureObject_t)bv.nodes_tex, b);
+        n1 = tex1Dfetch<float4>((cudaTextureObject_t)bv.nodes_tex, b + 1);
+        n2 = fs_ldg4(p + 2); n3 = fs_ldg4(p + 3);
+    } else {
+        n0 = fs_ldg4(p); n1 = fs_ldg4(p + 1); n2 = fs_ldg4(p + 2); n3 = fs_ldg4(p + 3);
+    }
+    fs_ray_prep r;
+    r.idx = s.idx; r.idy = s.idy; r.idz = s.idz; r.oodx = s.oodx; r.oody = s.oody; r.oodz = s.oodz;
+    bool h0, h1; float t0, t1;
+    fs_slab2(r, n0, n1, n2, tlimit, h0, h1, t0, t1);
+    const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
     if (!h0 && !h1) {
         s.node = s.sp ? stack[--s.sp] : TR_SENT;
     } else {
@@ -564,12 +547,6 @@ __device__ __forceinline__ void tr_node_step(const fs_bvh_view& bv, tr_state& s,
             int far_ = c1;
             if (ORDERED && t1 < t0) { far_ = c0; s.node = c1; }
             if (s.sp < FS_STACK_SIZE) stack[s.sp++] = far_; else *overflow = 1u;
-#if defined(FS_PREFETCH_FAR)
-            // the pushed subtree is visited later: pull its first record towards L1 now
-            const void* pf = far_ >= 0 ? (const void*)(bv.qnodes + (size_t)far_ * 2)
-                                       : (const void*)(bv.tris + (size_t)(((uint32_t)(~far_)) >> 3) * 4);
-            asm volatile("prefetch.global.L1 [%0];" :: "l"(pf));
-#endif
         }
     }
     tr_settle(s, stack);
@@ -594,7 +571,7 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
     int stack[FS_STACK_SIZE];
     tr_state s;
     s.node = TR_SENT; s.leaf = 0; s.sp = 0; s.tc = 0; s.te = 0;
-    s.o = fs_mk(0.f, 0.f, 0.f); s.d = s.o; s.sx = s.sy = s.sz = s.bx = s.by = s.bz = 0.f;
+    s.o = fs_mk(0.f, 0.f, 0.f); s.d = s.o; s.idx = s.idy = s.idz = s.oodx = s.oody = s.oodz = 0.f;
     bool running = false, exhausted = false;
     uint32_t j = 0, ovf = 0, guard = 0;
     float bt = 0.f; int best = -1;
@@ -640,7 +617,8 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
                 if (!__any_sync(FULLM, has)) break;
                 if (has) {
                     const float4* tq = bv.tris + (size_t)s.tc * 4;
-                    const float4 a = fs_ldg4(tq), b = fs_ldg4(tq + 1), c = fs_ldg4(tq + 2);
+                    const float4 a = (TEX == 3) ? tex1Dfetch<float4>((cudaTextureObject_t)bv.tris_tex, (int)(s.tc * 4u)) : fs_ldg4(tq);
+                    const float4 b = fs_ldg4(tq + 1), c = fs_ldg4(tq + 2);
                     if (COUNT) vc.tris++;
                     float t;
                     if (fs_intersect_tri(s.o, s.d, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z), fs_mk(c.x, c.y, c.z), t) && t <= bt) {
@@ -669,8 +647,8 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
 }
 
 // connection rays: (F.xyz, tmax) (dir.xyz, path id); unoccluded paths are appended to conn_queue
-template <bool COUNT>
-__global__ void __launch_bounds__(TR_THREADS)
+template <bool COUNT, int TEX>
+__global__ void __launch_bounds__(TR_THREADS, FS_TR_MINBLOCKS)
 k_trace_any(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
             const uint32_t* __restrict__ count_ptr, uint32_t* __restrict__ cursor,
             uint32_t* __restrict__ conn_queue, uint32_t* __restrict__ conn_count,
@@ -681,7 +659,7 @@ k_trace_any(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4
     int stack[FS_STACK_SIZE];
     tr_state s;
     s.node = TR_SENT; s.leaf = 0; s.sp = 0; s.tc = 0; s.te = 0;
-    s.o = fs_mk(0.f, 0.f, 0.f); s.d = s.o; s.sx = s.sy = s.sz = s.bx = s.by = s.bz = 0.f;
+    s.o = fs_mk(0.f, 0.f, 0.f); s.d = s.o; s.idx = s.idy = s.idz = s.oodx = s.oody = s.oodz = 0.f;
     bool running = false, exhausted = false, occluded = false;
     uint32_t path = 0, ovf = 0, guard = 0;
     float tmax = 0.f;
@@ -713,7 +691,7 @@ k_trace_any(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4
                 if (!__any_sync(FULLM, can && s.leaf == 0)) break;
                 if (can) {
                     if (COUNT) vc.nodes++;
-                    tr_node_step<false, 0>(bv, s, stack, tmax, &ovf);
+                    tr_node_step<false, (TEX ? 2 : 0)>(bv, s, stack, tmax, &ovf);
                 }
             }
             tr_next_leaf(s, stack);
@@ -980,7 +958,7 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
     const fs_wave_buffers& wb = ctx->wb;
     static int occ_tr = 0, occ_any = 0;
     if (!occ_tr) occ_tr = resident_ctas(k_trace_closest<COUNT, 0>, TR_THREADS, 0);
-    if (!occ_any) occ_any = resident_ctas(k_trace_any<COUNT>, TR_THREADS, 0);
+    if (!occ_any) occ_any = resident_ctas(k_trace_any<COUNT, 0>, TR_THREADS, 0);
     const bool timing = (tp.flags & FS_FLAG_TIME_KERNELS) != 0;
     cudaEvent_t* ev = nullptr;
     if (timing) {
@@ -1012,10 +990,10 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
             ++ctx->stats.kernel_launches;
             if (k == D) break;
             const int texm = tp.bv.nodes_tex ? (int)ctx->tune_tex : 0;
-            if (texm == 1)
-                k_trace_closest<COUNT, 1><<<grid_tr, TR_THREADS, 0, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u],
+            if (texm == 3 && tp.bv.tris_tex)
+                k_trace_closest<COUNT, 3><<<grid_tr, TR_THREADS, 0, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u],
                     wb.q_count + k, wb.q_cursor + k, wb.hit, ctx->d_counters, ctx->tune_refill);
-            else if (texm == 2)
+            else if (texm >= 2)
                 k_trace_closest<COUNT, 2><<<grid_tr, TR_THREADS, 0, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u],
                     wb.q_count + k, wb.q_cursor + k, wb.hit, ctx->d_counters, ctx->tune_refill);
             else
@@ -1033,9 +1011,12 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
     uint32_t grid_any = (uint32_t)(ctx->sm_count * occ_any);
     const uint32_t ctas_any = (tp.batch + TR_THREADS - 1) / TR_THREADS;
     if (grid_any > ctas_any) grid_any = ctas_any ? ctas_any : 1;
-    k_trace_any<COUNT><<<grid_any, TR_THREADS, 0, st>>>(tp.bv, wb.st_pos[0], wb.st_nrm[0], wb.q_count + (D + 2),
-                                                     wb.q_cursor + (D + 2), wb.conn_queue, wb.q_count + (D + 1),
-                                                     ctx->d_counters, d_dbg, ctx->tune_refill);
+    if (tp.bv.nodes_tex && ctx->tune_tex)
+        k_trace_any<COUNT, 2><<<grid_any, TR_THREADS, 0, st>>>(tp.bv, wb.st_pos[0], wb.st_nrm[0], wb.q_count + (D + 2),
+            wb.q_cursor + (D + 2), wb.conn_queue, wb.q_count + (D + 1), ctx->d_counters, d_dbg, ctx->tune_refill);
+    else
+        k_trace_any<COUNT, 0><<<grid_any, TR_THREADS, 0, st>>>(tp.bv, wb.st_pos[0], wb.st_nrm[0], wb.q_count + (D + 2),
+            wb.q_cursor + (D + 2), wb.conn_queue, wb.q_count + (D + 1), ctx->d_counters, d_dbg, ctx->tune_refill);
     ctx->stats.kernel_launches += 2;
     if (timing) cudaEventRecord(ev[2], st);
     uint32_t grid_ev = (uint32_t)ctx->sm_count * 4u;
