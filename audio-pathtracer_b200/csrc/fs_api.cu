@@ -120,6 +120,7 @@ void fs_destroy(fs_ctx* ctx)
     cudaFree(ctx->d_hist); cudaFree(ctx->d_counters); cudaFree(ctx->d_src_pos); cudaFree(ctx->d_dbg);
     cudaFree(ctx->d_amp); cudaFree(ctx->d_energy);
     for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->tev) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -264,7 +265,7 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
     fs_trace_params tp;
     fill_params(ctx, &tp, lis_pos, n_paths, max_depth, seed);
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    ctx->kev_used = 0; ctx->stats.extend_launches = 0;
+    ctx->kev_used = 0; ctx->tev_used = 0; ctx->stats.extend_launches = 0;
     CK(fs_wave_reset_counters(ctx));
     for (uint64_t done = 0; done < g_count;) {
         uint64_t nb = g_count - done;
@@ -297,6 +298,11 @@ static int finish_stats(fs_ctx* ctx)
         }
         (void)cudaGetLastError();
         ctx->stats.extend_ms = ext; ctx->stats.connect_ms = con; ctx->stats.eval_ms = evl;
+        float tr = 0.f;
+        for (size_t i = 0; i + 1 < ctx->tev_used; i += 2)
+            if (cudaEventElapsedTime(&ms, ctx->tev[i], ctx->tev[i + 1]) == cudaSuccess) tr += ms;
+        (void)cudaGetLastError();
+        ctx->stats.trace_ms = tr;
     }
     if (ctx->timed) {
         float ms = 0.f;

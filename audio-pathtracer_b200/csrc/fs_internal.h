@@ -103,6 +103,7 @@ struct fs_ctx {
     fs_stats stats;
     cudaEvent_t ev0, ev1; bool timed;
     std::vector<cudaEvent_t> kev; size_t kev_used;   // FS_FLAG_TIME_KERNELS: 4 events per batch
+    std::vector<cudaEvent_t> tev; size_t tev_used;   //   + one (begin, end) pair per k_trace_closest launch
     int sm_count;
     uint32_t tune_refill, tune_leaf_max, tune_tex;      // experiment knobs (env FS_TUNE_REFILL / FS_TUNE_LEAF_MAX)
     // IR / conv

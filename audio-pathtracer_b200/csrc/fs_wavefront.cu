@@ -990,6 +990,17 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
             ++ctx->stats.kernel_launches;
             if (k == D) break;
             const int texm = tp.bv.nodes_tex ? (int)ctx->tune_tex : 0;
+            cudaEvent_t* te = nullptr;
+            if (timing) {
+                if (ctx->tev.size() < ctx->tev_used + 2) {
+                    size_t old = ctx->tev.size();
+                    ctx->tev.resize(ctx->tev_used + 2);
+                    for (size_t i = old; i < ctx->tev.size(); ++i) cudaEventCreate(&ctx->tev[i]);
+                }
+                te = &ctx->tev[ctx->tev_used];
+                ctx->tev_used += 2;
+                cudaEventRecord(te[0], st);
+            }
             if (texm == 3 && tp.bv.tris_tex)
                 k_trace_closest<COUNT, 3><<<grid_tr, TR_THREADS, 0, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u],
                     wb.q_count + k, wb.q_cursor + k, wb.hit, ctx->d_counters, ctx->tune_refill);
@@ -999,6 +1010,7 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
             else
                 k_trace_closest<COUNT, 0><<<grid_tr, TR_THREADS, 0, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u],
                     wb.q_count + k, wb.q_cursor + k, wb.hit, ctx->d_counters, ctx->tune_refill);
+            if (timing) cudaEventRecord(te[1], st);
             ++ctx->stats.kernel_launches;
             ++ctx->stats.extend_launches;
         }

@@ -226,6 +226,7 @@ def run_b200(args):
         step_device(SEED0 + k); torch.cuda.synchronize()
         s = ctx.stats(); per.append(s)
     ext_ms = float(np.mean([s["extend_ms"] for s in per])); con_ms = float(np.mean([s["connect_ms"] for s in per]))
+    trc_ms = float(np.mean([s["trace_ms"] for s in per]))
     evl_ms = float(np.mean([s["eval_ms"] for s in per])); ext_launches = per[0]["extend_launches"]
     rays = float(np.mean([s["ext_rays"] + s["shadow_rays"] for s in per]))
     ext_rays = float(np.mean([s["ext_rays"] for s in per]))
@@ -242,11 +243,14 @@ def run_b200(args):
     en = float(np.mean([c["node_visits"] - c["shadow_node_visits"] for c in cnt]))
     et = float(np.mean([c["tri_tests"] - c["shadow_tri_tests"] for c in cnt]))
     er = float(np.mean([c["ext_rays"] for c in cnt]))
-    # bytes_ray = 64 * n_node + 48 * n_tri + 32 (ray/state read) + 16 (record write)
-    ext_bytes = 64.0 * en + 48.0 * et + 48.0 * er
+    # SURVEY.md 8(d) per-ray figure with this build's record sizes:
+    # bytes_ray = 64 * n_node (BVH2 node, both child boxes) + 48 * n_tri (v0,e1,e2) + 32 (ray record read) + 8 (hit write)
+    ext_bytes = 64.0 * en + 48.0 * et + 40.0 * er
     peak, peak_src = measured_peak()
-    achieved = ext_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else None
-    roofline = {"bound": "hbm", "kernel": "k_extend (BVH closest-hit traversal + shading), %d launches per step" % ext_launches,
+    achieved = ext_bytes / (trc_ms * 1e-3) / 1e9 if trc_ms > 0 else None
+    ext_ms_all = ext_ms
+    ext_ms = trc_ms
+    roofline = {"bound": "hbm", "kernel": "k_trace_closest (persistent BVH closest-hit traversal), %d launches per step" % ext_launches,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": None, "peak_source": peak_src,
                 "bytes_per_launch": ext_bytes / max(ext_launches, 1), "ms_per_launch": ext_ms / max(ext_launches, 1),
@@ -299,7 +303,7 @@ def run_b200(args):
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu,
                 "mrays_per_s": rays * N / (dev_ms / K * 1e-3) / 1e6, "ms_per_ir_update": dev_ms / K,
-                "stage_ms": {"extend": ext_ms, "connect": con_ms, "eval_splat": evl_ms},
+                "stage_ms": {"trace_closest": trc_ms, "shade_gen": ext_ms_all - trc_ms, "connect": con_ms, "eval_splat": evl_ms},
                 "rays_per_step_per_gpu": rays, "ext_rays_per_step_per_gpu": ext_rays, "connected_per_step_per_gpu": connected,
                 "triangles": int(sc.n_tris)}
         print(json.dumps(line), flush=True)

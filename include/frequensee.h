@@ -99,10 +99,11 @@ typedef struct fs_stats {
     uint64_t bvh_max_leaf;     /* triangles in the largest leaf */
     float    last_trace_ms;    /* device time of the last fs_trace*, CUDA events on the context stream */
     float    last_ir_ms;
-    float    extend_ms;        /* only with FS_FLAG_TIME_KERNELS: sum over the k_extend launches of the last trace */
+    float    extend_ms;        /* only with FS_FLAG_TIME_KERNELS: extension stage (k_shade_gen + k_trace_closest, or k_extend) */
     float    connect_ms;       /*   "   k_connect */
     float    eval_ms;          /*   "   k_eval (evaluate + splat) */
-    uint32_t extend_launches;  /* k_extend launches in the last trace */
+    uint32_t extend_launches;  /* closest-hit traversal launches (k_trace_closest / k_extend) in the last trace */
+    float    trace_ms;         /* only with FS_FLAG_TIME_KERNELS: sum over the k_trace_closest launches alone */
 } fs_stats;
 
 /* per-path debug record, same layout as fso_path_dbg in oracle/fs_oracle.h */
