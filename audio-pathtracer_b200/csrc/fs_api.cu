@@ -471,7 +471,7 @@ int fs_get_histogram(fs_ctx* ctx, uint64_t* hist_out)
     return finish_stats(ctx);
 }
 
-static int ir_common(fs_ctx* ctx, uint32_t source, const float* energy, float* ir_out)
+static int ir_common(fs_ctx* ctx, uint32_t hist_source, uint32_t source, const float* energy, float* ir_out)
 {
     const fs_config& c = ctx->cfg;
     if (source >= ctx->conv_cap || !ctx->conv[source].ir) {
@@ -488,7 +488,7 @@ static int ir_common(fs_ctx* ctx, uint32_t source, const float* energy, float* i
         CK(cudaMemcpyAsync(ctx->d_energy, energy, sizeof(float) * c.n_bins, cudaMemcpyHostToDevice, ctx->stream));
         d_energy = ctx->d_energy;
     }
-    const unsigned long long* hsrc = ctx->d_hist ? ctx->d_hist + (size_t)source * c.n_bands * c.n_bins : nullptr;
+    const unsigned long long* hsrc = ctx->d_hist ? ctx->d_hist + (size_t)hist_source * c.n_bands * c.n_bins : nullptr;
     CK(fs_ir_build(ctx, hsrc, ctx->hist_n_paths, d_energy, s.ir));
     { std::lock_guard<std::mutex> lk(ctx->conv_mu); CK(fs_conv_update_ir(ctx, source, ctx->stream)); }
     CK(cudaEventRecord(b, ctx->stream));
@@ -508,7 +508,17 @@ int fs_build_ir(fs_ctx* ctx, uint32_t source, float* ir_out)
     if (!ctx->d_hist || source >= ctx->hist_sources || ctx->hist_n_paths == 0)
         return fail(ctx, FS_ERR_STATE, "fs_build_ir: no histogram for this source (call fs_trace or fs_set_histogram)");
     dev_guard g(ctx->device);
-    return ir_common(ctx, source, nullptr, ir_out);
+    return ir_common(ctx, source, source, nullptr, ir_out);
+}
+
+int fs_build_ir_to(fs_ctx* ctx, uint32_t hist_source, uint32_t conv_source, float* ir_out)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    if (!ctx->d_hist || hist_source >= ctx->hist_sources || ctx->hist_n_paths == 0)
+        return fail(ctx, FS_ERR_STATE, "fs_build_ir_to: no histogram for this source (call fs_trace or fs_set_histogram)");
+    if (conv_source >= 4096) return fail(ctx, FS_ERR_INVALID, "source id too large");
+    dev_guard g(ctx->device);
+    return ir_common(ctx, hist_source, conv_source, nullptr, ir_out);
 }
 
 int fs_build_ir_from_energy(fs_ctx* ctx, uint32_t source, const float* energy, float* ir_out)
@@ -516,7 +526,7 @@ int fs_build_ir_from_energy(fs_ctx* ctx, uint32_t source, const float* energy, f
     if (!ctx) return FS_ERR_INVALID;
     if (!energy) return fail(ctx, FS_ERR_INVALID, "fs_build_ir_from_energy: null energy");
     dev_guard g(ctx->device);
-    return ir_common(ctx, source, energy, ir_out);
+    return ir_common(ctx, 0, source, energy, ir_out);
 }
 
 int fs_set_ir(fs_ctx* ctx, uint32_t source, const float* ir)

@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "fs_scene_set_triangles", "fs_scene_set_materials", "fs_scene_commit",
     "fs_trace", "fs_trace_range_device", "fs_trace_range", "fs_trace_debug",
     "fs_debug_closest_hits", "fs_debug_any_hits",
-    "fs_build_ir", "fs_build_ir_from_energy", "fs_set_histogram", "fs_set_histogram_device",
+    "fs_build_ir", "fs_build_ir_to", "fs_build_ir_from_energy", "fs_set_histogram", "fs_set_histogram_device",
     "fs_get_histogram", "fs_set_ir",
     "fs_conv_init_source", "fs_conv_release_source", "fs_conv_process", "fs_conv_process_many",
     "fs_debug_rfft", "fs_get_stats",
@@ -105,6 +105,7 @@ def load():
     L.fs_debug_closest_hits.argtypes = [vp, vp, u64, vp, vp]
     L.fs_debug_any_hits.argtypes = [vp, vp, vp, u64, vp]
     L.fs_build_ir.argtypes = [vp, u32, vp]
+    L.fs_build_ir_to.argtypes = [vp, u32, u32, vp]
     L.fs_build_ir_from_energy.argtypes = [vp, u32, vp, vp]
     L.fs_set_histogram.argtypes = [vp, vp, u32, u64]
     L.fs_set_histogram_device.argtypes = [vp, vp, u32, u64]
@@ -262,6 +263,11 @@ class Context:
     def build_ir(self, source=0, want_ir=True):
         ir = np.zeros((self.cfg.n_channels, self.cfg.sample_rate), dtype=np.float32) if want_ir else None
         self._ck(self.L.fs_build_ir(self.h, source, ir.ctypes.data if want_ir else None))
+        return ir
+
+    def build_ir_to(self, hist_source, conv_source, want_ir=True):
+        ir = np.zeros((self.cfg.n_channels, self.cfg.sample_rate), dtype=np.float32) if want_ir else None
+        self._ck(self.L.fs_build_ir_to(self.h, hist_source, conv_source, ir.ctypes.data if want_ir else None))
         return ir
 
     def build_ir_from_energy(self, energy, source=0):

@@ -176,6 +176,9 @@ int fs_debug_any_hits(fs_ctx* ctx, const float* rays, const float* tmax, uint64_
  * (or set by fs_set_histogram), normalised by 1/n_paths (SUB.cpp:164).  Also refreshes that
  * source's convolver partition spectra.  ir_out: host [C][sample_rate] float, may be NULL. */
 int fs_build_ir(fs_ctx* ctx, uint32_t source, float* ir_out);
+/* same, with the histogram slot and the convolver slot named separately (a per-component update
+ * traces one source into histogram slot 0 and publishes the IR to that component's own slot) */
+int fs_build_ir_to(fs_ctx* ctx, uint32_t hist_source, uint32_t conv_source, float* ir_out);
 /* seam 1 of the reference taken literally: EnergyBuffer float[K] -> IR (AddEnergyAtDelay users) */
 int fs_build_ir_from_energy(fs_ctx* ctx, uint32_t source, const float* energy /*[K]*/, float* ir_out);
 /* install an already reduced histogram (host [S][B][K]) and its path count, e.g. after an NCCL reduce */
