@@ -41,13 +41,17 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--paths", type=int, default=1 << 20)
     ap.add_argument("--depth", type=int, default=16)
+    ap.add_argument("--scene", default="furnished_room", choices=["furnished_room", "mine_tunnels", "concert_hall", "shoebox"],
+                    help="default furnished_room = BASELINE.json configs[1]; the others are extra measurements")
     ap.add_argument("--cpu-sample-paths", type=int, default=1 << 16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
 def config_dict(args, n):
-    return {"workload": WORKLOAD, "scene": "furnished_room(seed=1)", "paths_per_gpu_per_step": args.paths,
+    wl = WORKLOAD if (args.scene == "furnished_room" and args.paths == 1 << 20 and args.depth == 16) else \
+        "%s_%d_paths_depth%d_8bands" % (args.scene, args.paths, args.depth)
+    return {"workload": wl, "scene": "%s (seeded procedural)" % args.scene, "paths_per_gpu_per_step": args.paths,
             "max_depth": args.depth, "bands": 8, "bins": 1000, "sources": 1, "rr_prob": 0.9,
             "parallelism": "path-range sharding x%d, replicated BVH, one int64 reduce" % n,
             "l2": "no explicit flush: per-step wavefront state+records (~0.6 GB) exceed the 126 MB L2; "
@@ -102,6 +106,22 @@ class Clocks:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def traffic_from_profiles(args):
+    """dram__bytes_read.sum + dram__bytes_write.sum per k_trace_closest launch from the committed ncu --set full
+    capture of this workload (profiles/*_traffic.json); None for workloads that were not captured"""
+    if not (args.scene == "furnished_room" and args.paths == 1 << 20 and args.depth == 16):
+        return None
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for f in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if f.endswith("_traffic.json"):
+            try:
+                best = float(json.load(open(os.path.join(pdir, f)))["dram_bytes_per_launch"])
+            except Exception:
+                pass
+    return best
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -119,7 +139,8 @@ def cpu_oracle_rate(args, n_paths, threads, repeats=1, seed=SEED0):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle as po
     from frequensee import scenes
-    sc = scenes.furnished_room()
+    sc = scenes.by_name(args.scene)
+    sc.sources = sc.sources[:1]
     S = po.Scene(sc.verts, sc.tri_mat, sc.absorption, use_bvh=True)
     cfg = po.default_config()
     times = []
@@ -174,7 +195,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N, K, W = world, args.steps, args.warmup
     P, D = args.paths, args.depth
-    sc = scenes.furnished_room()
+    sc = scenes.by_name(args.scene)
+    sc.sources = sc.sources[:1]
     ctx = fs.Context(device=local, flags=capi.FLAG_TIME_KERNELS)
     ctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
     stream = torch.cuda.Stream()                            # a real (non-NULL) stream: the C-ABI treats NULL as "own stream"
@@ -254,7 +276,7 @@ def run_b200(args):
     ext_ms = trc_ms
     roofline = {"bound": "hbm", "kernel": "k_trace_closest (persistent BVH closest-hit traversal), %d launches per step" % ext_launches,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic_from_profiles(args), "peak_source": peak_src,
                 "bytes_per_launch": ext_bytes / max(ext_launches, 1), "ms_per_launch": ext_ms / max(ext_launches, 1),
                 "nodes_per_ray": en / er, "tris_per_ray": et / er,
                 "note": "BVH (~11 MB) is L2-resident: achieved is algorithmic fetch bandwidth, served mostly by L2, "
