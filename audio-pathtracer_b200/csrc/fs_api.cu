@@ -79,7 +79,8 @@ int fs_create(const fs_config* cfg, fs_ctx** out)
     ctx->cfg = *cfg;
     if (ctx->cfg.max_batch_paths == 0) ctx->cfg.max_batch_paths = 1u << 20;
     ctx->device = dev;
-    ctx->tune_refill = 8; ctx->tune_leaf_max = FS_LEAF_MAX; ctx->tune_tex = 2;
+    ctx->tune_refill = 8; ctx->tune_leaf_max = FS_LEAF_MAX; ctx->tune_tex = 2; ctx->tune_builder = 1;
+    if (const char* e4 = getenv("FS_TUNE_BUILDER")) ctx->tune_builder = (uint32_t)atoi(e4);
     if (const char* e3 = getenv("FS_TUNE_TEX")) ctx->tune_tex = (uint32_t)atoi(e3);
     if (const char* e1 = getenv("FS_TUNE_REFILL")) { int v = atoi(e1); if (v >= 1 && v <= 32) ctx->tune_refill = (uint32_t)v; }
     if (const char* e2 = getenv("FS_TUNE_LEAF_MAX")) { int v = atoi(e2); if (v >= 1 && v <= 8) ctx->tune_leaf_max = (uint32_t)v; }
@@ -200,7 +201,7 @@ int fs_scene_commit(fs_ctx* ctx)
             if (m[i] >= ctx->n_mats) return fail(ctx, FS_ERR_INVALID, "triangle material id out of range");
     }
     CK(fs_bvh_build(ctx->stream, ctx->d_verts, ctx->d_tri_mat, ctx->n_tris, &ctx->bvh, &ctx->stats.kernel_launches,
-                    ctx->tune_leaf_max));
+                    ctx->tune_leaf_max, ctx->tune_builder));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stats.bvh_nodes = ctx->bvh.n_inner;
     ctx->stats.bvh_max_leaf = ctx->bvh.max_leaf;

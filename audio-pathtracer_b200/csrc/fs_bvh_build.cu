@@ -16,6 +16,7 @@
 // Replaces UAudioRayTracingSubsystem::RegisterGeometry (SUB.h:99-100) + the Chaos scene query
 // acceleration behind UWorld::LineTraceSingleByObjectType (SUB.cpp:252, 340).
 #include "fs_internal.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -338,6 +339,126 @@ __global__ void k_emit(int n, const int2* __restrict__ children, const int2* __r
     nodes[(size_t)i * 4 + 3] = make_float4(__int_as_float(e0), __int_as_float(e1), 0.f, 0.f);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// PLOC: parallel locally-ordered clustering (Meister & Bittner 2018) over the Morton-sorted
+// triangles.  Every round each cluster looks R neighbours to the left and right in the cluster
+// array for the partner minimising the surface area of the merged box; mutual nearest neighbours
+// merge into one inner node.  Bottom-up agglomeration by surface area gives near-SAH trees
+// (the LBVH topology splits on Morton bits only).  One triangle per leaf; inner node ids are
+// handed out from the back so the root ends up at index 0 and the top of the tree is contiguous.
+// ---------------------------------------------------------------------------------------------
+// search radius: FS_TUNE_PLOC_R (default 10)
+
+__device__ __forceinline__ float box_area(float4 lo, float4 hi)
+{
+    float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void k_ploc_init(uint32_t n, const float4* __restrict__ bb_lo, const float4* __restrict__ bb_hi,
+                            float4* __restrict__ clo, float4* __restrict__ chi, int* __restrict__ cref)
+{
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    clo[j] = bb_lo[(n - 1) + j];
+    chi[j] = bb_hi[(n - 1) + j];
+    cref[j] = ~(int)(j << 3);                       // leaf: triangle j, count 1
+}
+
+__global__ void k_ploc_nn(uint32_t n, const float4* __restrict__ clo, const float4* __restrict__ chi,
+                          uint32_t* __restrict__ nn, const int PLOC_R)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 lo = clo[i], hi = chi[i];
+    float best = INFINITY; uint32_t bj = i;
+    const uint32_t j0 = i > (uint32_t)PLOC_R ? i - PLOC_R : 0u;
+    const uint32_t j1 = min(n - 1u, i + (uint32_t)PLOC_R);
+    for (uint32_t j = j0; j <= j1; ++j) {
+        if (j == i) continue;
+        const float4 l = clo[j], h = chi[j];
+        const float4 ul = make_float4(fminf(lo.x, l.x), fminf(lo.y, l.y), fminf(lo.z, l.z), 0.f);
+        const float4 uh = make_float4(fmaxf(hi.x, h.x), fmaxf(hi.y, h.y), fmaxf(hi.z, h.z), 0.f);
+        const float a = box_area(ul, uh);
+        if (a < best) { best = a; bj = j; }          // ties keep the lower index: deterministic
+    }
+    nn[i] = bj;
+}
+
+// flags[i] = 1 if cluster i survives this round (it is not the right half of a merging pair);
+// mflag[i] = 1 if cluster i is the left half of a merging pair (creates one inner node)
+__global__ void k_ploc_flags(uint32_t n, const uint32_t* __restrict__ nn, uint32_t* __restrict__ keep,
+                             uint32_t* __restrict__ mflag)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = nn[i];
+    const bool mutual = (j != i) && (nn[j] == i);
+    keep[i] = (mutual && j < i) ? 0u : 1u;
+    mflag[i] = (mutual && i < j) ? 1u : 0u;
+}
+
+__global__ void k_ploc_merge(uint32_t n, const uint32_t* __restrict__ nn, const uint32_t* __restrict__ keep_scan,
+                             const uint32_t* __restrict__ merge_scan, const uint32_t* __restrict__ keep,
+                             const uint32_t* __restrict__ mflag, uint32_t nodes_made, uint32_t n_inner,
+                             const float4* __restrict__ clo, const float4* __restrict__ chi, const int* __restrict__ cref,
+                             float4* __restrict__ nlo, float4* __restrict__ nhi, int* __restrict__ nref,
+                             float4* __restrict__ nodes)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !keep[i]) return;
+    const uint32_t pos = keep_scan[i];
+    if (mflag[i]) {
+        const uint32_t j = nn[i];
+        const float4 l0 = clo[i], h0 = chi[i], l1 = clo[j], h1 = chi[j];
+        const uint32_t id = n_inner - 1u - (nodes_made + merge_scan[i]);      // root (made last) gets id 0
+        const float p0 = box_pad(l0, h0), p1 = box_pad(l1, h1);
+        nodes[(size_t)id * 4 + 0] = make_float4(l0.x - p0, h0.x + p0, l0.y - p0, h0.y + p0);
+        nodes[(size_t)id * 4 + 1] = make_float4(l1.x - p1, h1.x + p1, l1.y - p1, h1.y + p1);
+        nodes[(size_t)id * 4 + 2] = make_float4(l0.z - p0, h0.z + p0, l1.z - p1, h1.z + p1);
+        nodes[(size_t)id * 4 + 3] = make_float4(__int_as_float(cref[i]), __int_as_float(cref[j]), 0.f, 0.f);
+        nlo[pos] = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.f);
+        nhi[pos] = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f);
+        nref[pos] = (int)id;
+    } else {
+        nlo[pos] = clo[i]; nhi[pos] = chi[i]; nref[pos] = cref[i];
+    }
+}
+
+// three-phase exclusive scan of n u32 (tile sums -> scan of tile sums by one CTA -> add)
+constexpr int SCAN_TILE = 1024;
+__global__ void __launch_bounds__(SCAN_TILE) k_scan_tiles(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                           uint32_t n, uint32_t* __restrict__ tile_sums)
+{
+    __shared__ uint32_t ws[32];
+    const uint32_t i = blockIdx.x * SCAN_TILE + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t v = i < n ? in[i] : 0u;
+    uint32_t x = v;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if ((int)lane >= o) x += y; }
+    if (lane == 31) ws[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = ws[lane];
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if ((int)lane >= o) w += y; }
+        ws[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t incl = x + (warp ? ws[warp - 1] : 0u);
+    if (i < n) out[i] = incl - v;
+    if (threadIdx.x == SCAN_TILE - 1) tile_sums[blockIdx.x] = incl;
+}
+__global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t n, const uint32_t* __restrict__ tile_offs)
+{
+    const uint32_t i = blockIdx.x * SCAN_TILE + threadIdx.x;
+    if (i < n) out[i] += tile_offs[blockIdx.x];
+}
+// total[0] = last exclusive value + last input (after the add phase)
+__global__ void k_scan_total(const uint32_t* __restrict__ in, const uint32_t* __restrict__ out, uint32_t n, uint32_t* total)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) *total = n ? out[n - 1] + in[n - 1] : 0u;
+}
+
 // single-triangle scene: root whose second child is a far-away point box (never entered in practice)
 __global__ void k_emit_single(const float4* __restrict__ bb_lo, const float4* __restrict__ bb_hi,
                               float4* __restrict__ nodes)
@@ -385,10 +506,73 @@ __global__ void k_leaf_stats(int n, const int2* __restrict__ ranges, uint32_t* _
 
 }  // namespace
 
+
+
 #define BCHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = e_; goto fail; } } while (0)
 
+// exclusive scan helper (device arrays); tile_sums must hold ceil(n/1024) + 1 entries
+static void scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tile_sums,
+                     uint32_t* total, uint64_t* launches)
+{
+    const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_tiles<<<tiles, SCAN_TILE, 0, st>>>(in, out, n, tile_sums);
+    k_sort_scan<<<1, 1024, 0, st>>>(tile_sums, tiles);
+    k_scan_add<<<tiles, SCAN_TILE, 0, st>>>(out, n, tile_sums);
+    k_scan_total<<<1, 32, 0, st>>>(in, out, n, total);
+    *launches += 4;
+}
+
+static cudaError_t ploc_build(cudaStream_t st, uint32_t n, const float4* bb_lo, const float4* bb_hi, float4* nodes,
+                              uint64_t* launches)
+{
+    int radius = 10;
+    if (const char* e = getenv("FS_TUNE_PLOC_R")) { int v = atoi(e); if (v >= 1 && v <= 256) radius = v; }
+    cudaError_t err = cudaSuccess;
+    float4 *lo[2] = {nullptr, nullptr}, *hi[2] = {nullptr, nullptr};
+    int* ref[2] = {nullptr, nullptr};
+    uint32_t *nn = nullptr, *keep = nullptr, *mflag = nullptr, *keep_scan = nullptr, *merge_scan = nullptr,
+             *tile_sums = nullptr, *totals = nullptr;
+    const uint32_t n_inner = n - 1;
+    const int TPB = 256;
+    uint32_t cur = n, made = 0;
+    int pp = 0;
+    for (int k = 0; k < 2; ++k) {
+        BCHECK(cudaMalloc(&lo[k], sizeof(float4) * n));
+        BCHECK(cudaMalloc(&hi[k], sizeof(float4) * n));
+        BCHECK(cudaMalloc(&ref[k], sizeof(int) * n));
+    }
+    BCHECK(cudaMalloc(&nn, 4ull * n)); BCHECK(cudaMalloc(&keep, 4ull * n)); BCHECK(cudaMalloc(&mflag, 4ull * n));
+    BCHECK(cudaMalloc(&keep_scan, 4ull * n)); BCHECK(cudaMalloc(&merge_scan, 4ull * n));
+    BCHECK(cudaMalloc(&tile_sums, 4ull * ((n + SCAN_TILE - 1) / SCAN_TILE + 2)));
+    BCHECK(cudaMalloc(&totals, 4 * 2));
+    k_ploc_init<<<(n + TPB - 1) / TPB, TPB, 0, st>>>(n, bb_lo, bb_hi, lo[0], hi[0], ref[0]); ++*launches;
+    for (int round = 0; cur > 1 && round < 4096; ++round) {
+        const uint32_t g = (cur + TPB - 1) / TPB;
+        k_ploc_nn<<<g, TPB, 0, st>>>(cur, lo[pp], hi[pp], nn, radius);
+        k_ploc_flags<<<g, TPB, 0, st>>>(cur, nn, keep, mflag);
+        *launches += 2;
+        scan_u32(st, keep, keep_scan, cur, tile_sums, totals, launches);
+        scan_u32(st, mflag, merge_scan, cur, tile_sums, totals + 1, launches);
+        k_ploc_merge<<<g, TPB, 0, st>>>(cur, nn, keep_scan, merge_scan, keep, mflag, made, n_inner, lo[pp], hi[pp], ref[pp],
+                                        lo[pp ^ 1], hi[pp ^ 1], ref[pp ^ 1], nodes);
+        ++*launches;
+        uint32_t h[2];
+        BCHECK(cudaMemcpyAsync(h, totals, sizeof(h), cudaMemcpyDeviceToHost, st));
+        BCHECK(cudaStreamSynchronize(st));
+        if (h[1] == 0 || h[0] >= cur) { err = cudaErrorUnknown; goto fail; }      // no progress: cannot happen (the global minimum pair is mutual)
+        made += h[1];
+        cur = h[0];
+        pp ^= 1;
+    }
+    if (cur != 1 || made != n_inner) err = cudaErrorUnknown;
+fail:
+    for (int k = 0; k < 2; ++k) { cudaFree(lo[k]); cudaFree(hi[k]); cudaFree(ref[k]); }
+    cudaFree(nn); cudaFree(keep); cudaFree(mflag); cudaFree(keep_scan); cudaFree(merge_scan); cudaFree(tile_sums); cudaFree(totals);
+    return err;
+}
+
 cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* d_mats, uint64_t T64,
-                         fs_bvh_device* out, uint64_t* launches, uint32_t leaf_max_u)
+                         fs_bvh_device* out, uint64_t* launches, uint32_t leaf_max_u, uint32_t builder)
 {
     const int leaf_max = (int)(leaf_max_u < 1 ? 1 : (leaf_max_u > 8 ? 8 : leaf_max_u));
     cudaError_t err = cudaSuccess;
@@ -453,6 +637,10 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
     if (n == 1) {
         k_emit_single<<<1, 1, 0, st>>>(bb_lo, bb_hi, out->nodes); ++*launches;
         out->max_leaf = 1;
+    } else if (builder == 1 && n >= 3) {
+        // PLOC over the Morton-sorted leaves; nodes are emitted as clusters merge
+        BCHECK(ploc_build(st, n, bb_lo, bb_hi, out->nodes, launches));
+        out->max_leaf = 1;
     } else {
         k_karras<<<gb, TPB, 0, st>>>(keys0, (int)n, children, ranges, parent); ++*launches;
         k_refit<<<gb, TPB, 0, st>>>((int)n, children, parent, bb_lo, bb_hi, arrive); ++*launches;
@@ -479,7 +667,7 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
         BCHECK(cudaMemcpyAsync(h, misc, sizeof(h), cudaMemcpyDeviceToHost, st));
         BCHECK(cudaStreamSynchronize(st));
         out->n_top = h[7];
-        if (n > 1) out->max_leaf = h[8] ? h[8] : 1;
+        if (n > 1 && !(builder == 1 && n >= 3)) out->max_leaf = h[8] ? h[8] : 1;
         out->extent = ord2f(h[6]);
     }
 fail:

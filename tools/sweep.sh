@@ -1,5 +1,5 @@
 #!/bin/bash
-for tex in 3 2; do
-  echo -n "tex=$tex : "
-  FS_TUNE_TEX=$tex timeout 60 python tools/profile_step.py 0 3 | tail -1 | cut -c1-130
+for b in 0 1; do
+  echo "builder=$b : "
+  FS_TUNE_BUILDER=$b timeout 200 python tools/profile_step.py 1 2 concert_hall 32 | tail -2 | cut -c1-330
 done
