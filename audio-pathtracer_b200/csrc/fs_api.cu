@@ -79,7 +79,8 @@ int fs_create(const fs_config* cfg, fs_ctx** out)
     ctx->cfg = *cfg;
     if (ctx->cfg.max_batch_paths == 0) ctx->cfg.max_batch_paths = 1u << 20;
     ctx->device = dev;
-    ctx->tune_refill = 8; ctx->tune_leaf_max = FS_LEAF_MAX; ctx->tune_tex = 2; ctx->tune_builder = 1;
+    ctx->tune_refill = 8; ctx->tune_leaf_max = FS_LEAF_MAX; ctx->tune_tex = 2; ctx->tune_builder = 1; ctx->tune_wide = 1;
+    if (const char* e5 = getenv("FS_TUNE_WIDE")) ctx->tune_wide = (uint32_t)atoi(e5);
     if (const char* e4 = getenv("FS_TUNE_BUILDER")) ctx->tune_builder = (uint32_t)atoi(e4);
     if (const char* e3 = getenv("FS_TUNE_TEX")) ctx->tune_tex = (uint32_t)atoi(e3);
     if (const char* e1 = getenv("FS_TUNE_REFILL")) { int v = atoi(e1); if (v >= 1 && v <= 32) ctx->tune_refill = (uint32_t)v; }
@@ -217,6 +218,9 @@ static void fill_params(fs_ctx* ctx, fs_trace_params* tp, const float lis[3], ui
     memset(tp, 0, sizeof(*tp));
     tp->bv.nodes_tex = (ctx->tune_tex && ctx->bvh.nodes_tex) ? (unsigned long long)ctx->bvh.nodes_tex : 0ull;
     tp->bv.tris_tex = (ctx->tune_tex && ctx->bvh.tris_tex) ? (unsigned long long)ctx->bvh.tris_tex : 0ull;
+    tp->bv.wnodes = ctx->tune_wide ? ctx->bvh.wnodes : nullptr;
+    tp->bv.wnodes_tex = (ctx->tune_tex && ctx->bvh.wnodes_tex) ? (unsigned long long)ctx->bvh.wnodes_tex : 0ull;
+    for (int a = 0; a < 3; ++a) { tp->bv.qbase[a] = ctx->bvh.qbase[a]; tp->bv.qscale[a] = ctx->bvh.qscale[a]; }
     tp->bv.nodes = ctx->bvh.nodes; tp->bv.tris = ctx->bvh.tris; tp->bv.tri_orig = ctx->bvh.tri_orig;
     tp->bv.tri_mat = ctx->bvh.tri_mat; tp->bv.n_tris = ctx->bvh.n_tris; tp->bv.n_inner = ctx->bvh.n_inner;
     tp->top = ctx->bvh.top_nodes; tp->n_top = ctx->bvh.n_top;

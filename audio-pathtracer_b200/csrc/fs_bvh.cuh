@@ -18,6 +18,14 @@
 // A 32 B node format (16-bit quantised boxes, octant plane selection by PRMT) halves those
 // wavefronts (48 %) but was measured no faster: the kernel then waits on load latency with the
 // ALU pipe as the busiest unit (profiles/r1_experiments.md); it is not kept in the tree.
+//   wnodes : uint4[n_inner][4]   64 B per 4-WIDE node (production traversal format).  Wide node i holds the
+//             grandchildren of BVH2 node i (a leaf child stays one slot), so it shares BVH2's indexing and a
+//             ray takes about half as many dependent steps.  Boxes are quantised to 16 bits per coordinate
+//             on a scene-wide grid, rounded outward plus one spare quantum:
+//               u_k = (lo.x | hi.x << 16, lo.y | hi.y << 16, lo.z | hi.z << 16, child_k), k = 0..3
+//             empty slot: inverted box (lo = 65535, hi = 0).  Dequantisation is folded into the slab FMA:
+//             t = fma(2^23 + q, s, b'), s = qscale * idir, b' = (qbase - o) * idir - 2^23 s (one PRMT per
+//             plane, chosen by the ray octant so there is no per-axis min/max).
 // Boxes are padded at build time so that the slab test (FMA form, not bit-reproducible against
 // the oracle and not required to be) is conservative: any triangle whose exact-arithmetic
 // fs_intersect_tri() succeeds is reached.  The hit itself comes from fs_intersect_tri() only.
@@ -42,6 +50,9 @@
 struct fs_bvh_view {
     unsigned long long nodes_tex;   // cudaTextureObject_t over `nodes` (float4 texels), 0 if absent
     unsigned long long tris_tex;    // same over `tris`
+    unsigned long long wnodes_tex;  // cudaTextureObject_t over `wnodes` (uint4 texels)
+    const uint4* wnodes;            // 4-wide quantised nodes (below), indexed like `nodes`
+    float qbase[3], qscale[3];      // world = qbase + q * qscale, q in [0, 65535]
     const float4* nodes;
     const float4* tris;
     const uint32_t* tri_orig;

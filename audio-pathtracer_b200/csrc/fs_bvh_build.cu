@@ -459,6 +459,76 @@ __global__ void k_scan_total(const uint32_t* __restrict__ in, const uint32_t* __
     if (threadIdx.x == 0 && blockIdx.x == 0) *total = n ? out[n - 1] + in[n - 1] : 0u;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// 4-wide quantised nodes from the finished BVH2 (see fs_bvh.cuh).  One thread per BVH2 node.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t quant_lo(float v, float base, float inv_scale)
+{
+    float q = floorf((v - base) * inv_scale) - 1.0f;          // outward + one spare quantum
+    return (uint32_t)fminf(fmaxf(q, 0.0f), 65535.0f);
+}
+__device__ __forceinline__ uint32_t quant_hi(float v, float base, float inv_scale)
+{
+    float q = ceilf((v - base) * inv_scale) + 1.0f;
+    return (uint32_t)fminf(fmaxf(q, 0.0f), 65535.0f);
+}
+
+// grid[0..2] = qbase, grid[3..5] = qscale from the root's two (padded) child boxes
+__global__ void k_quant_grid(const float4* __restrict__ nodes, float* __restrict__ grid)
+{
+    const int a = threadIdx.x;
+    if (a >= 3) return;
+    const float4 n0 = nodes[0], n1 = nodes[1], n2 = nodes[2];
+    float lo, hi;
+    if (a == 0) { lo = fminf(n0.x, n1.x); hi = fmaxf(n0.y, n1.y); }
+    else if (a == 1) { lo = fminf(n0.z, n1.z); hi = fmaxf(n0.w, n1.w); }
+    else { lo = fminf(n2.x, n2.z); hi = fmaxf(n2.y, n2.w); }
+    if (!(hi < 1e29f)) hi = (a == 0) ? n0.y : (a == 1 ? n0.w : n2.y);     // single-triangle root: ignore the dummy child
+    if (!(lo < 1e29f)) lo = (a == 0) ? n0.x : (a == 1 ? n0.z : n2.x);
+    float scale = (hi - lo) / 65500.0f;
+    if (!(scale > 1e-12f)) scale = 1e-12f;
+    grid[a] = lo - 16.0f * scale;
+    grid[3 + a] = scale;
+}
+
+__device__ __forceinline__ uint4 quant_box(float lox, float hix, float loy, float hiy, float loz, float hiz, int ref,
+                                           const float* __restrict__ g)
+{
+    const float ix = 1.0f / g[3], iy = 1.0f / g[4], iz = 1.0f / g[5];
+    uint4 u;
+    u.x = quant_lo(lox, g[0], ix) | (quant_hi(hix, g[0], ix) << 16);
+    u.y = quant_lo(loy, g[1], iy) | (quant_hi(hiy, g[1], iy) << 16);
+    u.z = quant_lo(loz, g[2], iz) | (quant_hi(hiz, g[2], iz) << 16);
+    u.w = (uint32_t)ref;
+    return u;
+}
+
+__global__ void k_emit4(uint32_t n_inner, const float4* __restrict__ nodes, const float* __restrict__ grid,
+                        uint4* __restrict__ wnodes)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_inner) return;
+    const uint4 EMPTY = make_uint4(0x0000ffffu, 0x0000ffffu, 0x0000ffffu, 0x7fffffffu);   // lo = 65535 > hi = 0
+    uint4 out[4] = {EMPTY, EMPTY, EMPTY, EMPTY};
+    int k = 0;
+    const float4 a0 = nodes[(size_t)i * 4], a1 = nodes[(size_t)i * 4 + 1], a2 = nodes[(size_t)i * 4 + 2], a3 = nodes[(size_t)i * 4 + 3];
+    const int c[2] = {__float_as_int(a3.x), __float_as_int(a3.y)};
+    for (int s = 0; s < 2; ++s) {
+        if (c[s] >= 0) {                              // inner child: its two children become slots
+            const size_t b = (size_t)c[s] * 4;
+            const float4 g0 = nodes[b], g1 = nodes[b + 1], g2 = nodes[b + 2], g3 = nodes[b + 3];
+            out[k++] = quant_box(g0.x, g0.y, g0.z, g0.w, g2.x, g2.y, __float_as_int(g3.x), grid);
+            out[k++] = quant_box(g1.x, g1.y, g1.z, g1.w, g2.z, g2.w, __float_as_int(g3.y), grid);
+        } else if (s == 0) {
+            out[k++] = quant_box(a0.x, a0.y, a0.z, a0.w, a2.x, a2.y, c[0], grid);
+        } else {
+            out[k++] = quant_box(a1.x, a1.y, a1.z, a1.w, a2.z, a2.w, c[1], grid);
+        }
+    }
+    for (int j = 0; j < 4; ++j) wnodes[(size_t)i * 4 + j] = out[j];
+}
+
 // single-triangle scene: root whose second child is a far-away point box (never entered in practice)
 __global__ void k_emit_single(const float4* __restrict__ bb_lo, const float4* __restrict__ bb_hi,
                               float4* __restrict__ nodes)
@@ -585,6 +655,7 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
     float4 *tlo = nullptr, *thi = nullptr, *bb_lo = nullptr, *bb_hi = nullptr;
     uint64_t *keys0 = nullptr, *keys1 = nullptr;
     uint32_t *vals0 = nullptr, *vals1 = nullptr, *block_hist = nullptr, *misc = nullptr, *arrive = nullptr;
+    float* grid = nullptr;
     int2 *children = nullptr, *ranges = nullptr;
     int *parent = nullptr, *queue = nullptr;
     const int TPB = 256;
@@ -606,6 +677,8 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
     BCHECK(cudaMalloc(&parent, 4ull * 2 * n));
     BCHECK(cudaMalloc(&queue, 4ull * FS_TOP_CAP));
     BCHECK(cudaMalloc(&out->nodes, sizeof(float4) * 4ull * n_inner));
+    BCHECK(cudaMalloc(&out->wnodes, sizeof(uint4) * 4ull * n_inner));
+    BCHECK(cudaMalloc(&grid, sizeof(float) * 8));
     BCHECK(cudaMalloc(&out->tris, sizeof(float4) * 4ull * n));
     BCHECK(cudaMalloc(&out->tri_orig, 4ull * n));
     BCHECK(cudaMalloc(&out->tri_mat, 4ull * n));
@@ -647,6 +720,8 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
         k_emit<<<gb, TPB, 0, st>>>((int)n, children, ranges, bb_lo, bb_hi, out->nodes, leaf_max); ++*launches;
         k_leaf_stats<<<gb, TPB, 0, st>>>((int)n, ranges, misc + 8, leaf_max); ++*launches;
     }
+    k_quant_grid<<<1, 32, 0, st>>>(out->nodes, grid); ++*launches;
+    k_emit4<<<(n_inner + TPB - 1) / TPB, TPB, 0, st>>>(n_inner, out->nodes, grid, out->wnodes); ++*launches;
     {
         cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
         rd.resType = cudaResourceTypeLinear;
@@ -659,6 +734,10 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
         rd.res.linear.devPtr = out->tris;
         rd.res.linear.sizeInBytes = sizeof(float4) * 4ull * n;
         if (cudaCreateTextureObject(&out->tris_tex, &rd, &td, nullptr) != cudaSuccess) { out->tris_tex = 0; (void)cudaGetLastError(); }
+        rd.res.linear.devPtr = out->wnodes;
+        rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
+        rd.res.linear.sizeInBytes = sizeof(uint4) * 4ull * n_inner;
+        if (cudaCreateTextureObject(&out->wnodes_tex, &rd, &td, nullptr) != cudaSuccess) { out->wnodes_tex = 0; (void)cudaGetLastError(); }
     }
     k_top_treelet<<<1, 32, 0, st>>>(out->nodes, n_inner, FS_TOP_CAP, out->top_nodes, misc + 7, queue); ++*launches;
     BCHECK(cudaGetLastError());
@@ -669,11 +748,14 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
         out->n_top = h[7];
         if (n > 1 && !(builder == 1 && n >= 3)) out->max_leaf = h[8] ? h[8] : 1;
         out->extent = ord2f(h[6]);
+        float hg[6];
+        BCHECK(cudaMemcpy(hg, grid, sizeof(hg), cudaMemcpyDeviceToHost));
+        for (int a = 0; a < 3; ++a) { out->qbase[a] = hg[a]; out->qscale[a] = hg[3 + a]; }
     }
 fail:
     cudaFree(tlo); cudaFree(thi); cudaFree(bb_lo); cudaFree(bb_hi); cudaFree(keys0); cudaFree(keys1);
     cudaFree(vals0); cudaFree(vals1); cudaFree(block_hist); cudaFree(misc); cudaFree(arrive);
-    cudaFree(children); cudaFree(ranges); cudaFree(parent); cudaFree(queue);
+    cudaFree(children); cudaFree(ranges); cudaFree(parent); cudaFree(queue); cudaFree(grid);
     if (err != cudaSuccess) fs_bvh_free(out);
     return err;
 }
@@ -682,6 +764,7 @@ void fs_bvh_free(fs_bvh_device* b)
 {
     if (b->nodes_tex) cudaDestroyTextureObject(b->nodes_tex);
     if (b->tris_tex) cudaDestroyTextureObject(b->tris_tex);
-    cudaFree(b->nodes); cudaFree(b->tris); cudaFree(b->tri_orig); cudaFree(b->tri_mat); cudaFree(b->top_nodes);
+    if (b->wnodes_tex) cudaDestroyTextureObject(b->wnodes_tex);
+    cudaFree(b->nodes); cudaFree(b->wnodes); cudaFree(b->tris); cudaFree(b->tri_orig); cudaFree(b->tri_mat); cudaFree(b->top_nodes);
     memset(b, 0, sizeof(*b));
 }

@@ -21,7 +21,9 @@ struct fs_bvh_device {
     uint32_t* tri_orig;
     uint32_t* tri_mat;
     float4* top_nodes;
-    cudaTextureObject_t nodes_tex, tris_tex;
+    cudaTextureObject_t nodes_tex, tris_tex, wnodes_tex;
+    uint4* wnodes;
+    float qbase[3], qscale[3];
     uint32_t n_tris, n_inner, n_top, max_leaf;
     float extent;
 };
@@ -105,7 +107,7 @@ struct fs_ctx {
     std::vector<cudaEvent_t> kev; size_t kev_used;   // FS_FLAG_TIME_KERNELS: 4 events per batch
     std::vector<cudaEvent_t> tev; size_t tev_used;   //   + one (begin, end) pair per k_trace_closest launch
     int sm_count;
-    uint32_t tune_refill, tune_leaf_max, tune_tex, tune_builder;      // experiment knobs (env FS_TUNE_REFILL / FS_TUNE_LEAF_MAX)
+    uint32_t tune_refill, tune_leaf_max, tune_tex, tune_builder, tune_wide;      // experiment knobs (env FS_TUNE_REFILL / FS_TUNE_LEAF_MAX)
     // IR / conv
     float* d_energy;            // [K] scratch
     float* d_amp;               // [K]

@@ -493,31 +493,73 @@ k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_d
 // per-lane traversal state shared by the two trace kernels
 struct tr_state {
     fs_vec3 o, d;
+    // BVH2 float nodes: (idir, o * idir).  4-wide quantised nodes: (s, b') with t(q) = fma(2^23 + q, s, b')
     float idx, idy, idz, oodx, oody, oodz;
     int node, leaf, sp;
     uint32_t tc, te;
 };
 
+template <bool WIDE>
 __device__ __forceinline__ void tr_init(tr_state& s, const fs_bvh_view& bv, fs_vec3 o, fs_vec3 d)
 {
     const fs_ray_prep r = fs_prep_ray(o, d);
     s.o = o; s.d = d;
-    s.idx = r.idx; s.idy = r.idy; s.idz = r.idz; s.oodx = r.oodx; s.oody = r.oody; s.oodz = r.oodz;
+    if (WIDE) {
+        s.idx = bv.qscale[0] * r.idx; s.idy = bv.qscale[1] * r.idy; s.idz = bv.qscale[2] * r.idz;
+        // b' = (qbase - o) * idir - 2^23 * s: its rounding error is below half a quantum, which the spare quantum of
+        // outward rounding at build time covers
+        s.oodx = fmaf(-8388608.0f, s.idx, (bv.qbase[0] - o.x) * r.idx);
+        s.oody = fmaf(-8388608.0f, s.idy, (bv.qbase[1] - o.y) * r.idy);
+        s.oodz = fmaf(-8388608.0f, s.idz, (bv.qbase[2] - o.z) * r.idz);
+    } else {
+        s.idx = r.idx; s.idy = r.idy; s.idz = r.idz; s.oodx = r.oodx; s.oody = r.oody; s.oodz = r.oodz;
+    }
     s.node = bv.n_tris ? 0 : TR_SENT; s.leaf = 0; s.sp = 0; s.tc = 0; s.te = 0;
 }
 
+// 2^23 + (16 bits of w chosen by the PRMT selector) as a float.  0x7410 = low half, 0x7432 = high half
+__device__ __forceinline__ float q_sel(uint32_t w, uint32_t sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)); }
+__device__ __forceinline__ uint4 ldg_u4(const uint4* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// Traversal stack: the first FS_SSTACK entries of every thread live in shared memory (column
+// layout [depth][thread]: bank-conflict free, ~30-cycle latency), deeper entries in local memory.
+// ncu showed 12 % of the kernel's stall samples on the instruction consuming a local-memory pop
+// (37 % of those loads missed L1, and the 256 B/thread stacks competed with BVH nodes for L1).
+#define FS_SSTACK 12
+#define TR_SMEM (FS_SSTACK * TR_THREADS * sizeof(int))
+struct tr_stack {
+    int* sh;        // &smem[threadIdx.x], stride blockDim.x
+    int* loc;       // per-thread local array for entries >= FS_SSTACK
+    __device__ __forceinline__ void push(int& sp, int v) const
+    {
+        if (sp < FS_SSTACK) sh[sp * TR_THREADS] = v; else loc[sp - FS_SSTACK] = v;
+        ++sp;
+    }
+    __device__ __forceinline__ int pop(int& sp) const
+    {
+        if (sp == 0) return TR_SENT;
+        --sp;
+        return (sp < FS_SSTACK) ? sh[sp * TR_THREADS] : loc[sp - FS_SSTACK];
+    }
+};
+
 // Speculative traversal (Aila & Laine): the first leaf a lane reaches is POSTPONED and the lane
 // keeps walking; a second leaf makes it wait (node stays < 0) for the warp's triangle phase.
-__device__ __forceinline__ void tr_settle(tr_state& s, const int* stack)
+__device__ __forceinline__ void tr_settle(tr_state& s, const tr_stack& stack)
 {
     if (s.node < 0 && s.leaf == 0) {            // one postponed leaf; a second one makes the lane wait
         s.leaf = s.node;
-        s.node = s.sp ? stack[--s.sp] : TR_SENT;
+        s.node = stack.pop(s.sp);
     }
 }
 
 template <bool ORDERED, int TEX>
-__device__ __forceinline__ void tr_node_step(const fs_bvh_view& bv, tr_state& s, int* stack, float tlimit,
+__device__ __forceinline__ void tr_node_step(const fs_bvh_view& bv, tr_state& s, const tr_stack& stack, float tlimit,
                                              uint32_t* overflow)
 {
     const float4* p = bv.nodes + (size_t)s.node * 4;
@@ -540,27 +582,83 @@ __device__ __forceinline__ void tr_node_step(const fs_bvh_view& bv, tr_state& s,
     fs_slab2(r, n0, n1, n2, tlimit, h0, h1, t0, t1);
     const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
     if (!h0 && !h1) {
-        s.node = s.sp ? stack[--s.sp] : TR_SENT;
+        s.node = stack.pop(s.sp);
     } else {
         s.node = h0 ? c0 : c1;
         if (h0 && h1) {
             int far_ = c1;
             if (ORDERED && t1 < t0) { far_ = c0; s.node = c1; }
-            if (s.sp < FS_STACK_SIZE) stack[s.sp++] = far_; else *overflow = 1u;
+            if (s.sp < FS_STACK_SIZE) stack.push(s.sp, far_); else *overflow = 1u;
         }
     }
     tr_settle(s, stack);
 }
 
+
+#define FS_CSWAP(ka, va, kb, vb) { const bool sw_ = kb < ka; const float tk_ = sw_ ? kb : ka; kb = sw_ ? ka : kb; ka = tk_; \
+                                   const int tv_ = sw_ ? vb : va; vb = sw_ ? va : vb; va = tv_; }
+
+// one step through a 4-wide quantised node: near/far planes picked by the ray octant, hits sorted near-to-far
+template <bool ORDERED, int TEX>
+__device__ __forceinline__ void tr_node_step4(const fs_bvh_view& bv, tr_state& s, const tr_stack& stack, float tlimit,
+                                              uint32_t* overflow)
+{
+    const uint4* p = bv.wnodes + (size_t)s.node * 4;
+    uint4 u0, u1, u2, u3;
+    if (TEX >= 2) {                      // two quarters through the texture data pipe, two through LSU
+        const int b = s.node * 4;
+        u0 = tex1Dfetch<uint4>((cudaTextureObject_t)bv.wnodes_tex, b);
+        u1 = tex1Dfetch<uint4>((cudaTextureObject_t)bv.wnodes_tex, b + 1);
+        u2 = ldg_u4(p + 2); u3 = ldg_u4(p + 3);
+    } else {
+        u0 = ldg_u4(p); u1 = ldg_u4(p + 1); u2 = ldg_u4(p + 2); u3 = ldg_u4(p + 3);
+    }
+    // ray octant (sign of s = sign of the direction): with a negative direction the HIGH plane is entered first
+    const uint32_t nx = (s.idx < 0.0f) ? 0x7432u : 0x7410u, ny = (s.idy < 0.0f) ? 0x7432u : 0x7410u,
+                   nz = (s.idz < 0.0f) ? 0x7432u : 0x7410u;
+    const uint32_t fx = nx ^ 0x0022u, fy = ny ^ 0x0022u, fz = nz ^ 0x0022u;
+    const float INF = __int_as_float(0x7f800000);
+#define FS_CHILD(u, key, val)                                                                                         \
+    {                                                                                                                 \
+        const float tn = fmaxf(fmaxf(fmaxf(fmaf(q_sel(u.x, nx), s.idx, s.oodx), fmaf(q_sel(u.y, ny), s.idy, s.oody)), \
+                                     fmaf(q_sel(u.z, nz), s.idz, s.oodz)), 0.0f);                                     \
+        const float tf = fminf(fminf(fminf(fmaf(q_sel(u.x, fx), s.idx, s.oodx), fmaf(q_sel(u.y, fy), s.idy, s.oody)), \
+                                     fmaf(q_sel(u.z, fz), s.idz, s.oodz)), tlimit);                                   \
+        key = (tn <= tf) ? tn : INF;                                                                                  \
+        val = (int)u.w;                                                                                               \
+    }
+    float k0, k1, k2, k3; int v0, v1, v2, v3;
+    FS_CHILD(u0, k0, v0) FS_CHILD(u1, k1, v1) FS_CHILD(u2, k2, v2) FS_CHILD(u3, k3, v3)
+#undef FS_CHILD
+    if (ORDERED) {                       // 5-comparator network; misses (INF) sink to the end
+        FS_CSWAP(k0, v0, k1, v1) FS_CSWAP(k2, v2, k3, v3) FS_CSWAP(k0, v0, k2, v2) FS_CSWAP(k1, v1, k3, v3) FS_CSWAP(k1, v1, k2, v2)
+    } else {                             // any-hit rays: only move the hits to the front
+        if (k0 == INF) { k0 = k1; v0 = v1; k1 = INF; }
+        if (k0 == INF) { k0 = k2; v0 = v2; k2 = INF; }
+        if (k0 == INF) { k0 = k3; v0 = v3; k3 = INF; }
+    }
+    if (k0 == INF) {
+        s.node = stack.pop(s.sp);
+    } else {
+        s.node = v0;
+        if (s.sp + 3 <= FS_STACK_SIZE) {
+            if (k3 != INF) stack.push(s.sp, v3);    // farthest first, so the nearest is popped first
+            if (k2 != INF) stack.push(s.sp, v2);
+            if (k1 != INF) stack.push(s.sp, v1);
+        } else *overflow = 1u;
+    }
+    tr_settle(s, stack);
+}
+
 // after a triangle step that exhausted the open range: open the postponed leaf, then re-settle
-__device__ __forceinline__ void tr_next_leaf(tr_state& s, const int* stack)
+__device__ __forceinline__ void tr_next_leaf(tr_state& s, const tr_stack& stack)
 {
     if (s.tc == s.te) {
         if (s.leaf != 0) { leaf_range(s.leaf, s.tc, s.te); s.leaf = 0; tr_settle(s, stack); }
     }
 }
 
-template <bool COUNT, int TEX>
+template <bool COUNT, int TEX, bool WIDE>
 __global__ void __launch_bounds__(TR_THREADS, FS_TR_MINBLOCKS)
 k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
                 const uint32_t* __restrict__ count_ptr, uint32_t* __restrict__ cursor,
@@ -568,7 +666,9 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
 {
     const uint32_t lane = lane_id();
     const uint32_t count = *count_ptr;
-    int stack[FS_STACK_SIZE];
+    extern __shared__ int smem_stack[];
+    int lstack[FS_STACK_SIZE - FS_SSTACK];
+    tr_stack stack; stack.sh = smem_stack + threadIdx.x; stack.loc = lstack;
     tr_state s;
     s.node = TR_SENT; s.leaf = 0; s.sp = 0; s.tc = 0; s.te = 0;
     s.o = fs_mk(0.f, 0.f, 0.f); s.d = s.o; s.idx = s.idy = s.idz = s.oodx = s.oody = s.oodz = 0.f;
@@ -589,7 +689,7 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
                 const uint32_t jj = base + (uint32_t)__popc(m_idle & ((1u << lane) - 1u));
                 if (jj < count) {
                     const float4 a = ray_o[jj], b = ray_d[jj];
-                    tr_init(s, bv, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z));
+                    tr_init<WIDE>(s, bv, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z));
                     bt = __int_as_float(0x7f800000); best = -1;
                     j = jj; running = true;
                 }
@@ -607,7 +707,8 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
                 if (!__any_sync(FULLM, can && s.leaf == 0)) break;
                 if (can) {
                     if (COUNT) vc.nodes++;
-                    tr_node_step<true, TEX>(bv, s, stack, bt, &ovf);
+                    if (WIDE) tr_node_step4<true, TEX>(bv, s, stack, bt, &ovf);
+                    else tr_node_step<true, TEX>(bv, s, stack, bt, &ovf);
                 }
             }
             // triangles: one test per lane per step until every pending leaf of the warp is done
@@ -617,8 +718,7 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
                 if (!__any_sync(FULLM, has)) break;
                 if (has) {
                     const float4* tq = bv.tris + (size_t)s.tc * 4;
-                    const float4 a = (TEX == 3) ? tex1Dfetch<float4>((cudaTextureObject_t)bv.tris_tex, (int)(s.tc * 4u)) : fs_ldg4(tq);
-                    const float4 b = fs_ldg4(tq + 1), c = fs_ldg4(tq + 2);
+                    const float4 a = fs_ldg4(tq), b = fs_ldg4(tq + 1), c = fs_ldg4(tq + 2);
                     if (COUNT) vc.tris++;
                     float t;
                     if (fs_intersect_tri(s.o, s.d, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z), fs_mk(c.x, c.y, c.z), t) && t <= bt) {
@@ -647,7 +747,7 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
 }
 
 // connection rays: (F.xyz, tmax) (dir.xyz, path id); unoccluded paths are appended to conn_queue
-template <bool COUNT, int TEX>
+template <bool COUNT, int TEX, bool WIDE>
 __global__ void __launch_bounds__(TR_THREADS, FS_TR_MINBLOCKS)
 k_trace_any(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
             const uint32_t* __restrict__ count_ptr, uint32_t* __restrict__ cursor,
@@ -656,7 +756,9 @@ k_trace_any(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4
 {
     const uint32_t lane = lane_id();
     const uint32_t count = *count_ptr;
-    int stack[FS_STACK_SIZE];
+    extern __shared__ int smem_stack[];
+    int lstack[FS_STACK_SIZE - FS_SSTACK];
+    tr_stack stack; stack.sh = smem_stack + threadIdx.x; stack.loc = lstack;
     tr_state s;
     s.node = TR_SENT; s.leaf = 0; s.sp = 0; s.tc = 0; s.te = 0;
     s.o = fs_mk(0.f, 0.f, 0.f); s.d = s.o; s.idx = s.idy = s.idz = s.oodx = s.oody = s.oodz = 0.f;
@@ -676,7 +778,7 @@ k_trace_any(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4
                 const uint32_t jj = base + (uint32_t)__popc(m_idle & ((1u << lane) - 1u));
                 if (jj < count) {
                     const float4 a = ray_o[jj], b = ray_d[jj];
-                    tr_init(s, bv, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z));
+                    tr_init<WIDE>(s, bv, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z));
                     tmax = a.w; path = __float_as_uint(b.w); occluded = false; running = true;
                 }
             }
@@ -691,7 +793,8 @@ k_trace_any(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4
                 if (!__any_sync(FULLM, can && s.leaf == 0)) break;
                 if (can) {
                     if (COUNT) vc.nodes++;
-                    tr_node_step<false, (TEX ? 2 : 0)>(bv, s, stack, tmax, &ovf);
+                    if (WIDE) tr_node_step4<false, (TEX ? 2 : 0)>(bv, s, stack, tmax, &ovf);
+                    else tr_node_step<false, (TEX ? 2 : 0)>(bv, s, stack, tmax, &ovf);
                 }
             }
             tr_next_leaf(s, stack);
@@ -957,8 +1060,8 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
     cudaStream_t st = ctx->stream;
     const fs_wave_buffers& wb = ctx->wb;
     static int occ_tr = 0, occ_any = 0;
-    if (!occ_tr) occ_tr = resident_ctas(k_trace_closest<COUNT, 0>, TR_THREADS, 0);
-    if (!occ_any) occ_any = resident_ctas(k_trace_any<COUNT, 0>, TR_THREADS, 0);
+    if (!occ_tr) occ_tr = resident_ctas(k_trace_closest<COUNT, 2, true>, TR_THREADS, TR_SMEM);
+    if (!occ_any) occ_any = resident_ctas(k_trace_any<COUNT, 2, true>, TR_THREADS, TR_SMEM);
     const bool timing = (tp.flags & FS_FLAG_TIME_KERNELS) != 0;
     cudaEvent_t* ev = nullptr;
     if (timing) {
@@ -989,7 +1092,8 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
             k_shade_gen<<<grid_sh, WF_THREADS, 0, st>>>(tp, wb, k, ctx->d_counters);
             ++ctx->stats.kernel_launches;
             if (k == D) break;
-            const int texm = tp.bv.nodes_tex ? (int)ctx->tune_tex : 0;
+            const bool wide = tp.bv.wnodes != nullptr;
+            const int texm = (wide ? tp.bv.wnodes_tex : tp.bv.nodes_tex) ? (int)ctx->tune_tex : 0;
             cudaEvent_t* te = nullptr;
             if (timing) {
                 if (ctx->tev.size() < ctx->tev_used + 2) {
@@ -1001,15 +1105,12 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
                 ctx->tev_used += 2;
                 cudaEventRecord(te[0], st);
             }
-            if (texm == 3 && tp.bv.tris_tex)
-                k_trace_closest<COUNT, 3><<<grid_tr, TR_THREADS, 0, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u],
-                    wb.q_count + k, wb.q_cursor + k, wb.hit, ctx->d_counters, ctx->tune_refill);
-            else if (texm >= 2)
-                k_trace_closest<COUNT, 2><<<grid_tr, TR_THREADS, 0, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u],
-                    wb.q_count + k, wb.q_cursor + k, wb.hit, ctx->d_counters, ctx->tune_refill);
-            else
-                k_trace_closest<COUNT, 0><<<grid_tr, TR_THREADS, 0, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u],
-                    wb.q_count + k, wb.q_cursor + k, wb.hit, ctx->d_counters, ctx->tune_refill);
+#define FS_LAUNCH_TRACE(TEXV, WIDEV)                                                                                   \
+            k_trace_closest<COUNT, TEXV, WIDEV><<<grid_tr, TR_THREADS, TR_SMEM, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u], \
+                wb.q_count + k, wb.q_cursor + k, wb.hit, ctx->d_counters, ctx->tune_refill)
+            if (wide) { if (texm >= 2) FS_LAUNCH_TRACE(2, true); else FS_LAUNCH_TRACE(0, true); }
+            else { if (texm >= 2) FS_LAUNCH_TRACE(2, false); else FS_LAUNCH_TRACE(0, false); }
+#undef FS_LAUNCH_TRACE
             if (timing) cudaEventRecord(te[1], st);
             ++ctx->stats.kernel_launches;
             ++ctx->stats.extend_launches;
@@ -1023,12 +1124,16 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
     uint32_t grid_any = (uint32_t)(ctx->sm_count * occ_any);
     const uint32_t ctas_any = (tp.batch + TR_THREADS - 1) / TR_THREADS;
     if (grid_any > ctas_any) grid_any = ctas_any ? ctas_any : 1;
-    if (tp.bv.nodes_tex && ctx->tune_tex)
-        k_trace_any<COUNT, 2><<<grid_any, TR_THREADS, 0, st>>>(tp.bv, wb.st_pos[0], wb.st_nrm[0], wb.q_count + (D + 2),
-            wb.q_cursor + (D + 2), wb.conn_queue, wb.q_count + (D + 1), ctx->d_counters, d_dbg, ctx->tune_refill);
-    else
-        k_trace_any<COUNT, 0><<<grid_any, TR_THREADS, 0, st>>>(tp.bv, wb.st_pos[0], wb.st_nrm[0], wb.q_count + (D + 2),
-            wb.q_cursor + (D + 2), wb.conn_queue, wb.q_count + (D + 1), ctx->d_counters, d_dbg, ctx->tune_refill);
+    {
+        const bool wide = tp.bv.wnodes != nullptr;
+        const bool tex = (wide ? tp.bv.wnodes_tex : tp.bv.nodes_tex) && ctx->tune_tex;
+#define FS_LAUNCH_ANY(TEXV, WIDEV)                                                                                     \
+        k_trace_any<COUNT, TEXV, WIDEV><<<grid_any, TR_THREADS, TR_SMEM, st>>>(tp.bv, wb.st_pos[0], wb.st_nrm[0], wb.q_count + (D + 2), \
+            wb.q_cursor + (D + 2), wb.conn_queue, wb.q_count + (D + 1), ctx->d_counters, d_dbg, ctx->tune_refill)
+        if (wide) { if (tex) FS_LAUNCH_ANY(2, true); else FS_LAUNCH_ANY(0, true); }
+        else { if (tex) FS_LAUNCH_ANY(2, false); else FS_LAUNCH_ANY(0, false); }
+#undef FS_LAUNCH_ANY
+    }
     ctx->stats.kernel_launches += 2;
     if (timing) cudaEventRecord(ev[2], st);
     uint32_t grid_ev = (uint32_t)ctx->sm_count * 4u;

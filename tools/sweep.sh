@@ -1,5 +1,7 @@
 #!/bin/bash
-for b in 0 1; do
-  echo "builder=$b : "
-  FS_TUNE_BUILDER=$b timeout 200 python tools/profile_step.py 1 2 concert_hall 32 | tail -2 | cut -c1-330
+for w in 1 0; do
+  echo -n "wide=$w : "
+  FS_TUNE_WIDE=$w timeout 100 python tools/profile_step.py 1 3 | tail -1 | cut -c1-330
+  echo -n "wide=$w nocount: "
+  FS_TUNE_WIDE=$w timeout 100 python tools/profile_step.py 0 3 | tail -1 | cut -c1-130
 done
