@@ -63,7 +63,7 @@ struct fs_trace_params {
 struct fs_wave_buffers {
     float4* st_pos[2];          // ping-pong subpath state: (pos.xyz, bits(sp_id))
     float4* st_nrm[2];          //                          (nrm.xyz, bits(depth))
-    float4* rec;                // [max_depth+1][2*cap]: (d, bits(mat), prob, -)
+    float4* rec;                // [max_depth+1][2*cap]: (segment length, bits(mat), pdf, pdf^pdf_exponent) of node k of subpath sp_id
     float4* end_pos;            // [2*cap]: (end.xyz, bits(n_nodes))
     float2* hit;                // [2*cap]: closest-hit records (t, bits(sorted triangle index or -1))
     uint32_t* conn_queue;       // [cap] path ids whose connection is unoccluded
@@ -107,7 +107,7 @@ struct fs_ctx {
     std::vector<cudaEvent_t> kev; size_t kev_used;   // FS_FLAG_TIME_KERNELS: 4 events per batch
     std::vector<cudaEvent_t> tev; size_t tev_used;   //   + one (begin, end) pair per k_trace_closest launch
     int sm_count;
-    uint32_t tune_refill, tune_leaf_max, tune_tex, tune_builder, tune_wide;      // experiment knobs (env FS_TUNE_REFILL / FS_TUNE_LEAF_MAX)
+    uint32_t tune_refill, tune_leaf_max, tune_tex, tune_builder, tune_wide, tune_node_min, tune_tri_min;      // experiment knobs (env FS_TUNE_REFILL / FS_TUNE_LEAF_MAX)
     // IR / conv
     float* d_energy;            // [K] scratch
     float* d_amp;               // [K]

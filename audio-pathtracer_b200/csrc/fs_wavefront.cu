@@ -16,7 +16,7 @@
 //
 // HBM layout (SoA, float4 granularity so every lane moves 16 B):
 //   st_pos/st_nrm[2][2*cap]  ping-pong compacted subpath state
-//   rec[(k)*2*cap + sp_id]   node record k>=1 of subpath sp_id: (segment length, material, pdf)
+//   rec[k][sp_id]            node record k>=1 of subpath sp_id: (segment length, material, pdf, pdf^pdf_exponent)
 //   end_pos[sp_id]           last node position + node count
 #include "fs_internal.h"
 
@@ -111,7 +111,7 @@ k_extend(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, int in_
     const float4* __restrict__ in_nrm = wb.st_nrm[in_buf];
     float4* __restrict__ out_pos = wb.st_pos[in_buf ^ 1];
     float4* __restrict__ out_nrm = wb.st_nrm[in_buf ^ 1];
-    const uint32_t stride = 2u * wb.cap;
+    const uint32_t stride = 2u * wb.cap;             // rec[k][sp_id]: one plane per node index (writes of a bounce stay semi-coalesced)
     fs_visit_counters vc; vc.nodes = 0; vc.tris = 0;
     uint32_t rays_local = 0;
     for (;;) {
@@ -173,7 +173,7 @@ k_extend(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, int in_
                     float seg = sqrtf(fs_dot(dl, dl));
                     uint32_t mat = __ldg(tp.bv.tri_mat + tri);
                     wb.rec[(size_t)(k + 1) * stride + sp_id] =
-                        make_float4(seg, __uint_as_float(mat), prob, 0.f);
+                        make_float4(seg, __uint_as_float(mat), prob, fs_pow(prob, tp.ep.pdf_exponent));
                     pos = np; nrm = fn;
                     n_nodes = k + 2;
                     terminated = (k + 1 >= tp.max_depth);        // PARAM: ray budget per subpath
@@ -269,10 +269,10 @@ k_connect(const fs_trace_params tp, const fs_wave_buffers wb, fs_dev_counters* _
 // ---------------------------------------------------------------------------------------------
 // k_eval: EvaluatePath over F nodes ++ reverse(B nodes), then the splat
 // ---------------------------------------------------------------------------------------------
-// Sum of `v` over the lanes of `peers` (all lanes holding the same histogram key), result valid
+// Sum of `v` over the lanes of `peers` (all lanes holding the same histogram address), result valid
 // in the group's lowest lane.  Tree reduction over an arbitrary lane subset: in every round the
 // even-ranked lanes absorb their next higher peer, odd-ranked lanes drop out.
-__device__ __forceinline__ void reduce_peers8(uint32_t peers, unsigned long long v[FS_MAX_BANDS], int nb)
+__device__ __forceinline__ unsigned long long reduce_peers(uint32_t peers, unsigned long long v)
 {
     const uint32_t group = peers;
     const uint32_t lane = lane_id();
@@ -280,91 +280,120 @@ __device__ __forceinline__ void reduce_peers8(uint32_t peers, unsigned long long
     peers &= (0xfffffffeu << lane);                       // peers above me
     while (__any_sync(group, peers)) {
         const int next = __ffs(peers);                    // 1-based, 0 = none
-        for (int b = 0; b < nb; ++b) {
-            unsigned long long t = __shfl_sync(group, v[b], next ? next - 1 : (int)lane);
-            if (next) v[b] += t;
-        }
+        const unsigned long long t = __shfl_sync(group, v, next ? next - 1 : (int)lane);
+        if (next) v += t;
         const bool done = rel & 1u;
         if (done) peers = 0;
         peers &= __ballot_sync(group, !done);
         rel >>= 1;
     }
+    return v;
 }
 
+// one band of one segment of EvaluatePath (SUB.cpp:368-399); P = prob^pdf_exponent comes from the node record
+__device__ __forceinline__ void eval_seg_band(const fs_eval_params& ep, float bs, float P, float d, float air_b, float& E)
+{
+    if (d < ep.min_seg) return;                           // SUB.cpp:375-378 (the caller has already added d to the delay)
+    const float G = 1.0f / (FS_FOUR_PI * (d * d));        // :391
+    float e = E;
+    e *= bs;                                              // :392
+    e *= G;                                               // :393
+    e *= fs_exp(-air_b * d);                              // :395-397
+    e /= P;                                               // :398
+    E = e;
+}
+
+// 8 lanes per connected path, one absorption band each (4 paths per warp): the walk over the node
+// records is uniform across the 8 lanes of a path, so SIMD efficiency no longer depends on the band
+// loop (the one-thread-per-path version ran at 8.9 of 32 lanes, profiles/r1e_summary.md).
 __global__ void __launch_bounds__(WF_THREADS)
 k_eval(const fs_trace_params tp, const fs_wave_buffers wb, unsigned long long* __restrict__ hist,
        fs_dev_counters* __restrict__ dc, fs_path_dbg* __restrict__ dbg)
 {
     const uint32_t lane = lane_id();
+    const uint32_t sub = lane >> 3, b = lane & 7u;
     const uint32_t qi = tp.max_depth + 1;
     const uint32_t count = wb.q_count[qi];
-    const uint32_t stride = 2u * wb.cap;
+    const uint32_t stride = 2u * wb.cap;             // rec[k][sp_id]: one plane per node index (writes of a bounce stay semi-coalesced)
     const uint32_t NBr = tp.ep.n_bands;
+    const bool band_on = b < NBr;
+    const float air_b = band_on ? tp.ep.air[b] : 0.0f;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&dc->connected, (unsigned long long)count);
-    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < count;
-         base += gridDim.x * blockDim.x) {
-        const uint32_t j = base + lane;
-        const bool valid = j < count;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t base = warp_global * 4u; base < count; base += n_warps * 4u) {
+        const uint32_t j = base + sub;
+        const bool valid = (j < count) && band_on;
+        unsigned long long q = 0ull;
         uint32_t key = 0xffffffffu;
-        unsigned long long q[FS_MAX_BANDS];
-#pragma unroll
-        for (int b = 0; b < FS_MAX_BANDS; ++b) q[b] = 0ull;
-        uint32_t s = 0, bin = 0;
+        size_t hidx = 0;
         if (valid) {
             const uint32_t p = wb.conn_queue[j];
             const float len = wb.conn_len[p];
             const uint32_t sf = 2u * p, sb = 2u * p + 1u;
             const uint32_t nf = __float_as_uint(wb.end_pos[sf].w);
             const uint32_t nb = __float_as_uint(wb.end_pos[sb].w);
-            float E[FS_MAX_BANDS];
+            float E = 1.0f, total = 0.0f;
+            float bs = 1.0f, P = 1.0f;                    // node 0 of the source subpath: no material, probability 1
+            const float4* __restrict__ rf = wb.rec + sf;
+            const float4* __restrict__ rb = wb.rec + sb;
+            // records are fetched four at a time so their latencies overlap
+            for (uint32_t i0 = 1; i0 < nf; i0 += 4) {     // segments F_{i-1} -> F_i
+                float4 r[4];
 #pragma unroll
-            for (int b = 0; b < FS_MAX_BANDS; ++b) E[b] = 1.0f;
-            float total = 0.0f;
-            const float* row = nullptr;           // node 0 of the source subpath: no material
-            float prob = 1.0f;
-            for (uint32_t i = 1; i < nf; ++i) {   // segments F_{i-1} -> F_i
-                float4 r = wb.rec[(size_t)i * stride + sf];
-                fs_eval_segment<FS_MAX_BANDS>(tp.ep, row, prob, r.x, total, E);
-                row = tp.refl_over_pi + (size_t)__float_as_uint(r.y) * NBr;
-                prob = r.z;
+                for (uint32_t u = 0; u < 4; ++u) r[u] = (i0 + u < nf) ? rf[(size_t)(i0 + u) * stride] : make_float4(0.f, 0.f, 1.f, 1.f);
+#pragma unroll
+                for (uint32_t u = 0; u < 4; ++u) {
+                    if (i0 + u < nf) {
+                        total += r[u].x;                  // ScaledDistance += NodeDistance, SUB.cpp:374
+                        eval_seg_band(tp.ep, bs, P, r[u].x, air_b, E);
+                        bs = __ldg(tp.refl_over_pi + (size_t)__float_as_uint(r[u].y) * NBr + b);
+                        P = r[u].w;
+                    }
+                }
             }
-            fs_eval_segment<FS_MAX_BANDS>(tp.ep, row, prob, len, total, E);     // connection F_last -> B_last
-            for (uint32_t i = nb - 1; i >= 1; --i) {                             // B_i -> B_{i-1}
-                float4 r = wb.rec[(size_t)i * stride + sb];
-                fs_eval_segment<FS_MAX_BANDS>(tp.ep, tp.refl_over_pi + (size_t)__float_as_uint(r.y) * NBr,
-                                              r.z, r.x, total, E);
+            total += len;
+            eval_seg_band(tp.ep, bs, P, len, air_b, E);   // connection F_last -> B_last
+            for (int i0 = (int)nb - 1; i0 >= 1; i0 -= 4) { // B_i -> B_{i-1}
+                float4 r[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) r[u] = (i0 - u >= 1) ? rb[(size_t)(i0 - u) * stride] : make_float4(0.f, 0.f, 1.f, 1.f);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (i0 - u >= 1) {
+                        total += r[u].x;
+                        eval_seg_band(tp.ep, __ldg(tp.refl_over_pi + (size_t)__float_as_uint(r[u].y) * NBr + b), r[u].w, r[u].x, air_b, E);
+                    }
+                }
             }
             const float delay = total / tp.sound_speed;                           // SUB.cpp:419
             const float fb = floorf((delay * 1000.0f) / tp.bin_ms);               // COMP.h:89
+            uint32_t bin;
             if (!(fb >= 0.0f)) bin = 0;
             else if (fb >= (float)(tp.n_bins - 1)) bin = tp.n_bins - 1;
             else bin = (uint32_t)fb;
             const uint64_t g = tp.g_first + p;
-            s = (uint32_t)(g / tp.n_paths);
-            key = s * tp.n_bins + bin;
-#pragma unroll
-            for (int b = 0; b < FS_MAX_BANDS; ++b) {
-                if (b < (int)NBr) {
-                    float e = E[b];
-                    e = (e < tp.energy_clamp) ? e : tp.energy_clamp;              // SUB.cpp:410
-                    e = e * tp.energy_gain;                                       // SUB.cpp:413
-                    q[b] = (unsigned long long)(e * 4294967296.0f);               // Q32.32
-                    if (dbg) dbg[p].energy[b] = e;
-                }
+            const uint32_t s = (uint32_t)(g / tp.n_paths);
+            float e = E;
+            e = (e < tp.energy_clamp) ? e : tp.energy_clamp;                      // SUB.cpp:410
+            e = e * tp.energy_gain;                                               // SUB.cpp:413
+            q = (unsigned long long)(e * 4294967296.0f);                          // Q32.32
+            hidx = ((size_t)s * NBr + b) * tp.n_bins + bin;
+            key = (s * tp.n_bins + bin) * 8u + b;
+            if (dbg) {
+                dbg[p].energy[b] = e;
+                if (b == 0) { dbg[p].bin = (int32_t)bin; dbg[p].delay_s = delay; dbg[p].total_dist = total; }
             }
-            if (dbg) { dbg[p].bin = (int32_t)bin; dbg[p].delay_s = delay; dbg[p].total_dist = total; }
         }
-        // splat: lanes with the same (source, bin) combine first, one RED.64 per band per group
+        // splat: lanes with the same (source, band, bin) combine first, one RED.64 per group
         const uint32_t active = __ballot_sync(0xffffffffu, valid);
         if (valid) {
-            unsigned long long* h = hist + ((size_t)s * NBr) * tp.n_bins + bin;
             if (tp.flags & FS_FLAG_NO_SPLAT_AGG) {
-                for (uint32_t b = 0; b < NBr; ++b) atomicAdd(h + (size_t)b * tp.n_bins, q[b]);
+                atomicAdd(hist + hidx, q);
             } else {
                 const uint32_t peers = __match_any_sync(active, key);
-                if (peers != (1u << lane)) reduce_peers8(peers, q, (int)NBr);
-                if ((uint32_t)(__ffs(peers) - 1) == lane)
-                    for (uint32_t b = 0; b < NBr; ++b) atomicAdd(h + (size_t)b * tp.n_bins, q[b]);
+                if (peers != (1u << lane)) q = reduce_peers(peers, q);
+                if ((uint32_t)(__ffs(peers) - 1) == lane) atomicAdd(hist + hidx, q);
             }
         }
     }
@@ -414,7 +443,7 @@ k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_d
     const float4* __restrict__ in_d = wb.st_nrm[in];
     float4* __restrict__ out_o = wb.st_pos[out];
     float4* __restrict__ out_d = wb.st_nrm[out];
-    const uint32_t stride = 2u * wb.cap;
+    const uint32_t stride = 2u * wb.cap;             // rec[k][sp_id]: one plane per node index (writes of a bounce stay semi-coalesced)
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < count_in;
          base += gridDim.x * blockDim.x) {
         const uint32_t j = base + lane;
@@ -453,7 +482,7 @@ k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_d
                     const fs_vec3 dl = fs_sub(pos, o);
                     const float seg = sqrtf(fs_dot(dl, dl));
                     const uint32_t mat = __ldg(tp.bv.tri_mat + tri);
-                    wb.rec[(size_t)k * stride + sp_id] = make_float4(seg, __uint_as_float(mat), b.w, 0.f);
+                    wb.rec[(size_t)k * stride + sp_id] = make_float4(seg, __uint_as_float(mat), b.w, fs_pow(b.w, tp.ep.pdf_exponent));
                     nrm = fn;
                     nodes = k + 1;
                     if (k >= tp.max_depth) {      // PARAM: ray budget per subpath exhausted
@@ -662,7 +691,8 @@ template <bool COUNT, int TEX, bool WIDE>
 __global__ void __launch_bounds__(TR_THREADS, FS_TR_MINBLOCKS)
 k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
                 const uint32_t* __restrict__ count_ptr, uint32_t* __restrict__ cursor,
-                float2* __restrict__ hits, fs_dev_counters* __restrict__ dc, const uint32_t REFILL_MIN)
+                float2* __restrict__ hits, fs_dev_counters* __restrict__ dc, const uint32_t REFILL_MIN,
+                const uint32_t NODE_MIN, const uint32_t TRI_MIN)
 {
     const uint32_t lane = lane_id();
     const uint32_t count = *count_ptr;
@@ -705,6 +735,8 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
             for (;;) {
                 const bool can = running && s.node >= 0 && s.node != TR_SENT;
                 if (!__any_sync(FULLM, can && s.leaf == 0)) break;
+                // leave early for the triangle phase once too few lanes still walk and triangle work is waiting
+                if (NODE_MIN && (uint32_t)__popc(__ballot_sync(FULLM, can)) < NODE_MIN && __any_sync(FULLM, s.leaf != 0)) break;
                 if (can) {
                     if (COUNT) vc.nodes++;
                     if (WIDE) tr_node_step4<true, TEX>(bv, s, stack, bt, &ovf);
@@ -713,9 +745,13 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
             }
             // triangles: one test per lane per step until every pending leaf of the warp is done
             tr_next_leaf(s, stack);
-            for (;;) {
+            for (uint32_t it = 0;; ++it) {
                 const bool has = s.tc < s.te;
-                if (!__any_sync(FULLM, has)) break;
+                const uint32_t m_has = __ballot_sync(FULLM, has);
+                if (m_has == 0u) break;
+                // after at least one step: go back to walking once few lanes have triangles left and others can walk
+                if (TRI_MIN && it && (uint32_t)__popc(m_has) < TRI_MIN &&
+                    __any_sync(FULLM, running && s.node >= 0 && s.node != TR_SENT && s.leaf == 0)) break;
                 if (has) {
                     const float4* tq = bv.tris + (size_t)s.tc * 4;
                     const float4 a = fs_ldg4(tq), b = fs_ldg4(tq + 1), c = fs_ldg4(tq + 2);
@@ -732,7 +768,7 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
                 }
             }
             // retire finished rays (8 B hit record), then decide whether to refill
-            if (running && s.node == TR_SENT && s.leaf == 0) {
+            if (running && s.node == TR_SENT && s.leaf == 0 && s.tc == s.te) {
                 hits[j] = make_float2(bt, __int_as_float(best));
                 running = false;
             }
@@ -752,7 +788,8 @@ __global__ void __launch_bounds__(TR_THREADS, FS_TR_MINBLOCKS)
 k_trace_any(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
             const uint32_t* __restrict__ count_ptr, uint32_t* __restrict__ cursor,
             uint32_t* __restrict__ conn_queue, uint32_t* __restrict__ conn_count,
-            fs_dev_counters* __restrict__ dc, fs_path_dbg* __restrict__ dbg, const uint32_t REFILL_MIN)
+            fs_dev_counters* __restrict__ dc, fs_path_dbg* __restrict__ dbg, const uint32_t REFILL_MIN,
+            const uint32_t NODE_MIN)
 {
     const uint32_t lane = lane_id();
     const uint32_t count = *count_ptr;
@@ -791,6 +828,7 @@ k_trace_any(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4
             for (;;) {
                 const bool can = running && s.node >= 0 && s.node != TR_SENT;
                 if (!__any_sync(FULLM, can && s.leaf == 0)) break;
+                if (NODE_MIN && (uint32_t)__popc(__ballot_sync(FULLM, can)) < NODE_MIN && __any_sync(FULLM, s.leaf != 0)) break;
                 if (can) {
                     if (COUNT) vc.nodes++;
                     if (WIDE) tr_node_step4<false, (TEX ? 2 : 0)>(bv, s, stack, tmax, &ovf);
@@ -1040,8 +1078,9 @@ static cudaError_t launch_batch(fs_ctx* ctx, const fs_trace_params& tp, unsigned
     k_connect<COUNT, MODE><<<grid_con, WF_THREADS, smem, st>>>(tp, wb, ctx->d_counters, d_dbg);
     ++ctx->stats.kernel_launches;
     if (timing) cudaEventRecord(ev[2], st);
-    uint32_t grid_ev = (uint32_t)ctx->sm_count * 4u;
-    if (grid_ev > ctas_con) grid_ev = ctas_con ? ctas_con : 1;
+    uint32_t grid_ev = (uint32_t)ctx->sm_count * 8u;
+    const uint32_t ctas_ev = (tp.batch / 4u + WF_THREADS / 32 - 1) / (WF_THREADS / 32) + 1;
+    if (grid_ev > ctas_ev) grid_ev = ctas_ev;
     k_eval<<<grid_ev, WF_THREADS, 0, st>>>(tp, wb, d_hist, ctx->d_counters, d_dbg);
     ++ctx->stats.kernel_launches;
     if (timing) cudaEventRecord(ev[3], st);
@@ -1107,7 +1146,7 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
             }
 #define FS_LAUNCH_TRACE(TEXV, WIDEV)                                                                                   \
             k_trace_closest<COUNT, TEXV, WIDEV><<<grid_tr, TR_THREADS, TR_SMEM, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u], \
-                wb.q_count + k, wb.q_cursor + k, wb.hit, ctx->d_counters, ctx->tune_refill)
+                wb.q_count + k, wb.q_cursor + k, wb.hit, ctx->d_counters, ctx->tune_refill, ctx->tune_node_min, ctx->tune_tri_min)
             if (wide) { if (texm >= 2) FS_LAUNCH_TRACE(2, true); else FS_LAUNCH_TRACE(0, true); }
             else { if (texm >= 2) FS_LAUNCH_TRACE(2, false); else FS_LAUNCH_TRACE(0, false); }
 #undef FS_LAUNCH_TRACE
@@ -1129,15 +1168,16 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
         const bool tex = (wide ? tp.bv.wnodes_tex : tp.bv.nodes_tex) && ctx->tune_tex;
 #define FS_LAUNCH_ANY(TEXV, WIDEV)                                                                                     \
         k_trace_any<COUNT, TEXV, WIDEV><<<grid_any, TR_THREADS, TR_SMEM, st>>>(tp.bv, wb.st_pos[0], wb.st_nrm[0], wb.q_count + (D + 2), \
-            wb.q_cursor + (D + 2), wb.conn_queue, wb.q_count + (D + 1), ctx->d_counters, d_dbg, ctx->tune_refill)
+            wb.q_cursor + (D + 2), wb.conn_queue, wb.q_count + (D + 1), ctx->d_counters, d_dbg, ctx->tune_refill, ctx->tune_node_min)
         if (wide) { if (tex) FS_LAUNCH_ANY(2, true); else FS_LAUNCH_ANY(0, true); }
         else { if (tex) FS_LAUNCH_ANY(2, false); else FS_LAUNCH_ANY(0, false); }
 #undef FS_LAUNCH_ANY
     }
     ctx->stats.kernel_launches += 2;
     if (timing) cudaEventRecord(ev[2], st);
-    uint32_t grid_ev = (uint32_t)ctx->sm_count * 4u;
-    if (grid_ev > ctas_any) grid_ev = ctas_any ? ctas_any : 1;
+    uint32_t grid_ev = (uint32_t)ctx->sm_count * 8u;
+    const uint32_t ctas_ev = (tp.batch / 4u + WF_THREADS / 32 - 1) / (WF_THREADS / 32) + 1;   // 4 paths per warp
+    if (grid_ev > ctas_ev) grid_ev = ctas_ev;
     k_eval<<<grid_ev, WF_THREADS, 0, st>>>(tp, wb, d_hist, ctx->d_counters, d_dbg);
     ++ctx->stats.kernel_launches;
     if (timing) cudaEventRecord(ev[3], st);

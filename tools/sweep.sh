@@ -1,7 +1,9 @@
 #!/bin/bash
-for w in 1 0; do
-  echo -n "wide=$w : "
-  FS_TUNE_WIDE=$w timeout 100 python tools/profile_step.py 1 3 | tail -1 | cut -c1-330
-  echo -n "wide=$w nocount: "
-  FS_TUNE_WIDE=$w timeout 100 python tools/profile_step.py 0 3 | tail -1 | cut -c1-130
+for m in 1 4 8 12 16; do
+  echo -n "refill=$m : "
+  FS_TUNE_REFILL=$m timeout 100 python tools/profile_step.py 0 3 | tail -1 | cut -c1-130
+done
+for m in 12 16; do
+  echo -n "node_min=$m : "
+  FS_TUNE_NODE_MIN=$m timeout 100 python tools/profile_step.py 0 3 | tail -1 | cut -c1-130
 done
