@@ -224,7 +224,7 @@ static void fill_params(fs_ctx* ctx, fs_trace_params* tp, const float lis[3], ui
     tp->bv.wnodes_tex = (ctx->tune_tex && ctx->bvh.wnodes_tex) ? (unsigned long long)ctx->bvh.wnodes_tex : 0ull;
     for (int a = 0; a < 3; ++a) { tp->bv.qbase[a] = ctx->bvh.qbase[a]; tp->bv.qscale[a] = ctx->bvh.qscale[a]; }
     tp->bv.nodes = ctx->bvh.nodes; tp->bv.tris = ctx->bvh.tris; tp->bv.tri_orig = ctx->bvh.tri_orig;
-    tp->bv.tri_mat = ctx->bvh.tri_mat; tp->bv.n_tris = ctx->bvh.n_tris; tp->bv.n_inner = ctx->bvh.n_inner;
+    tp->bv.tri_mat = ctx->bvh.tri_mat; tp->bv.tri_nm = ctx->bvh.tri_nm; tp->bv.n_tris = ctx->bvh.n_tris; tp->bv.n_inner = ctx->bvh.n_inner;
     tp->top = ctx->bvh.top_nodes; tp->n_top = ctx->bvh.n_top;
     tp->refl_over_pi = ctx->d_refl_over_pi; tp->n_mats = ctx->n_mats;
     tp->ep.min_seg = c.min_seg; tp->ep.pdf_exponent = c.pdf_exponent; tp->ep.n_bands = c.n_bands;

@@ -57,6 +57,7 @@ struct fs_bvh_view {
     const float4* tris;
     const uint32_t* tri_orig;
     const uint32_t* tri_mat;
+    const float4* tri_nm;           // [T] (unit normal.xyz, bits(material)) in leaf order: one 16 B fetch per hit when shading
     uint32_t n_tris;
     uint32_t n_inner;
 };

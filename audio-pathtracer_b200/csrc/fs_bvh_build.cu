@@ -219,7 +219,8 @@ __global__ void k_pack(const float* __restrict__ verts, const uint32_t* __restri
                        const uint32_t* __restrict__ sorted_ids, uint32_t n,
                        const float4* __restrict__ tlo, const float4* __restrict__ thi,
                        float4* __restrict__ tris, uint32_t* __restrict__ tri_orig,
-                       uint32_t* __restrict__ tri_mat, float4* __restrict__ bb_lo, float4* __restrict__ bb_hi)
+                       uint32_t* __restrict__ tri_mat, float4* __restrict__ tri_nm, float4* __restrict__ bb_lo,
+                       float4* __restrict__ bb_hi)
 {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
@@ -236,6 +237,7 @@ __global__ void k_pack(const float* __restrict__ verts, const uint32_t* __restri
     tris[(size_t)j * 4 + 3] = make_float4(__uint_as_float(id), __uint_as_float(mat), 0.f, 0.f);
     tri_orig[j] = id;
     tri_mat[j] = mat;
+    tri_nm[j] = make_float4(nn.x, nn.y, nn.z, __uint_as_float(mat));
     bb_lo[(n - 1) + j] = tlo[id];
     bb_hi[(n - 1) + j] = thi[id];
 }
@@ -682,6 +684,7 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
     BCHECK(cudaMalloc(&out->tris, sizeof(float4) * 4ull * n));
     BCHECK(cudaMalloc(&out->tri_orig, 4ull * n));
     BCHECK(cudaMalloc(&out->tri_mat, 4ull * n));
+    BCHECK(cudaMalloc(&out->tri_nm, sizeof(float4) * (size_t)n));
     BCHECK(cudaMalloc(&out->top_nodes, sizeof(float4) * 4ull * FS_TOP_CAP));
     out->n_inner = n_inner;
 
@@ -705,7 +708,7 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
         }
         // 8 passes: result is back in keys0/vals0
     }
-    k_pack<<<gb, TPB, 0, st>>>(d_verts, d_mats, vals0, n, tlo, thi, out->tris, out->tri_orig, out->tri_mat, bb_lo, bb_hi);
+    k_pack<<<gb, TPB, 0, st>>>(d_verts, d_mats, vals0, n, tlo, thi, out->tris, out->tri_orig, out->tri_mat, out->tri_nm, bb_lo, bb_hi);
     ++*launches;
     if (n == 1) {
         k_emit_single<<<1, 1, 0, st>>>(bb_lo, bb_hi, out->nodes); ++*launches;
@@ -765,6 +768,6 @@ void fs_bvh_free(fs_bvh_device* b)
     if (b->nodes_tex) cudaDestroyTextureObject(b->nodes_tex);
     if (b->tris_tex) cudaDestroyTextureObject(b->tris_tex);
     if (b->wnodes_tex) cudaDestroyTextureObject(b->wnodes_tex);
-    cudaFree(b->nodes); cudaFree(b->wnodes); cudaFree(b->tris); cudaFree(b->tri_orig); cudaFree(b->tri_mat); cudaFree(b->top_nodes);
+    cudaFree(b->nodes); cudaFree(b->wnodes); cudaFree(b->tris); cudaFree(b->tri_orig); cudaFree(b->tri_mat); cudaFree(b->tri_nm); cudaFree(b->top_nodes);
     memset(b, 0, sizeof(*b));
 }

@@ -20,6 +20,7 @@ struct fs_bvh_device {
     float4* tris;
     uint32_t* tri_orig;
     uint32_t* tri_mat;
+    float4* tri_nm;
     float4* top_nodes;
     cudaTextureObject_t nodes_tex, tris_tex, wnodes_tex;
     uint4* wnodes;

@@ -473,15 +473,15 @@ k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_d
                     cont = false;
                 } else {                          // SUB.cpp:343-348
                     const float t = h.x;
-                    const float4* tq = tp.bv.tris + (size_t)tri * 4;
-                    fs_vec3 fn = fs_mk(fs_ldg4(tq).w, fs_ldg4(tq + 1).w, fs_ldg4(tq + 2).w);
+                    const float4 nm = fs_ldg4(tp.bv.tri_nm + tri);
+                    fs_vec3 fn = fs_mk(nm.x, nm.y, nm.z);
                     if (fs_dot(fn, d) > 0.0f) { fn.x = -fn.x; fn.y = -fn.y; fn.z = -fn.z; }
                     pos.x = fmaf(tp.eps_offset, fn.x, fmaf(t, d.x, o.x));
                     pos.y = fmaf(tp.eps_offset, fn.y, fmaf(t, d.y, o.y));
                     pos.z = fmaf(tp.eps_offset, fn.z, fmaf(t, d.z, o.z));
                     const fs_vec3 dl = fs_sub(pos, o);
                     const float seg = sqrtf(fs_dot(dl, dl));
-                    const uint32_t mat = __ldg(tp.bv.tri_mat + tri);
+                    const uint32_t mat = __float_as_uint(nm.w);
                     wb.rec[(size_t)k * stride + sp_id] = make_float4(seg, __uint_as_float(mat), b.w, fs_pow(b.w, tp.ep.pdf_exponent));
                     nrm = fn;
                     nodes = k + 1;
