@@ -978,6 +978,34 @@ k_debug_rays(const fs_trace_params tp, const float* __restrict__ rays, const flo
     }
 }
 
+
+// ---- debug rays through the PRODUCTION traversal kernels (intersector parity tests) ----
+__global__ void k_dbg_pack(const float* __restrict__ rays, const float* __restrict__ tmax, uint64_t n,
+                           float4* __restrict__ ro, float4* __restrict__ rd, uint32_t* __restrict__ count, uint8_t* __restrict__ out_hit)
+{
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i == 0) *count = (uint32_t)n;
+    if (i >= n) return;
+    const float w0 = tmax ? tmax[i] : __uint_as_float((uint32_t)i);
+    ro[i] = make_float4(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2], w0);
+    rd[i] = make_float4(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5], tmax ? __uint_as_float((uint32_t)i) : 0.f);
+    if (out_hit) out_hit[i] = 1;          // any-hit: rays the kernel reports as unoccluded are cleared afterwards
+}
+__global__ void k_dbg_unpack_closest(const fs_bvh_view bv, const float2* __restrict__ hits, uint64_t n,
+                                     float* __restrict__ out_t, uint32_t* __restrict__ out_tri)
+{
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int tri = __float_as_int(hits[i].y);
+    out_t[i] = hits[i].x;
+    out_tri[i] = tri >= 0 ? bv.tri_orig[tri] : 0xffffffffu;
+}
+__global__ void k_dbg_unpack_any(const uint32_t* __restrict__ conn, const uint32_t* __restrict__ conn_count, uint8_t* __restrict__ out_hit)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < *conn_count) out_hit[conn[i]] = 0;
+}
+
 template <typename K>
 int resident_ctas(K kernel, int threads, size_t smem)
 {
@@ -1214,6 +1242,38 @@ cudaError_t fs_wave_debug_rays(fs_ctx* ctx, const fs_trace_params& tp, const flo
 {
     cudaStream_t st = ctx->stream;
     const int mode = pick_mode(tp);
+    if (!(tp.flags & (FS_FLAG_FUSED_EXTEND | FS_FLAG_BRUTE_FORCE)) && n < 0xffffffffull) {
+        // default: the same k_trace_closest / k_trace_any the BDPT update runs (4-wide nodes, smem stack, ...)
+        float4 *ro = nullptr, *rd = nullptr; float2* hits = nullptr; uint32_t *misc = nullptr, *conn = nullptr;
+        cudaError_t e;
+        if ((e = cudaMalloc(&ro, sizeof(float4) * n)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&rd, sizeof(float4) * n)) != cudaSuccess) { cudaFree(ro); return e; }
+        if ((e = cudaMalloc(&hits, sizeof(float2) * n)) != cudaSuccess) { cudaFree(ro); cudaFree(rd); return e; }
+        if ((e = cudaMalloc(&conn, 4 * n)) != cudaSuccess) { cudaFree(ro); cudaFree(rd); cudaFree(hits); return e; }
+        if ((e = cudaMalloc(&misc, 4 * 4)) != cudaSuccess) { cudaFree(ro); cudaFree(rd); cudaFree(hits); cudaFree(conn); return e; }
+        cudaMemsetAsync(misc, 0, 16, st);            // [0] ray count, [1] cursor, [2] connected count
+        const uint32_t g = (uint32_t)((n + 255) / 256);
+        k_dbg_pack<<<g, 256, 0, st>>>(d_rays, d_hit ? d_tmax : nullptr, n, ro, rd, misc, d_hit);
+        const bool wide = tp.bv.wnodes != nullptr;
+        const bool tex = (wide ? tp.bv.wnodes_tex : tp.bv.nodes_tex) && ctx->tune_tex;
+        uint32_t grid = (uint32_t)((n + TR_THREADS - 1) / TR_THREADS);
+        if (grid > (uint32_t)ctx->sm_count * 5u) grid = (uint32_t)ctx->sm_count * 5u;
+        if (d_hit) {
+#define FS_DBG_ANY(TEXV, WIDEV) k_trace_any<false, TEXV, WIDEV><<<grid, TR_THREADS, TR_SMEM, st>>>(tp.bv, ro, rd, misc, misc + 1, conn, misc + 2, ctx->d_counters, nullptr, ctx->tune_refill, ctx->tune_node_min)
+            if (wide) { if (tex) FS_DBG_ANY(2, true); else FS_DBG_ANY(0, true); } else { if (tex) FS_DBG_ANY(2, false); else FS_DBG_ANY(0, false); }
+#undef FS_DBG_ANY
+            k_dbg_unpack_any<<<g, 256, 0, st>>>(conn, misc + 2, d_hit);
+        } else {
+#define FS_DBG_CL(TEXV, WIDEV) k_trace_closest<false, TEXV, WIDEV><<<grid, TR_THREADS, TR_SMEM, st>>>(tp.bv, ro, rd, misc, misc + 1, hits, ctx->d_counters, ctx->tune_refill, ctx->tune_node_min, ctx->tune_tri_min)
+            if (wide) { if (tex) FS_DBG_CL(2, true); else FS_DBG_CL(0, true); } else { if (tex) FS_DBG_CL(2, false); else FS_DBG_CL(0, false); }
+#undef FS_DBG_CL
+            k_dbg_unpack_closest<<<g, 256, 0, st>>>(tp.bv, hits, n, d_t, d_tri);
+        }
+        ctx->stats.kernel_launches += 3;
+        e = cudaStreamSynchronize(st);
+        cudaFree(ro); cudaFree(rd); cudaFree(hits); cudaFree(conn); cudaFree(misc);
+        return e != cudaSuccess ? e : cudaGetLastError();
+    }
     const size_t smem = (mode == MODE_TOP) ? (size_t)tp.n_top * 64 : 0;
     uint32_t grid = (uint32_t)((n + WF_THREADS - 1) / WF_THREADS);
     if (grid > (uint32_t)ctx->sm_count * 8u) grid = (uint32_t)ctx->sm_count * 8u;

@@ -31,11 +31,11 @@ def test_bvh_equals_brute_force_and_oracle(fs, oracle, scene_name, kw, lo, hi):
     else:
         rays = _rays(rng, lo, hi, n)
     rays[:64, 3:] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 64)] * rng.choice([-1, 1], (64, 1))  # axis-parallel
-    with fs.Context() as a, fs.Context(flags=capi.FLAG_BRUTE_FORCE) as b, fs.Context(flags=capi.FLAG_SMEM_TREELET) as c:
+    with fs.Context() as a, fs.Context(flags=capi.FLAG_BRUTE_FORCE) as b, fs.Context(flags=capi.FLAG_FUSED_EXTEND) as c:
         for ctx in (a, b, c):
             ctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
-        ta, ia = a.closest_hits(rays)
-        tc, ic = c.closest_hits(rays)
+        ta, ia = a.closest_hits(rays)            # production kernels: 4-wide quantised nodes, smem stack, ray replacement
+        tc, ic = c.closest_hits(rays)            # per-thread traversal of the BVH2 float nodes
         nb = 6000
         tb, ib = b.closest_hits(rays[:nb])
         assert np.array_equal(ta, tc) and np.array_equal(ia, ic)
@@ -44,6 +44,7 @@ def test_bvh_equals_brute_force_and_oracle(fs, oracle, scene_name, kw, lo, hi):
         tmax = (ta * rng.uniform(0.5, 1.5, n)).astype(np.float32)
         tmax[~np.isfinite(tmax)] = 10.0
         ha = a.any_hits(rays, tmax)
+        assert np.array_equal(ha, c.any_hits(rays, tmax))
         hb = b.any_hits(rays[:nb], tmax[:nb])
         assert np.array_equal(ha[:nb], hb)
     S = oracle.Scene(sc.verts, sc.tri_mat, sc.absorption, use_bvh=True)
