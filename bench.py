@@ -188,6 +188,10 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything native code prints there (e.g. "NCCL version ...") goes to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
@@ -330,7 +334,8 @@ def run_b200(args):
                 "stage_ms": {"trace_closest": trc_ms, "shade_gen": ext_ms_all - trc_ms, "connect": con_ms, "eval_splat": evl_ms},
                 "rays_per_step_per_gpu": rays, "ext_rays_per_step_per_gpu": ext_rays, "connected_per_step_per_gpu": connected,
                 "triangles": int(sc.n_tris)}
-        print(json.dumps(line), flush=True)
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     ctx.close()
     if N > 1:
         dist.barrier()
