@@ -79,7 +79,8 @@ int fs_create(const fs_config* cfg, fs_ctx** out)
     ctx->cfg = *cfg;
     if (ctx->cfg.max_batch_paths == 0) ctx->cfg.max_batch_paths = 1u << 20;
     ctx->device = dev;
-    ctx->tune_refill = 4; ctx->tune_leaf_max = FS_LEAF_MAX; ctx->tune_tex = 2; ctx->tune_builder = 1; ctx->tune_wide = 1; ctx->tune_node_min = 14; ctx->tune_tri_min = 4;
+    ctx->tune_refill = 4; ctx->tune_leaf_max = FS_LEAF_MAX; ctx->tune_tex = 2; ctx->tune_builder = 1; ctx->tune_wide = 1; ctx->tune_node_min = 14; ctx->tune_tri_min = 4; ctx->tune_sched = 0;
+    if (const char* e8 = getenv("FS_TUNE_SCHED")) ctx->tune_sched = (uint32_t)atoi(e8);
     if (const char* e7 = getenv("FS_TUNE_TRI_MIN")) ctx->tune_tri_min = (uint32_t)atoi(e7);
     if (const char* e6 = getenv("FS_TUNE_NODE_MIN")) ctx->tune_node_min = (uint32_t)atoi(e6);
     if (const char* e5 = getenv("FS_TUNE_WIDE")) ctx->tune_wide = (uint32_t)atoi(e5);

@@ -559,7 +559,9 @@ __device__ __forceinline__ uint4 ldg_u4(const uint4* p)
 // layout [depth][thread]: bank-conflict free, ~30-cycle latency), deeper entries in local memory.
 // ncu showed 12 % of the kernel's stall samples on the instruction consuming a local-memory pop
 // (37 % of those loads missed L1, and the 256 B/thread stacks competed with BVH nodes for L1).
+#ifndef FS_SSTACK
 #define FS_SSTACK 12
+#endif
 #define TR_SMEM (FS_SSTACK * TR_THREADS * sizeof(int))
 struct tr_stack {
     int* sh;        // &smem[threadIdx.x], stride blockDim.x
@@ -628,7 +630,7 @@ __device__ __forceinline__ void tr_node_step(const fs_bvh_view& bv, tr_state& s,
                                    const int tv_ = sw_ ? vb : va; vb = sw_ ? va : vb; va = tv_; }
 
 // one step through a 4-wide quantised node: near/far planes picked by the ray octant, hits sorted near-to-far
-template <bool ORDERED, int TEX>
+template <bool ORDERED, int TEX, bool SETTLE = true>
 __device__ __forceinline__ void tr_node_step4(const fs_bvh_view& bv, tr_state& s, const tr_stack& stack, float tlimit,
                                               uint32_t* overflow)
 {
@@ -659,8 +661,14 @@ __device__ __forceinline__ void tr_node_step4(const fs_bvh_view& bv, tr_state& s
     float k0, k1, k2, k3; int v0, v1, v2, v3;
     FS_CHILD(u0, k0, v0) FS_CHILD(u1, k1, v1) FS_CHILD(u2, k2, v2) FS_CHILD(u3, k3, v3)
 #undef FS_CHILD
-    if (ORDERED) {                       // 5-comparator network; misses (INF) sink to the end
+    if (ORDERED) {
+#if defined(FS_SORT_MIN_ONLY)
+        // 3 comparators: slot 0 = nearest hit, the others stay unordered
+        FS_CSWAP(k0, v0, k1, v1) FS_CSWAP(k2, v2, k3, v3) FS_CSWAP(k0, v0, k2, v2)
+#else
+        // 5-comparator network; misses (INF) sink to the end
         FS_CSWAP(k0, v0, k1, v1) FS_CSWAP(k2, v2, k3, v3) FS_CSWAP(k0, v0, k2, v2) FS_CSWAP(k1, v1, k3, v3) FS_CSWAP(k1, v1, k2, v2)
+#endif
     } else {                             // any-hit rays: only move the hits to the front
         if (k0 == INF) { k0 = k1; v0 = v1; k1 = INF; }
         if (k0 == INF) { k0 = k2; v0 = v2; k2 = INF; }
@@ -676,7 +684,7 @@ __device__ __forceinline__ void tr_node_step4(const fs_bvh_view& bv, tr_state& s
             if (k1 != INF) stack.push(s.sp, v1);
         } else *overflow = 1u;
     }
-    tr_settle(s, stack);
+    if (SETTLE) tr_settle(s, stack);
 }
 
 // after a triangle step that exhausted the open range: open the postponed leaf, then re-settle
@@ -687,7 +695,7 @@ __device__ __forceinline__ void tr_next_leaf(tr_state& s, const tr_stack& stack)
     }
 }
 
-template <bool COUNT, int TEX, bool WIDE>
+template <bool COUNT, int TEX, bool WIDE, int SCHED>
 __global__ void __launch_bounds__(TR_THREADS, FS_TR_MINBLOCKS)
 k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
                 const uint32_t* __restrict__ count_ptr, uint32_t* __restrict__ cursor,
@@ -726,7 +734,40 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
             }
         }
         if (!__any_sync(FULLM, running)) break;
-        // ---- walk until enough lanes have retired their ray ("while-while" with postponed leaves)
+        // ---- schedule 1 ("if-if"): every iteration a lane takes one wide-node step and, when that leaves it at a
+        // leaf, tests one triangle right away.  A wide-node step costs ~3x a triangle test, so running the cheap
+        // triangle part under-occupied every iteration beats batching it in phases: no lane ever waits for a phase.
+        if (SCHED == 1) {
+            for (;;) {
+                if (running && s.node >= 0 && s.node != TR_SENT) {
+                    if (COUNT) vc.nodes++;
+                    tr_node_step4<true, TEX, false>(bv, s, stack, bt, &ovf);
+                }
+                if (running && s.node < 0) {
+                    if (s.tc == s.te) leaf_range(s.node, s.tc, s.te);
+                    const float4* tq = bv.tris + (size_t)s.tc * 4;
+                    const float4 a = fs_ldg4(tq), b = fs_ldg4(tq + 1), c = fs_ldg4(tq + 2);
+                    if (COUNT) vc.tris++;
+                    float t;
+                    if (fs_intersect_tri(s.o, s.d, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z), fs_mk(c.x, c.y, c.z), t) && t <= bt) {
+                        if (t < bt || __float_as_uint(fs_ldg4(tq + 3).x) < __float_as_uint(fs_ldg4(bv.tris + (size_t)best * 4 + 3).x)) {
+                            bt = t; best = (int)s.tc;
+                        }
+                    }
+                    ++s.tc;
+                    if (s.tc == s.te) s.node = stack.pop(s.sp);
+                }
+                if (running && s.node == TR_SENT) {
+                    hits[j] = make_float2(bt, __int_as_float(best));
+                    running = false;
+                }
+                const uint32_t m_run = __ballot_sync(FULLM, running);
+                if (m_run == 0u) break;
+                if (!exhausted && 32u - (uint32_t)__popc(m_run) >= REFILL_MIN) break;
+            }
+            continue;
+        }
+        // ---- schedule 0: walk until enough lanes have retired their ray ("while-while" with postponed leaves)
         for (;;) {
 #if defined(FS_TRAVERSAL_GUARD)
             if (++guard > (1u << 22)) { ovf = 2u; running = false; exhausted = true; break; }   // bring-up guard
@@ -1127,7 +1168,7 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
     cudaStream_t st = ctx->stream;
     const fs_wave_buffers& wb = ctx->wb;
     static int occ_tr = 0, occ_any = 0;
-    if (!occ_tr) occ_tr = resident_ctas(k_trace_closest<COUNT, 2, true>, TR_THREADS, TR_SMEM);
+    if (!occ_tr) occ_tr = resident_ctas(k_trace_closest<COUNT, 2, true, 0>, TR_THREADS, TR_SMEM);
     if (!occ_any) occ_any = resident_ctas(k_trace_any<COUNT, 2, true>, TR_THREADS, TR_SMEM);
     const bool timing = (tp.flags & FS_FLAG_TIME_KERNELS) != 0;
     cudaEvent_t* ev = nullptr;
@@ -1172,11 +1213,12 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
                 ctx->tev_used += 2;
                 cudaEventRecord(te[0], st);
             }
-#define FS_LAUNCH_TRACE(TEXV, WIDEV)                                                                                   \
-            k_trace_closest<COUNT, TEXV, WIDEV><<<grid_tr, TR_THREADS, TR_SMEM, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u], \
+#define FS_LAUNCH_TRACE(TEXV, WIDEV, SCHEDV)                                                                                 \
+            k_trace_closest<COUNT, TEXV, WIDEV, SCHEDV><<<grid_tr, TR_THREADS, TR_SMEM, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u], \
                 wb.q_count + k, wb.q_cursor + k, wb.hit, ctx->d_counters, ctx->tune_refill, ctx->tune_node_min, ctx->tune_tri_min)
-            if (wide) { if (texm >= 2) FS_LAUNCH_TRACE(2, true); else FS_LAUNCH_TRACE(0, true); }
-            else { if (texm >= 2) FS_LAUNCH_TRACE(2, false); else FS_LAUNCH_TRACE(0, false); }
+            if (wide && ctx->tune_sched == 1) { if (texm >= 2) FS_LAUNCH_TRACE(2, true, 1); else FS_LAUNCH_TRACE(0, true, 1); }
+            else if (wide) { if (texm >= 2) FS_LAUNCH_TRACE(2, true, 0); else FS_LAUNCH_TRACE(0, true, 0); }
+            else { if (texm >= 2) FS_LAUNCH_TRACE(2, false, 0); else FS_LAUNCH_TRACE(0, false, 0); }
 #undef FS_LAUNCH_TRACE
             if (timing) cudaEventRecord(te[1], st);
             ++ctx->stats.kernel_launches;
@@ -1264,7 +1306,7 @@ cudaError_t fs_wave_debug_rays(fs_ctx* ctx, const fs_trace_params& tp, const flo
 #undef FS_DBG_ANY
             k_dbg_unpack_any<<<g, 256, 0, st>>>(conn, misc + 2, d_hit);
         } else {
-#define FS_DBG_CL(TEXV, WIDEV) k_trace_closest<false, TEXV, WIDEV><<<grid, TR_THREADS, TR_SMEM, st>>>(tp.bv, ro, rd, misc, misc + 1, hits, ctx->d_counters, ctx->tune_refill, ctx->tune_node_min, ctx->tune_tri_min)
+#define FS_DBG_CL(TEXV, WIDEV) k_trace_closest<false, TEXV, WIDEV, 0><<<grid, TR_THREADS, TR_SMEM, st>>>(tp.bv, ro, rd, misc, misc + 1, hits, ctx->d_counters, ctx->tune_refill, ctx->tune_node_min, ctx->tune_tri_min)
             if (wide) { if (tex) FS_DBG_CL(2, true); else FS_DBG_CL(0, true); } else { if (tex) FS_DBG_CL(2, false); else FS_DBG_CL(0, false); }
 #undef FS_DBG_CL
             k_dbg_unpack_closest<<<g, 256, 0, st>>>(tp.bv, hits, n, d_t, d_tri);
