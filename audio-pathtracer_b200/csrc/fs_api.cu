@@ -79,8 +79,8 @@ int fs_create(const fs_config* cfg, fs_ctx** out)
     ctx->cfg = *cfg;
     if (ctx->cfg.max_batch_paths == 0) ctx->cfg.max_batch_paths = 1u << 20;
     ctx->device = dev;
-    ctx->tune_refill = 4; ctx->tune_leaf_max = FS_LEAF_MAX; ctx->tune_tex = 2; ctx->tune_builder = 1; ctx->tune_wide = 1; ctx->tune_node_min = 14; ctx->tune_tri_min = 4; ctx->tune_sched = 0;
-    if (const char* e8 = getenv("FS_TUNE_SCHED")) ctx->tune_sched = (uint32_t)atoi(e8);
+    ctx->tune_refill = 4; ctx->tune_leaf_max = FS_LEAF_MAX; ctx->tune_tex = 2; ctx->tune_builder = 1; ctx->tune_wide = 1; ctx->tune_node_min = 14; ctx->tune_tri_min = 4; ctx->tune_collapse = 1;
+    if (const char* e9 = getenv("FS_TUNE_COLLAPSE")) ctx->tune_collapse = (uint32_t)atoi(e9);
     if (const char* e7 = getenv("FS_TUNE_TRI_MIN")) ctx->tune_tri_min = (uint32_t)atoi(e7);
     if (const char* e6 = getenv("FS_TUNE_NODE_MIN")) ctx->tune_node_min = (uint32_t)atoi(e6);
     if (const char* e5 = getenv("FS_TUNE_WIDE")) ctx->tune_wide = (uint32_t)atoi(e5);
@@ -205,9 +205,11 @@ int fs_scene_commit(fs_ctx* ctx)
             if (m[i] >= ctx->n_mats) return fail(ctx, FS_ERR_INVALID, "triangle material id out of range");
     }
     CK(fs_bvh_build(ctx->stream, ctx->d_verts, ctx->d_tri_mat, ctx->n_tris, &ctx->bvh, &ctx->stats.kernel_launches,
-                    ctx->tune_leaf_max, ctx->tune_builder));
+                    ctx->tune_leaf_max, ctx->tune_builder, ctx->tune_collapse));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stats.bvh_nodes = ctx->bvh.n_inner;
+    if (getenv("FS_VERBOSE")) fprintf(stderr, "[frequensee] BVH: %u triangles, %u BVH2 nodes, %u reachable 4-wide nodes (%.1f MB)\n",
+                                      ctx->bvh.n_tris, ctx->bvh.n_inner, ctx->bvh.n_wide, ctx->bvh.n_wide * 64.0 / 1e6);
     ctx->stats.bvh_max_leaf = ctx->bvh.max_leaf;
     ctx->committed = true;
     return FS_OK;

@@ -18,9 +18,10 @@
 // A 32 B node format (16-bit quantised boxes, octant plane selection by PRMT) halves those
 // wavefronts (48 %) but was measured no faster: the kernel then waits on load latency with the
 // ALU pipe as the busiest unit (profiles/r1_experiments.md); it is not kept in the tree.
-//   wnodes : uint4[n_inner][4]   64 B per 4-WIDE node (production traversal format).  Wide node i holds the
-//             grandchildren of BVH2 node i (a leaf child stays one slot), so it shares BVH2's indexing and a
-//             ray takes about half as many dependent steps.  Boxes are quantised to 16 bits per coordinate
+//   wnodes : uint4[n_wide][4]    64 B per 4-WIDE node (production traversal format).  A wide node is a BVH2
+//             node with up to two of its descendants opened (greedy by surface area), so a ray takes about
+//             half as many dependent steps; only the nodes reachable from the root are kept, in a dense
+//             breadth-first array (children of a node adjacent).  Boxes are quantised to 16 bits per coordinate
 //             on a scene-wide grid, rounded outward plus one spare quantum:
 //               u_k = (lo.x | hi.x << 16, lo.y | hi.y << 16, lo.z | hi.z << 16, child_k), k = 0..3
 //             empty slot: inverted box (lo = 65535, hi = 0).  Dequantisation is folded into the slab FMA:

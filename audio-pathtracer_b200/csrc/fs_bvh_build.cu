@@ -506,29 +506,87 @@ __device__ __forceinline__ uint4 quant_box(float lox, float hix, float loy, floa
     return u;
 }
 
+// Wide node i = BVH2 node i with up to two of its descendants opened.  collapse = 1 (default): greedy by
+// surface area -- repeatedly replace the inner child with the largest box by its two children until there are
+// four slots (Wald et al. 2008 / Ylitie et al. 2017 collapse, restricted to width 4): every slot is used and the
+// big, often-hit boxes are the ones that get resolved one level further.  collapse = 0: the four grandchildren
+// (a leaf child leaves a slot empty).  Child references stay BVH2 node indices, so every BVH2 node can be emitted
+// independently; the ones no wide node refers to are simply never visited.
+struct cbox { float lx, hx, ly, hy, lz, hz; int ref; };
+__device__ __forceinline__ void load_children(const float4* __restrict__ nodes, int i, cbox& a, cbox& b)
+{
+    const float4 n0 = nodes[(size_t)i * 4], n1 = nodes[(size_t)i * 4 + 1], n2 = nodes[(size_t)i * 4 + 2], n3 = nodes[(size_t)i * 4 + 3];
+    a.lx = n0.x; a.hx = n0.y; a.ly = n0.z; a.hy = n0.w; a.lz = n2.x; a.hz = n2.y; a.ref = __float_as_int(n3.x);
+    b.lx = n1.x; b.hx = n1.y; b.ly = n1.z; b.hy = n1.w; b.lz = n2.z; b.hz = n2.w; b.ref = __float_as_int(n3.y);
+}
+__device__ __forceinline__ float cbox_area(const cbox& c)
+{
+    const float dx = c.hx - c.lx, dy = c.hy - c.ly, dz = c.hz - c.lz;
+    return dx * dy + dy * dz + dz * dx;
+}
+
 __global__ void k_emit4(uint32_t n_inner, const float4* __restrict__ nodes, const float* __restrict__ grid,
-                        uint4* __restrict__ wnodes)
+                        uint4* __restrict__ wnodes, int collapse)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_inner) return;
     const uint4 EMPTY = make_uint4(0x0000ffffu, 0x0000ffffu, 0x0000ffffu, 0x7fffffffu);   // lo = 65535 > hi = 0
-    uint4 out[4] = {EMPTY, EMPTY, EMPTY, EMPTY};
-    int k = 0;
-    const float4 a0 = nodes[(size_t)i * 4], a1 = nodes[(size_t)i * 4 + 1], a2 = nodes[(size_t)i * 4 + 2], a3 = nodes[(size_t)i * 4 + 3];
-    const int c[2] = {__float_as_int(a3.x), __float_as_int(a3.y)};
-    for (int s = 0; s < 2; ++s) {
-        if (c[s] >= 0) {                              // inner child: its two children become slots
-            const size_t b = (size_t)c[s] * 4;
-            const float4 g0 = nodes[b], g1 = nodes[b + 1], g2 = nodes[b + 2], g3 = nodes[b + 3];
-            out[k++] = quant_box(g0.x, g0.y, g0.z, g0.w, g2.x, g2.y, __float_as_int(g3.x), grid);
-            out[k++] = quant_box(g1.x, g1.y, g1.z, g1.w, g2.z, g2.w, __float_as_int(g3.y), grid);
-        } else if (s == 0) {
-            out[k++] = quant_box(a0.x, a0.y, a0.z, a0.w, a2.x, a2.y, c[0], grid);
-        } else {
-            out[k++] = quant_box(a1.x, a1.y, a1.z, a1.w, a2.z, a2.w, c[1], grid);
+    cbox c[4];
+    int k = 2;
+    load_children(nodes, (int)i, c[0], c[1]);
+    if (collapse) {
+        while (k < 4) {
+            int pick = -1; float best = -1.0f;
+            for (int j = 0; j < k; ++j)
+                if (c[j].ref >= 0) { const float a = cbox_area(c[j]); if (a > best) { best = a; pick = j; } }
+            if (pick < 0) break;
+            const int r = c[pick].ref;
+            load_children(nodes, r, c[pick], c[k]);
+            ++k;
         }
+    } else {
+        const int r0 = c[0].ref, r1 = c[1].ref;
+        if (r1 >= 0) { load_children(nodes, r1, c[1], c[k]); ++k; }
+        if (r0 >= 0) { load_children(nodes, r0, c[0], c[k]); ++k; }
     }
-    for (int j = 0; j < 4; ++j) wnodes[(size_t)i * 4 + j] = out[j];
+    for (int j = 0; j < 4; ++j)
+        wnodes[(size_t)i * 4 + j] = (j < k) ? quant_box(c[j].lx, c[j].hx, c[j].ly, c[j].hy, c[j].lz, c[j].hz, c[j].ref, grid) : EMPTY;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dense breadth-first relayout of the REACHABLE wide nodes.  k_emit4 makes a wide node for every BVH2
+// node, but a traversal that starts at the root only ever visits the ones other wide nodes refer to
+// (about half with the grandchild collapse, fewer with the greedy one); left interleaved in memory the
+// unreachable ones halve the useful part of every 128 B line and of the L1/L2 capacity.  Level by
+// level: count the inner children of the frontier, exclusive scan, copy each frontier node to its
+// dense slot with its inner-child references rewritten.  The children of a node get consecutive
+// slots (one or two lines), the top of the tree is a contiguous prefix.  Deterministic.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool wide_is_inner(uint32_t ref) { return (int)ref >= 0 && ref != 0x7fffffffu; }
+
+__global__ void k_wide_count(const uint4* __restrict__ src, const int* __restrict__ frontier, uint32_t nf, uint32_t* __restrict__ cnt)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nf) return;
+    const uint4* p = src + (size_t)frontier[t] * 4;
+    uint32_t c = 0;
+    for (int j = 0; j < 4; ++j) c += wide_is_inner(p[j].w) ? 1u : 0u;
+    cnt[t] = c;
+}
+
+__global__ void k_wide_place(const uint4* __restrict__ src, uint4* __restrict__ dst, const int* __restrict__ frontier, uint32_t nf,
+                             const uint32_t* __restrict__ off, uint32_t level_base, int* __restrict__ next_frontier)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nf) return;
+    const uint4* p = src + (size_t)frontier[t] * 4;
+    uint4* q = dst + (size_t)(level_base + t) * 4;
+    uint32_t o = off[t];
+    for (int j = 0; j < 4; ++j) {
+        uint4 u = p[j];
+        if (wide_is_inner(u.w)) { next_frontier[o] = (int)u.w; u.w = level_base + nf + o; ++o; }
+        q[j] = u;
+    }
 }
 
 // single-triangle scene: root whose second child is a far-away point box (never entered in practice)
@@ -643,10 +701,47 @@ fail:
     return err;
 }
 
+// sparse (one wide node per BVH2 node) -> dense breadth-first array; *dense_out is allocated here
+static cudaError_t wide_compact(cudaStream_t st, uint32_t n_inner, const uint4* sparse, uint4** dense_out, uint32_t* n_wide_out,
+                                uint64_t* launches)
+{
+    cudaError_t err = cudaSuccess;
+    int* fr[2] = {nullptr, nullptr};
+    uint32_t *cnt = nullptr, *off = nullptr, *tile_sums = nullptr, *total = nullptr;
+    uint4* dense = nullptr;
+    const int TPB = 256;
+    uint32_t nf = 1, base = 0;
+    int pp = 0;
+    const int zero = 0;
+    BCHECK(cudaMalloc(&fr[0], 4ull * n_inner)); BCHECK(cudaMalloc(&fr[1], 4ull * n_inner));
+    BCHECK(cudaMalloc(&cnt, 4ull * n_inner)); BCHECK(cudaMalloc(&off, 4ull * n_inner));
+    BCHECK(cudaMalloc(&tile_sums, 4ull * ((n_inner + SCAN_TILE - 1) / SCAN_TILE + 2)));
+    BCHECK(cudaMalloc(&total, 4));
+    BCHECK(cudaMalloc(&dense, sizeof(uint4) * 4ull * n_inner));
+    BCHECK(cudaMemcpyAsync(fr[0], &zero, 4, cudaMemcpyHostToDevice, st));
+    while (nf) {
+        const uint32_t g = (nf + TPB - 1) / TPB;
+        uint32_t next = 0;
+        k_wide_count<<<g, TPB, 0, st>>>(sparse, fr[pp], nf, cnt); ++*launches;
+        scan_u32(st, cnt, off, nf, tile_sums, total, launches);
+        k_wide_place<<<g, TPB, 0, st>>>(sparse, dense, fr[pp], nf, off, base, fr[pp ^ 1]); ++*launches;
+        BCHECK(cudaMemcpyAsync(&next, total, 4, cudaMemcpyDeviceToHost, st));
+        BCHECK(cudaStreamSynchronize(st));
+        base += nf; nf = next; pp ^= 1;
+        if (base + nf > n_inner) { err = cudaErrorUnknown; goto fail; }     // cannot happen for a tree
+    }
+    BCHECK(cudaGetLastError());
+    *dense_out = dense; dense = nullptr; *n_wide_out = base;
+fail:
+    cudaFree(fr[0]); cudaFree(fr[1]); cudaFree(cnt); cudaFree(off); cudaFree(tile_sums); cudaFree(total); cudaFree(dense);
+    return err;
+}
+
 cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* d_mats, uint64_t T64,
-                         fs_bvh_device* out, uint64_t* launches, uint32_t leaf_max_u, uint32_t builder)
+                         fs_bvh_device* out, uint64_t* launches, uint32_t leaf_max_u, uint32_t builder, uint32_t collapse_u)
 {
     const int leaf_max = (int)(leaf_max_u < 1 ? 1 : (leaf_max_u > 8 ? 8 : leaf_max_u));
+    const int collapse = (int)collapse_u;     // bit 0: greedy surface-area collapse, bit 1: skip the dense relayout
     cudaError_t err = cudaSuccess;
     const uint32_t n = (uint32_t)T64;
     fs_bvh_free(out);
@@ -724,7 +819,13 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
         k_leaf_stats<<<gb, TPB, 0, st>>>((int)n, ranges, misc + 8, leaf_max); ++*launches;
     }
     k_quant_grid<<<1, 32, 0, st>>>(out->nodes, grid); ++*launches;
-    k_emit4<<<(n_inner + TPB - 1) / TPB, TPB, 0, st>>>(n_inner, out->nodes, grid, out->wnodes); ++*launches;
+    k_emit4<<<(n_inner + TPB - 1) / TPB, TPB, 0, st>>>(n_inner, out->nodes, grid, out->wnodes, collapse & 1); ++*launches;
+    out->n_wide = n_inner;
+    if (!(collapse & 2)) {                          // FS_TUNE_COLLAPSE bit 1 keeps the sparse layout (A/B)
+        uint4* dense = nullptr; uint32_t n_wide = 0;
+        BCHECK(wide_compact(st, n_inner, out->wnodes, &dense, &n_wide, launches));
+        cudaFree(out->wnodes); out->wnodes = dense; out->n_wide = n_wide;
+    }
     {
         cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
         rd.resType = cudaResourceTypeLinear;
@@ -739,7 +840,7 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
         if (cudaCreateTextureObject(&out->tris_tex, &rd, &td, nullptr) != cudaSuccess) { out->tris_tex = 0; (void)cudaGetLastError(); }
         rd.res.linear.devPtr = out->wnodes;
         rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
-        rd.res.linear.sizeInBytes = sizeof(uint4) * 4ull * n_inner;
+        rd.res.linear.sizeInBytes = sizeof(uint4) * 4ull * out->n_wide;
         if (cudaCreateTextureObject(&out->wnodes_tex, &rd, &td, nullptr) != cudaSuccess) { out->wnodes_tex = 0; (void)cudaGetLastError(); }
     }
     k_top_treelet<<<1, 32, 0, st>>>(out->nodes, n_inner, FS_TOP_CAP, out->top_nodes, misc + 7, queue); ++*launches;

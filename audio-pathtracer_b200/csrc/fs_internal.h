@@ -26,11 +26,13 @@ struct fs_bvh_device {
     uint4* wnodes;
     float qbase[3], qscale[3];
     uint32_t n_tris, n_inner, n_top, max_leaf;
+    uint32_t n_wide;             // wide nodes reachable from the root (dense breadth-first array)
     float extent;
 };
 
 cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* d_mats, uint64_t n_tris,
-                         fs_bvh_device* out, uint64_t* launches, uint32_t leaf_max, uint32_t builder /*0 LBVH, 1 PLOC*/);
+                         fs_bvh_device* out, uint64_t* launches, uint32_t leaf_max, uint32_t builder /*0 LBVH, 1 PLOC*/,
+                         uint32_t collapse /*wide nodes: bit 0 greedy by surface area (else grandchildren), bit 1 keep the sparse layout*/);
 void fs_bvh_free(fs_bvh_device* b);
 
 // device-side counters of one trace call
@@ -108,7 +110,7 @@ struct fs_ctx {
     std::vector<cudaEvent_t> kev; size_t kev_used;   // FS_FLAG_TIME_KERNELS: 4 events per batch
     std::vector<cudaEvent_t> tev; size_t tev_used;   //   + one (begin, end) pair per k_trace_closest launch
     int sm_count;
-    uint32_t tune_refill, tune_leaf_max, tune_tex, tune_builder, tune_wide, tune_node_min, tune_tri_min, tune_sched;      // experiment knobs (env FS_TUNE_REFILL / FS_TUNE_LEAF_MAX)
+    uint32_t tune_refill, tune_leaf_max, tune_tex, tune_builder, tune_wide, tune_node_min, tune_tri_min, tune_collapse;      // experiment knobs (env FS_TUNE_REFILL / FS_TUNE_LEAF_MAX)
     // IR / conv
     float* d_energy;            // [K] scratch
     float* d_amp;               // [K]

@@ -559,38 +559,83 @@ __device__ __forceinline__ uint4 ldg_u4(const uint4* p)
 // layout [depth][thread]: bank-conflict free, ~30-cycle latency), deeper entries in local memory.
 // ncu showed 12 % of the kernel's stall samples on the instruction consuming a local-memory pop
 // (37 % of those loads missed L1, and the 256 B/thread stacks competed with BVH nodes for L1).
+//
+// DIST = true (closest-hit rays): an entry is (node, entry distance of its box).  A pop skips every
+// entry whose box is entered beyond the current best hit (boxes are conservative, ties t == best are
+// kept), so a subtree that became irrelevant after it was pushed costs one LDS instead of a 64 B node
+// fetch + four slab tests that all miss.  ncu (r1h): 30 % of the node steps hit no child at all.
 #ifndef FS_SSTACK
 #define FS_SSTACK 12
 #endif
-#define TR_SMEM (FS_SSTACK * TR_THREADS * sizeof(int))
+template <bool DIST> struct tr_entry_t { typedef int type; };
+template <> struct tr_entry_t<true> { typedef uint2 type; };
+#ifndef FS_STACK_DIST
+#define FS_STACK_DIST 0      // measured (r1i): culling removes only 2 % of the node visits, 8 B entries cost more than that
+#endif
+#define TR_SMEM_CLOSEST (FS_SSTACK * TR_THREADS * sizeof(tr_entry_t<FS_STACK_DIST != 0>::type))
+#define TR_SMEM_ANY (FS_SSTACK * TR_THREADS * sizeof(int))
+template <bool DIST>
 struct tr_stack {
-    int* sh;        // &smem[threadIdx.x], stride blockDim.x
-    int* loc;       // per-thread local array for entries >= FS_SSTACK
-    __device__ __forceinline__ void push(int& sp, int v) const
+    typedef typename tr_entry_t<DIST>::type entry;
+    entry* sh;        // &smem[threadIdx.x], stride blockDim.x
+    entry* loc;       // per-thread local array for entries >= FS_SSTACK
+    static __device__ __forceinline__ uint2 mk(int v, float d, uint2*) { return make_uint2((uint32_t)v, __float_as_uint(d)); }
+    static __device__ __forceinline__ int mk(int v, float, int*) { return v; }
+    static __device__ __forceinline__ int node_of(uint2 e) { return (int)e.x; }
+    static __device__ __forceinline__ int node_of(int e) { return e; }
+    static __device__ __forceinline__ bool live(uint2 e, float tbest) { return __uint_as_float(e.y) <= tbest; }
+    static __device__ __forceinline__ bool live(int, float) { return true; }
+    __device__ __forceinline__ void push(int& sp, int v, float d) const
     {
-        if (sp < FS_SSTACK) sh[sp * TR_THREADS] = v; else loc[sp - FS_SSTACK] = v;
+        const entry e = mk(v, d, (entry*)nullptr);
+        if (sp < FS_SSTACK) sh[sp * TR_THREADS] = e; else loc[sp - FS_SSTACK] = e;
         ++sp;
     }
-    __device__ __forceinline__ int pop(int& sp) const
+    // up to three entries at once, farthest first (e3, e2, e1; h3 implies h2 implies h1 = true)
+    __device__ __forceinline__ void push3(int& sp, bool h2, bool h3, int v1, float d1, int v2, float d2, int v3, float d3,
+                                          uint32_t* overflow) const
     {
-        if (sp == 0) return TR_SENT;
-        --sp;
-        return (sp < FS_SSTACK) ? sh[sp * TR_THREADS] : loc[sp - FS_SSTACK];
+        const int n = 1 + (int)h2 + (int)h3;
+        if (sp + 3 <= FS_SSTACK) {                    // common case: straight-line predicated shared stores
+            entry* q = sh + sp * TR_THREADS;
+            if (h3) q[0] = mk(v3, d3, (entry*)nullptr);
+            if (h2) q[h3 ? TR_THREADS : 0] = mk(v2, d2, (entry*)nullptr);
+            q[(n - 1) * TR_THREADS] = mk(v1, d1, (entry*)nullptr);
+            sp += n;
+        } else if (sp + 3 <= FS_STACK_SIZE) {
+            if (h3) push(sp, v3, d3);
+            if (h2) push(sp, v2, d2);
+            push(sp, v1, d1);
+        } else *overflow = 1u;
+    }
+    // next entry that can still hold a hit not beyond tbest; TR_SENT when the stack is empty
+    __device__ __forceinline__ int pop(int& sp, float tbest) const
+    {
+        while (sp > 0) {
+            --sp;
+            const entry e = (sp < FS_SSTACK) ? sh[sp * TR_THREADS] : loc[sp - FS_SSTACK];
+            if (live(e, tbest)) return node_of(e);
+        }
+        return TR_SENT;
     }
 };
 
 // Speculative traversal (Aila & Laine): the first leaf a lane reaches is POSTPONED and the lane
 // keeps walking; a second leaf makes it wait (node stays < 0) for the warp's triangle phase.
-__device__ __forceinline__ void tr_settle(tr_state& s, const tr_stack& stack)
+#define TR_POP (-0x7fffffff - 1)        // "take the next node from the stack" marker (never a valid leaf code)
+template <bool DIST>
+__device__ __forceinline__ void tr_advance(tr_state& s, const tr_stack<DIST>& stack, int cand, float tbest)
 {
-    if (s.node < 0 && s.leaf == 0) {            // one postponed leaf; a second one makes the lane wait
-        s.leaf = s.node;
-        s.node = stack.pop(s.sp);
+    for (;;) {
+        if (cand == TR_POP) cand = stack.pop(s.sp, tbest);
+        if (cand < 0 && s.leaf == 0) { s.leaf = cand; cand = TR_POP; continue; }   // one postponed leaf
+        break;
     }
+    s.node = cand;
 }
 
-template <bool ORDERED, int TEX>
-__device__ __forceinline__ void tr_node_step(const fs_bvh_view& bv, tr_state& s, const tr_stack& stack, float tlimit,
+template <bool ORDERED, int TEX, bool DIST>
+__device__ __forceinline__ void tr_node_step(const fs_bvh_view& bv, tr_state& s, const tr_stack<DIST>& stack, float tlimit,
                                              uint32_t* overflow)
 {
     const float4* p = bv.nodes + (size_t)s.node * 4;
@@ -612,17 +657,16 @@ __device__ __forceinline__ void tr_node_step(const fs_bvh_view& bv, tr_state& s,
     bool h0, h1; float t0, t1;
     fs_slab2(r, n0, n1, n2, tlimit, h0, h1, t0, t1);
     const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-    if (!h0 && !h1) {
-        s.node = stack.pop(s.sp);
-    } else {
-        s.node = h0 ? c0 : c1;
+    int cand = TR_POP;
+    if (h0 || h1) {
+        cand = h0 ? c0 : c1;
         if (h0 && h1) {
-            int far_ = c1;
-            if (ORDERED && t1 < t0) { far_ = c0; s.node = c1; }
-            if (s.sp < FS_STACK_SIZE) stack.push(s.sp, far_); else *overflow = 1u;
+            int far_ = c1; float tfar = t1;
+            if (ORDERED && t1 < t0) { far_ = c0; tfar = t0; cand = c1; }
+            if (s.sp < FS_STACK_SIZE) stack.push(s.sp, far_, tfar); else *overflow = 1u;
         }
     }
-    tr_settle(s, stack);
+    tr_advance(s, stack, cand, tlimit);
 }
 
 
@@ -630,8 +674,8 @@ __device__ __forceinline__ void tr_node_step(const fs_bvh_view& bv, tr_state& s,
                                    const int tv_ = sw_ ? vb : va; vb = sw_ ? va : vb; va = tv_; }
 
 // one step through a 4-wide quantised node: near/far planes picked by the ray octant, hits sorted near-to-far
-template <bool ORDERED, int TEX, bool SETTLE = true>
-__device__ __forceinline__ void tr_node_step4(const fs_bvh_view& bv, tr_state& s, const tr_stack& stack, float tlimit,
+template <bool ORDERED, int TEX, bool DIST>
+__device__ __forceinline__ void tr_node_step4(const fs_bvh_view& bv, tr_state& s, const tr_stack<DIST>& stack, float tlimit,
                                               uint32_t* overflow)
 {
     const uint4* p = bv.wnodes + (size_t)s.node * 4;
@@ -662,40 +706,39 @@ __device__ __forceinline__ void tr_node_step4(const fs_bvh_view& bv, tr_state& s
     FS_CHILD(u0, k0, v0) FS_CHILD(u1, k1, v1) FS_CHILD(u2, k2, v2) FS_CHILD(u3, k3, v3)
 #undef FS_CHILD
     if (ORDERED) {
-#if defined(FS_SORT_MIN_ONLY)
-        // 3 comparators: slot 0 = nearest hit, the others stay unordered
-        FS_CSWAP(k0, v0, k1, v1) FS_CSWAP(k2, v2, k3, v3) FS_CSWAP(k0, v0, k2, v2)
-#else
         // 5-comparator network; misses (INF) sink to the end
         FS_CSWAP(k0, v0, k1, v1) FS_CSWAP(k2, v2, k3, v3) FS_CSWAP(k0, v0, k2, v2) FS_CSWAP(k1, v1, k3, v3) FS_CSWAP(k1, v1, k2, v2)
-#endif
     } else {                             // any-hit rays: only move the hits to the front
         if (k0 == INF) { k0 = k1; v0 = v1; k1 = INF; }
         if (k0 == INF) { k0 = k2; v0 = v2; k2 = INF; }
         if (k0 == INF) { k0 = k3; v0 = v3; k3 = INF; }
     }
-    if (k0 == INF) {
-        s.node = stack.pop(s.sp);
-    } else {
-        s.node = v0;
+    if (ORDERED) {
+        // hits are a prefix of the sorted order: push the 2nd..4th (farthest first, so the nearest is popped first)
+        if (k1 != INF) stack.push3(s.sp, k2 != INF, k3 != INF, v1, k1, v2, k2, v3, k3, overflow);
+    } else if (k0 != INF) {
         if (s.sp + 3 <= FS_STACK_SIZE) {
-            if (k3 != INF) stack.push(s.sp, v3);    // farthest first, so the nearest is popped first
-            if (k2 != INF) stack.push(s.sp, v2);
-            if (k1 != INF) stack.push(s.sp, v1);
+            if (k3 != INF) stack.push(s.sp, v3, k3);
+            if (k2 != INF) stack.push(s.sp, v2, k2);
+            if (k1 != INF) stack.push(s.sp, v1, k1);
         } else *overflow = 1u;
     }
-    if (SETTLE) tr_settle(s, stack);
+    tr_advance(s, stack, (k0 != INF) ? v0 : TR_POP, tlimit);
 }
 
 // after a triangle step that exhausted the open range: open the postponed leaf, then re-settle
-__device__ __forceinline__ void tr_next_leaf(tr_state& s, const tr_stack& stack)
+template <bool DIST>
+__device__ __forceinline__ void tr_next_leaf(tr_state& s, const tr_stack<DIST>& stack, float tbest)
 {
     if (s.tc == s.te) {
-        if (s.leaf != 0) { leaf_range(s.leaf, s.tc, s.te); s.leaf = 0; tr_settle(s, stack); }
+        if (s.leaf != 0) {
+            leaf_range(s.leaf, s.tc, s.te); s.leaf = 0;
+            if (s.node < 0) tr_advance(s, stack, s.node, tbest);      // a waiting second leaf becomes the postponed one
+        }
     }
 }
 
-template <bool COUNT, int TEX, bool WIDE, int SCHED>
+template <bool COUNT, int TEX, bool WIDE>
 __global__ void __launch_bounds__(TR_THREADS, FS_TR_MINBLOCKS)
 k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
                 const uint32_t* __restrict__ count_ptr, uint32_t* __restrict__ cursor,
@@ -704,14 +747,16 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
 {
     const uint32_t lane = lane_id();
     const uint32_t count = *count_ptr;
-    extern __shared__ int smem_stack[];
-    int lstack[FS_STACK_SIZE - FS_SSTACK];
-    tr_stack stack; stack.sh = smem_stack + threadIdx.x; stack.loc = lstack;
+    typedef tr_stack<FS_STACK_DIST != 0> stack_t;
+    extern __shared__ __align__(8) unsigned char smem_raw[];
+    stack_t::entry lstack[FS_STACK_SIZE - FS_SSTACK];
+    stack_t stack; stack.sh = reinterpret_cast<stack_t::entry*>(smem_raw) + threadIdx.x; stack.loc = lstack;
     tr_state s;
     s.node = TR_SENT; s.leaf = 0; s.sp = 0; s.tc = 0; s.te = 0;
     s.o = fs_mk(0.f, 0.f, 0.f); s.d = s.o; s.idx = s.idy = s.idz = s.oodx = s.oody = s.oodz = 0.f;
     bool running = false, exhausted = false;
-    uint32_t j = 0, ovf = 0, guard = 0;
+    uint32_t j = 0, guard = 0;
+    uint32_t* const ovf_p = &dc->overflow;       // rare: written straight to global memory, no register carried
     float bt = 0.f; int best = -1;
     fs_visit_counters vc; vc.nodes = 0; vc.tris = 0;
     for (;;) {
@@ -734,58 +779,26 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
             }
         }
         if (!__any_sync(FULLM, running)) break;
-        // ---- schedule 1 ("if-if"): every iteration a lane takes one wide-node step and, when that leaves it at a
-        // leaf, tests one triangle right away.  A wide-node step costs ~3x a triangle test, so running the cheap
-        // triangle part under-occupied every iteration beats batching it in phases: no lane ever waits for a phase.
-        if (SCHED == 1) {
-            for (;;) {
-                if (running && s.node >= 0 && s.node != TR_SENT) {
-                    if (COUNT) vc.nodes++;
-                    tr_node_step4<true, TEX, false>(bv, s, stack, bt, &ovf);
-                }
-                if (running && s.node < 0) {
-                    if (s.tc == s.te) leaf_range(s.node, s.tc, s.te);
-                    const float4* tq = bv.tris + (size_t)s.tc * 4;
-                    const float4 a = fs_ldg4(tq), b = fs_ldg4(tq + 1), c = fs_ldg4(tq + 2);
-                    if (COUNT) vc.tris++;
-                    float t;
-                    if (fs_intersect_tri(s.o, s.d, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z), fs_mk(c.x, c.y, c.z), t) && t <= bt) {
-                        if (t < bt || __float_as_uint(fs_ldg4(tq + 3).x) < __float_as_uint(fs_ldg4(bv.tris + (size_t)best * 4 + 3).x)) {
-                            bt = t; best = (int)s.tc;
-                        }
-                    }
-                    ++s.tc;
-                    if (s.tc == s.te) s.node = stack.pop(s.sp);
-                }
-                if (running && s.node == TR_SENT) {
-                    hits[j] = make_float2(bt, __int_as_float(best));
-                    running = false;
-                }
-                const uint32_t m_run = __ballot_sync(FULLM, running);
-                if (m_run == 0u) break;
-                if (!exhausted && 32u - (uint32_t)__popc(m_run) >= REFILL_MIN) break;
-            }
-            continue;
-        }
-        // ---- schedule 0: walk until enough lanes have retired their ray ("while-while" with postponed leaves)
+        // ---- walk until enough lanes have retired their ray ("while-while" with postponed leaves)
         for (;;) {
 #if defined(FS_TRAVERSAL_GUARD)
-            if (++guard > (1u << 22)) { ovf = 2u; running = false; exhausted = true; break; }   // bring-up guard
+            if (++guard > (1u << 22)) { *ovf_p = 2u; running = false; exhausted = true; break; }   // bring-up guard
 #endif
             // inner nodes, until every lane that can still walk has triangle work pending
             for (;;) {
                 const bool can = running && s.node >= 0 && s.node != TR_SENT;
-                if (!__any_sync(FULLM, can && s.leaf == 0)) break;
+                const uint32_t m_can = __ballot_sync(FULLM, can), m_leaf = __ballot_sync(FULLM, s.leaf != 0);
+                if ((m_can & ~m_leaf) == 0u) break;
                 // leave early for the triangle phase once too few lanes still walk and triangle work is waiting
-                if (NODE_MIN && (uint32_t)__popc(__ballot_sync(FULLM, can)) < NODE_MIN && __any_sync(FULLM, s.leaf != 0)) break;
+                if (NODE_MIN && (uint32_t)__popc(m_can) < NODE_MIN && m_leaf != 0u) break;
                 if (can) {
                     if (COUNT) vc.nodes++;
-                    if (WIDE) tr_node_step4<true, TEX>(bv, s, stack, bt, &ovf);
-                    else tr_node_step<true, TEX>(bv, s, stack, bt, &ovf);
+                    if (WIDE) tr_node_step4<true, TEX>(bv, s, stack, bt, ovf_p);
+                    else tr_node_step<true, TEX>(bv, s, stack, bt, ovf_p);
                 }
             }
             // triangles: one test per lane per step until every pending leaf of the warp is done
-            tr_next_leaf(s, stack);
+            tr_next_leaf(s, stack, bt);
             for (uint32_t it = 0;; ++it) {
                 const bool has = s.tc < s.te;
                 const uint32_t m_has = __ballot_sync(FULLM, has);
@@ -805,7 +818,7 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
                         }
                     }
                     ++s.tc;
-                    tr_next_leaf(s, stack);
+                    tr_next_leaf(s, stack, bt);
                 }
             }
             // retire finished rays (8 B hit record), then decide whether to refill
@@ -818,7 +831,6 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
             if (!exhausted && 32u - (uint32_t)__popc(m_run) >= REFILL_MIN) break;
         }
     }
-    if (ovf) dc->overflow = ovf;
     (void)guard;
     if (COUNT) flush_counters(dc, vc);
 }
@@ -836,12 +848,13 @@ k_trace_any(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4
     const uint32_t count = *count_ptr;
     extern __shared__ int smem_stack[];
     int lstack[FS_STACK_SIZE - FS_SSTACK];
-    tr_stack stack; stack.sh = smem_stack + threadIdx.x; stack.loc = lstack;
+    tr_stack<false> stack; stack.sh = smem_stack + threadIdx.x; stack.loc = lstack;
     tr_state s;
     s.node = TR_SENT; s.leaf = 0; s.sp = 0; s.tc = 0; s.te = 0;
     s.o = fs_mk(0.f, 0.f, 0.f); s.d = s.o; s.idx = s.idy = s.idz = s.oodx = s.oody = s.oodz = 0.f;
     bool running = false, exhausted = false, occluded = false;
-    uint32_t path = 0, ovf = 0, guard = 0;
+    uint32_t path = 0, guard = 0;
+    uint32_t* const ovf_p = &dc->overflow;
     float tmax = 0.f;
     fs_visit_counters vc; vc.nodes = 0; vc.tris = 0;
     for (;;) {
@@ -864,7 +877,7 @@ k_trace_any(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4
         if (!__any_sync(FULLM, running)) break;
         for (;;) {
 #if defined(FS_TRAVERSAL_GUARD)
-            if (++guard > (1u << 22)) { ovf = 2u; running = false; exhausted = true; break; }   // bring-up guard
+            if (++guard > (1u << 22)) { *ovf_p = 2u; running = false; exhausted = true; break; }   // bring-up guard
 #endif
             for (;;) {
                 const bool can = running && s.node >= 0 && s.node != TR_SENT;
@@ -872,11 +885,11 @@ k_trace_any(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4
                 if (NODE_MIN && (uint32_t)__popc(__ballot_sync(FULLM, can)) < NODE_MIN && __any_sync(FULLM, s.leaf != 0)) break;
                 if (can) {
                     if (COUNT) vc.nodes++;
-                    if (WIDE) tr_node_step4<false, (TEX ? 2 : 0)>(bv, s, stack, tmax, &ovf);
-                    else tr_node_step<false, (TEX ? 2 : 0)>(bv, s, stack, tmax, &ovf);
+                    if (WIDE) tr_node_step4<false, (TEX ? 2 : 0)>(bv, s, stack, tmax, ovf_p);
+                    else tr_node_step<false, (TEX ? 2 : 0)>(bv, s, stack, tmax, ovf_p);
                 }
             }
-            tr_next_leaf(s, stack);
+            tr_next_leaf(s, stack, tmax);
             for (;;) {
                 const bool has = s.tc < s.te;
                 if (!__any_sync(FULLM, has)) break;
@@ -889,7 +902,7 @@ k_trace_any(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4
                     if (fs_intersect_tri(s.o, s.d, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z), fs_mk(c.x, c.y, c.z), t)
                         && t < tmax) {           // any hit ends the ray
                         occluded = true; s.tc = s.te; s.node = TR_SENT; s.leaf = 0; s.sp = 0;
-                    } else tr_next_leaf(s, stack);
+                    } else tr_next_leaf(s, stack, tmax);
                 }
             }
             const bool done = running && s.node == TR_SENT && s.leaf == 0;
@@ -910,7 +923,6 @@ k_trace_any(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4
             if (!exhausted && 32u - (uint32_t)__popc(m_run) >= REFILL_MIN) break;
         }
     }
-    if (ovf) dc->overflow = ovf;
     (void)guard;
     if (COUNT) flush_counters(dc, vc, true);
 }
@@ -1168,8 +1180,8 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
     cudaStream_t st = ctx->stream;
     const fs_wave_buffers& wb = ctx->wb;
     static int occ_tr = 0, occ_any = 0;
-    if (!occ_tr) occ_tr = resident_ctas(k_trace_closest<COUNT, 2, true, 0>, TR_THREADS, TR_SMEM);
-    if (!occ_any) occ_any = resident_ctas(k_trace_any<COUNT, 2, true>, TR_THREADS, TR_SMEM);
+    if (!occ_tr) occ_tr = resident_ctas(k_trace_closest<COUNT, 2, true>, TR_THREADS, TR_SMEM_CLOSEST);
+    if (!occ_any) occ_any = resident_ctas(k_trace_any<COUNT, 2, true>, TR_THREADS, TR_SMEM_ANY);
     const bool timing = (tp.flags & FS_FLAG_TIME_KERNELS) != 0;
     cudaEvent_t* ev = nullptr;
     if (timing) {
@@ -1213,12 +1225,11 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
                 ctx->tev_used += 2;
                 cudaEventRecord(te[0], st);
             }
-#define FS_LAUNCH_TRACE(TEXV, WIDEV, SCHEDV)                                                                                 \
-            k_trace_closest<COUNT, TEXV, WIDEV, SCHEDV><<<grid_tr, TR_THREADS, TR_SMEM, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u], \
+#define FS_LAUNCH_TRACE(TEXV, WIDEV)                                                                                   \
+            k_trace_closest<COUNT, TEXV, WIDEV><<<grid_tr, TR_THREADS, TR_SMEM_CLOSEST, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u], \
                 wb.q_count + k, wb.q_cursor + k, wb.hit, ctx->d_counters, ctx->tune_refill, ctx->tune_node_min, ctx->tune_tri_min)
-            if (wide && ctx->tune_sched == 1) { if (texm >= 2) FS_LAUNCH_TRACE(2, true, 1); else FS_LAUNCH_TRACE(0, true, 1); }
-            else if (wide) { if (texm >= 2) FS_LAUNCH_TRACE(2, true, 0); else FS_LAUNCH_TRACE(0, true, 0); }
-            else { if (texm >= 2) FS_LAUNCH_TRACE(2, false, 0); else FS_LAUNCH_TRACE(0, false, 0); }
+            if (wide) { if (texm >= 2) FS_LAUNCH_TRACE(2, true); else FS_LAUNCH_TRACE(0, true); }
+            else { if (texm >= 2) FS_LAUNCH_TRACE(2, false); else FS_LAUNCH_TRACE(0, false); }
 #undef FS_LAUNCH_TRACE
             if (timing) cudaEventRecord(te[1], st);
             ++ctx->stats.kernel_launches;
@@ -1237,7 +1248,7 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
         const bool wide = tp.bv.wnodes != nullptr;
         const bool tex = (wide ? tp.bv.wnodes_tex : tp.bv.nodes_tex) && ctx->tune_tex;
 #define FS_LAUNCH_ANY(TEXV, WIDEV)                                                                                     \
-        k_trace_any<COUNT, TEXV, WIDEV><<<grid_any, TR_THREADS, TR_SMEM, st>>>(tp.bv, wb.st_pos[0], wb.st_nrm[0], wb.q_count + (D + 2), \
+        k_trace_any<COUNT, TEXV, WIDEV><<<grid_any, TR_THREADS, TR_SMEM_ANY, st>>>(tp.bv, wb.st_pos[0], wb.st_nrm[0], wb.q_count + (D + 2), \
             wb.q_cursor + (D + 2), wb.conn_queue, wb.q_count + (D + 1), ctx->d_counters, d_dbg, ctx->tune_refill, ctx->tune_node_min)
         if (wide) { if (tex) FS_LAUNCH_ANY(2, true); else FS_LAUNCH_ANY(0, true); }
         else { if (tex) FS_LAUNCH_ANY(2, false); else FS_LAUNCH_ANY(0, false); }
@@ -1301,12 +1312,12 @@ cudaError_t fs_wave_debug_rays(fs_ctx* ctx, const fs_trace_params& tp, const flo
         uint32_t grid = (uint32_t)((n + TR_THREADS - 1) / TR_THREADS);
         if (grid > (uint32_t)ctx->sm_count * 5u) grid = (uint32_t)ctx->sm_count * 5u;
         if (d_hit) {
-#define FS_DBG_ANY(TEXV, WIDEV) k_trace_any<false, TEXV, WIDEV><<<grid, TR_THREADS, TR_SMEM, st>>>(tp.bv, ro, rd, misc, misc + 1, conn, misc + 2, ctx->d_counters, nullptr, ctx->tune_refill, ctx->tune_node_min)
+#define FS_DBG_ANY(TEXV, WIDEV) k_trace_any<false, TEXV, WIDEV><<<grid, TR_THREADS, TR_SMEM_ANY, st>>>(tp.bv, ro, rd, misc, misc + 1, conn, misc + 2, ctx->d_counters, nullptr, ctx->tune_refill, ctx->tune_node_min)
             if (wide) { if (tex) FS_DBG_ANY(2, true); else FS_DBG_ANY(0, true); } else { if (tex) FS_DBG_ANY(2, false); else FS_DBG_ANY(0, false); }
 #undef FS_DBG_ANY
             k_dbg_unpack_any<<<g, 256, 0, st>>>(conn, misc + 2, d_hit);
         } else {
-#define FS_DBG_CL(TEXV, WIDEV) k_trace_closest<false, TEXV, WIDEV, 0><<<grid, TR_THREADS, TR_SMEM, st>>>(tp.bv, ro, rd, misc, misc + 1, hits, ctx->d_counters, ctx->tune_refill, ctx->tune_node_min, ctx->tune_tri_min)
+#define FS_DBG_CL(TEXV, WIDEV) k_trace_closest<false, TEXV, WIDEV><<<grid, TR_THREADS, TR_SMEM_CLOSEST, st>>>(tp.bv, ro, rd, misc, misc + 1, hits, ctx->d_counters, ctx->tune_refill, ctx->tune_node_min, ctx->tune_tri_min)
             if (wide) { if (tex) FS_DBG_CL(2, true); else FS_DBG_CL(0, true); } else { if (tex) FS_DBG_CL(2, false); else FS_DBG_CL(0, false); }
 #undef FS_DBG_CL
             k_dbg_unpack_closest<<<g, 256, 0, st>>>(tp.bv, hits, n, d_t, d_tri);

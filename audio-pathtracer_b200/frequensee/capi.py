@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(HERE), "lib", "libfrequensee.so")
+LIB_PATH = os.environ.get("FS_LIB_PATH") or os.path.join(os.path.dirname(HERE), "lib", "libfrequensee.so")   # FS_LIB_PATH: A/B builds (tools/)
 MAX_BANDS = 8
 
 FS_OK = 0
