@@ -79,7 +79,13 @@ int fs_create(const fs_config* cfg, fs_ctx** out)
     ctx->cfg = *cfg;
     if (ctx->cfg.max_batch_paths == 0) ctx->cfg.max_batch_paths = 1u << 20;
     ctx->device = dev;
-    ctx->tune_refill = 4; ctx->tune_leaf_max = FS_LEAF_MAX; ctx->tune_tex = 2; ctx->tune_builder = 1; ctx->tune_wide = 1; ctx->tune_node_min = 14; ctx->tune_tri_min = 4; ctx->tune_collapse = 1;
+    ctx->tune_refill = 4; ctx->tune_leaf_max = FS_LEAF_MAX; ctx->tune_tex = 2; ctx->tune_builder = 1; ctx->tune_wide = 1; ctx->tune_node_min = 14; ctx->tune_tri_min = 4; ctx->tune_collapse = 1; ctx->tune_l2pin_mb = 0; ctx->tune_tq = 1; ctx->tune_tq_node_min = 8; ctx->tune_tq_flush = 24;
+    if (const char* e11 = getenv("FS_TUNE_TQ")) ctx->tune_tq = (uint32_t)atoi(e11);
+    if (const char* e12 = getenv("FS_TUNE_TQ_NODE_MIN")) ctx->tune_tq_node_min = (uint32_t)atoi(e12);
+    if (const char* e13 = getenv("FS_TUNE_TQ_FLUSH")) ctx->tune_tq_flush = (uint32_t)atoi(e13);
+    if (ctx->tune_tq_flush < 1) ctx->tune_tq_flush = 1;
+    if (ctx->tune_tq_flush > 32) ctx->tune_tq_flush = 32;       // FS_TQ_CAP assumes <= 31 entries carried into a node step
+    if (const char* e10 = getenv("FS_TUNE_L2PIN")) ctx->tune_l2pin_mb = (uint32_t)atoi(e10);
     if (const char* e9 = getenv("FS_TUNE_COLLAPSE")) ctx->tune_collapse = (uint32_t)atoi(e9);
     if (const char* e7 = getenv("FS_TUNE_TRI_MIN")) ctx->tune_tri_min = (uint32_t)atoi(e7);
     if (const char* e6 = getenv("FS_TUNE_NODE_MIN")) ctx->tune_node_min = (uint32_t)atoi(e6);
@@ -132,10 +138,13 @@ void fs_destroy(fs_ctx* ctx)
     delete ctx;
 }
 
+static void apply_l2_policy(fs_ctx* ctx);
+
 int fs_set_stream(fs_ctx* ctx, void* cuda_stream)
 {
     if (!ctx) return FS_ERR_INVALID;
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    if (ctx->committed) { dev_guard g(ctx->device); apply_l2_policy(ctx); }
     return FS_OK;
 }
 
@@ -152,7 +161,7 @@ int fs_scene_set_triangles(fs_ctx* ctx, const float* verts, const uint32_t* tri_
 {
     if (!ctx) return FS_ERR_INVALID;
     if (n_tris && (!verts || !tri_material)) return fail(ctx, FS_ERR_INVALID, "fs_scene_set_triangles: null array");
-    if (n_tris >= (1ull << 28)) return fail(ctx, FS_ERR_INVALID, "too many triangles (< 2^28 supported)");
+    if (n_tris >= (1ull << 27)) return fail(ctx, FS_ERR_INVALID, "too many triangles (< 2^27 supported)");
     dev_guard g(ctx->device);
     for (uint64_t i = 0; i < n_tris * 9; ++i)
         if (!(verts[i] == verts[i]) || fabsf(verts[i]) > 1e18f) return fail(ctx, FS_ERR_INVALID, "non-finite vertex");
@@ -192,6 +201,32 @@ int fs_scene_set_materials(fs_ctx* ctx, const float* absorption, uint32_t n_mate
     return FS_OK;
 }
 
+// The breadth-first wide-node array starts with the top of the tree: pin that prefix in L2 (persisting
+// access-policy window on the context's stream) so the per-step streaming state (ray queues, node records:
+// hundreds of MB) cannot evict the nodes every ray visits.  FS_TUNE_L2PIN = MB to pin (0 = off).
+static void apply_l2_policy(fs_ctx* ctx)
+{
+    if (!ctx->bvh.wnodes || !ctx->tune_l2pin_mb) return;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+    size_t want = (size_t)ctx->tune_l2pin_mb << 20;
+    const size_t have = (size_t)ctx->bvh.n_wide * 64u;
+    if (want > have) want = have;
+    if (want > (size_t)max_persist) want = (size_t)max_persist;
+    if (want > (size_t)max_window) want = (size_t)max_window;
+    if (!want) return;
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    cudaStreamAttrValue v; memset(&v, 0, sizeof(v));
+    v.accessPolicyWindow.base_ptr = ctx->bvh.wnodes;
+    v.accessPolicyWindow.num_bytes = want;
+    v.accessPolicyWindow.hitRatio = 1.0f;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    if (cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) (void)cudaGetLastError();
+    if (getenv("FS_VERBOSE")) fprintf(stderr, "[frequensee] L2 persisting window: %.1f MB of wide nodes (device max %d MB)\n", want / 1048576.0, max_persist >> 20);
+}
+
 int fs_scene_commit(fs_ctx* ctx)
 {
     if (!ctx) return FS_ERR_INVALID;
@@ -211,6 +246,7 @@ int fs_scene_commit(fs_ctx* ctx)
     if (getenv("FS_VERBOSE")) fprintf(stderr, "[frequensee] BVH: %u triangles, %u BVH2 nodes, %u reachable 4-wide nodes (%.1f MB)\n",
                                       ctx->bvh.n_tris, ctx->bvh.n_inner, ctx->bvh.n_wide, ctx->bvh.n_wide * 64.0 / 1e6);
     ctx->stats.bvh_max_leaf = ctx->bvh.max_leaf;
+    apply_l2_policy(ctx);
     ctx->committed = true;
     return FS_OK;
 }

@@ -110,7 +110,7 @@ struct fs_ctx {
     std::vector<cudaEvent_t> kev; size_t kev_used;   // FS_FLAG_TIME_KERNELS: 4 events per batch
     std::vector<cudaEvent_t> tev; size_t tev_used;   //   + one (begin, end) pair per k_trace_closest launch
     int sm_count;
-    uint32_t tune_refill, tune_leaf_max, tune_tex, tune_builder, tune_wide, tune_node_min, tune_tri_min, tune_collapse;      // experiment knobs (env FS_TUNE_REFILL / FS_TUNE_LEAF_MAX)
+    uint32_t tune_refill, tune_leaf_max, tune_tex, tune_builder, tune_wide, tune_node_min, tune_tri_min, tune_collapse, tune_l2pin_mb, tune_tq, tune_tq_node_min, tune_tq_flush;      // experiment knobs (env FS_TUNE_REFILL / FS_TUNE_LEAF_MAX)
     // IR / conv
     float* d_energy;            // [K] scratch
     float* d_amp;               // [K]

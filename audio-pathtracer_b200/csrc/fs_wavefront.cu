@@ -569,6 +569,9 @@ __device__ __forceinline__ uint4 ldg_u4(const uint4* p)
 #endif
 template <bool DIST> struct tr_entry_t { typedef int type; };
 template <> struct tr_entry_t<true> { typedef uint2 type; };
+#ifndef FS_ANY_ORDERED
+#define FS_ANY_ORDERED 0     // connection rays: visit the hit children near-to-far (1) or in slot order (0)
+#endif
 #ifndef FS_STACK_DIST
 #define FS_STACK_DIST 0      // measured (r1i): culling removes only 2 % of the node visits, 8 B entries cost more than that
 #endif
@@ -673,10 +676,11 @@ __device__ __forceinline__ void tr_node_step(const fs_bvh_view& bv, tr_state& s,
 #define FS_CSWAP(ka, va, kb, vb) { const bool sw_ = kb < ka; const float tk_ = sw_ ? kb : ka; kb = sw_ ? ka : kb; ka = tk_; \
                                    const int tv_ = sw_ ? vb : va; vb = sw_ ? va : vb; va = tv_; }
 
-// one step through a 4-wide quantised node: near/far planes picked by the ray octant, hits sorted near-to-far
-template <bool ORDERED, int TEX, bool DIST>
-__device__ __forceinline__ void tr_node_step4(const fs_bvh_view& bv, tr_state& s, const tr_stack<DIST>& stack, float tlimit,
-                                              uint32_t* overflow)
+// the four children of a 4-wide quantised node against the ray: near/far planes picked by the ray octant,
+// entry distances k (INF = miss) and references v; ORDER 1: sorted near-to-far, 0: hits moved to the front, 2: slot order
+template <int ORDER, int TEX>
+__device__ __forceinline__ void wide_children(const fs_bvh_view& bv, const tr_state& s, float tlimit,
+                                              float& k0, float& k1, float& k2, float& k3, int& v0, int& v1, int& v2, int& v3)
 {
     const uint4* p = bv.wnodes + (size_t)s.node * 4;
     uint4 u0, u1, u2, u3;
@@ -702,17 +706,26 @@ __device__ __forceinline__ void tr_node_step4(const fs_bvh_view& bv, tr_state& s
         key = (tn <= tf) ? tn : INF;                                                                                  \
         val = (int)u.w;                                                                                               \
     }
-    float k0, k1, k2, k3; int v0, v1, v2, v3;
     FS_CHILD(u0, k0, v0) FS_CHILD(u1, k1, v1) FS_CHILD(u2, k2, v2) FS_CHILD(u3, k3, v3)
 #undef FS_CHILD
-    if (ORDERED) {
+    if (ORDER == 1) {
         // 5-comparator network; misses (INF) sink to the end
         FS_CSWAP(k0, v0, k1, v1) FS_CSWAP(k2, v2, k3, v3) FS_CSWAP(k0, v0, k2, v2) FS_CSWAP(k1, v1, k3, v3) FS_CSWAP(k1, v1, k2, v2)
-    } else {                             // any-hit rays: only move the hits to the front
+    } else if (ORDER == 0) {             // any-hit rays: only move the hits to the front
         if (k0 == INF) { k0 = k1; v0 = v1; k1 = INF; }
         if (k0 == INF) { k0 = k2; v0 = v2; k2 = INF; }
         if (k0 == INF) { k0 = k3; v0 = v3; k3 = INF; }
     }
+}
+
+// one step through a 4-wide node: test, push the farther hits, move on to the nearest (or pop)
+template <bool ORDERED, int TEX, bool DIST>
+__device__ __forceinline__ void tr_node_step4(const fs_bvh_view& bv, tr_state& s, const tr_stack<DIST>& stack, float tlimit,
+                                              uint32_t* overflow)
+{
+    const float INF = __int_as_float(0x7f800000);
+    float k0, k1, k2, k3; int v0, v1, v2, v3;
+    wide_children<ORDERED ? 1 : 0, TEX>(bv, s, tlimit, k0, k1, k2, k3, v0, v1, v2, v3);
     if (ORDERED) {
         // hits are a prefix of the sorted order: push the 2nd..4th (farthest first, so the nearest is popped first)
         if (k1 != INF) stack.push3(s.sp, k2 != INF, k3 != INF, v1, k1, v2, k2, v3, k3, overflow);
@@ -835,6 +848,168 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
     if (COUNT) flush_counters(dc, vc);
 }
 
+// =============================================================================================
+// k_trace_closest_q: closest-hit traversal with a WARP-SHARED TRIANGLE QUEUE.
+//
+// ncu on k_trace_closest (r1h/r1i, SASS-level counters): a ray needs ~2 550 thread-instructions, the kernel
+// spends 3 100 -- but only 17.9 of 32 lanes are active per issued instruction.  The lost lanes are phase
+// mismatch: in the node phase 11 lanes sit out (waiting at a second leaf, or done with a postponed leaf), and
+// the triangle phase runs with 10.6 lanes because only the lanes that happen to hold a leaf take part.
+//
+// Here a lane never holds a leaf.  Every leaf child (one triangle) whose box the ray enters is appended as
+// (owner lane, triangle) to a queue shared by the warp (shared memory, one ATOMS per node step) and the lane
+// keeps walking; the traversal stack only holds inner nodes.  When >= FLUSH_MIN entries are waiting (or
+// nobody can walk) the warp tests them CONVERGED: lane i takes entry i whoever owns it, fetches the owner's
+// ray by shuffle, and merges a hit into the owner's best (t, triangle) -- a 64-bit key in shared memory,
+// updated by compare-and-swap with the oracle's exact tie rule (equal t: lower original id).  The node phase
+// loses only the lanes that are out of rays; the triangle phase runs at up to 32 of 32.
+// Results are unchanged by construction: the closest hit is min (t, original id) over the triangles whose
+// boxes the ray enters at or before the best t known so far -- any order, any delay.
+// =============================================================================================
+// at most FLUSH_MIN - 1 (<= 31) entries are waiting when a node-phase iteration starts and it adds at most 4 x 32
+#define FS_TQ_CAP 160
+#define TQ_INVALID 0xffffffffu
+#define TQ_WARPS (TR_THREADS / 32)
+#define TR_SMEM_TQ (FS_SSTACK * TR_THREADS * sizeof(int) + TR_THREADS * sizeof(unsigned long long) + \
+                    TQ_WARPS * FS_TQ_CAP * sizeof(uint32_t) + TQ_WARPS * sizeof(uint32_t))
+
+template <bool COUNT, int TEX>
+__global__ void __launch_bounds__(TR_THREADS, FS_TR_MINBLOCKS)
+k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+                  const uint32_t* __restrict__ count_ptr, uint32_t* __restrict__ cursor,
+                  float2* __restrict__ hits, fs_dev_counters* __restrict__ dc, const uint32_t REFILL_MIN,
+                  const uint32_t NODE_MIN, const uint32_t FLUSH_MIN)
+{
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t count = *count_ptr;
+    extern __shared__ __align__(8) unsigned char smem_raw[];
+    int* const sstack = reinterpret_cast<int*>(smem_raw);
+    unsigned long long* const skey = reinterpret_cast<unsigned long long*>(sstack + FS_SSTACK * TR_THREADS);
+    uint32_t* const squeue = reinterpret_cast<uint32_t*>(skey + TR_THREADS) + warp * FS_TQ_CAP;
+    uint32_t* const sqcount = reinterpret_cast<uint32_t*>(skey + TR_THREADS) + TQ_WARPS * FS_TQ_CAP + warp;
+    unsigned long long* const mykey = skey + threadIdx.x;
+    unsigned long long* const wkey = skey + (threadIdx.x & ~31u);
+    int lstack[FS_STACK_SIZE - FS_SSTACK];
+    tr_stack<false> stack; stack.sh = sstack + threadIdx.x; stack.loc = lstack;
+    const unsigned long long KEY_NONE = ((unsigned long long)0x7f800000u << 32) | 0xffffffffull;
+    for (uint32_t i = lane; i < (uint32_t)FS_TQ_CAP; i += 32) squeue[i] = TQ_INVALID;
+    if (lane == 0) *sqcount = 0u;
+    *mykey = KEY_NONE;
+    __syncwarp();
+    tr_state s;
+    s.node = TR_SENT; s.leaf = 0; s.sp = 0; s.tc = 0; s.te = 0;
+    s.o = fs_mk(0.f, 0.f, 0.f); s.d = s.o; s.idx = s.idy = s.idz = s.oodx = s.oody = s.oodz = 0.f;
+    bool running = false, exhausted = false;
+    uint32_t j = 0;
+    uint32_t* const ovf_p = &dc->overflow;
+    float bt = __int_as_float(0x7f800000);
+    fs_visit_counters vc; vc.nodes = 0; vc.tris = 0;
+    for (;;) {
+        // ---- refill idle lanes from the ray queue: one atomic per warp
+        const uint32_t m_idle = __ballot_sync(FULLM, !running);
+        if (!exhausted && ((uint32_t)__popc(m_idle) >= REFILL_MIN)) {
+            const uint32_t n = (uint32_t)__popc(m_idle);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(cursor, n);
+            base = __shfl_sync(FULLM, base, 0);
+            if (base + n >= count) exhausted = true;
+            if (!running) {
+                const uint32_t jj = base + (uint32_t)__popc(m_idle & ((1u << lane) - 1u));
+                if (jj < count) {
+                    const float4 a = ray_o[jj], b = ray_d[jj];
+                    tr_init<true>(s, bv, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z));
+                    bt = __int_as_float(0x7f800000); *mykey = KEY_NONE;
+                    j = jj; running = true;
+                }
+            }
+        }
+        if (!__any_sync(FULLM, running)) break;
+        for (;;) {
+            // ---- node phase: every lane with a ray walks; leaves go to the queue
+            for (;;) {
+                const bool can = running && s.node >= 0 && s.node != TR_SENT;
+                const uint32_t m_can = __ballot_sync(FULLM, can);
+                const uint32_t qn = *(volatile uint32_t*)sqcount;
+                if (m_can == 0u || qn >= FLUSH_MIN) break;
+                if (NODE_MIN && qn && (uint32_t)__popc(m_can) < NODE_MIN) break;   // few walkers left and triangle work waits
+                if (can) {
+                    if (COUNT) vc.nodes++;
+                    const float INF = __int_as_float(0x7f800000);
+                    float k0, k1, k2, k3; int v0, v1, v2, v3;
+                    wide_children<2, TEX>(bv, s, bt, k0, k1, k2, k3, v0, v1, v2, v3);
+                    // every leaf child the ray enters goes to the queue right away (single-triangle leaves), so the
+                    // stack only ever holds inner nodes and the step is straight-line code
+                    const bool l0 = k0 != INF && v0 < 0, l1 = k1 != INF && v1 < 0, l2 = k2 != INF && v2 < 0, l3 = k3 != INF && v3 < 0;
+                    const uint32_t nl = (uint32_t)l0 + (uint32_t)l1 + (uint32_t)l2 + (uint32_t)l3;
+                    if (nl) {
+                        uint32_t* q = squeue + atomicAdd(sqcount, nl);
+                        if (l0) { *q++ = ((uint32_t)(~v0) >> 3 << 5) | lane; k0 = INF; }
+                        if (l1) { *q++ = ((uint32_t)(~v1) >> 3 << 5) | lane; k1 = INF; }
+                        if (l2) { *q++ = ((uint32_t)(~v2) >> 3 << 5) | lane; k2 = INF; }
+                        if (l3) { *q = ((uint32_t)(~v3) >> 3 << 5) | lane; k3 = INF; }
+                    }
+                    FS_CSWAP(k0, v0, k1, v1) FS_CSWAP(k2, v2, k3, v3) FS_CSWAP(k0, v0, k2, v2) FS_CSWAP(k1, v1, k3, v3) FS_CSWAP(k1, v1, k2, v2)
+                    if (k1 != INF) stack.push3(s.sp, k2 != INF, k3 != INF, v1, k1, v2, k2, v3, k3, ovf_p);
+                    s.node = (k0 != INF) ? v0 : stack.pop(s.sp, 0.f);
+                }
+                __syncwarp();
+            }
+            // ---- triangle phase: the queue, 32 entries at a time, whoever owns them
+            __syncwarp();
+            const uint32_t total = *(volatile uint32_t*)sqcount;
+            for (uint32_t base = 0; base < total; base += 32) {
+                const uint32_t idx = base + lane;
+                const uint32_t e = idx < total ? squeue[idx] : TQ_INVALID;
+                const uint32_t owner = e & 31u;
+                const float ox = __shfl_sync(FULLM, s.o.x, owner), oy = __shfl_sync(FULLM, s.o.y, owner), oz = __shfl_sync(FULLM, s.o.z, owner);
+                const float dx = __shfl_sync(FULLM, s.d.x, owner), dy = __shfl_sync(FULLM, s.d.y, owner), dz = __shfl_sync(FULLM, s.d.z, owner);
+                const float bto = __shfl_sync(FULLM, bt, owner);
+                if (e != TQ_INVALID) {
+                    const uint32_t tri = e >> 5;
+                    const float4* tq = bv.tris + (size_t)tri * 4;
+                    const float4 a = fs_ldg4(tq), b = fs_ldg4(tq + 1), c = fs_ldg4(tq + 2);
+                    if (COUNT) vc.tris++;
+                    squeue[idx] = TQ_INVALID;
+                    float t;
+                    if (fs_intersect_tri(fs_mk(ox, oy, oz), fs_mk(dx, dy, dz), fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z), fs_mk(c.x, c.y, c.z), t)
+                        && t <= bto) {
+                        // merge into the owner's best: min over (t, ORIGINAL triangle id); ids are fetched only on a tie
+                        const unsigned long long mine = ((unsigned long long)__float_as_uint(t) << 32) | tri;
+                        unsigned long long old = *(volatile unsigned long long*)(wkey + owner);
+                        for (;;) {
+                            const float told = __uint_as_float((uint32_t)(old >> 32));
+                            bool better = t < told;
+                            if (t == told) {
+                                const uint32_t otri = (uint32_t)old;
+                                better = otri == 0xffffffffu ||
+                                         __float_as_uint(fs_ldg4(tq + 3).x) < __float_as_uint(fs_ldg4(bv.tris + (size_t)otri * 4 + 3).x);
+                            }
+                            if (!better) break;
+                            const unsigned long long prev = atomicCAS(wkey + owner, old, mine);
+                            if (prev == old) break;
+                            old = prev;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) *sqcount = 0u;
+            const unsigned long long kk = *(volatile unsigned long long*)mykey;
+            bt = __uint_as_float((uint32_t)(kk >> 32));
+            __syncwarp();
+            // ---- retire finished rays (nothing of theirs is left in the queue)
+            if (running && s.node == TR_SENT) {
+                hits[j] = make_float2(bt, __int_as_float((int)(uint32_t)kk));
+                running = false;
+            }
+            const uint32_t m_run = __ballot_sync(FULLM, running);
+            if (m_run == 0u) break;
+            if (!exhausted && 32u - (uint32_t)__popc(m_run) >= REFILL_MIN) break;
+        }
+    }
+    if (COUNT) flush_counters(dc, vc);
+}
+
 // connection rays: (F.xyz, tmax) (dir.xyz, path id); unoccluded paths are appended to conn_queue
 template <bool COUNT, int TEX, bool WIDE>
 __global__ void __launch_bounds__(TR_THREADS, FS_TR_MINBLOCKS)
@@ -885,7 +1060,7 @@ k_trace_any(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4
                 if (NODE_MIN && (uint32_t)__popc(__ballot_sync(FULLM, can)) < NODE_MIN && __any_sync(FULLM, s.leaf != 0)) break;
                 if (can) {
                     if (COUNT) vc.nodes++;
-                    if (WIDE) tr_node_step4<false, (TEX ? 2 : 0)>(bv, s, stack, tmax, ovf_p);
+                    if (WIDE) tr_node_step4<FS_ANY_ORDERED != 0, (TEX ? 2 : 0)>(bv, s, stack, tmax, ovf_p);
                     else tr_node_step<false, (TEX ? 2 : 0)>(bv, s, stack, tmax, ovf_p);
                 }
             }
@@ -1179,8 +1354,9 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
 {
     cudaStream_t st = ctx->stream;
     const fs_wave_buffers& wb = ctx->wb;
-    static int occ_tr = 0, occ_any = 0;
+    static int occ_tr = 0, occ_any = 0, occ_tq = 0;
     if (!occ_tr) occ_tr = resident_ctas(k_trace_closest<COUNT, 2, true>, TR_THREADS, TR_SMEM_CLOSEST);
+    if (!occ_tq) occ_tq = resident_ctas(k_trace_closest_q<COUNT, 2>, TR_THREADS, TR_SMEM_TQ);
     if (!occ_any) occ_any = resident_ctas(k_trace_any<COUNT, 2, true>, TR_THREADS, TR_SMEM_ANY);
     const bool timing = (tp.flags & FS_FLAG_TIME_KERNELS) != 0;
     cudaEvent_t* ev = nullptr;
@@ -1200,7 +1376,8 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
     const uint32_t n_sub = 2u * tp.batch;
     uint32_t grid_sh = (n_sub + WF_THREADS - 1) / WF_THREADS;
     if (grid_sh > (uint32_t)ctx->sm_count * 8u) grid_sh = (uint32_t)ctx->sm_count * 8u;
-    uint32_t grid_tr = (uint32_t)(ctx->sm_count * occ_tr);
+    const bool use_tq = ctx->tune_tq && tp.bv.wnodes != nullptr && ctx->bvh.max_leaf == 1;    // queue entries are single triangles
+    uint32_t grid_tr = (uint32_t)(ctx->sm_count * (use_tq ? occ_tq : occ_tr));
     const uint32_t ctas_needed = (n_sub + TR_THREADS - 1) / TR_THREADS;
     if (grid_tr > ctas_needed) grid_tr = ctas_needed ? ctas_needed : 1;
     if (timing) cudaEventRecord(ev[0], st);
@@ -1228,8 +1405,13 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
 #define FS_LAUNCH_TRACE(TEXV, WIDEV)                                                                                   \
             k_trace_closest<COUNT, TEXV, WIDEV><<<grid_tr, TR_THREADS, TR_SMEM_CLOSEST, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u], \
                 wb.q_count + k, wb.q_cursor + k, wb.hit, ctx->d_counters, ctx->tune_refill, ctx->tune_node_min, ctx->tune_tri_min)
-            if (wide) { if (texm >= 2) FS_LAUNCH_TRACE(2, true); else FS_LAUNCH_TRACE(0, true); }
+#define FS_LAUNCH_TQ(TEXV)                                                                                             \
+            k_trace_closest_q<COUNT, TEXV><<<grid_tr, TR_THREADS, TR_SMEM_TQ, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u],   \
+                wb.q_count + k, wb.q_cursor + k, wb.hit, ctx->d_counters, ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush)
+            if (use_tq) { if (texm >= 2) FS_LAUNCH_TQ(2); else FS_LAUNCH_TQ(0); }
+            else if (wide) { if (texm >= 2) FS_LAUNCH_TRACE(2, true); else FS_LAUNCH_TRACE(0, true); }
             else { if (texm >= 2) FS_LAUNCH_TRACE(2, false); else FS_LAUNCH_TRACE(0, false); }
+#undef FS_LAUNCH_TQ
 #undef FS_LAUNCH_TRACE
             if (timing) cudaEventRecord(te[1], st);
             ++ctx->stats.kernel_launches;
@@ -1318,7 +1500,10 @@ cudaError_t fs_wave_debug_rays(fs_ctx* ctx, const fs_trace_params& tp, const flo
             k_dbg_unpack_any<<<g, 256, 0, st>>>(conn, misc + 2, d_hit);
         } else {
 #define FS_DBG_CL(TEXV, WIDEV) k_trace_closest<false, TEXV, WIDEV><<<grid, TR_THREADS, TR_SMEM_CLOSEST, st>>>(tp.bv, ro, rd, misc, misc + 1, hits, ctx->d_counters, ctx->tune_refill, ctx->tune_node_min, ctx->tune_tri_min)
-            if (wide) { if (tex) FS_DBG_CL(2, true); else FS_DBG_CL(0, true); } else { if (tex) FS_DBG_CL(2, false); else FS_DBG_CL(0, false); }
+#define FS_DBG_TQ(TEXV) k_trace_closest_q<false, TEXV><<<grid, TR_THREADS, TR_SMEM_TQ, st>>>(tp.bv, ro, rd, misc, misc + 1, hits, ctx->d_counters, ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush)
+            if (wide && ctx->tune_tq && ctx->bvh.max_leaf == 1) { if (tex) FS_DBG_TQ(2); else FS_DBG_TQ(0); }
+            else if (wide) { if (tex) FS_DBG_CL(2, true); else FS_DBG_CL(0, true); } else { if (tex) FS_DBG_CL(2, false); else FS_DBG_CL(0, false); }
+#undef FS_DBG_TQ
 #undef FS_DBG_CL
             k_dbg_unpack_closest<<<g, 256, 0, st>>>(tp.bv, hits, n, d_t, d_tri);
         }
