@@ -528,19 +528,32 @@ struct tr_state {
     uint32_t tc, te;
 };
 
+__device__ __forceinline__ float fs_rcp_fast(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 template <bool WIDE>
 __device__ __forceinline__ void tr_init(tr_state& s, const fs_bvh_view& bv, fs_vec3 o, fs_vec3 d)
 {
-    const fs_ray_prep r = fs_prep_ray(o, d);
     s.o = o; s.d = d;
     if (WIDE) {
-        s.idx = bv.qscale[0] * r.idx; s.idy = bv.qscale[1] * r.idy; s.idz = bv.qscale[2] * r.idz;
+        // 1 / d by MUFU.RCP (<= 1 ulp): the box test only has to be conservative, and a 2^-23 relative error of t is far
+        // inside the spare quantum of the outward rounding (an IEEE division costs ~15 instructions per axis and ray)
+        const float dx = (fabsf(d.x) > 1e-30f) ? d.x : ((d.x < 0.0f) ? -1e-30f : 1e-30f);
+        const float dy = (fabsf(d.y) > 1e-30f) ? d.y : ((d.y < 0.0f) ? -1e-30f : 1e-30f);
+        const float dz = (fabsf(d.z) > 1e-30f) ? d.z : ((d.z < 0.0f) ? -1e-30f : 1e-30f);
+        const float ix = fs_rcp_fast(dx), iy = fs_rcp_fast(dy), iz = fs_rcp_fast(dz);
+        s.idx = bv.qscale[0] * ix; s.idy = bv.qscale[1] * iy; s.idz = bv.qscale[2] * iz;
         // b' = (qbase - o) * idir - 2^23 * s: its rounding error is below half a quantum, which the spare quantum of
         // outward rounding at build time covers
-        s.oodx = fmaf(-8388608.0f, s.idx, (bv.qbase[0] - o.x) * r.idx);
-        s.oody = fmaf(-8388608.0f, s.idy, (bv.qbase[1] - o.y) * r.idy);
-        s.oodz = fmaf(-8388608.0f, s.idz, (bv.qbase[2] - o.z) * r.idz);
+        s.oodx = fmaf(-8388608.0f, s.idx, (bv.qbase[0] - o.x) * ix);
+        s.oody = fmaf(-8388608.0f, s.idy, (bv.qbase[1] - o.y) * iy);
+        s.oodz = fmaf(-8388608.0f, s.idz, (bv.qbase[2] - o.z) * iz);
     } else {
+        const fs_ray_prep r = fs_prep_ray(o, d);
         s.idx = r.idx; s.idy = r.idy; s.idz = r.idz; s.oodx = r.oodx; s.oody = r.oody; s.oodz = r.oodz;
     }
     s.node = bv.n_tris ? 0 : TR_SENT; s.leaf = 0; s.sp = 0; s.tc = 0; s.te = 0;
@@ -903,6 +916,7 @@ k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const 
     uint32_t j = 0;
     uint32_t* const ovf_p = &dc->overflow;
     float bt = __int_as_float(0x7f800000);
+    uint32_t qn = 0;                                 // entries in the warp's triangle queue (warp-uniform)
     fs_visit_counters vc; vc.nodes = 0; vc.tris = 0;
     for (;;) {
         // ---- refill idle lanes from the ray queue: one atomic per warp
@@ -929,34 +943,40 @@ k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const 
             for (;;) {
                 const bool can = running && s.node >= 0 && s.node != TR_SENT;
                 const uint32_t m_can = __ballot_sync(FULLM, can);
-                const uint32_t qn = *(volatile uint32_t*)sqcount;
                 if (m_can == 0u || qn >= FLUSH_MIN) break;
                 if (NODE_MIN && qn && (uint32_t)__popc(m_can) < NODE_MIN) break;   // few walkers left and triangle work waits
+                uint32_t nl = 0;
                 if (can) {
                     if (COUNT) vc.nodes++;
                     const float INF = __int_as_float(0x7f800000);
                     float k0, k1, k2, k3; int v0, v1, v2, v3;
                     wide_children<2, TEX>(bv, s, bt, k0, k1, k2, k3, v0, v1, v2, v3);
                     // every leaf child the ray enters goes to the queue right away (single-triangle leaves), so the
-                    // stack only ever holds inner nodes and the step is straight-line code
+                    // stack only ever holds inner nodes and the step is straight-line code.
+                    // leaf code v = ~(first << 3): entry = first << 5 | lane = -4 v + (lane - 4)
                     const bool l0 = k0 != INF && v0 < 0, l1 = k1 != INF && v1 < 0, l2 = k2 != INF && v2 < 0, l3 = k3 != INF && v3 < 0;
-                    const uint32_t nl = (uint32_t)l0 + (uint32_t)l1 + (uint32_t)l2 + (uint32_t)l3;
+                    nl = (uint32_t)l0 + (uint32_t)l1 + (uint32_t)l2 + (uint32_t)l3;
                     if (nl) {
                         uint32_t* q = squeue + atomicAdd(sqcount, nl);
-                        if (l0) { *q++ = ((uint32_t)(~v0) >> 3 << 5) | lane; k0 = INF; }
-                        if (l1) { *q++ = ((uint32_t)(~v1) >> 3 << 5) | lane; k1 = INF; }
-                        if (l2) { *q++ = ((uint32_t)(~v2) >> 3 << 5) | lane; k2 = INF; }
-                        if (l3) { *q = ((uint32_t)(~v3) >> 3 << 5) | lane; k3 = INF; }
+                        const uint32_t lm4 = lane - 4u;
+                        if (l0) *q = (uint32_t)v0 * 0xfffffffcu + lm4;
+                        q += l0;
+                        if (l1) *q = (uint32_t)v1 * 0xfffffffcu + lm4;
+                        q += l1;
+                        if (l2) *q = (uint32_t)v2 * 0xfffffffcu + lm4;
+                        q += l2;
+                        if (l3) *q = (uint32_t)v3 * 0xfffffffcu + lm4;
                     }
+                    k0 = l0 ? INF : k0; k1 = l1 ? INF : k1; k2 = l2 ? INF : k2; k3 = l3 ? INF : k3;
                     FS_CSWAP(k0, v0, k1, v1) FS_CSWAP(k2, v2, k3, v3) FS_CSWAP(k0, v0, k2, v2) FS_CSWAP(k1, v1, k3, v3) FS_CSWAP(k1, v1, k2, v2)
                     if (k1 != INF) stack.push3(s.sp, k2 != INF, k3 != INF, v1, k1, v2, k2, v3, k3, ovf_p);
                     s.node = (k0 != INF) ? v0 : stack.pop(s.sp, 0.f);
                 }
-                __syncwarp();
+                qn += __reduce_add_sync(FULLM, nl);         // the queue length, tracked in a (uniform) register
             }
             // ---- triangle phase: the queue, 32 entries at a time, whoever owns them
             __syncwarp();
-            const uint32_t total = *(volatile uint32_t*)sqcount;
+            const uint32_t total = qn;
             for (uint32_t base = 0; base < total; base += 32) {
                 const uint32_t idx = base + lane;
                 const uint32_t e = idx < total ? squeue[idx] : TQ_INVALID;
@@ -994,6 +1014,7 @@ k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const 
             }
             __syncwarp();
             if (lane == 0) *sqcount = 0u;
+            qn = 0u;
             const unsigned long long kk = *(volatile unsigned long long*)mykey;
             bt = __uint_as_float((uint32_t)(kk >> 32));
             __syncwarp();
