@@ -77,7 +77,7 @@ int fs_create(const fs_config* cfg, fs_ctx** out)
     fs_ctx* ctx = new (std::nothrow) fs_ctx();
     if (!ctx) return fail(nullptr, FS_ERR_NOMEM, "out of host memory");
     ctx->cfg = *cfg;
-    if (ctx->cfg.max_batch_paths == 0) ctx->cfg.max_batch_paths = 1u << 20;
+    if (ctx->cfg.max_batch_paths == 0) ctx->cfg.max_batch_paths = 1u << 21;
     ctx->device = dev;
     ctx->tune_refill = 4; ctx->tune_leaf_max = FS_LEAF_MAX; ctx->tune_tex = 2; ctx->tune_builder = 1; ctx->tune_wide = 1; ctx->tune_node_min = 14; ctx->tune_tri_min = 4; ctx->tune_collapse = 1; ctx->tune_l2pin_mb = 0; ctx->tune_tq = 1; ctx->tune_tq_node_min = 8; ctx->tune_tq_flush = 24;
     if (const char* e11 = getenv("FS_TUNE_TQ")) ctx->tune_tq = (uint32_t)atoi(e11);
@@ -305,8 +305,11 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
         ctx->src_cap = n_sources;
     }
     CK(cudaMemcpyAsync(ctx->d_src_pos, src_pos, sizeof(float) * 3 * n_sources, cudaMemcpyHostToDevice, ctx->stream));
+    // equal batches: every bounce of a batch is a pair of launches whose cost has a fixed part (launch + the tail of the
+    // slowest rays), so 1.25 M pairs run as 1 x 1.25 M or 2 x 0.63 M, never as 1 M + a 0.25 M remainder
     const uint32_t cap_cfg = ctx->cfg.max_batch_paths;
-    uint32_t cap = (uint32_t)(g_count < cap_cfg ? (g_count ? g_count : 1) : cap_cfg);
+    const uint64_t n_batches = g_count ? (g_count + cap_cfg - 1) / cap_cfg : 1;
+    uint32_t cap = (uint32_t)(g_count ? (g_count + n_batches - 1) / n_batches : 1);
     CK(fs_wave_alloc(ctx, cap, max_depth));
     fs_trace_params tp;
     fill_params(ctx, &tp, lis_pos, n_paths, max_depth, seed);
@@ -315,7 +318,7 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
     CK(fs_wave_reset_counters(ctx));
     for (uint64_t done = 0; done < g_count;) {
         uint64_t nb = g_count - done;
-        if (nb > ctx->wb.cap) nb = ctx->wb.cap;
+        if (nb > cap) nb = cap;
         tp.g_first = g_first + done;
         tp.batch = (uint32_t)nb;
         CK(fs_wave_trace_batch(ctx, tp, d_hist, d_dbg ? d_dbg + done : nullptr));

@@ -78,7 +78,7 @@ typedef struct fs_config {
     uint32_t conv_block;       /* AudioCallbackBufferFrameSize = 1024 (Config/DefaultEngine.ini:15) */
     uint32_t conv_clamp;       /* clamp to +-1 (REV.cpp:162-168) */
     float    conv_wet;         /* MixAlpha = 1 (REV.cpp:161) */
-    uint32_t max_batch_paths;  /* path pairs in flight per wavefront batch; 0 = default (1<<20) */
+    uint32_t max_batch_paths;  /* path pairs in flight per wavefront batch; 0 = default (1<<21) */
     uint32_t flags;            /* FS_FLAG_* */
     int32_t  device;           /* CUDA device ordinal; -1 = current device */
 } fs_config;
