@@ -444,9 +444,12 @@ k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_d
     float4* __restrict__ out_o = wb.st_pos[out];
     float4* __restrict__ out_d = wb.st_nrm[out];
     const uint32_t stride = 2u * wb.cap;             // rec[k][sp_id]: one plane per node index (writes of a bounce stay semi-coalesced)
-    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < count_in;
-         base += gridDim.x * blockDim.x) {
-        const uint32_t j = base + lane;
+    // One queue-slot atomic per CTA tile, not per warp: ncu (r1i) had 43 % of this kernel's stall samples on the return
+    // of the per-warp atomicAdd -- 10^5 same-address atomics per launch run at about one per nanosecond.
+    __shared__ uint32_t s_cnt[WF_THREADS / 32], s_base;
+    const uint32_t warp = threadIdx.x >> 5;
+    for (uint32_t tile = blockIdx.x * blockDim.x; tile < count_in; tile += gridDim.x * blockDim.x) {
+        const uint32_t j = tile + threadIdx.x;
         bool emit = false;
         fs_vec3 pos = fs_mk(0.f, 0.f, 0.f), dir = fs_mk(0.f, 0.f, 0.f);
         uint32_t sp_id = 0; float prob = 1.0f;
@@ -506,17 +509,23 @@ k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_d
             }
         }
         const uint32_t m = __ballot_sync(FULLM, emit);
-        if (m) {
-            uint32_t slot = 0;
-            if (lane == 0) { slot = atomicAdd(&wb.q_count[k], (uint32_t)__popc(m)); atomicAdd(&dc->ext_rays, (unsigned long long)__popc(m)); }
-            slot = __shfl_sync(FULLM, slot, 0);
-            if (emit) {
-                const uint32_t o = slot + __popc(m & ((1u << lane) - 1u));
-                out_o[o] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(sp_id));
-                out_d[o] = make_float4(dir.x, dir.y, dir.z, prob);
-            }
+        if (lane == 0) s_cnt[warp] = (uint32_t)__popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < WF_THREADS / 32; ++w) { const uint32_t c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+            s_base = tot ? atomicAdd(&wb.q_count[k], tot) : 0u;      // ext_rays = sum of the queue lengths (k_connect_gen)
         }
+        __syncthreads();
+        if (emit) {
+            const uint32_t o = s_base + s_cnt[warp] + __popc(m & ((1u << lane) - 1u));
+            out_o[o] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(sp_id));
+            out_d[o] = make_float4(dir.x, dir.y, dir.z, prob);
+        }
+        __syncthreads();                                   // s_cnt / s_base are rewritten by the next tile
     }
+    (void)dc;
 }
 
 // per-lane traversal state shared by the two trace kernels
@@ -1132,6 +1141,11 @@ k_connect_gen(const fs_trace_params tp, const fs_wave_buffers wb, fs_dev_counter
     const uint32_t qc = tp.max_depth + 1, qs = tp.max_depth + 2;
     float4* __restrict__ sh_o = wb.st_pos[0];
     float4* __restrict__ sh_d = wb.st_nrm[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {              // extension rays of this batch = the lengths of its ray queues
+        unsigned long long ext = 0;
+        for (uint32_t k = 0; k < tp.max_depth; ++k) ext += wb.q_count[k];
+        atomicAdd(&dc->ext_rays, ext);
+    }
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < tp.batch;
          base += gridDim.x * blockDim.x) {
         const uint32_t p = base + lane;
