@@ -3,6 +3,7 @@
 #include "fs_internal.h"
 
 #include <stdio.h>
+#include <utility>
 #include <stdlib.h>
 #include <new>
 #include <vector>
@@ -79,7 +80,8 @@ int fs_create(const fs_config* cfg, fs_ctx** out)
     ctx->cfg = *cfg;
     if (ctx->cfg.max_batch_paths == 0) ctx->cfg.max_batch_paths = 1u << 21;
     ctx->device = dev;
-    ctx->tune_refill = 4; ctx->tune_leaf_max = FS_LEAF_MAX; ctx->tune_tex = 2; ctx->tune_builder = 1; ctx->tune_wide = 1; ctx->tune_node_min = 14; ctx->tune_tri_min = 4; ctx->tune_collapse = 1; ctx->tune_l2pin_mb = 0; ctx->tune_tq = 1; ctx->tune_tq_node_min = 8; ctx->tune_tq_flush = 24;
+    ctx->tune_refill = 4; ctx->tune_leaf_max = FS_LEAF_MAX; ctx->tune_tex = 2; ctx->tune_builder = 1; ctx->tune_wide = 1; ctx->tune_node_min = 14; ctx->tune_tri_min = 4; ctx->tune_collapse = 1; ctx->tune_l2pin_mb = 0; ctx->tune_streams = 2;
+    if (const char* e14 = getenv("FS_TUNE_STREAMS")) { int v = atoi(e14); if (v >= 1 && v <= FS_MAX_LANES) ctx->tune_streams = (uint32_t)v; } ctx->tune_tq = 1; ctx->tune_tq_node_min = 8; ctx->tune_tq_flush = 24;
     if (const char* e11 = getenv("FS_TUNE_TQ")) ctx->tune_tq = (uint32_t)atoi(e11);
     if (const char* e12 = getenv("FS_TUNE_TQ_NODE_MIN")) ctx->tune_tq_node_min = (uint32_t)atoi(e12);
     if (const char* e13 = getenv("FS_TUNE_TQ_FLUSH")) ctx->tune_tq_flush = (uint32_t)atoi(e13);
@@ -108,6 +110,12 @@ int fs_create(const fs_config* cfg, fs_ctx** out)
         if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaStreamCreate"); break; }
         ctx->stream = ctx->own_stream;
         if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaEventCreate"); break; }
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaEventCreate"); break; }
+        for (int l = 0; l < FS_MAX_LANES - 1 && e == cudaSuccess; ++l) {
+            if ((e = cudaStreamCreateWithFlags(&ctx->lanes[l].stream, cudaStreamNonBlocking)) != cudaSuccess) break;
+            e = cudaEventCreateWithFlags(&ctx->lanes[l].done, cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess) { rc = fail_cuda(nullptr, e, "batch lanes"); break; }
         if ((e = cudaMalloc(&ctx->d_counters, sizeof(fs_dev_counters))) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaMalloc counters"); break; }
         if ((e = cudaMemset(ctx->d_counters, 0, sizeof(fs_dev_counters))) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaMemset"); break; }
         if ((e = cudaMalloc(&ctx->d_amp, sizeof(float) * cfg->n_bins)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaMalloc amp"); break; }
@@ -126,6 +134,12 @@ void fs_destroy(fs_ctx* ctx)
     cudaDeviceSynchronize();
     fs_conv_teardown(ctx);
     fs_wave_free(&ctx->wb);
+    for (int l = 0; l < FS_MAX_LANES - 1; ++l) {
+        fs_wave_free(&ctx->lanes[l].wb);
+        if (ctx->lanes[l].stream) cudaStreamDestroy(ctx->lanes[l].stream);
+        if (ctx->lanes[l].done) cudaEventDestroy(ctx->lanes[l].done);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     fs_bvh_free(&ctx->bvh);
     cudaFree(ctx->d_verts); cudaFree(ctx->d_tri_mat); cudaFree(ctx->d_refl_over_pi);
     cudaFree(ctx->d_hist); cudaFree(ctx->d_counters); cudaFree(ctx->d_src_pos); cudaFree(ctx->d_dbg);
@@ -306,23 +320,56 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
     }
     CK(cudaMemcpyAsync(ctx->d_src_pos, src_pos, sizeof(float) * 3 * n_sources, cudaMemcpyHostToDevice, ctx->stream));
     // equal batches: every bounce of a batch is a pair of launches whose cost has a fixed part (launch + the tail of the
-    // slowest rays), so 1.25 M pairs run as 1 x 1.25 M or 2 x 0.63 M, never as 1 M + a 0.25 M remainder
+    // slowest rays), so 1.25 M pairs run as 1 x 1.25 M or 2 x 0.63 M, never as 1 M + a 0.25 M remainder.
+    // Batches alternate between up to tune_streams lanes (own stream + own wavefront buffers): a traversal launch ends
+    // with a tail of a few long rays on an almost empty GPU, and the other lane's kernels fill it.  Histogram sums are
+    // integer atomics, so the result does not depend on how batches interleave.  Per-kernel timing (FS_FLAG_TIME_KERNELS)
+    // and the debug record path run on one lane so that every kernel is timed alone.
     const uint32_t cap_cfg = ctx->cfg.max_batch_paths;
-    const uint64_t n_batches = g_count ? (g_count + cap_cfg - 1) / cap_cfg : 1;
-    uint32_t cap = (uint32_t)(g_count ? (g_count + n_batches - 1) / n_batches : 1);
+    uint32_t n_lanes = ctx->tune_streams;
+    if ((ctx->cfg.flags & FS_FLAG_TIME_KERNELS) || d_dbg) n_lanes = 1;
+    while (n_lanes > 1 && g_count / n_lanes < (1u << 17)) --n_lanes;            // small jobs: not worth a second set of launches
+    uint64_t n_batches = g_count ? (g_count + cap_cfg - 1) / cap_cfg : 1;
+    if (n_batches < n_lanes) n_batches = n_lanes;
+    if (n_batches % n_lanes) n_batches += n_lanes - n_batches % n_lanes;
+    const uint32_t cap = (uint32_t)(g_count ? (g_count + n_batches - 1) / n_batches : 1);
     CK(fs_wave_alloc(ctx, cap, max_depth));
+    for (uint32_t l = 1; l < n_lanes; ++l) {
+        std::swap(ctx->wb, ctx->lanes[l - 1].wb);
+        cudaError_t ea = fs_wave_alloc(ctx, cap, max_depth);
+        std::swap(ctx->wb, ctx->lanes[l - 1].wb);
+        CK(ea);
+    }
     fs_trace_params tp;
     fill_params(ctx, &tp, lis_pos, n_paths, max_depth, seed);
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     ctx->kev_used = 0; ctx->tev_used = 0; ctx->stats.extend_launches = 0;
     CK(fs_wave_reset_counters(ctx));
-    for (uint64_t done = 0; done < g_count;) {
+    if (n_lanes > 1) {
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        for (uint32_t l = 1; l < n_lanes; ++l) CK(cudaStreamWaitEvent(ctx->lanes[l - 1].stream, ctx->ev_fork, 0));
+    }
+    uint32_t b = 0;
+    for (uint64_t done = 0; done < g_count; ++b) {
         uint64_t nb = g_count - done;
         if (nb > cap) nb = cap;
         tp.g_first = g_first + done;
         tp.batch = (uint32_t)nb;
-        CK(fs_wave_trace_batch(ctx, tp, d_hist, d_dbg ? d_dbg + done : nullptr));
+        const uint32_t l = b % n_lanes;
+        cudaError_t eb;
+        if (l == 0) eb = fs_wave_trace_batch(ctx, tp, d_hist, d_dbg ? d_dbg + done : nullptr);
+        else {                                       // run the batch with the lane's stream and buffers swapped in
+            cudaStream_t main_stream = ctx->stream;
+            std::swap(ctx->wb, ctx->lanes[l - 1].wb); ctx->stream = ctx->lanes[l - 1].stream;
+            eb = fs_wave_trace_batch(ctx, tp, d_hist, nullptr);
+            std::swap(ctx->wb, ctx->lanes[l - 1].wb); ctx->stream = main_stream;
+        }
+        CK(eb);
         done += nb;
+    }
+    for (uint32_t l = 1; l < n_lanes; ++l) {
+        CK(cudaEventRecord(ctx->lanes[l - 1].done, ctx->lanes[l - 1].stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->lanes[l - 1].done, 0));
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->timed = true;
@@ -348,8 +395,12 @@ static int finish_stats(fs_ctx* ctx)
         (void)cudaGetLastError();
         ctx->stats.extend_ms = ext; ctx->stats.connect_ms = con; ctx->stats.eval_ms = evl;
         float tr = 0.f;
+        const bool verbose = getenv("FS_VERBOSE") != nullptr;
         for (size_t i = 0; i + 1 < ctx->tev_used; i += 2)
-            if (cudaEventElapsedTime(&ms, ctx->tev[i], ctx->tev[i + 1]) == cudaSuccess) tr += ms;
+            if (cudaEventElapsedTime(&ms, ctx->tev[i], ctx->tev[i + 1]) == cudaSuccess) {
+                tr += ms;
+                if (verbose) fprintf(stderr, "[frequensee] trace launch %zu: %.3f ms\n", i / 2, ms);
+            }
         (void)cudaGetLastError();
         ctx->stats.trace_ms = tr;
     }

@@ -87,6 +87,8 @@ struct fs_conv_source {
     uint32_t head;              // FDL head slot
 };
 
+#define FS_MAX_LANES 4
+
 struct fs_ctx {
     fs_config cfg;
     int device;
@@ -100,6 +102,9 @@ struct fs_ctx {
     fs_bvh_device bvh;
     // trace
     fs_wave_buffers wb;
+    // extra batch lanes: while one batch's traversal launch drains its slowest rays, the other lane's kernels fill the SMs
+    struct lane_t { cudaStream_t stream; fs_wave_buffers wb; cudaEvent_t done; } lanes[FS_MAX_LANES - 1];
+    cudaEvent_t ev_fork; uint32_t tune_streams;
     unsigned long long* d_hist; uint32_t hist_sources;   // [S][B][K]
     uint64_t hist_n_paths;
     fs_dev_counters* d_counters;

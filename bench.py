@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--depth", type=int, default=16)
     ap.add_argument("--scene", default="furnished_room", choices=["furnished_room", "mine_tunnels", "concert_hall", "shoebox"],
                     help="default furnished_room = BASELINE.json configs[1]; the others are extra measurements")
-    ap.add_argument("--cpu-sample-paths", type=int, default=1 << 16)
+    ap.add_argument("--cpu-sample-paths", type=int, default=1 << 19)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -157,7 +157,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    sample = min(args.paths, 1 << 15)
+    sample = min(args.paths, 1 << 17)
     cpu_oracle_rate(args, sample, threads, repeats=max(1, min(args.warmup, 1)))
     times, st = cpu_oracle_rate(args, sample, threads, repeats=args.steps)
     total = sum(times)
@@ -201,7 +201,7 @@ def run_b200(args):
     P, D = args.paths, args.depth
     sc = scenes.by_name(args.scene)
     sc.sources = sc.sources[:1]
-    ctx = fs.Context(device=local, flags=capi.FLAG_TIME_KERNELS)
+    ctx = fs.Context(device=local)                          # production configuration: no per-kernel events, batch lanes on
     ctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
     stream = torch.cuda.Stream()                            # a real (non-NULL) stream: the C-ABI treats NULL as "own stream"
     torch.cuda.set_stream(stream)
@@ -248,11 +248,19 @@ def run_b200(args):
     dev_ms = float(t.item())
     value = P * N * K / (dev_ms * 1e-3)
 
-    # per-kernel-class device time: average over the timed steps' seeds (re-run outside the timed region)
+    # per-kernel-class device time: the same steps (same seeds) re-run on a second context with FS_FLAG_TIME_KERNELS,
+    # i.e. CUDA events on the launching stream around every stage and every k_trace_closest launch.  That context runs
+    # its batches on ONE lane, so each kernel is timed alone (in the headline run two batch lanes overlap their kernels).
+    tctx = fs.Context(device=local, flags=capi.FLAG_TIME_KERNELS)
+    tctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
+    tctx.set_stream(stream.cuda_stream)
     per = []
-    for k in range(min(K, 5)):
-        step_device(SEED0 + k); torch.cuda.synchronize()
-        s = ctx.stats(); per.append(s)
+    for k in range(-1, min(K, 5)):
+        tctx.trace_range_device(sc.sources, sc.listener, n_global, g_first, g_count, D, SEED0 + k, d_hist.data_ptr(), True)
+        torch.cuda.synchronize()
+        if k >= 0:
+            per.append(tctx.stats())
+    tctx.close()
     ext_ms = float(np.mean([s["extend_ms"] for s in per])); con_ms = float(np.mean([s["connect_ms"] for s in per]))
     trc_ms = float(np.mean([s["trace_ms"] for s in per]))
     evl_ms = float(np.mean([s["eval_ms"] for s in per])); ext_launches = per[0]["extend_launches"]
