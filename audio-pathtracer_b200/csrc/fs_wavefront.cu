@@ -417,9 +417,12 @@ k_eval(const fs_trace_params tp, const fs_wave_buffers wb, unsigned long long* _
 //   k_connect_gen / k_trace_any  the same for the connection (shadow) rays.
 // Ray record (32 B): (origin.xyz, sp_id | tmax) (dir.xyz, pdf | path id); hit record 8 B (t, tri).
 // =============================================================================================
-constexpr int TR_THREADS = 256;
+#ifndef FS_TR_THREADS
+#define FS_TR_THREADS 256
+#endif
+constexpr int TR_THREADS = FS_TR_THREADS;
 #ifndef FS_TR_MINBLOCKS
-#define FS_TR_MINBLOCKS 5      // <= 51 registers: 5 CTAs (40 warps) per SM
+#define FS_TR_MINBLOCKS (1280 / FS_TR_THREADS)      // <= 51 registers: 1280 threads (40 warps) per SM
 #endif
 // refill a warp once this many lanes are idle (kernel argument, default FS_REFILL_DEFAULT)
 #define FS_REFILL_DEFAULT 8u
