@@ -189,3 +189,57 @@ def test_error_behaviour(fs, shoebox):
         fs.Context(n_bands=9)
     with pytest.raises(fs.FrequenSeeError):
         fs.Context(conv_block=1000)
+
+
+class _env:
+    """FS_TUNE_* knobs are read by fs_create: set them around the creation of a context"""
+    def __init__(self, **kv):
+        self.kv = {k: str(v) for k, v in kv.items()}
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        os.environ.update(self.kv)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_every_traversal_kernel_and_bvh_layout_gives_the_same_histogram(fs, oracle, room):
+    """queue kernel (default) / phased kernel, greedy / grandchild collapse, dense / sparse wide-node layout,
+    BVH2 float nodes, LBVH with multi-triangle leaves: the closest hit does not depend on the structure"""
+    S = oracle.Scene(room.verts, room.tri_mat, room.absorption, use_bvh=True)
+    ho, so = S.trace(oracle.default_config(), room.sources, room.listener, 8192, 16, 1, n_threads=16)
+    for env in ({}, {"FS_TUNE_TQ": 0}, {"FS_TUNE_COLLAPSE": 0}, {"FS_TUNE_COLLAPSE": 3}, {"FS_TUNE_TQ": 0, "FS_TUNE_COLLAPSE": 2},
+                {"FS_TUNE_WIDE": 0}, {"FS_TUNE_BUILDER": 0}, {"FS_TUNE_BUILDER": 0, "FS_TUNE_LEAF_MAX": 1},
+                {"FS_TUNE_TQ_FLUSH": 1}, {"FS_TUNE_TQ_FLUSH": 32, "FS_TUNE_TQ_NODE_MIN": 0}, {"FS_TUNE_REFILL": 1},
+                {"FS_TUNE_L2PIN": 8}):
+        with _env(**env):
+            ctx = _ctx(fs, room)
+        with ctx:
+            h = ctx.trace(room.sources, room.listener, 8192, 16, 1)
+            st = ctx.stats()
+        assert np.array_equal(h, ho), "env=%r" % (env,)
+        assert st["ext_rays"] == so["ext_rays"] and st["connected"] == so["connected"], "env=%r" % (env,)
+
+
+def test_batch_lanes_and_batch_splits_are_bit_exact(fs, oracle, shoebox):
+    """jobs above 2^18 pairs run as equal batches on two lanes (streams): same integers as one lane, as many
+    small batches, and as the oracle"""
+    n = 600000
+    S = oracle.Scene(shoebox.verts, shoebox.tri_mat, shoebox.absorption, use_bvh=False)
+    ho, so = S.trace(oracle.default_config(), shoebox.sources, shoebox.listener, n, 8, 77, n_threads=16)
+    for env, over in (({}, {}), ({"FS_TUNE_STREAMS": 1}, {}), ({"FS_TUNE_STREAMS": 3}, {"max_batch_paths": 70001}),
+                      ({"FS_TUNE_STREAMS": 4}, {}), ({"FS_TUNE_STREAMS": 2}, {"max_batch_paths": 1 << 16})):
+        with _env(**env):
+            ctx = _ctx(fs, shoebox, **over)
+        with ctx:
+            h = ctx.trace(shoebox.sources, shoebox.listener, n, 8, 77)
+            st = ctx.stats()
+            h2 = ctx.trace(shoebox.sources, shoebox.listener, n, 8, 77)       # buffers reused, lanes re-joined
+        assert np.array_equal(h, ho), "env=%r over=%r" % (env, over)
+        assert np.array_equal(h2, ho)
+        assert [st["ext_rays"], st["shadow_rays"], st["connected"]] == [so["ext_rays"], so["shadow_rays"], so["connected"]]
