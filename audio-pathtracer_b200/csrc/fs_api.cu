@@ -385,6 +385,11 @@ static int finish_stats(fs_ctx* ctx)
     ctx->stats.ext_rays = h.ext_rays; ctx->stats.shadow_rays = h.shadow_rays; ctx->stats.connected = h.connected;
     ctx->stats.node_visits = h.node_visits; ctx->stats.tri_tests = h.tri_tests;
     ctx->stats.shadow_node_visits = h.shadow_node_visits; ctx->stats.shadow_tri_tests = h.shadow_tri_tests;
+    if (getenv("FS_VERBOSE") && h.max_steps) {
+        fprintf(stderr, "[frequensee] node steps per ray: max %u; rays by steps/8:", h.max_steps);
+        for (int b = 0; b < 16; ++b) fprintf(stderr, " %u", h.steps_hist[b]);
+        fprintf(stderr, "\n");
+    }
     if (ctx->kev_used) {
         float ext = 0.f, con = 0.f, evl = 0.f, ms;
         for (size_t i = 0; i + 3 < ctx->kev_used; i += 4) {

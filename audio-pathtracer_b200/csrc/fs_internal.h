@@ -39,7 +39,8 @@ void fs_bvh_free(fs_bvh_device* b);
 struct fs_dev_counters {
     unsigned long long ext_rays, shadow_rays, connected, node_visits, tri_tests;
     unsigned long long shadow_node_visits, shadow_tri_tests;
-    uint32_t overflow, pad;
+    uint32_t overflow, max_steps;      // max_steps: longest ray of the call in node steps (FS_FLAG_COUNT_VISITS builds)
+    uint32_t steps_hist[16];           // rays by node steps: [8 i, 8 i + 8), last bucket open-ended (same builds)
 };
 
 // constant-ish parameters every wavefront kernel needs

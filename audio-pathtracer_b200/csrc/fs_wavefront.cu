@@ -436,7 +436,10 @@ __device__ __forceinline__ void leaf_range(int leafnode, uint32_t& tc, uint32_t&
     te = tc + (payload & 7u) + 1u;
 }
 
-__global__ void __launch_bounds__(WF_THREADS)
+#ifndef FS_SHADE_MINBLOCKS
+#define FS_SHADE_MINBLOCKS 6
+#endif
+__global__ void __launch_bounds__(WF_THREADS, FS_SHADE_MINBLOCKS)
 k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_dev_counters* __restrict__ dc)
 {
     const uint32_t lane = lane_id();
@@ -929,6 +932,7 @@ k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const 
     uint32_t* const ovf_p = &dc->overflow;
     float bt = __int_as_float(0x7f800000);
     uint32_t qn = 0;                                 // entries in the warp's triangle queue (warp-uniform)
+    uint32_t ray_steps = 0;                          // COUNT builds: node steps of the current ray
     fs_visit_counters vc; vc.nodes = 0; vc.tris = 0;
     for (;;) {
         // ---- refill idle lanes from the ray queue: one atomic per warp
@@ -946,6 +950,7 @@ k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const 
                     tr_init<true>(s, bv, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z));
                     bt = __int_as_float(0x7f800000); *mykey = KEY_NONE;
                     j = jj; running = true;
+                    if (COUNT) ray_steps = 0;
                 }
             }
         }
@@ -959,7 +964,7 @@ k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const 
                 if (NODE_MIN && qn && (uint32_t)__popc(m_can) < NODE_MIN) break;   // few walkers left and triangle work waits
                 uint32_t nl = 0;
                 if (can) {
-                    if (COUNT) vc.nodes++;
+                    if (COUNT) { vc.nodes++; ray_steps++; }
                     const float INF = __int_as_float(0x7f800000);
                     float k0, k1, k2, k3; int v0, v1, v2, v3;
                     wide_children<2, TEX>(bv, s, bt, k0, k1, k2, k3, v0, v1, v2, v3);
@@ -1034,6 +1039,7 @@ k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const 
             if (running && s.node == TR_SENT) {
                 hits[j] = make_float2(bt, __int_as_float((int)(uint32_t)kk));
                 running = false;
+                if (COUNT) { atomicMax(&dc->max_steps, ray_steps); atomicAdd(&dc->steps_hist[ray_steps / 8u < 15u ? ray_steps / 8u : 15u], 1u); }
             }
             const uint32_t m_run = __ballot_sync(FULLM, running);
             if (m_run == 0u) break;
@@ -1214,7 +1220,8 @@ __global__ void k_reset_queues(uint32_t* q_count, uint32_t* q_cursor, uint32_t n
     if (reset_dc && i == 0) {
         dc->ext_rays = 0; dc->shadow_rays = 0; dc->connected = 0; dc->node_visits = 0; dc->tri_tests = 0;
         dc->shadow_node_visits = 0; dc->shadow_tri_tests = 0;
-        dc->overflow = 0;
+        dc->overflow = 0; dc->max_steps = 0;
+        for (int b = 0; b < 16; ++b) dc->steps_hist[b] = 0;
     }
 }
 
