@@ -899,8 +899,11 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
 #define TQ_INVALID 0xffffffffu
 #define TQ_WARPS (TR_THREADS / 32)
 #define TR_SMEM_TQ (FS_SSTACK * TR_THREADS * sizeof(int) + TR_THREADS * sizeof(unsigned long long) + \
-                    TQ_WARPS * FS_TQ_CAP * sizeof(uint32_t) + TQ_WARPS * sizeof(uint32_t))
+                    TQ_WARPS * FS_TQ_CAP * sizeof(uint32_t) + TQ_WARPS * sizeof(uint32_t) + TR_THREADS * sizeof(uint32_t))
 
+#ifndef FS_DRAIN_SPLIT
+#define FS_DRAIN_SPLIT 1
+#endif
 template <bool COUNT, int TEX>
 __global__ void __launch_bounds__(TR_THREADS, FS_TR_MINBLOCKS)
 k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
@@ -908,6 +911,7 @@ k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const 
                   float2* __restrict__ hits, fs_dev_counters* __restrict__ dc, const uint32_t REFILL_MIN,
                   const uint32_t NODE_MIN, const uint32_t FLUSH_MIN)
 {
+    constexpr bool DRAIN_SPLIT = FS_DRAIN_SPLIT != 0;
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t count = *count_ptr;
     extern __shared__ __align__(8) unsigned char smem_raw[];
@@ -915,6 +919,8 @@ k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const 
     unsigned long long* const skey = reinterpret_cast<unsigned long long*>(sstack + FS_SSTACK * TR_THREADS);
     uint32_t* const squeue = reinterpret_cast<uint32_t*>(skey + TR_THREADS) + warp * FS_TQ_CAP;
     uint32_t* const sqcount = reinterpret_cast<uint32_t*>(skey + TR_THREADS) + TQ_WARPS * FS_TQ_CAP + warp;
+    // helpers working for each lane's ray (drain splitting, below)
+    uint32_t* const whelp = reinterpret_cast<uint32_t*>(skey + TR_THREADS) + TQ_WARPS * FS_TQ_CAP + TQ_WARPS + (threadIdx.x & ~31u);
     unsigned long long* const mykey = skey + threadIdx.x;
     unsigned long long* const wkey = skey + (threadIdx.x & ~31u);
     int lstack[FS_STACK_SIZE - FS_SSTACK];
@@ -923,6 +929,8 @@ k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const 
     for (uint32_t i = lane; i < (uint32_t)FS_TQ_CAP; i += 32) squeue[i] = TQ_INVALID;
     if (lane == 0) *sqcount = 0u;
     *mykey = KEY_NONE;
+    whelp[lane] = 0u;
+    uint32_t owner = lane;                           // lane whose ray this lane is walking (itself, except for drain helpers)
     __syncwarp();
     tr_state s;
     s.node = TR_SENT; s.leaf = 0; s.sp = 0; s.tc = 0; s.te = 0;
@@ -975,7 +983,7 @@ k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const 
                     nl = (uint32_t)l0 + (uint32_t)l1 + (uint32_t)l2 + (uint32_t)l3;
                     if (nl) {
                         uint32_t* q = squeue + atomicAdd(sqcount, nl);
-                        const uint32_t lm4 = lane - 4u;
+                        const uint32_t lm4 = owner - 4u;
                         if (l0) *q = (uint32_t)v0 * 0xfffffffcu + lm4;
                         q += l0;
                         if (l1) *q = (uint32_t)v1 * 0xfffffffcu + lm4;
@@ -1032,14 +1040,55 @@ k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const 
             __syncwarp();
             if (lane == 0) *sqcount = 0u;
             qn = 0u;
-            const unsigned long long kk = *(volatile unsigned long long*)mykey;
+            const unsigned long long kk = *(volatile unsigned long long*)(wkey + owner);
             bt = __uint_as_float((uint32_t)(kk >> 32));
             __syncwarp();
-            // ---- retire finished rays (nothing of theirs is left in the queue)
-            if (running && s.node == TR_SENT) {
+            // ---- retire finished rays (nothing of theirs is left in the queue): helpers first, then the owners whose
+            // helpers are all done
+            const bool fin = running && s.node == TR_SENT;
+            if (fin && owner != lane) { atomicSub(whelp + owner, 1u); running = false; owner = lane; }
+            __syncwarp();
+            if (fin && running && *(volatile uint32_t*)(whelp + lane) == 0u) {
                 hits[j] = make_float2(bt, __int_as_float((int)(uint32_t)kk));
                 running = false;
                 if (COUNT) { atomicMax(&dc->max_steps, ray_steps); atomicAdd(&dc->steps_hist[ray_steps / 8u < 15u ? ray_steps / 8u : 15u], 1u); }
+            }
+            // ---- drain: once the ray queue is empty a launch lasts as long as its longest ray (up to 100 node steps in
+            // the room, 400 in the hall, against 16 / 27 on average).  The subtrees on a ray's stack are independent, and
+            // every triangle candidate ends up in the OWNER's key whoever found it -- so an idle lane takes the top half
+            // of a busy lane's stack and walks it as a helper of the same ray.  The result is the same set of candidates.
+            if (DRAIN_SPLIT && exhausted) {
+                const uint32_t m_free = __ballot_sync(FULLM, !running);
+                const bool give = running && s.node != TR_SENT && s.sp >= 1 && s.sp <= FS_SSTACK;
+                const uint32_t m_give = __ballot_sync(FULLM, give);
+                const uint32_t nf = (uint32_t)__popc(m_free), ng = (uint32_t)__popc(m_give);
+                const uint32_t n = nf < ng ? nf : ng;
+                if (n) {
+                    const uint32_t lt = (1u << lane) - 1u;
+                    const uint32_t rf = (uint32_t)__popc(m_free & lt), rg = (uint32_t)__popc(m_give & lt);
+                    const bool take = !running && rf < n;
+                    const uint32_t donor = take ? __fns(m_give, 0u, (int)rf + 1) : lane;      // k-th free lane <- k-th giver
+                    const int dsp = __shfl_sync(FULLM, s.sp, donor);
+                    const float ox = __shfl_sync(FULLM, s.o.x, donor), oy = __shfl_sync(FULLM, s.o.y, donor), oz = __shfl_sync(FULLM, s.o.z, donor);
+                    const float dx = __shfl_sync(FULLM, s.d.x, donor), dy = __shfl_sync(FULLM, s.d.y, donor), dz = __shfl_sync(FULLM, s.d.z, donor);
+                    const float ix = __shfl_sync(FULLM, s.idx, donor), iy = __shfl_sync(FULLM, s.idy, donor), iz = __shfl_sync(FULLM, s.idz, donor);
+                    const float px = __shfl_sync(FULLM, s.oodx, donor), py = __shfl_sync(FULLM, s.oody, donor), pz = __shfl_sync(FULLM, s.oodz, donor);
+                    const float dbt = __shfl_sync(FULLM, bt, donor);
+                    const uint32_t down = __shfl_sync(FULLM, owner, donor);
+                    if (take) {
+                        const int h = (dsp + 1) >> 1;
+                        const int* src = sstack + (threadIdx.x & ~31u) + donor;
+                        for (int i = 0; i < h; ++i) stack.sh[i * TR_THREADS] = src[(dsp - h + i) * TR_THREADS];
+                        s.o = fs_mk(ox, oy, oz); s.d = fs_mk(dx, dy, dz);
+                        s.idx = ix; s.idy = iy; s.idz = iz; s.oodx = px; s.oody = py; s.oodz = pz;
+                        s.sp = h; bt = dbt; owner = down;
+                        s.node = stack.pop(s.sp, 0.f);
+                        running = true;
+                        atomicAdd(whelp + down, 1u);
+                    }
+                    __syncwarp();
+                    if (give && rg < n) s.sp -= (s.sp + 1) >> 1;
+                }
             }
             const uint32_t m_run = __ballot_sync(FULLM, running);
             if (m_run == 0u) break;
