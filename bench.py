@@ -12,7 +12,7 @@ global N * 2^20 work range against a replicated BVH, one NCCL integer reduce per
 
 One JSON line on stdout (rank 0).  `value` = path pairs/s with everything resident in HBM;
 `e2e` = the same through the C-ABI with host buffers (positions in, histogram + IR out);
-`roofline` = k_extend (BVH traversal) algorithmic bytes / its CUDA-event time vs the measured HBM
+`roofline` = k_trace_closest_q (BVH traversal) algorithmic bytes / its CUDA-event time vs the measured HBM
 peak; `cpu_baseline` = the CPU oracle (a port of the reference's loop) on a bounded sample.
 """
 import argparse
@@ -286,13 +286,17 @@ def run_b200(args):
     achieved = ext_bytes / (trc_ms * 1e-3) / 1e9 if trc_ms > 0 else None
     ext_ms_all = ext_ms
     ext_ms = trc_ms
-    roofline = {"bound": "hbm", "kernel": "k_trace_closest (persistent BVH closest-hit traversal), %d launches per step" % ext_launches,
+    bvh_mb = (sc.n_tris * 0.5 * 64 + sc.n_tris * 64) / 1e6          # reachable 4-wide nodes (~T/2 x 64 B) + triangles (64 B)
+    roofline = {"bound": "hbm", "kernel": "k_trace_closest_q (persistent 4-wide BVH closest-hit traversal, warp-shared triangle "
+                                          "queue), %d launches per step on the one-lane timing context" % ext_launches,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": traffic_from_profiles(args), "peak_source": peak_src,
                 "bytes_per_launch": ext_bytes / max(ext_launches, 1), "ms_per_launch": ext_ms / max(ext_launches, 1),
                 "nodes_per_ray": en / er, "tris_per_ray": et / er,
-                "note": "BVH (~11 MB) is L2-resident: achieved is algorithmic fetch bandwidth, served mostly by L2, "
-                        "normalised by the measured HBM copy peak as SURVEY.md 8(d) prescribes"}
+                "note": ("nodes + triangles (~%.0f MB) are L2-resident: achieved is algorithmic fetch bandwidth, served mostly "
+                         "by L2/L1, normalised by the measured HBM copy peak as SURVEY.md 8(d) prescribes" % bvh_mb) if bvh_mb < 100
+                        else ("nodes + triangles (~%.0f MB) exceed the 126 MB L2: algorithmic fetch bandwidth against the "
+                              "measured HBM copy peak; n_node / n_tri counted by the instrumented build of the same kernel" % bvh_mb)}
 
     # e2e: the public C-ABI call with host buffers in and out, copies inside the timed region
     ctx.set_stream(None)
