@@ -736,3 +736,39 @@ int fs_get_stats(fs_ctx* ctx, fs_stats* out)
 }
 
 }  // extern "C"
+
+// ---- text float arrays (saved_ir.txt: one float per line, COMP.cpp:454-505); host only
+int fs_load_float_array(const char* path, float* out, uint64_t cap, uint64_t* n_out)
+{
+    if (!path || !n_out) return FS_ERR_INVALID;
+    FILE* f = fopen(path, "rb");
+    if (!f) return FS_ERR_INVALID;
+    uint64_t n = 0;
+    char line[256];
+    while (fgets(line, sizeof(line), f)) {
+        const char* p = line;
+        while (*p == ' ' || *p == '\t') ++p;
+        if (*p == '\0' || *p == '\n' || *p == '\r') continue;            // ParseIntoArray(..., CullEmpty = true)
+        char* end = nullptr;
+        const float v = strtof(p, &end);                                // FCString::Atof: 0 for a non-numeric line
+        if (out && n < cap) out[n] = (end == p) ? 0.0f : v;
+        ++n;
+    }
+    fclose(f);
+    *n_out = n;
+    return FS_OK;
+}
+
+int fs_save_float_array(const char* path, const float* data, uint64_t n)
+{
+    if (!path || (!data && n)) return FS_ERR_INVALID;
+    FILE* f = fopen(path, "wb");
+    if (!f) return FS_ERR_INVALID;
+    for (uint64_t i = 0; i < n; ++i) {
+        char buf[48];
+        snprintf(buf, sizeof(buf), "%.9g", (double)data[i]);
+        if (!strpbrk(buf, ".eEn")) strcat(buf, ".0");                    // SanitizeFloat keeps one fractional digit ("1.0")
+        if (fputs(buf, f) < 0 || (i + 1 < n && fputc('\n', f) == EOF)) { fclose(f); return FS_ERR_INVALID; }
+    }
+    return fclose(f) == 0 ? FS_OK : FS_ERR_INVALID;
+}

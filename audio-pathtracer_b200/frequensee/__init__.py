@@ -6,4 +6,4 @@ UFrequenSeeAudioComponent / UAudioRayTracingSubsystem / FFrequenSeeAudioReverbPl
 for this path on top of the C-ABI.
 """
 from . import capi, scenes  # noqa: F401
-from .capi import Context, FrequenSeeError, default_config  # noqa: F401
+from .capi import Context, FrequenSeeError, default_config, load_float_array, save_float_array  # noqa: F401

@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "fs_trace", "fs_trace_range_device", "fs_trace_range", "fs_trace_debug",
     "fs_debug_closest_hits", "fs_debug_any_hits",
     "fs_build_ir", "fs_build_ir_to", "fs_build_ir_from_energy", "fs_set_histogram", "fs_set_histogram_device",
-    "fs_get_histogram", "fs_set_ir",
+    "fs_get_histogram", "fs_set_ir", "fs_load_float_array", "fs_save_float_array",
     "fs_conv_init_source", "fs_conv_release_source", "fs_conv_process", "fs_conv_process_many",
     "fs_debug_rfft", "fs_get_stats",
 ]
@@ -111,6 +111,8 @@ def load():
     L.fs_set_histogram_device.argtypes = [vp, vp, u32, u64]
     L.fs_get_histogram.argtypes = [vp, vp]
     L.fs_set_ir.argtypes = [vp, u32, vp]
+    L.fs_load_float_array.argtypes = [C.c_char_p, vp, u64, C.POINTER(u64)]
+    L.fs_save_float_array.argtypes = [C.c_char_p, vp, u64]
     L.fs_conv_init_source.argtypes = [vp, u32]
     L.fs_conv_release_source.argtypes = [vp, u32]
     L.fs_conv_process.argtypes = [vp, u32, vp, vp, u32]
@@ -315,3 +317,26 @@ class Context:
         st = Stats()
         self._ck(self.L.fs_get_stats(self.h, C.byref(st)))
         return st.as_dict()
+
+
+def load_float_array(path):
+    """one float per line (the reference's saved_ir.txt, COMP.cpp:454-490); host only, no context"""
+    L = load()
+    n = C.c_uint64(0)
+    rc = L.fs_load_float_array(os.fsencode(path), None, 0, C.byref(n))
+    if rc != FS_OK:
+        raise FrequenSeeError(rc, "cannot read %s" % path)
+    out = np.zeros(n.value, np.float32)
+    rc = L.fs_load_float_array(os.fsencode(path), out.ctypes.data, n.value, C.byref(n))
+    if rc != FS_OK:
+        raise FrequenSeeError(rc, "cannot read %s" % path)
+    return out
+
+
+def save_float_array(path, data):
+    """COMP.cpp:492-505: one float per line, shortest form that reads back exactly"""
+    L = load()
+    data = np.ascontiguousarray(data, dtype=np.float32).ravel()
+    rc = L.fs_save_float_array(os.fsencode(path), data.ctypes.data, data.size)
+    if rc != FS_OK:
+        raise FrequenSeeError(rc, "cannot write %s" % path)

@@ -188,6 +188,14 @@ int fs_get_histogram(fs_ctx* ctx, uint64_t* hist_out /*[S][B][K]*/);
 /* install an external IR (host [C][sample_rate]) for `source`, e.g. a loaded saved_ir.txt
  * (COMP.cpp:454-490) */
 int fs_set_ir(fs_ctx* ctx, uint32_t source, const float* ir);
+/* text files with one float per line, the format of the reference's saved_ir.txt:
+ * replaces UFrequenSeeAudioComponent::LoadFloatArray (COMP.cpp:454-490; FCString::Atof per line, empty lines
+ * skipped) and SaveArrayToFile (COMP.cpp:492-505).  Host only: no context, no GPU.
+ * fs_load_float_array: values are written to out[0 .. min(*n_out, cap)); *n_out = number of values in the file
+ * (call with out = NULL, cap = 0 to size the buffer).  Returns FS_ERR_INVALID if the file cannot be read.
+ * fs_save_float_array writes the shortest decimal form that reads back to the same float ("%.9g"). */
+int fs_load_float_array(const char* path, float* out, uint64_t cap, uint64_t* n_out);
+int fs_save_float_array(const char* path, const float* data, uint64_t n);
 
 /* ---- convolution ----------------------------------------------------------------------------
  * replaces: IAudioReverb::OnInitSource / OnReleaseSource / ProcessSourceAudio (REV.h:39-47,

@@ -96,6 +96,30 @@ public:
             std::memcpy(ImpulseBuffer[c].data(), flat.data() + (size_t)c * SampleRate, sizeof(float) * SampleRate);
     }
     std::vector<std::vector<float>>& GetImpulseResponse() { return ImpulseBuffer; }                         // COMP.h:113
+    // COMP.cpp:454-490: one float per line into Data (resized to the file's length)
+    static bool LoadFloatArray(const std::string& FilePath, std::vector<float>& Data)
+    {
+        uint64_t n = 0;
+        if (fs_load_float_array(FilePath.c_str(), nullptr, 0, &n) != FS_OK) return false;
+        Data.resize((size_t)n);
+        return fs_load_float_array(FilePath.c_str(), Data.data(), n, &n) == FS_OK;
+    }
+    // COMP.cpp:492-505
+    static bool SaveArrayToFile(const std::vector<float>& Array, const std::string& FilePath)
+    {
+        return fs_save_float_array(FilePath.c_str(), Array.data(), Array.size()) == FS_OK;
+    }
+    // a loaded saved_ir.txt becomes this component's IR on both channels and is published to its convolver
+    bool UseImpulseResponse(const std::vector<float>& Mono)
+    {
+        if ((int)Mono.size() != SampleRate) return false;
+        std::vector<float> flat((size_t)NumChannels * SampleRate);
+        for (int c = 0; c < NumChannels; ++c) {
+            ImpulseBuffer[c] = Mono;
+            std::memcpy(flat.data() + (size_t)c * SampleRate, Mono.data(), sizeof(float) * SampleRate);
+        }
+        return Ctx->Check(fs_set_ir(Ctx->Get(), SourceId, flat.data())) == FS_OK;
+    }
     FVector3f GetActorLocation() const { return Location; }
     void SetActorLocation(FVector3f L) { Location = L; }
     uint32_t GetSourceId() const { return SourceId; }

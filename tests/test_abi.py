@@ -58,3 +58,22 @@ def test_product_does_not_reference_oracle():
                     bad.append(os.path.join(dp, f))
     # mentions in comments are allowed only in docs, not in code files
     assert bad == [], bad
+
+
+def test_float_array_text_files_round_trip(fs, tmp_path):
+    """saved_ir.txt format of the reference (COMP.cpp:454-505): one float per line; host only, no GPU needed"""
+    import numpy as np
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.normal(size=2000).astype(np.float32) * np.float32(1e-3),
+                        np.array([0.0, 1.0, -1.0, 1e-30, 3.4e38, -2.5e-7, 16777216.0], np.float32)])
+    p = str(tmp_path / "saved_ir.txt")
+    fs.save_float_array(p, x)
+    lines = open(p).read().split("\n")
+    assert len(lines) == len(x) and lines[-7:-4] == ["0.0", "1.0", "-1.0"]       # SanitizeFloat keeps one fractional digit
+    assert np.array_equal(fs.load_float_array(p), x)                             # bit-exact round trip
+    # files written by the reference: "%f"-style lines, blank lines, CRLF, a trailing newline, junk -> Atof gives 0
+    open(p, "w").write("0.500000\r\n\n-0.125000\n1e-3\nabc\n  2.000000  \n")
+    assert np.array_equal(fs.load_float_array(p), np.array([0.5, -0.125, 1e-3, 0.0, 2.0], np.float32))
+    import pytest
+    with pytest.raises(fs.FrequenSeeError):
+        fs.load_float_array(str(tmp_path / "missing.txt"))
