@@ -133,6 +133,7 @@ void fs_destroy(fs_ctx* ctx)
     dev_guard g(ctx->device);
     cudaDeviceSynchronize();
     fs_conv_teardown(ctx);
+    cudaFree(ctx->d_carriers); cudaFree(ctx->d_amp_bands);
     fs_wave_free(&ctx->wb);
     for (int l = 0; l < FS_MAX_LANES - 1; ++l) {
         fs_wave_free(&ctx->lanes[l].wb);
@@ -576,7 +577,8 @@ int fs_get_histogram(fs_ctx* ctx, uint64_t* hist_out)
     return finish_stats(ctx);
 }
 
-static int ir_common(fs_ctx* ctx, uint32_t hist_source, uint32_t source, const float* energy, float* ir_out)
+static int ir_common(fs_ctx* ctx, uint32_t hist_source, uint32_t source, const float* energy, float* ir_out,
+                     bool per_band = false, uint64_t noise_seed = 0)
 {
     const fs_config& c = ctx->cfg;
     if (source >= ctx->conv_cap || !ctx->conv[source].ir) {
@@ -594,7 +596,8 @@ static int ir_common(fs_ctx* ctx, uint32_t hist_source, uint32_t source, const f
         d_energy = ctx->d_energy;
     }
     const unsigned long long* hsrc = ctx->d_hist ? ctx->d_hist + (size_t)hist_source * c.n_bands * c.n_bins : nullptr;
-    CK(fs_ir_build(ctx, hsrc, ctx->hist_n_paths, d_energy, s.ir));
+    if (per_band) CK(fs_ir_build_bands(ctx, hsrc, ctx->hist_n_paths, noise_seed, s.ir));
+    else CK(fs_ir_build(ctx, hsrc, ctx->hist_n_paths, d_energy, s.ir));
     { std::lock_guard<std::mutex> lk(ctx->conv_mu); CK(fs_conv_update_ir(ctx, source, ctx->stream)); }
     CK(cudaEventRecord(b, ctx->stream));
     if (ir_out) {
@@ -624,6 +627,16 @@ int fs_build_ir_to(fs_ctx* ctx, uint32_t hist_source, uint32_t conv_source, floa
     if (conv_source >= 4096) return fail(ctx, FS_ERR_INVALID, "source id too large");
     dev_guard g(ctx->device);
     return ir_common(ctx, hist_source, conv_source, nullptr, ir_out);
+}
+
+int fs_build_ir_bands(fs_ctx* ctx, uint32_t hist_source, uint32_t conv_source, uint64_t noise_seed, float* ir_out)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    if (!ctx->d_hist || hist_source >= ctx->hist_sources || ctx->hist_n_paths == 0)
+        return fail(ctx, FS_ERR_STATE, "fs_build_ir_bands: no histogram for this source (call fs_trace or fs_set_histogram)");
+    if (conv_source >= 4096) return fail(ctx, FS_ERR_INVALID, "source id too large");
+    dev_guard g(ctx->device);
+    return ir_common(ctx, hist_source, conv_source, nullptr, ir_out, true, noise_seed);
 }
 
 int fs_build_ir_from_energy(fs_ctx* ctx, uint32_t source, const float* energy, float* ir_out)

@@ -120,6 +120,7 @@ struct fs_ctx {
     // IR / conv
     float* d_energy;            // [K] scratch
     float* d_amp;               // [K]
+    float* d_carriers; float* d_amp_bands; uint64_t carrier_seed;   // per-band IR synthesis: [C][B][fs] noise carriers, [B][K]
     float2* d_twiddle;          // [conv fft size / 2]
     uint32_t fft_n, n_part, n_freq;
     fs_conv_source* conv; uint32_t conv_cap;
@@ -138,6 +139,8 @@ cudaError_t fs_wave_debug_rays(fs_ctx* ctx, const fs_trace_params& tp, const flo
                                uint64_t n, float* d_t, uint32_t* d_tri, uint8_t* d_hit);
 
 // fs_ir.cu
+cudaError_t fs_ir_build_bands(fs_ctx* ctx, const unsigned long long* d_hist_src, uint64_t n_paths, uint64_t noise_seed,
+                              float* d_ir_out);
 cudaError_t fs_ir_build(fs_ctx* ctx, const unsigned long long* d_hist_src, uint64_t n_paths,
                         const float* d_energy_in, float* d_ir_out);
 

@@ -12,6 +12,8 @@
 //              mono IR (COMP.cpp:327-330).
 // Algorithmic bytes per update: read B*K*8, write C*sample_rate*4.
 #include "fs_internal.h"
+#include <math.h>
+#include <vector>
 
 namespace {
 
@@ -58,7 +60,99 @@ __global__ void k_ir(const float* __restrict__ amp, uint32_t n_bins, uint32_t sp
     for (uint32_t c = 0; c < n_channels; ++c) ir[(size_t)c * n_samples + i] = y;
 }
 
+// ---- per-band synthesis: band envelopes x band-limited noise carriers ------------------------
+// amp[b][k] = the mapping of COMP.cpp:339-346 applied to band b alone
+__global__ void k_energy_bands(const unsigned long long* __restrict__ hist, uint32_t n_bands, uint32_t n_bins,
+                               double inv_scale, float threshold, float* __restrict__ amp)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bands * n_bins) return;
+    const float e = (float)(((double)hist[i] * (1.0 / 4294967296.0)) * inv_scale);
+    const float Pi4 = sqrtf(4.0f * FS_PI);
+    amp[i] = (fabsf(e) >= threshold) ? e / sqrtf(e * Pi4) : 0.0f;
+}
+
+// ir[c][t] = sum_b ramp_b[t] * carrier[c][b][t]; the ramp is COMP.cpp:347-363 per band, no low-pass (band-limited carriers)
+__global__ void k_ir_bands(const float* __restrict__ amp, const float* __restrict__ carriers, uint32_t n_bands,
+                           uint32_t n_bins, uint32_t spb, uint32_t n_samples, uint32_t n_channels, float* __restrict__ ir)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_samples) return;
+    const uint32_t bin = t / spb, j = t - bin * spb;
+    const float w = (float)j / (float)spb;
+    for (uint32_t c = 0; c < n_channels; ++c) {
+        float acc = 0.0f;
+        if (bin < n_bins)
+            for (uint32_t b = 0; b < n_bands; ++b) {
+                const float e = amp[b * n_bins + bin], pe = bin ? amp[b * n_bins + bin - 1] : e;
+                const float raw = (1.0f - w) * pe + w * e;
+                acc = acc + raw * carriers[((size_t)c * n_bands + b) * n_samples + t];
+            }
+        ir[(size_t)c * n_samples + t] = acc;
+    }
+}
+
 }  // namespace
+
+// Noise carriers [C][B][sample_rate]: white noise from Philox4x32-10 (counter (t/4, 'IRNZ', channel, band), key = seed)
+// through two cascaded RBJ band-pass biquads (0 dB peak gain, Q = sqrt 2) at f_b = 62.5 * 2^b Hz (capped at 0.45 fs), in
+// double precision on the host, scaled to unit RMS.  Depends on (seed, B, C, fs) only: built once, cached on the device.
+static void band_carriers_host(const fs_config& c, uint64_t seed, std::vector<float>& out)
+{
+    const uint32_t NS = c.sample_rate, B = c.n_bands, Cn = c.n_channels;
+    const double fs = (double)c.sample_rate;
+    out.assign((size_t)Cn * B * NS, 0.0f);
+    std::vector<double> y(NS);
+    for (uint32_t ch = 0; ch < Cn; ++ch)
+        for (uint32_t b = 0; b < B; ++b) {
+            double fc = 62.5 * (double)(1u << b);
+            if (fc > 0.45 * fs) fc = 0.45 * fs;
+            const double w0 = 2.0 * 3.14159265358979323846 * fc / fs, q = 1.4142135623730951;
+            const double alpha = sin(w0) / (2.0 * q), a0 = 1.0 + alpha;
+            const double b0 = alpha / a0, b2 = -alpha / a0, a1 = -2.0 * cos(w0) / a0, a2 = (1.0 - alpha) / a0;
+            double x1 = 0, x2 = 0, u1 = 0, u2 = 0, v1 = 0, v2 = 0, ss = 0;
+            uint32_t r[4] = {0, 0, 0, 0};
+            for (uint32_t t = 0; t < NS; ++t) {
+                if ((t & 3u) == 0) fs_philox4x32_10(t >> 2, 0x49524E5Au, ch, b, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+                const double x = (double)r[t & 3u] * (2.0 / 4294967296.0) - 1.0;
+                const double u = b0 * x + b2 * x2 - a1 * u1 - a2 * u2;
+                const double v = b0 * u + b2 * u2 - a1 * v1 - a2 * v2;
+                x2 = x1; x1 = x; u2 = u1; u1 = u; v2 = v1; v1 = v;
+                y[t] = v; ss += v * v;
+            }
+            const double g = ss > 0.0 ? 1.0 / sqrt(ss / (double)NS) : 0.0;
+            float* o = out.data() + ((size_t)ch * B + b) * NS;
+            for (uint32_t t = 0; t < NS; ++t) o[t] = (float)(y[t] * g);
+        }
+}
+
+cudaError_t fs_ir_build_bands(fs_ctx* ctx, const unsigned long long* d_hist_src, uint64_t n_paths, uint64_t noise_seed,
+                              float* d_ir_out)
+{
+    const fs_config& c = ctx->cfg;
+    cudaError_t e;
+    const size_t ncar = (size_t)c.n_channels * c.n_bands * c.sample_rate;
+    if (!ctx->d_carriers || ctx->carrier_seed != noise_seed) {
+        std::vector<float> h;
+        band_carriers_host(c, noise_seed, h);
+        if (!ctx->d_carriers) {
+            if ((e = cudaMalloc(&ctx->d_carriers, sizeof(float) * ncar)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&ctx->d_amp_bands, sizeof(float) * c.n_bands * c.n_bins)) != cudaSuccess) return e;
+        }
+        if ((e = cudaMemcpyAsync(ctx->d_carriers, h.data(), sizeof(float) * ncar, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return e;     // h goes out of scope
+        ctx->carrier_seed = noise_seed;
+    }
+    const uint32_t spb = (uint32_t)((double)c.bin_ms * 1e-3 * c.sample_rate + 0.5);
+    const double inv_scale = n_paths ? 1.0 / (double)n_paths : 0.0;
+    const uint32_t nbk = c.n_bands * c.n_bins;
+    k_energy_bands<<<(nbk + 255) / 256, 256, 0, ctx->stream>>>(d_hist_src, c.n_bands, c.n_bins, inv_scale, c.ir_threshold,
+                                                              ctx->d_amp_bands);
+    k_ir_bands<<<(c.sample_rate + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_amp_bands, ctx->d_carriers, c.n_bands, c.n_bins, spb,
+                                                                      c.sample_rate, c.n_channels, d_ir_out);
+    ctx->stats.kernel_launches += 2;
+    return cudaGetLastError();
+}
 
 cudaError_t fs_ir_build(fs_ctx* ctx, const unsigned long long* d_hist_src, uint64_t n_paths,
                         const float* d_energy_in, float* d_ir_out)

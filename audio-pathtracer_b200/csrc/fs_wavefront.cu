@@ -904,6 +904,9 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
 #ifndef FS_DRAIN_SPLIT
 #define FS_DRAIN_SPLIT 1
 #endif
+#ifndef FS_PREFETCH_PUSHED
+#define FS_PREFETCH_PUSHED 0
+#endif
 template <bool COUNT, int TEX>
 __global__ void __launch_bounds__(TR_THREADS, FS_TR_MINBLOCKS)
 k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
@@ -994,7 +997,13 @@ k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const 
                     }
                     k0 = l0 ? INF : k0; k1 = l1 ? INF : k1; k2 = l2 ? INF : k2; k3 = l3 ? INF : k3;
                     FS_CSWAP(k0, v0, k1, v1) FS_CSWAP(k2, v2, k3, v3) FS_CSWAP(k0, v0, k2, v2) FS_CSWAP(k1, v1, k3, v3) FS_CSWAP(k1, v1, k2, v2)
-                    if (k1 != INF) stack.push3(s.sp, k2 != INF, k3 != INF, v1, k1, v2, k2, v3, k3, ovf_p);
+                    if (k1 != INF) {
+                        stack.push3(s.sp, k2 != INF, k3 != INF, v1, k1, v2, k2, v3, k3, ovf_p);
+#if FS_PREFETCH_PUSHED
+                        // the nearest pushed sibling is the next node this lane pops: pull its 64 B towards the SM now
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(bv.wnodes + (size_t)v1 * 4));
+#endif
+                    }
                     s.node = (k0 != INF) ? v0 : stack.pop(s.sp, 0.f);
                 }
                 qn += __reduce_add_sync(FULLM, nl);         // the queue length, tracked in a (uniform) register
@@ -1204,9 +1213,12 @@ k_connect_gen(const fs_trace_params tp, const fs_wave_buffers wb, fs_dev_counter
         for (uint32_t k = 0; k < tp.max_depth; ++k) ext += wb.q_count[k];
         atomicAdd(&dc->ext_rays, ext);
     }
-    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < tp.batch;
-         base += gridDim.x * blockDim.x) {
-        const uint32_t p = base + lane;
+    // one shadow-queue atomic per CTA tile (as in k_shade_gen: per-warp atomics on one address ran at ~1 per ns and were
+    // 63 % of this kernel's stall samples); the shadow-ray count is added once per CTA
+    __shared__ uint32_t s_cnt[WF_THREADS / 32], s_base;
+    const uint32_t warp = threadIdx.x >> 5;
+    for (uint32_t tile = blockIdx.x * blockDim.x; tile < tp.batch; tile += gridDim.x * blockDim.x) {
+        const uint32_t p = tile + threadIdx.x;
         bool shadow = false, direct = false;
         fs_vec3 F = fs_mk(0.f, 0.f, 0.f), dir = F;
         float tmax = 0.f;
@@ -1232,18 +1244,28 @@ k_connect_gen(const fs_trace_params tp, const fs_wave_buffers wb, fs_dev_counter
             }
         }
         const uint32_t ms = __ballot_sync(FULLM, shadow), md = __ballot_sync(FULLM, direct);
-        uint32_t slot_s = 0, slot_d = 0;
-        if (lane == 0) {
-            if (ms) { slot_s = atomicAdd(&wb.q_count[qs], (uint32_t)__popc(ms)); atomicAdd(&dc->shadow_rays, (unsigned long long)__popc(ms)); }
-            if (md) slot_d = atomicAdd(&wb.q_count[qc], (uint32_t)__popc(md));
+        if (lane == 0) s_cnt[warp] = (uint32_t)__popc(ms);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < WF_THREADS / 32; ++w) { const uint32_t c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+            s_base = 0u;
+            if (tot) { s_base = atomicAdd(&wb.q_count[qs], tot); atomicAdd(&dc->shadow_rays, (unsigned long long)tot); }
         }
-        slot_s = __shfl_sync(FULLM, slot_s, 0); slot_d = __shfl_sync(FULLM, slot_d, 0);
+        __syncthreads();
         if (shadow) {
-            const uint32_t o = slot_s + (uint32_t)__popc(ms & ((1u << lane) - 1u));
+            const uint32_t o = s_base + s_cnt[warp] + (uint32_t)__popc(ms & ((1u << lane) - 1u));
             sh_o[o] = make_float4(F.x, F.y, F.z, tmax);
             sh_d[o] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(p));
         }
-        if (direct) wb.conn_queue[slot_d + (uint32_t)__popc(md & ((1u << lane) - 1u))] = p;
+        if (md) {                                               // coincident end points: rare
+            uint32_t slot_d = 0;
+            if (lane == 0) slot_d = atomicAdd(&wb.q_count[qc], (uint32_t)__popc(md));
+            slot_d = __shfl_sync(FULLM, slot_d, 0);
+            if (direct) wb.conn_queue[slot_d + (uint32_t)__popc(md & ((1u << lane) - 1u))] = p;
+        }
+        __syncthreads();
     }
 }
 

@@ -179,6 +179,11 @@ int fs_build_ir(fs_ctx* ctx, uint32_t source, float* ir_out);
 /* same, with the histogram slot and the convolver slot named separately (a per-component update
  * traces one source into histogram slot 0 and publishes the IR to that component's own slot) */
 int fs_build_ir_to(fs_ctx* ctx, uint32_t hist_source, uint32_t conv_source, float* ir_out);
+/* per-band synthesis (EXTENDS the reference, whose IR is one low-passed broadband envelope,
+ * COMP.cpp:337-378): each band keeps its envelope (the mapping of COMP.cpp:339-363 per band) and modulates a unit-RMS
+ * octave-band noise carrier (f_b = 62.5 * 2^b Hz, Philox noise keyed by noise_seed through two RBJ band-pass biquads);
+ * ir[c][t] = sum_b ramp_b[t] * carrier[c][b][t], no low-pass.  Publishes to conv_source's convolver like fs_build_ir_to. */
+int fs_build_ir_bands(fs_ctx* ctx, uint32_t hist_source, uint32_t conv_source, uint64_t noise_seed, float* ir_out);
 /* seam 1 of the reference taken literally: EnergyBuffer float[K] -> IR (AddEnergyAtDelay users) */
 int fs_build_ir_from_energy(fs_ctx* ctx, uint32_t source, const float* energy /*[K]*/, float* ir_out);
 /* install an already reduced histogram (host [S][B][K]) and its path count, e.g. after an NCCL reduce */

@@ -95,6 +95,14 @@ public:
         for (int c = 0; c < NumChannels; ++c)
             std::memcpy(ImpulseBuffer[c].data(), flat.data() + (size_t)c * SampleRate, sizeof(float) * SampleRate);
     }
+    // per-band synthesis from the device histogram (extends COMP.cpp:337-378; fs_build_ir_bands)
+    void ReconstructImpulseResponsePerBand(uint64_t NoiseSeed)
+    {
+        std::vector<float> flat((size_t)NumChannels * SampleRate);
+        if (Ctx->Check(fs_build_ir_bands(Ctx->Get(), 0, SourceId, NoiseSeed, flat.data())) != FS_OK) return;
+        for (int c = 0; c < NumChannels; ++c)
+            std::memcpy(ImpulseBuffer[c].data(), flat.data() + (size_t)c * SampleRate, sizeof(float) * SampleRate);
+    }
     std::vector<std::vector<float>>& GetImpulseResponse() { return ImpulseBuffer; }                         // COMP.h:113
     // COMP.cpp:454-490: one float per line into Data (resized to the file's length)
     static bool LoadFloatArray(const std::string& FilePath, std::vector<float>& Data)

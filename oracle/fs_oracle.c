@@ -794,6 +794,81 @@ int fso_build_ir(const fso_config* cfg, const uint64_t* hist, uint64_t n_paths, 
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Per-band IR synthesis (EXTENDS the reference, which collapses its IR to one
+ * low-passed broadband envelope, COMP.cpp:337-378, README.md:118-122 "overly reverberant").
+ * Every band keeps its own envelope a_b[k] (the mapping of COMP.cpp:339-363 applied per band) and
+ * modulates a band-limited noise carrier:  ir[c][t] = sum_b ramp_b[t] * n_{c,b}[t].
+ *   bands      octave bands, centre f_b = 62.5 * 2^b Hz (62.5 Hz ... 8 kHz for B = 8), capped at 0.45 fs
+ *   carrier    white noise in [-1,1) from Philox4x32-10 (counter (t/4, 'IRNZ', c, b), key = seed), through
+ *              two cascaded RBJ band-pass biquads (constant 0 dB peak gain, Q = sqrt 2), double precision,
+ *              Direct Form I, then scaled to unit RMS over the 1 s; stored as float
+ * No one-pole low-pass in this mode: the carriers are band-limited already.
+ * ---------------------------------------------------------------------------------------- */
+void fso_band_carriers(const fso_config* cfg, uint64_t seed, float* out /* [C][B][NS] */)
+{
+    const uint32_t NS = cfg->sample_rate, B = cfg->n_bands, Cn = cfg->n_channels;
+    const double fs = (double)cfg->sample_rate;
+    double* y = (double*)malloc((size_t)NS * sizeof(double));
+    for (uint32_t c = 0; c < Cn; ++c)
+        for (uint32_t b = 0; b < B; ++b) {
+            double fc = 62.5 * (double)(1u << b);
+            if (fc > 0.45 * fs) fc = 0.45 * fs;
+            const double w0 = 2.0 * 3.14159265358979323846 * fc / fs, q = 1.4142135623730951;
+            const double alpha = sin(w0) / (2.0 * q), a0 = 1.0 + alpha;
+            const double b0 = alpha / a0, b2 = -alpha / a0, a1 = -2.0 * cos(w0) / a0, a2 = (1.0 - alpha) / a0;
+            double x1 = 0, x2 = 0, u1 = 0, u2 = 0, v1 = 0, v2 = 0, ss = 0;
+            uint32_t r[4] = {0, 0, 0, 0};
+            for (uint32_t t = 0; t < NS; ++t) {
+                if ((t & 3u) == 0) {
+                    const uint32_t ctr[4] = {t >> 2, 0x49524E5Au, c, b};
+                    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+                    fso_philox4x32_10(ctr, key, r);
+                }
+                const double x = (double)r[t & 3u] * (2.0 / 4294967296.0) - 1.0;
+                const double u = b0 * x + b2 * x2 - a1 * u1 - a2 * u2;        /* first section */
+                const double v = b0 * u + b2 * u2 - a1 * v1 - a2 * v2;        /* second section */
+                x2 = x1; x1 = x; u2 = u1; u1 = u; v2 = v1; v1 = v;
+                y[t] = v; ss += v * v;
+            }
+            const double g = ss > 0.0 ? 1.0 / sqrt(ss / (double)NS) : 0.0;
+            float* o = out + ((size_t)c * B + b) * NS;
+            for (uint32_t t = 0; t < NS; ++t) o[t] = (float)(y[t] * g);
+        }
+    free(y);
+}
+
+int fso_build_ir_bands(const fso_config* cfg, const uint64_t* hist, uint64_t n_paths, uint64_t noise_seed, float* ir_out)
+{
+    const uint32_t K = cfg->n_bins, NS = cfg->sample_rate, B = cfg->n_bands, Cn = cfg->n_channels;
+    const uint32_t spb = (uint32_t)((double)cfg->bin_ms * 1e-3 * cfg->sample_rate + 0.5);
+    const float Pi4 = sqrtf(4.0f * FSO_PI);
+    float* car = (float*)malloc((size_t)Cn * B * NS * 4);
+    float* amp = (float*)malloc((size_t)B * K * 4);
+    fso_band_carriers(cfg, noise_seed, car);
+    for (uint32_t b = 0; b < B; ++b)
+        for (uint32_t k = 0; k < K; ++k) {
+            const float e = (float)(((double)hist[(uint64_t)b * K + k] * (1.0 / 4294967296.0)) / (double)n_paths);
+            amp[b * K + k] = (fabsf(e) >= cfg->ir_threshold) ? e / sqrtf(e * Pi4) : 0.0f;    /* COMP.cpp:343-346 per band */
+        }
+    for (uint32_t c = 0; c < Cn; ++c)
+        for (uint32_t t = 0; t < NS; ++t) {
+            const uint32_t bin = t / spb, j = t - bin * spb;
+            float acc = 0.0f;
+            if (bin < K) {
+                const float w = (float)j / (float)spb;
+                for (uint32_t b = 0; b < B; ++b) {
+                    const float e = amp[b * K + bin], pe = bin ? amp[b * K + bin - 1] : e;   /* :347-363 */
+                    const float raw = (1.0f - w) * pe + w * e;
+                    acc = acc + raw * car[((size_t)c * B + b) * NS + t];
+                }
+            }
+            ir_out[(uint64_t)c * NS + t] = acc;
+        }
+    free(car); free(amp);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Convolution semantics: ProcessSourceAudio + ConvolveFFT, REV.cpp:118-213.
  * y[n] = sum_m h[m] x[n-m] for the newest block, history initially zero (CIRC.cpp:15-21),
  * the IR current at the time of the call applied to the whole retained history.  Direct form

@@ -118,6 +118,9 @@ int fso_trace(const fso_scene* sc, const fso_config* cfg, const float* src_pos, 
 int fso_build_ir(const fso_config* cfg, const uint64_t* hist, uint64_t n_paths, float* ir_out);
 /* float-histogram variant: the reference's own signature, EnergyBuffer float[K] -> IR */
 int fso_build_ir_from_energy(const fso_config* cfg, const float* energy, float* ir_out);
+/* per-band synthesis: band envelopes x band-limited noise carriers; carriers [C][B][sample_rate] */
+void fso_band_carriers(const fso_config* cfg, uint64_t seed, float* out);
+int fso_build_ir_bands(const fso_config* cfg, const uint64_t* hist, uint64_t n_paths, uint64_t noise_seed, float* ir_out);
 
 /* ---- convolution semantics (REV.cpp:118-213, CIRC.cpp:43-75) ---- */
 /* Streaming direct-form reference in double precision.  State = per-channel history of

@@ -102,6 +102,9 @@ def lib():
                                 C.c_void_p, C.POINTER(Stats), C.c_void_p, C.c_int]
         L.fso_build_ir.argtypes = [C.POINTER(Config), C.c_void_p, C.c_uint64, C.c_void_p]
         L.fso_build_ir_from_energy.argtypes = [C.POINTER(Config), C.c_void_p, C.c_void_p]
+        L.fso_band_carriers.argtypes = [C.POINTER(Config), C.c_uint64, C.c_void_p]
+        L.fso_band_carriers.restype = None
+        L.fso_build_ir_bands.argtypes = [C.POINTER(Config), C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
         L.fso_conv_create.restype = C.c_void_p
         L.fso_conv_create.argtypes = [C.POINTER(Config)]
         L.fso_conv_destroy.argtypes = [C.c_void_p]
@@ -228,6 +231,19 @@ def build_ir(cfg, hist, n_paths):
     hist = np.ascontiguousarray(hist, dtype=np.uint64)
     out = np.zeros((cfg.n_channels, cfg.sample_rate), dtype=np.float32)
     lib().fso_build_ir(C.byref(cfg), hist.ctypes.data, n_paths, out.ctypes.data)
+    return out
+
+
+def band_carriers(cfg, seed):
+    out = np.zeros((cfg.n_channels, cfg.n_bands, cfg.sample_rate), dtype=np.float32)
+    lib().fso_band_carriers(C.byref(cfg), seed, out.ctypes.data)
+    return out
+
+
+def build_ir_bands(cfg, hist, n_paths, noise_seed):
+    hist = np.ascontiguousarray(hist, dtype=np.uint64)
+    out = np.zeros((cfg.n_channels, cfg.sample_rate), dtype=np.float32)
+    lib().fso_build_ir_bands(C.byref(cfg), hist.ctypes.data, n_paths, noise_seed, out.ctypes.data)
     return out
 
 

@@ -129,3 +129,23 @@ def test_saved_ir_text_round_trip_drives_the_convolver(fs, oracle, tmp_path):
         y1 = ctx.conv_process_many(x, 1)
     assert np.array_equal(ir[0], ir[1])                     # both channels read the same mono histogram (COMP.cpp:325-329)
     assert np.array_equal(y0, y1)
+
+
+def test_per_band_ir_matches_oracle(fs, oracle):
+    """fs_build_ir_bands against the oracle on the histogram of a real trace; tolerance 1e-5 relative L2"""
+    from frequensee import scenes
+    sc = scenes.shoebox()
+    with fs.Context() as ctx:
+        ctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
+        h = ctx.trace(sc.sources, sc.listener, 16384, 8, 21)
+        ir = ctx.build_ir_bands(99)
+        ir_again = ctx.build_ir_bands(99)
+        ir_other = ctx.build_ir_bands(100)
+        ctx.conv_init_source(0)
+        x = np.zeros((1, 1024, 2), np.float32); x[0, 0] = 1.0
+        y = ctx.conv_process_many(x, 0)                                  # the convolver got the per-band IR (seed 100)
+    iro = oracle.build_ir_bands(oracle.default_config(), h[0], 16384, 99)
+    assert _rel(ir, iro) < 1e-5
+    assert np.array_equal(ir, ir_again) and not np.array_equal(ir, ir_other)
+    assert not np.array_equal(ir[0], ir[1])                               # decorrelated channels
+    assert _rel(y[0, :, 0], np.clip(ir_other[0, :1024], -1, 1)) < 1e-5

@@ -218,3 +218,43 @@ def test_golden_vectors(oracle):
     assert dbg[:64].tobytes() == g["shoebox_rr09_dbg64"].tobytes()
     ir = oracle.build_ir(cfg, h[0], 16384)
     assert np.array_equal(ir[0, :4800], g["shoebox_ir_first4800"])
+
+
+def test_band_carriers_are_unit_rms_octave_band_noise(oracle):
+    """per-band IR synthesis: carrier b is noise around f_b = 62.5 * 2^b Hz with unit RMS"""
+    cfg = oracle.default_config()
+    car = oracle.band_carriers(cfg, 1234)
+    assert car.shape == (cfg.n_channels, cfg.n_bands, cfg.sample_rate)
+    rms = np.sqrt((car.astype(np.float64) ** 2).mean(axis=2))
+    assert np.allclose(rms, 1.0, atol=1e-6)
+    f = np.fft.rfftfreq(cfg.sample_rate, 1.0 / cfg.sample_rate)
+    for b in range(cfg.n_bands):
+        P = np.abs(np.fft.rfft(car[0, b].astype(np.float64))) ** 2
+        fc = 62.5 * 2 ** b
+        assert P[(f >= fc / 2) & (f <= fc * 2)].sum() / P.sum() > 0.9
+    c01 = np.corrcoef(car[0, 4], car[1, 4])[0, 1]
+    assert abs(c01) < 0.05                                                  # the two channels are decorrelated
+    assert np.array_equal(car, oracle.band_carriers(cfg, 1234))            # deterministic
+    assert not np.array_equal(car[0, 3], oracle.band_carriers(cfg, 1235)[0, 3])
+
+
+def test_per_band_ir_single_bin_kat(oracle):
+    """one band, one bin: ir = (ramp of COMP.cpp:347-363 with a = sqrt(E) / (4 pi)^(1/4)) x that band's carrier"""
+    cfg = oracle.default_config()
+    B, K, NS = cfg.n_bands, cfg.n_bins, cfg.sample_rate
+    n_paths = 1000
+    hist = np.zeros((B, K), np.uint64)
+    E = 0.02
+    hist[5, 100] = int(E * n_paths * 2 ** 32)
+    ir = oracle.build_ir_bands(cfg, hist, n_paths, 77)
+    car = oracle.band_carriers(cfg, 77)
+    e = np.float32(np.float64(hist[5, 100]) / 2 ** 32 / n_paths)
+    a = e / np.sqrt(e * np.sqrt(np.float32(4.0) * np.float32(np.pi), dtype=np.float32), dtype=np.float32)
+    assert abs(float(a) - math.sqrt(E) / (4 * math.pi) ** 0.25) < 1e-6
+    j = np.arange(48, dtype=np.float32) / np.float32(48)
+    exp = np.zeros(NS, np.float32)
+    exp[4800:4848] = j * a                                                  # bin 100 ramps up from bin 99 (= 0)
+    exp[4848:4896] = (np.float32(1) - j) * a                                # bin 101 ramps down from bin 100
+    for c in range(cfg.n_channels):
+        assert np.allclose(ir[c], exp * car[c, 5], rtol=1e-6, atol=1e-9)
+    assert np.count_nonzero(ir[0, :4800]) == 0 and np.count_nonzero(ir[0, 4896:]) == 0
