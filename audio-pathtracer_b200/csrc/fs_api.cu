@@ -133,7 +133,7 @@ void fs_destroy(fs_ctx* ctx)
     dev_guard g(ctx->device);
     cudaDeviceSynchronize();
     fs_conv_teardown(ctx);
-    cudaFree(ctx->d_carriers); cudaFree(ctx->d_amp_bands);
+    cudaFree(ctx->d_carriers); cudaFree(ctx->d_amp_bands); cudaFree(ctx->d_amp_all);
     fs_wave_free(&ctx->wb);
     for (int l = 0; l < FS_MAX_LANES - 1; ++l) {
         fs_wave_free(&ctx->lanes[l].wb);
@@ -627,6 +627,42 @@ int fs_build_ir_to(fs_ctx* ctx, uint32_t hist_source, uint32_t conv_source, floa
     if (conv_source >= 4096) return fail(ctx, FS_ERR_INVALID, "source id too large");
     dev_guard g(ctx->device);
     return ir_common(ctx, hist_source, conv_source, nullptr, ir_out);
+}
+
+int fs_build_ir_all(fs_ctx* ctx, uint32_t n_sources, float* ir_out)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    if (!ctx->d_hist || n_sources == 0 || n_sources > ctx->hist_sources || ctx->hist_n_paths == 0)
+        return fail(ctx, FS_ERR_STATE, "fs_build_ir_all: no histogram for these sources (call fs_trace or fs_set_histogram)");
+    if (n_sources > 4096) return fail(ctx, FS_ERR_INVALID, "source id too large");
+    dev_guard g(ctx->device);
+    const fs_config& c = ctx->cfg;
+    for (uint32_t s = 0; s < n_sources; ++s)
+        if (s >= ctx->conv_cap || !ctx->conv[s].ir) {
+            cudaError_t e = fs_conv_source_alloc(ctx, s);
+            if (e != cudaSuccess) return fail_cuda(ctx, e, "fs_conv_source_alloc");
+        }
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    CK(cudaEventRecord(a, ctx->stream));
+    for (uint32_t s0 = 0; s0 < n_sources; s0 += FS_PTR_TABLE) {
+        const uint32_t n = n_sources - s0 < FS_PTR_TABLE ? n_sources - s0 : FS_PTR_TABLE;
+        fs_ptr_table tab;
+        for (uint32_t i = 0; i < n; ++i) { tab.p[i] = ctx->conv[s0 + i].ir; tab.q[i] = nullptr; }
+        CK(fs_ir_build_multi(ctx, ctx->d_hist, s0, n, ctx->hist_n_paths, tab));
+        { std::lock_guard<std::mutex> lk(ctx->conv_mu); CK(fs_conv_update_ir_multi(ctx, s0, n, ctx->stream)); }
+    }
+    CK(cudaEventRecord(b, ctx->stream));
+    if (ir_out) {
+        const size_t per = (size_t)c.n_channels * c.sample_rate;
+        for (uint32_t s = 0; s < n_sources; ++s)
+            CK(cudaMemcpyAsync(ir_out + s * per, ctx->conv[s].ir, sizeof(float) * per, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) ctx->stats.last_ir_ms = ms;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return FS_OK;
 }
 
 int fs_build_ir_bands(fs_ctx* ctx, uint32_t hist_source, uint32_t conv_source, uint64_t noise_seed, float* ir_out)

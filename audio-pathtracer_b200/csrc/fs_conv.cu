@@ -70,6 +70,27 @@ __global__ void k_ir_spectra(const float* __restrict__ ir, uint32_t ir_len, uint
     for (uint32_t f = threadIdx.x; f < nf; f += blockDim.x) dst[f] = r[f];
 }
 
+// the same for up to FS_PTR_TABLE sources in one launch: tab.p[s] = device IR, tab.q[s] = destination H of source s
+__global__ void k_ir_spectra_multi(fs_ptr_table tab, uint32_t ir_len, uint32_t bk, uint32_t n_ch,
+                                   const float2* __restrict__ tw, uint32_t tw_n)
+{
+    extern __shared__ float2 sm[];
+    const uint32_t n = 2u * bk, nf = bk + 1u;
+    float2* a = sm; float2* b = sm + n;
+    const uint32_t p = blockIdx.x, c = blockIdx.y;
+    const float* ir = (const float*)tab.p[blockIdx.z];
+    float2* H = (float2*)tab.q[blockIdx.z];
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t src = p * bk + i;
+        float v = (i < bk && src < ir_len) ? ir[(size_t)c * ir_len + src] : 0.0f;
+        a[i] = make_float2(v, 0.0f);
+    }
+    __syncthreads();
+    float2* r = fft_stockham(a, b, n, tw, tw_n, false);
+    float2* dst = H + ((size_t)p * n_ch + c) * nf;
+    for (uint32_t f = threadIdx.x; f < nf; f += blockDim.x) dst[f] = r[f];
+}
+
 struct conv_args {
     float2* fdl;            // [P][C][NF]
     const float2* H;        // [P][C][NF]
@@ -259,6 +280,33 @@ cudaError_t fs_conv_update_ir(fs_ctx* ctx, uint32_t source, cudaStream_t st)
     // the convolver runs on the same stream unless the caller moved it; publication is ordered by the stream
     s.h_published.store(nxt, std::memory_order_release);
     s.h_valid = 1;
+    return cudaSuccess;
+}
+
+// sources [s0, s0 + n), n <= FS_PTR_TABLE: all partition spectra in one launch, then publish each
+cudaError_t fs_conv_update_ir_multi(fs_ctx* ctx, uint32_t s0, uint32_t n, cudaStream_t st)
+{
+    const fs_config& c = ctx->cfg;
+    fs_ptr_table tab;
+    int nxt[FS_PTR_TABLE];
+    for (uint32_t i = 0; i < n; ++i) {
+        fs_conv_source& s = ctx->conv[s0 + i];
+        nxt[i] = 1 - s.h_published.load(std::memory_order_acquire);
+        tab.p[i] = s.ir; tab.q[i] = s.H[nxt[i]];
+    }
+    const size_t smem = sizeof(float2) * 2 * ctx->fft_n;
+    const uint32_t tw_n = ctx->fft_n > 4096u ? ctx->fft_n : 4096u;
+    uint32_t threads = c.conv_block < 1024u ? c.conv_block : 1024u;
+    k_ir_spectra_multi<<<dim3(ctx->n_part, c.n_channels, n), threads, smem, st>>>(tab, c.sample_rate, c.conv_block, c.n_channels,
+                                                                                   ctx->d_twiddle, tw_n);
+    ++ctx->stats.kernel_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    for (uint32_t i = 0; i < n; ++i) {
+        fs_conv_source& s = ctx->conv[s0 + i];
+        s.h_published.store(nxt[i], std::memory_order_release);
+        s.h_valid = 1;
+    }
     return cudaSuccess;
 }
 

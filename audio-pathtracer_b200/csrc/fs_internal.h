@@ -89,6 +89,8 @@ struct fs_conv_source {
 };
 
 #define FS_MAX_LANES 4
+#define FS_PTR_TABLE 64
+struct fs_ptr_table { void* p[FS_PTR_TABLE]; void* q[FS_PTR_TABLE]; };   // per-source device pointers passed by value
 
 struct fs_ctx {
     fs_config cfg;
@@ -120,6 +122,7 @@ struct fs_ctx {
     // IR / conv
     float* d_energy;            // [K] scratch
     float* d_amp;               // [K]
+    float* d_amp_all; uint32_t amp_all_cap;   // [FS_PTR_TABLE][K]: multi-source IR build
     float* d_carriers; float* d_amp_bands; uint64_t carrier_seed;   // per-band IR synthesis: [C][B][fs] noise carriers, [B][K]
     float2* d_twiddle;          // [conv fft size / 2]
     uint32_t fft_n, n_part, n_freq;
@@ -139,6 +142,9 @@ cudaError_t fs_wave_debug_rays(fs_ctx* ctx, const fs_trace_params& tp, const flo
                                uint64_t n, float* d_t, uint32_t* d_tri, uint8_t* d_hit);
 
 // fs_ir.cu
+cudaError_t fs_ir_build_multi(fs_ctx* ctx, const unsigned long long* d_hist, uint32_t s0, uint32_t n, uint64_t n_paths,
+                              const fs_ptr_table& d_ir);
+cudaError_t fs_conv_update_ir_multi(fs_ctx* ctx, uint32_t s0, uint32_t n, cudaStream_t st);
 cudaError_t fs_ir_build_bands(fs_ctx* ctx, const unsigned long long* d_hist_src, uint64_t n_paths, uint64_t noise_seed,
                               float* d_ir_out);
 cudaError_t fs_ir_build(fs_ctx* ctx, const unsigned long long* d_hist_src, uint64_t n_paths,

@@ -92,7 +92,56 @@ __global__ void k_ir_bands(const float* __restrict__ amp, const float* __restric
     }
 }
 
+// ---- all sources of a multi-emitter update in one launch each (config 4: 64 sources x 58 us of tiny serial launches) ----
+__global__ void k_energy_multi(const unsigned long long* __restrict__ hist, uint32_t n_bands, uint32_t n_bins, double inv_scale,
+                               float threshold, float* __restrict__ amp /*[S][K]*/)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x, src = blockIdx.y;
+    if (k >= n_bins) return;
+    const unsigned long long* h = hist + (size_t)src * n_bands * n_bins;
+    unsigned long long sum = 0;
+    for (uint32_t b = 0; b < n_bands; ++b) sum += h[(size_t)b * n_bins + k];
+    const float e = (float)(((double)sum * (1.0 / 4294967296.0)) * inv_scale);
+    const float Pi4 = sqrtf(4.0f * FS_PI);
+    amp[(size_t)src * n_bins + k] = (fabsf(e) >= threshold) ? e / sqrtf(e * Pi4) : 0.0f;
+}
+
+__global__ void k_ir_multi(const float* __restrict__ amp, uint32_t n_bins, uint32_t spb, uint32_t n_samples,
+                           uint32_t n_channels, float a, fs_ptr_table tab)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, src = blockIdx.y;
+    if (i >= n_samples) return;
+    const float* am = amp + (size_t)src * n_bins;
+    uint32_t j0 = i >= (uint32_t)IR_WINDOW ? i - IR_WINDOW : 0u;
+    float y = raw_sample(am, j0, spb, n_bins);
+    if (j0 > 0) y = a * y;
+    for (uint32_t j = j0 + 1; j <= i; ++j) y = a * raw_sample(am, j, spb, n_bins) + (1.0f - a) * y;
+    float* ir = (float*)tab.p[src];
+    for (uint32_t c = 0; c < n_channels; ++c) ir[(size_t)c * n_samples + i] = y;
+}
+
 }  // namespace
+
+// same arithmetic as fs_ir_build, for sources [s0, s0 + n) (n <= FS_PTR_TABLE): d_ir[i] = device IR of source s0 + i
+cudaError_t fs_ir_build_multi(fs_ctx* ctx, const unsigned long long* d_hist, uint32_t s0, uint32_t n, uint64_t n_paths,
+                              const fs_ptr_table& d_ir)
+{
+    const fs_config& c = ctx->cfg;
+    cudaError_t e;
+    if (ctx->amp_all_cap < n) {
+        cudaFree(ctx->d_amp_all); ctx->d_amp_all = nullptr;
+        if ((e = cudaMalloc(&ctx->d_amp_all, sizeof(float) * (size_t)FS_PTR_TABLE * c.n_bins)) != cudaSuccess) return e;
+        ctx->amp_all_cap = FS_PTR_TABLE;
+    }
+    const uint32_t spb = (uint32_t)((double)c.bin_ms * 1e-3 * c.sample_rate + 0.5);
+    const double inv_scale = n_paths ? 1.0 / (double)n_paths : 0.0;
+    k_energy_multi<<<dim3((c.n_bins + 255) / 256, n), 256, 0, ctx->stream>>>(d_hist + (size_t)s0 * c.n_bands * c.n_bins, c.n_bands,
+                                                                            c.n_bins, inv_scale, c.ir_threshold, ctx->d_amp_all);
+    k_ir_multi<<<dim3((c.sample_rate + 255) / 256, n), 256, 0, ctx->stream>>>(ctx->d_amp_all, c.n_bins, spb, c.sample_rate,
+                                                                             c.n_channels, c.ir_lowpass, d_ir);
+    ctx->stats.kernel_launches += 2;
+    return cudaGetLastError();
+}
 
 // Noise carriers [C][B][sample_rate]: white noise from Philox4x32-10 (counter (t/4, 'IRNZ', channel, band), key = seed)
 // through two cascaded RBJ band-pass biquads (0 dB peak gain, Q = sqrt 2) at f_b = 62.5 * 2^b Hz (capped at 0.45 fs), in

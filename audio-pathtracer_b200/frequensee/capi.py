@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "fs_scene_set_triangles", "fs_scene_set_materials", "fs_scene_commit",
     "fs_trace", "fs_trace_range_device", "fs_trace_range", "fs_trace_debug",
     "fs_debug_closest_hits", "fs_debug_any_hits",
-    "fs_build_ir", "fs_build_ir_to", "fs_build_ir_bands", "fs_build_ir_from_energy", "fs_set_histogram", "fs_set_histogram_device",
+    "fs_build_ir", "fs_build_ir_to", "fs_build_ir_all", "fs_build_ir_bands", "fs_build_ir_from_energy", "fs_set_histogram", "fs_set_histogram_device",
     "fs_get_histogram", "fs_set_ir", "fs_load_float_array", "fs_save_float_array",
     "fs_conv_init_source", "fs_conv_release_source", "fs_conv_process", "fs_conv_process_many",
     "fs_debug_rfft", "fs_get_stats",
@@ -112,6 +112,7 @@ def load():
     L.fs_get_histogram.argtypes = [vp, vp]
     L.fs_set_ir.argtypes = [vp, u32, vp]
     L.fs_build_ir_bands.argtypes = [vp, u32, u32, u64, vp]
+    L.fs_build_ir_all.argtypes = [vp, u32, vp]
     L.fs_load_float_array.argtypes = [C.c_char_p, vp, u64, C.POINTER(u64)]
     L.fs_save_float_array.argtypes = [C.c_char_p, vp, u64]
     L.fs_conv_init_source.argtypes = [vp, u32]
@@ -272,6 +273,12 @@ class Context:
         ir = np.zeros((self.cfg.n_channels, self.cfg.sample_rate), dtype=np.float32) if want_ir else None
         self._ck(self.L.fs_build_ir_to(self.h, hist_source, conv_source, ir.ctypes.data if want_ir else None))
         return ir
+
+    def build_ir_all(self, n_sources, want_ir=True):
+        """all sources of a multi-emitter update, IR kernels launched once per 64 sources"""
+        out = np.zeros((n_sources, self.cfg.n_channels, self.cfg.sample_rate), dtype=np.float32) if want_ir else None
+        self._ck(self.L.fs_build_ir_all(self.h, n_sources, out.ctypes.data if want_ir else None))
+        return out
 
     def build_ir_bands(self, noise_seed, hist_source=0, conv_source=0, want_ir=True):
         """per-band synthesis: band envelopes x octave-band noise carriers"""

@@ -43,16 +43,19 @@ def parse():
     ap.add_argument("--depth", type=int, default=16)
     ap.add_argument("--scene", default="furnished_room", choices=["furnished_room", "mine_tunnels", "concert_hall", "shoebox"],
                     help="default furnished_room = BASELINE.json configs[1]; the others are extra measurements")
+    ap.add_argument("--sources", type=int, default=1,
+                    help="emitters (BASELINE configs[3]: 64 in the mine tunnels); --paths stays the path pairs per GPU per step, "
+                         "split evenly over the sources")
     ap.add_argument("--cpu-sample-paths", type=int, default=1 << 19)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
 def config_dict(args, n):
-    wl = WORKLOAD if (args.scene == "furnished_room" and args.paths == 1 << 20 and args.depth == 16) else \
-        "%s_%d_paths_depth%d_8bands" % (args.scene, args.paths, args.depth)
+    wl = WORKLOAD if (args.scene == "furnished_room" and args.paths == 1 << 20 and args.depth == 16 and args.sources == 1) else \
+        "%s_%d_paths_depth%d_8bands%s" % (args.scene, args.paths, args.depth, "_%dsources" % args.sources if args.sources > 1 else "")
     return {"workload": wl, "scene": "%s (seeded procedural)" % args.scene, "paths_per_gpu_per_step": args.paths,
-            "max_depth": args.depth, "bands": 8, "bins": 1000, "sources": 1, "rr_prob": 0.9,
+            "max_depth": args.depth, "bands": 8, "bins": 1000, "sources": args.sources, "rr_prob": 0.9,
             "parallelism": "path-range sharding x%d, replicated BVH, one int64 reduce" % n,
             "l2": "no explicit flush: per-step wavefront state+records (~0.6 GB) exceed the 126 MB L2; "
                   "the ~11 MB BVH is L2-resident by design, as in steady-state 60 Hz refresh"}
@@ -140,14 +143,16 @@ def cpu_oracle_rate(args, n_paths, threads, repeats=1, seed=SEED0):
     import pyoracle as po
     from frequensee import scenes
     sc = scenes.by_name(args.scene)
-    sc.sources = sc.sources[:1]
+    sc.sources = sc.sources[:args.sources]
     S = po.Scene(sc.verts, sc.tri_mat, sc.absorption, use_bvh=True)
     cfg = po.default_config()
     times = []
     for r in range(repeats):
         t0 = time.perf_counter()
-        h, st = S.trace(cfg, sc.sources, sc.listener, n_paths, args.depth, seed + r, n_threads=threads)
-        po.build_ir(cfg, h[0], n_paths)
+        per_source = max(1, n_paths // len(sc.sources))      # n_paths = path pairs over all sources
+        h, st = S.trace(cfg, sc.sources, sc.listener, per_source, args.depth, seed + r, n_threads=threads)
+        for si in range(len(sc.sources)):
+            po.build_ir(cfg, h[si], per_source)
         times.append(time.perf_counter() - t0)
     return times, st
 
@@ -200,7 +205,10 @@ def run_b200(args):
     N, K, W = world, args.steps, args.warmup
     P, D = args.paths, args.depth
     sc = scenes.by_name(args.scene)
-    sc.sources = sc.sources[:1]
+    sc.sources = sc.sources[:args.sources]
+    NS_ = len(sc.sources)
+    if P * N % NS_:
+        raise SystemExit("--paths x --gpus must be a multiple of --sources")
     ctx = fs.Context(device=local)                          # production configuration: no per-kernel events, batch lanes on
     ctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
     stream = torch.cuda.Stream()                            # a real (non-NULL) stream: the C-ABI treats NULL as "own stream"
@@ -208,17 +216,20 @@ def run_b200(args):
     assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     B, Kb = ctx.cfg.n_bands, ctx.cfg.n_bins
-    d_hist = torch.zeros((1, B, Kb), dtype=torch.int64, device="cuda")
-    n_global = P * N                                        # per-source path count of the whole job
-    g_first, g_count = shard_range(n_global, rank, N)
+    d_hist = torch.zeros((NS_, B, Kb), dtype=torch.int64, device="cuda")
+    n_global = P * N // NS_                                 # per-source path count of the whole job
+    g_first, g_count = shard_range(n_global * NS_, rank, N) # contiguous range of the global index g = source * n + i
 
     def step_device(seed):
         ctx.trace_range_device(sc.sources, sc.listener, n_global, g_first, g_count, D, seed, d_hist.data_ptr(), True)
         if N > 1:
             dist.reduce(d_hist, dst=0, op=dist.ReduceOp.SUM)
         if rank == 0:
-            ctx.set_histogram_device(d_hist.data_ptr(), 1, n_global)
-            ctx.build_ir(0, want_ir=False)
+            ctx.set_histogram_device(d_hist.data_ptr(), NS_, n_global)
+            if NS_ == 1:
+                ctx.build_ir(0, want_ir=False)
+            else:
+                ctx.build_ir_all(NS_, want_ir=False)
 
     def barrier():
         if N > 1:
@@ -304,8 +315,8 @@ def run_b200(args):
     if rank == 0 or N > 1:
         def step_host(seed):
             if N == 1:
-                h = ctx.trace(sc.sources, sc.listener, P, D, seed)           # positions H2D, histogram D2H
-                ir = ctx.build_ir(0)                                          # IR D2H
+                h = ctx.trace(sc.sources, sc.listener, n_global, D, seed)    # positions H2D, histogram D2H
+                ir = ctx.build_ir(0) if NS_ == 1 else ctx.build_ir_all(NS_)  # IR D2H
                 return h, ir
             h = ctx.trace_range(sc.sources, sc.listener, n_global, g_first, g_count, D, seed)
             return h, None
@@ -319,16 +330,16 @@ def run_b200(args):
                 dist.reduce(d_hist, dst=0, op=dist.ReduceOp.SUM)
                 if rank == 0:
                     ctx.set_histogram(d_hist.cpu().numpy().view(np.uint64), n_global)
-                    ir = ctx.build_ir(0)
+                    ir = ctx.build_ir(0) if NS_ == 1 else ctx.build_ir_all(NS_)
         barrier()
         wall = time.perf_counter() - t0
         tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
         if N > 1:
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
         wall = float(tw.item())
-        hb = 1 * B * Kb * 8
+        hb = NS_ * B * Kb * 8
         e2e = {"value": P * N * K / wall, "unit": UNIT, "h2d_bytes_per_step": int(sc.sources.nbytes + sc.listener.nbytes),
-               "d2h_bytes_per_step": int(hb + ctx.cfg.n_channels * ctx.cfg.sample_rate * 4), "ms_per_step": 1e3 * wall / K}
+               "d2h_bytes_per_step": int(hb + NS_ * ctx.cfg.n_channels * ctx.cfg.sample_rate * 4), "ms_per_step": 1e3 * wall / K}
     cpu = None
     if rank == 0 and N == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

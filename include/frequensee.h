@@ -179,6 +179,9 @@ int fs_build_ir(fs_ctx* ctx, uint32_t source, float* ir_out);
 /* same, with the histogram slot and the convolver slot named separately (a per-component update
  * traces one source into histogram slot 0 and publishes the IR to that component's own slot) */
 int fs_build_ir_to(fs_ctx* ctx, uint32_t hist_source, uint32_t conv_source, float* ir_out);
+/* multi-emitter update (BASELINE configs[3]: 64 sources): fs_build_ir for sources 0 .. n_sources-1 with the three IR kernels
+ * launched once per 64 sources instead of once per source; same arithmetic.  ir_out: host [n_sources][C][sample_rate] or NULL. */
+int fs_build_ir_all(fs_ctx* ctx, uint32_t n_sources, float* ir_out);
 /* per-band synthesis (EXTENDS the reference, whose IR is one low-passed broadband envelope,
  * COMP.cpp:337-378): each band keeps its envelope (the mapping of COMP.cpp:339-363 per band) and modulates a unit-RMS
  * octave-band noise carrier (f_b = 62.5 * 2^b Hz, Philox noise keyed by noise_seed through two RBJ band-pass biquads);

@@ -149,3 +149,30 @@ def test_per_band_ir_matches_oracle(fs, oracle):
     assert np.array_equal(ir, ir_again) and not np.array_equal(ir, ir_other)
     assert not np.array_equal(ir[0], ir[1])                               # decorrelated channels
     assert _rel(y[0, :, 0], np.clip(ir_other[0, :1024], -1, 1)) < 1e-5
+
+
+def test_build_ir_all_equals_per_source_builds(fs, oracle):
+    """fs_build_ir_all (one launch per kernel for all emitters) gives exactly the IRs and convolver state of fs_build_ir"""
+    from frequensee import scenes
+    sc = scenes.shoebox()
+    srcs = np.array([[1.5, 1.2, 1.0], [3.0, 2.0, 1.5], [5.5, 4.0, 2.0], [2.0, 4.2, 0.8], [6.1, 1.1, 2.4]], np.float32)
+    x = np.zeros((2, 1024, 2), np.float32); x[0, 0] = 1.0; x[1, 5] = -0.5
+    with fs.Context() as ctx:
+        ctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
+        h = ctx.trace(srcs, sc.listener, 4096, 8, 31)
+        one = np.stack([ctx.build_ir(s) for s in range(len(srcs))])
+        for s in range(len(srcs)):
+            ctx.conv_init_source(s)
+        y_one = np.stack([ctx.conv_process_many(x, s) for s in range(len(srcs))])
+    with fs.Context() as ctx:
+        ctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
+        ctx.trace(srcs, sc.listener, 4096, 8, 31)
+        allir = ctx.build_ir_all(len(srcs))
+        for s in range(len(srcs)):
+            ctx.conv_init_source(s)
+        y_all = np.stack([ctx.conv_process_many(x, s) for s in range(len(srcs))])
+    assert np.array_equal(one, allir) and np.array_equal(y_one, y_all)
+    cfg = oracle.default_config()
+    for s in range(len(srcs)):
+        assert _rel(allir[s], oracle.build_ir(cfg, h[s], 4096)) < 1e-5
+    assert not np.array_equal(allir[0], allir[1])

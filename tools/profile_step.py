@@ -12,7 +12,7 @@ import time
 ctx = fs.Context(flags=flags | (0 if os.environ.get('PS_NOTIME') else capi.FLAG_TIME_KERNELS))   # PS_NOTIME=1: no per-kernel events (batch lanes overlap)
 t0 = time.time(); ctx.set_scene(sc.verts, sc.tri_mat, sc.absorption); print('commit %d tris %.3f s' % (sc.n_tris, time.time() - t0))
 for i in range(steps):
-    ctx.trace(sc.sources[:1], sc.listener, int(os.environ.get('PS_PATHS', 1 << 20)), depth, 1000 + i, want_hist=False)
+    ctx.trace(sc.sources[:int(os.environ.get('PS_SOURCES', 1))], sc.listener, int(os.environ.get('PS_PATHS', 1 << 20)), depth, 1000 + i, want_hist=False)
     ctx.build_ir(0, want_ir=False)
     st = ctx.stats()
     print("step", i, {k: st[k] for k in ("last_trace_ms", "extend_ms", "connect_ms", "node_visits", "tri_tests", "ext_rays")})
