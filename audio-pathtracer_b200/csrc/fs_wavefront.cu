@@ -877,7 +877,7 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
 }
 
 // =============================================================================================
-// k_trace_closest_q: closest-hit traversal with a WARP-SHARED TRIANGLE QUEUE.
+// k_trace_q: traversal with a WARP-SHARED TRIANGLE QUEUE (closest hit of extension rays; any hit of connection rays).
 //
 // ncu on k_trace_closest (r1h/r1i, SASS-level counters): a ray needs ~2 550 thread-instructions, the kernel
 // spends 3 100 -- but only 17.9 of 32 lanes are active per issued instruction.  The lost lanes are phase
@@ -907,12 +907,20 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
 #ifndef FS_PREFETCH_PUSHED
 #define FS_PREFETCH_PUSHED 0
 #endif
-template <bool COUNT, int TEX>
+#ifndef FS_PREFETCH_TRIS
+#define FS_PREFETCH_TRIS 0
+#endif
+// ANY = false: closest hit of extension rays -> hits[j] = (t, triangle).
+// ANY = true : connection rays (F.xyz, tmax) (dir.xyz, path id): any triangle closer than tmax occludes; the paths that
+//              stay visible are appended to conn_queue.  Same node phase and queue; the "best key" of a lane degenerates
+//              to an occluded flag (any store wins), and bt is the constant tmax.
+template <bool COUNT, int TEX, bool ANY>
 __global__ void __launch_bounds__(TR_THREADS, FS_TR_MINBLOCKS)
-k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
-                  const uint32_t* __restrict__ count_ptr, uint32_t* __restrict__ cursor,
-                  float2* __restrict__ hits, fs_dev_counters* __restrict__ dc, const uint32_t REFILL_MIN,
-                  const uint32_t NODE_MIN, const uint32_t FLUSH_MIN)
+k_trace_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+          const uint32_t* __restrict__ count_ptr, uint32_t* __restrict__ cursor,
+          float2* __restrict__ hits, uint32_t* __restrict__ conn_queue, uint32_t* __restrict__ conn_count,
+          fs_path_dbg* __restrict__ dbg, fs_dev_counters* __restrict__ dc, const uint32_t REFILL_MIN,
+          const uint32_t NODE_MIN, const uint32_t FLUSH_MIN)
 {
     constexpr bool DRAIN_SPLIT = FS_DRAIN_SPLIT != 0;
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
@@ -959,8 +967,8 @@ k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const 
                 if (jj < count) {
                     const float4 a = ray_o[jj], b = ray_d[jj];
                     tr_init<true>(s, bv, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z));
-                    bt = __int_as_float(0x7f800000); *mykey = KEY_NONE;
-                    j = jj; running = true;
+                    bt = ANY ? a.w : __int_as_float(0x7f800000); *mykey = KEY_NONE;
+                    j = ANY ? __float_as_uint(b.w) : jj; running = true;
                     if (COUNT) ray_steps = 0;
                 }
             }
@@ -987,13 +995,19 @@ k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const 
                     if (nl) {
                         uint32_t* q = squeue + atomicAdd(sqcount, nl);
                         const uint32_t lm4 = owner - 4u;
-                        if (l0) *q = (uint32_t)v0 * 0xfffffffcu + lm4;
+#if FS_PREFETCH_TRIS
+#define FS_PF_TRI(v) asm volatile("prefetch.global.L2 [%0];" :: "l"(bv.tris + (size_t)((uint32_t)(~(v)) >> 3) * 4))
+#else
+#define FS_PF_TRI(v)
+#endif
+                        if (l0) { *q = (uint32_t)v0 * 0xfffffffcu + lm4; FS_PF_TRI(v0); }
                         q += l0;
-                        if (l1) *q = (uint32_t)v1 * 0xfffffffcu + lm4;
+                        if (l1) { *q = (uint32_t)v1 * 0xfffffffcu + lm4; FS_PF_TRI(v1); }
                         q += l1;
-                        if (l2) *q = (uint32_t)v2 * 0xfffffffcu + lm4;
+                        if (l2) { *q = (uint32_t)v2 * 0xfffffffcu + lm4; FS_PF_TRI(v2); }
                         q += l2;
-                        if (l3) *q = (uint32_t)v3 * 0xfffffffcu + lm4;
+                        if (l3) { *q = (uint32_t)v3 * 0xfffffffcu + lm4; FS_PF_TRI(v3); }
+#undef FS_PF_TRI
                     }
                     k0 = l0 ? INF : k0; k1 = l1 ? INF : k1; k2 = l2 ? INF : k2; k3 = l3 ? INF : k3;
                     FS_CSWAP(k0, v0, k1, v1) FS_CSWAP(k2, v2, k3, v3) FS_CSWAP(k0, v0, k2, v2) FS_CSWAP(k1, v1, k3, v3) FS_CSWAP(k1, v1, k2, v2)
@@ -1025,8 +1039,11 @@ k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const 
                     if (COUNT) vc.tris++;
                     squeue[idx] = TQ_INVALID;
                     float t;
-                    if (fs_intersect_tri(fs_mk(ox, oy, oz), fs_mk(dx, dy, dz), fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z), fs_mk(c.x, c.y, c.z), t)
-                        && t <= bto) {
+                    const bool hit = fs_intersect_tri(fs_mk(ox, oy, oz), fs_mk(dx, dy, dz), fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z),
+                                                      fs_mk(c.x, c.y, c.z), t);
+                    if (ANY) {
+                        if (hit && t < bto) *(volatile unsigned long long*)(wkey + owner) = 0ull;      // occluded: any store wins
+                    } else if (hit && t <= bto) {
                         // merge into the owner's best: min over (t, ORIGINAL triangle id); ids are fetched only on a tie
                         const unsigned long long mine = ((unsigned long long)__float_as_uint(t) << 32) | tri;
                         unsigned long long old = *(volatile unsigned long long*)(wkey + owner);
@@ -1050,14 +1067,29 @@ k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const 
             if (lane == 0) *sqcount = 0u;
             qn = 0u;
             const unsigned long long kk = *(volatile unsigned long long*)(wkey + owner);
-            bt = __uint_as_float((uint32_t)(kk >> 32));
+            if (ANY) { if (running && kk != KEY_NONE) { s.node = TR_SENT; s.sp = 0; } }     // the owner's ray is occluded: stop walking
+            else bt = __uint_as_float((uint32_t)(kk >> 32));
             __syncwarp();
             // ---- retire finished rays (nothing of theirs is left in the queue): helpers first, then the owners whose
             // helpers are all done
             const bool fin = running && s.node == TR_SENT;
             if (fin && owner != lane) { atomicSub(whelp + owner, 1u); running = false; owner = lane; }
             __syncwarp();
-            if (fin && running && *(volatile uint32_t*)(whelp + lane) == 0u) {
+            const bool retire = fin && running && *(volatile uint32_t*)(whelp + lane) == 0u;
+            if (ANY) {
+                const bool conn = retire && kk == KEY_NONE;
+                const uint32_t mc = __ballot_sync(FULLM, conn);
+                if (mc) {                             // ballot-compacted append of the visible pairs
+                    uint32_t slot = 0;
+                    if (lane == 0) slot = atomicAdd(conn_count, (uint32_t)__popc(mc));
+                    slot = __shfl_sync(FULLM, slot, 0);
+                    if (conn) {
+                        conn_queue[slot + (uint32_t)__popc(mc & ((1u << lane) - 1u))] = j;
+                        if (dbg) dbg[j].connected = 1u;
+                    }
+                }
+                if (retire) running = false;
+            } else if (retire) {
                 hits[j] = make_float2(bt, __int_as_float((int)(uint32_t)kk));
                 running = false;
                 if (COUNT) { atomicMax(&dc->max_steps, ray_steps); atomicAdd(&dc->steps_hist[ray_steps / 8u < 15u ? ray_steps / 8u : 15u], 1u); }
@@ -1104,7 +1136,7 @@ k_trace_closest_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const 
             if (!exhausted && 32u - (uint32_t)__popc(m_run) >= REFILL_MIN) break;
         }
     }
-    if (COUNT) flush_counters(dc, vc);
+    if (COUNT) flush_counters(dc, vc, ANY);
 }
 
 // connection rays: (F.xyz, tmax) (dir.xyz, path id); unoccluded paths are appended to conn_queue
@@ -1472,7 +1504,7 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
     const fs_wave_buffers& wb = ctx->wb;
     static int occ_tr = 0, occ_any = 0, occ_tq = 0;
     if (!occ_tr) occ_tr = resident_ctas(k_trace_closest<COUNT, 2, true>, TR_THREADS, TR_SMEM_CLOSEST);
-    if (!occ_tq) occ_tq = resident_ctas(k_trace_closest_q<COUNT, 2>, TR_THREADS, TR_SMEM_TQ);
+    if (!occ_tq) occ_tq = resident_ctas(k_trace_q<COUNT, 2, false>, TR_THREADS, TR_SMEM_TQ);
     if (!occ_any) occ_any = resident_ctas(k_trace_any<COUNT, 2, true>, TR_THREADS, TR_SMEM_ANY);
     const bool timing = (tp.flags & FS_FLAG_TIME_KERNELS) != 0;
     cudaEvent_t* ev = nullptr;
@@ -1522,8 +1554,9 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
             k_trace_closest<COUNT, TEXV, WIDEV><<<grid_tr, TR_THREADS, TR_SMEM_CLOSEST, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u], \
                 wb.q_count + k, wb.q_cursor + k, wb.hit, ctx->d_counters, ctx->tune_refill, ctx->tune_node_min, ctx->tune_tri_min)
 #define FS_LAUNCH_TQ(TEXV)                                                                                             \
-            k_trace_closest_q<COUNT, TEXV><<<grid_tr, TR_THREADS, TR_SMEM_TQ, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u],   \
-                wb.q_count + k, wb.q_cursor + k, wb.hit, ctx->d_counters, ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush)
+            k_trace_q<COUNT, TEXV, false><<<grid_tr, TR_THREADS, TR_SMEM_TQ, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u],   \
+                wb.q_count + k, wb.q_cursor + k, wb.hit, nullptr, nullptr, nullptr, ctx->d_counters, ctx->tune_refill,           \
+                ctx->tune_tq_node_min, ctx->tune_tq_flush)
             if (use_tq) { if (texm >= 2) FS_LAUNCH_TQ(2); else FS_LAUNCH_TQ(0); }
             else if (wide) { if (texm >= 2) FS_LAUNCH_TRACE(2, true); else FS_LAUNCH_TRACE(0, true); }
             else { if (texm >= 2) FS_LAUNCH_TRACE(2, false); else FS_LAUNCH_TRACE(0, false); }
@@ -1539,7 +1572,7 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
     if (grid_cg > (uint32_t)ctx->sm_count * 8u) grid_cg = (uint32_t)ctx->sm_count * 8u;
     if (!grid_cg) grid_cg = 1;
     k_connect_gen<<<grid_cg, WF_THREADS, 0, st>>>(tp, wb, ctx->d_counters, d_dbg);
-    uint32_t grid_any = (uint32_t)(ctx->sm_count * occ_any);
+    uint32_t grid_any = (uint32_t)(ctx->sm_count * ((use_tq && ctx->tune_tq >= 2) ? occ_tq : occ_any));
     const uint32_t ctas_any = (tp.batch + TR_THREADS - 1) / TR_THREADS;
     if (grid_any > ctas_any) grid_any = ctas_any ? ctas_any : 1;
     {
@@ -1548,8 +1581,14 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
 #define FS_LAUNCH_ANY(TEXV, WIDEV)                                                                                     \
         k_trace_any<COUNT, TEXV, WIDEV><<<grid_any, TR_THREADS, TR_SMEM_ANY, st>>>(tp.bv, wb.st_pos[0], wb.st_nrm[0], wb.q_count + (D + 2), \
             wb.q_cursor + (D + 2), wb.conn_queue, wb.q_count + (D + 1), ctx->d_counters, d_dbg, ctx->tune_refill, ctx->tune_node_min)
-        if (wide) { if (tex) FS_LAUNCH_ANY(2, true); else FS_LAUNCH_ANY(0, true); }
+#define FS_LAUNCH_ANYQ(TEXV)                                                                                           \
+        k_trace_q<COUNT, TEXV, true><<<grid_any, TR_THREADS, TR_SMEM_TQ, st>>>(tp.bv, wb.st_pos[0], wb.st_nrm[0], wb.q_count + (D + 2), \
+            wb.q_cursor + (D + 2), nullptr, wb.conn_queue, wb.q_count + (D + 1), d_dbg, ctx->d_counters, ctx->tune_refill,       \
+            ctx->tune_tq_node_min, ctx->tune_tq_flush)
+        if (use_tq && ctx->tune_tq >= 2) { if (tex) FS_LAUNCH_ANYQ(2); else FS_LAUNCH_ANYQ(0); }
+        else if (wide) { if (tex) FS_LAUNCH_ANY(2, true); else FS_LAUNCH_ANY(0, true); }
         else { if (tex) FS_LAUNCH_ANY(2, false); else FS_LAUNCH_ANY(0, false); }
+#undef FS_LAUNCH_ANYQ
 #undef FS_LAUNCH_ANY
     }
     ctx->stats.kernel_launches += 2;
@@ -1616,7 +1655,7 @@ cudaError_t fs_wave_debug_rays(fs_ctx* ctx, const fs_trace_params& tp, const flo
             k_dbg_unpack_any<<<g, 256, 0, st>>>(conn, misc + 2, d_hit);
         } else {
 #define FS_DBG_CL(TEXV, WIDEV) k_trace_closest<false, TEXV, WIDEV><<<grid, TR_THREADS, TR_SMEM_CLOSEST, st>>>(tp.bv, ro, rd, misc, misc + 1, hits, ctx->d_counters, ctx->tune_refill, ctx->tune_node_min, ctx->tune_tri_min)
-#define FS_DBG_TQ(TEXV) k_trace_closest_q<false, TEXV><<<grid, TR_THREADS, TR_SMEM_TQ, st>>>(tp.bv, ro, rd, misc, misc + 1, hits, ctx->d_counters, ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush)
+#define FS_DBG_TQ(TEXV) k_trace_q<false, TEXV, false><<<grid, TR_THREADS, TR_SMEM_TQ, st>>>(tp.bv, ro, rd, misc, misc + 1, hits, nullptr, nullptr, nullptr, ctx->d_counters, ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush)
             if (wide && ctx->tune_tq && ctx->bvh.max_leaf == 1) { if (tex) FS_DBG_TQ(2); else FS_DBG_TQ(0); }
             else if (wide) { if (tex) FS_DBG_CL(2, true); else FS_DBG_CL(0, true); } else { if (tex) FS_DBG_CL(2, false); else FS_DBG_CL(0, false); }
 #undef FS_DBG_TQ

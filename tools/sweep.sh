@@ -1,8 +1,8 @@
 #!/bin/bash
-export FS_VERBOSE=1
-run() { echo "== $1"; python tools/profile_step.py 0 3 $2 $3 2>&1 | grep "rotation\|commit\|step 2" | cut -c1-110; python tools/profile_step.py 1 1 $2 $3 2>&1 | grep "step 0" | cut -c110-230; }
-for r in 0 3 8; do
-FS_TUNE_ROTATE=$r run "room rotate=$r" furnished_room 16
-FS_TUNE_ROTATE=$r run "hall rotate=$r" concert_hall 32
-FS_TUNE_ROTATE=$r run "tunnels rotate=$r" mine_tunnels 16
-done
+run() { echo "== $1"; python tools/profile_step.py 0 3 $2 $3 2>&1 | grep "step 2" | cut -c1-130; }
+run "room any phased" furnished_room 16
+FS_TUNE_TQ=2 run "room any queue" furnished_room 16
+run "hall any phased" concert_hall 32
+FS_TUNE_TQ=2 run "hall any queue" concert_hall 32
+run "tunnels any phased" mine_tunnels 16
+FS_TUNE_TQ=2 run "tunnels any queue" mine_tunnels 16
