@@ -1650,7 +1650,10 @@ cudaError_t fs_wave_debug_rays(fs_ctx* ctx, const fs_trace_params& tp, const flo
         if (grid > (uint32_t)ctx->sm_count * 5u) grid = (uint32_t)ctx->sm_count * 5u;
         if (d_hit) {
 #define FS_DBG_ANY(TEXV, WIDEV) k_trace_any<false, TEXV, WIDEV><<<grid, TR_THREADS, TR_SMEM_ANY, st>>>(tp.bv, ro, rd, misc, misc + 1, conn, misc + 2, ctx->d_counters, nullptr, ctx->tune_refill, ctx->tune_node_min)
-            if (wide) { if (tex) FS_DBG_ANY(2, true); else FS_DBG_ANY(0, true); } else { if (tex) FS_DBG_ANY(2, false); else FS_DBG_ANY(0, false); }
+#define FS_DBG_ANYQ(TEXV) k_trace_q<false, TEXV, true><<<grid, TR_THREADS, TR_SMEM_TQ, st>>>(tp.bv, ro, rd, misc, misc + 1, nullptr, conn, misc + 2, nullptr, ctx->d_counters, ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush)
+            if (wide && ctx->tune_tq >= 2 && ctx->bvh.max_leaf == 1) { if (tex) FS_DBG_ANYQ(2); else FS_DBG_ANYQ(0); }
+            else if (wide) { if (tex) FS_DBG_ANY(2, true); else FS_DBG_ANY(0, true); } else { if (tex) FS_DBG_ANY(2, false); else FS_DBG_ANY(0, false); }
+#undef FS_DBG_ANYQ
 #undef FS_DBG_ANY
             k_dbg_unpack_any<<<g, 256, 0, st>>>(conn, misc + 2, d_hit);
         } else {
