@@ -327,9 +327,20 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
     // with a tail of a few long rays on an almost empty GPU, and the other lane's kernels fill it.  Histogram sums are
     // integer atomics, so the result does not depend on how batches interleave.  Per-kernel timing (FS_FLAG_TIME_KERNELS)
     // and the debug record path run on one lane so that every kernel is timed alone.
-    const uint32_t cap_cfg = ctx->cfg.max_batch_paths;
+    uint32_t cap_cfg = ctx->cfg.max_batch_paths;
     uint32_t n_lanes = ctx->tune_streams;
     if ((ctx->cfg.flags & FS_FLAG_TIME_KERNELS) || d_dbg) n_lanes = 1;
+    if (ctx->cfg.flags & FS_FLAG_CONNECT_ALL) {
+        // up to (depth+1)^2 connection rays per pair: keep a batch's ray queue near 2^24 entries; ids are pair << 12 | s << 6 | t
+        if (max_depth > 63) return fail(ctx, FS_ERR_INVALID, "FS_FLAG_CONNECT_ALL: max_depth <= 63");
+        if (d_dbg) return fail(ctx, FS_ERR_INVALID, "FS_FLAG_CONNECT_ALL: no per-path debug records");
+        if (ctx->cfg.flags & (FS_FLAG_FUSED_EXTEND | FS_FLAG_BRUTE_FORCE)) return fail(ctx, FS_ERR_INVALID, "FS_FLAG_CONNECT_ALL needs the wavefront path");
+        uint32_t lim = (1u << 24) / ((max_depth + 1u) * (max_depth + 1u));
+        if (lim < 256u) lim = 256u;
+        if (lim > (1u << 20)) lim = 1u << 20;
+        if (cap_cfg > lim) cap_cfg = lim;
+        n_lanes = 1;
+    }
     while (n_lanes > 1 && g_count / n_lanes < (1u << 17)) --n_lanes;            // small jobs: not worth a second set of launches
     uint64_t n_batches = g_count ? (g_count + cap_cfg - 1) / cap_cfg : 1;
     if (n_batches < n_lanes) n_batches = n_lanes;

@@ -75,6 +75,11 @@ struct fs_wave_buffers {
     uint32_t* q_count;          // [max_depth+4]: [k] rays of bounce k, [D+1] connected pairs, [D+2] shadow rays
     uint32_t* q_cursor;         // [max_depth+4] work cursors of the persistent kernels
     uint32_t cap, depth_cap;
+    // FS_FLAG_CONNECT_ALL: node positions of every subpath and the (s, t) connection rays of a batch
+    float4* npos;               // [max_depth+1][2*cap]: position of node k >= 1 of subpath sp_id
+    float4 *all_o, *all_d;      // [all_cap] connection rays (F.xyz, tmax) (dir.xyz, bits(pair << 12 | (s-1) << 6 | (t-1)))
+    uint32_t* all_conn;         // [all_cap] ids of the visible connections
+    uint64_t all_cap;
 };
 
 struct fs_conv_source {

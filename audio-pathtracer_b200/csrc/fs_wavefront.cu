@@ -306,6 +306,20 @@ __device__ __forceinline__ void eval_seg_band(const fs_eval_params& ep, float bs
 // 8 lanes per connected path, one absorption band each (4 paths per warp): the walk over the node
 // records is uniform across the 8 lanes of a path, so SIMD efficiency no longer depends on the band
 // loop (the one-thread-per-path version ran at 8.9 of 32 lanes, profiles/r1e_summary.md).
+// position of node k of subpath sp (node 0 = the source / the listener); FS_FLAG_CONNECT_ALL only
+__device__ __forceinline__ fs_vec3 node_pos(const fs_trace_params& tp, const fs_wave_buffers& wb, uint32_t sp, uint32_t k, uint32_t stride)
+{
+    if (k == 0) {
+        if (sp & 1u) return fs_mk(tp.lis[0], tp.lis[1], tp.lis[2]);
+        const uint64_t g = tp.g_first + (sp >> 1);
+        const uint32_t s = (uint32_t)(g / tp.n_paths);
+        return fs_mk(__ldg(tp.src_pos + 3 * s), __ldg(tp.src_pos + 3 * s + 1), __ldg(tp.src_pos + 3 * s + 2));
+    }
+    const float4 v = wb.npos[(size_t)k * stride + sp];
+    return fs_mk(v.x, v.y, v.z);
+}
+
+template <bool ALL>
 __global__ void __launch_bounds__(WF_THREADS)
 k_eval(const fs_trace_params tp, const fs_wave_buffers wb, unsigned long long* __restrict__ hist,
        fs_dev_counters* __restrict__ dc, fs_path_dbg* __restrict__ dbg)
@@ -328,11 +342,18 @@ k_eval(const fs_trace_params tp, const fs_wave_buffers wb, unsigned long long* _
         uint32_t key = 0xffffffffu;
         size_t hidx = 0;
         if (valid) {
-            const uint32_t p = wb.conn_queue[j];
-            const float len = wb.conn_len[p];
+            // ALL: the queue entry names a prefix pair (pair << 12 | (s-1) << 6 | (t-1)); the path is F[0..s) ++ reverse(B[0..t)),
+            // its connecting segment is recomputed from the node positions, its weight is 1 / (s + t - 1)
+            const uint32_t id = ALL ? wb.all_conn[j] : wb.conn_queue[j];
+            const uint32_t p = ALL ? (id >> 12) : id;
             const uint32_t sf = 2u * p, sb = 2u * p + 1u;
-            const uint32_t nf = __float_as_uint(wb.end_pos[sf].w);
-            const uint32_t nb = __float_as_uint(wb.end_pos[sb].w);
+            const uint32_t nf = ALL ? ((id >> 6) & 63u) + 1u : __float_as_uint(wb.end_pos[sf].w);
+            const uint32_t nb = ALL ? (id & 63u) + 1u : __float_as_uint(wb.end_pos[sb].w);
+            float len;
+            if (ALL) {
+                const fs_vec3 dl = fs_sub(node_pos(tp, wb, sb, nb - 1u, stride), node_pos(tp, wb, sf, nf - 1u, stride));
+                len = sqrtf(fs_dot(dl, dl));
+            } else len = wb.conn_len[p];
             float E = 1.0f, total = 0.0f;
             float bs = 1.0f, P = 1.0f;                    // node 0 of the source subpath: no material, probability 1
             const float4* __restrict__ rf = wb.rec + sf;
@@ -377,6 +398,7 @@ k_eval(const fs_trace_params tp, const fs_wave_buffers wb, unsigned long long* _
             float e = E;
             e = (e < tp.energy_clamp) ? e : tp.energy_clamp;                      // SUB.cpp:410
             e = e * tp.energy_gain;                                               // SUB.cpp:413
+            if (ALL && nf + nb > 2u) e = e * (1.0f / (float)(nf + nb - 1u));      // one over the strategies of this path length
             q = (unsigned long long)(e * 4294967296.0f);                          // Q32.32
             hidx = ((size_t)s * NBr + b) * tp.n_bins + bin;
             key = (s * tp.n_bins + bin) * 8u + b;
@@ -492,6 +514,7 @@ k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_d
                     const float seg = sqrtf(fs_dot(dl, dl));
                     const uint32_t mat = __float_as_uint(nm.w);
                     wb.rec[(size_t)k * stride + sp_id] = make_float4(seg, __uint_as_float(mat), b.w, fs_pow(b.w, tp.ep.pdf_exponent));
+                    if (wb.npos) wb.npos[(size_t)k * stride + sp_id] = make_float4(pos.x, pos.y, pos.z, 0.0f);
                     nrm = fn;
                     nodes = k + 1;
                     if (k >= tp.max_depth) {      // PARAM: ray budget per subpath exhausted
@@ -1301,6 +1324,45 @@ k_connect_gen(const fs_trace_params tp, const fs_wave_buffers wb, fs_dev_counter
     }
 }
 
+// FS_FLAG_CONNECT_ALL: the connection ray of every prefix pair (s, t) of every path pair.  One thread per pair reserves
+// nf * nb queue slots; a pair closer than eps_connect is visible by definition and travels as a ray with tmax = 0 (no
+// triangle has t < 0), so every (s, t) has exactly one queue entry.
+__global__ void __launch_bounds__(WF_THREADS)
+k_connect_all_gen(const fs_trace_params tp, const fs_wave_buffers wb, fs_dev_counters* __restrict__ dc)
+{
+    const uint32_t qs = tp.max_depth + 2;
+    const uint32_t stride = 2u * wb.cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long ext = 0;
+        for (uint32_t k = 0; k < tp.max_depth; ++k) ext += wb.q_count[k];
+        atomicAdd(&dc->ext_rays, ext);
+    }
+    unsigned long long n_shadow = 0;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < tp.batch; p += gridDim.x * blockDim.x) {
+        const uint32_t nf = __float_as_uint(wb.end_pos[2u * p].w), nb = __float_as_uint(wb.end_pos[2u * p + 1u].w);
+        uint32_t o = atomicAdd(&wb.q_count[qs], nf * nb);
+        for (uint32_t s = 1; s <= nf; ++s) {
+            const fs_vec3 F = node_pos(tp, wb, 2u * p, s - 1u, stride);
+            for (uint32_t t = 1; t <= nb; ++t, ++o) {
+                const fs_vec3 B = node_pos(tp, wb, 2u * p + 1u, t - 1u, stride);
+                const fs_vec3 dl = fs_sub(B, F);
+                const float len = sqrtf(fs_dot(dl, dl));
+                float tmax = len - tp.eps_connect;                  // SUB.cpp:253
+                fs_vec3 dir = fs_mk(1.0f, 0.0f, 0.0f);
+                if (tmax > 0.0f) {
+                    const float inv = 1.0f / len;
+                    dir = fs_mk(dl.x * inv, dl.y * inv, dl.z * inv);
+                    ++n_shadow;
+                } else tmax = 0.0f;
+                wb.all_o[o] = make_float4(F.x, F.y, F.z, tmax);
+                wb.all_d[o] = make_float4(dir.x, dir.y, dir.z, __uint_as_float((p << 12) | ((s - 1u) << 6) | (t - 1u)));
+            }
+        }
+    }
+    for (int of = 16; of; of >>= 1) n_shadow += __shfl_xor_sync(0xffffffffu, n_shadow, of);
+    if (lane_id() == 0 && n_shadow) atomicAdd(&dc->shadow_rays, n_shadow);
+}
+
 // max_depth == 0: no ray is ever extended, both subpaths consist of node 0 only
 __global__ void k_init_ends(const fs_trace_params tp, const fs_wave_buffers wb)
 {
@@ -1420,6 +1482,14 @@ cudaError_t fs_wave_alloc(fs_ctx* ctx, uint32_t cap, uint32_t max_depth)
     if ((e = cudaMalloc(&wb->hit, sizeof(float2) * n2)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&wb->q_count, 4ull * (max_depth + 4))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&wb->q_cursor, 4ull * (max_depth + 4))) != cudaSuccess) return e;
+    if (ctx->cfg.flags & FS_FLAG_CONNECT_ALL) {
+        const uint64_t per = (uint64_t)(max_depth + 1) * (max_depth + 1);
+        wb->all_cap = (uint64_t)cap * per;
+        if ((e = cudaMalloc(&wb->npos, sizeof(float4) * n2 * (max_depth + 1ull))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&wb->all_o, sizeof(float4) * wb->all_cap)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&wb->all_d, sizeof(float4) * wb->all_cap)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&wb->all_conn, 4ull * wb->all_cap)) != cudaSuccess) return e;
+    }
     wb->cap = cap; wb->depth_cap = max_depth;
     return cudaSuccess;
 }
@@ -1429,6 +1499,7 @@ void fs_wave_free(fs_wave_buffers* wb)
     for (int i = 0; i < 2; ++i) { cudaFree(wb->st_pos[i]); cudaFree(wb->st_nrm[i]); }
     cudaFree(wb->rec); cudaFree(wb->end_pos); cudaFree(wb->conn_queue); cudaFree(wb->conn_len);
     cudaFree(wb->q_count); cudaFree(wb->q_cursor); cudaFree(wb->hit);
+    cudaFree(wb->npos); cudaFree(wb->all_o); cudaFree(wb->all_d); cudaFree(wb->all_conn);
     memset(wb, 0, sizeof(*wb));
 }
 
@@ -1485,7 +1556,7 @@ static cudaError_t launch_batch(fs_ctx* ctx, const fs_trace_params& tp, unsigned
     uint32_t grid_ev = (uint32_t)ctx->sm_count * 8u;
     const uint32_t ctas_ev = (tp.batch / 4u + WF_THREADS / 32 - 1) / (WF_THREADS / 32) + 1;
     if (grid_ev > ctas_ev) grid_ev = ctas_ev;
-    k_eval<<<grid_ev, WF_THREADS, 0, st>>>(tp, wb, d_hist, ctx->d_counters, d_dbg);
+    k_eval<false><<<grid_ev, WF_THREADS, 0, st>>>(tp, wb, d_hist, ctx->d_counters, d_dbg);
     ++ctx->stats.kernel_launches;
     if (timing) cudaEventRecord(ev[3], st);
     return cudaGetLastError();
@@ -1571,20 +1642,25 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
     uint32_t grid_cg = (tp.batch + WF_THREADS - 1) / WF_THREADS;
     if (grid_cg > (uint32_t)ctx->sm_count * 8u) grid_cg = (uint32_t)ctx->sm_count * 8u;
     if (!grid_cg) grid_cg = 1;
-    k_connect_gen<<<grid_cg, WF_THREADS, 0, st>>>(tp, wb, ctx->d_counters, d_dbg);
+    const bool all = (tp.flags & FS_FLAG_CONNECT_ALL) != 0;        // every prefix pair (s, t) instead of the two end points
+    if (all) k_connect_all_gen<<<grid_cg, WF_THREADS, 0, st>>>(tp, wb, ctx->d_counters);
+    else k_connect_gen<<<grid_cg, WF_THREADS, 0, st>>>(tp, wb, ctx->d_counters, d_dbg);
     uint32_t grid_any = (uint32_t)(ctx->sm_count * ((use_tq && ctx->tune_tq >= 2) ? occ_tq : occ_any));
     const uint32_t ctas_any = (tp.batch + TR_THREADS - 1) / TR_THREADS;
-    if (grid_any > ctas_any) grid_any = ctas_any ? ctas_any : 1;
+    if (!all && grid_any > ctas_any) grid_any = ctas_any ? ctas_any : 1;
+    const float4* any_o = all ? wb.all_o : wb.st_pos[0];
+    const float4* any_d = all ? wb.all_d : wb.st_nrm[0];
+    uint32_t* any_conn = all ? wb.all_conn : wb.conn_queue;
     {
         const bool wide = tp.bv.wnodes != nullptr;
         const bool tex = (wide ? tp.bv.wnodes_tex : tp.bv.nodes_tex) && ctx->tune_tex;
 #define FS_LAUNCH_ANY(TEXV, WIDEV)                                                                                     \
-        k_trace_any<COUNT, TEXV, WIDEV><<<grid_any, TR_THREADS, TR_SMEM_ANY, st>>>(tp.bv, wb.st_pos[0], wb.st_nrm[0], wb.q_count + (D + 2), \
-            wb.q_cursor + (D + 2), wb.conn_queue, wb.q_count + (D + 1), ctx->d_counters, d_dbg, ctx->tune_refill, ctx->tune_node_min)
+        k_trace_any<COUNT, TEXV, WIDEV><<<grid_any, TR_THREADS, TR_SMEM_ANY, st>>>(tp.bv, any_o, any_d, wb.q_count + (D + 2), \
+            wb.q_cursor + (D + 2), any_conn, wb.q_count + (D + 1), ctx->d_counters, all ? nullptr : d_dbg, ctx->tune_refill, ctx->tune_node_min)
 #define FS_LAUNCH_ANYQ(TEXV)                                                                                           \
-        k_trace_q<COUNT, TEXV, true><<<grid_any, TR_THREADS, TR_SMEM_TQ, st>>>(tp.bv, wb.st_pos[0], wb.st_nrm[0], wb.q_count + (D + 2), \
-            wb.q_cursor + (D + 2), nullptr, wb.conn_queue, wb.q_count + (D + 1), d_dbg, ctx->d_counters, ctx->tune_refill,       \
-            ctx->tune_tq_node_min, ctx->tune_tq_flush)
+        k_trace_q<COUNT, TEXV, true><<<grid_any, TR_THREADS, TR_SMEM_TQ, st>>>(tp.bv, any_o, any_d, wb.q_count + (D + 2),     \
+            wb.q_cursor + (D + 2), nullptr, any_conn, wb.q_count + (D + 1), all ? nullptr : d_dbg, ctx->d_counters,               \
+            ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush)
         if (use_tq && ctx->tune_tq >= 2) { if (tex) FS_LAUNCH_ANYQ(2); else FS_LAUNCH_ANYQ(0); }
         else if (wide) { if (tex) FS_LAUNCH_ANY(2, true); else FS_LAUNCH_ANY(0, true); }
         else { if (tex) FS_LAUNCH_ANY(2, false); else FS_LAUNCH_ANY(0, false); }
@@ -1595,8 +1671,9 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
     if (timing) cudaEventRecord(ev[2], st);
     uint32_t grid_ev = (uint32_t)ctx->sm_count * 8u;
     const uint32_t ctas_ev = (tp.batch / 4u + WF_THREADS / 32 - 1) / (WF_THREADS / 32) + 1;   // 4 paths per warp
-    if (grid_ev > ctas_ev) grid_ev = ctas_ev;
-    k_eval<<<grid_ev, WF_THREADS, 0, st>>>(tp, wb, d_hist, ctx->d_counters, d_dbg);
+    if (!all && grid_ev > ctas_ev) grid_ev = ctas_ev;
+    if (all) k_eval<true><<<grid_ev, WF_THREADS, 0, st>>>(tp, wb, d_hist, ctx->d_counters, nullptr);
+    else k_eval<false><<<grid_ev, WF_THREADS, 0, st>>>(tp, wb, d_hist, ctx->d_counters, d_dbg);
     ++ctx->stats.kernel_launches;
     if (timing) cudaEventRecord(ev[3], st);
     return cudaGetLastError();

@@ -52,6 +52,10 @@ typedef enum fs_status {
 #define FS_FLAG_SMEM_TREELET   4u   /* fused path only: stage the top BVH treelet in shared memory */
 #define FS_FLAG_BRUTE_FORCE    8u   /* test every triangle (debug/parity only, tiny scenes) */
 #define FS_FLAG_TIME_KERNELS  16u   /* CUDA events around each kernel class -> fs_stats.*_ms */
+#define FS_FLAG_CONNECT_ALL   64u   /* connect every source prefix s with every listener prefix t (the reference's
+                                       unfinished Is_NaiveConnections, SUB.cpp:508-535), each connected path evaluated like the
+                                       endpoint connection and weighted 1 / (s + t - 1); (1, 1) is the deterministic direct path.
+                                       Up to (depth+1)^2 connection rays per pair: batches shrink to ~2^24 / (depth+1)^2 pairs */
 #define FS_FLAG_FUSED_EXTEND  32u   /* A/B: fused RR+sample+traverse+shade kernel per bounce instead of the
                                        split shade/trace wavefront with per-lane ray replacement */
 

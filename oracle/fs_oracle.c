@@ -608,6 +608,65 @@ static inline void eval_segment(const fso_scene* sc, const fso_config* cfg, int3
     }
 }
 
+/* EvaluatePath over F[0..nf) ++ reverse(B[0..nb)) (SUB.cpp:259-267, 360-420), then AddEnergyAtDelay (COMP.h:87-91).
+ * `len` = length of the connecting segment F[nf-1] -> B[nb-1]; `weight` multiplies the clamped, gained energy
+ * (1 for the reference's endpoint connection). */
+static void splat_path(const fso_scene* sc, const fso_config* cfg, const pnode* fn, uint32_t nf, const pnode* bn, uint32_t nb,
+                       float len, float weight, uint64_t* hist_src, fso_path_dbg* dbg)
+{
+    float E[FSO_MAX_BANDS];
+    for (uint32_t b = 0; b < cfg->n_bands; ++b) E[b] = 1.0f;
+    float total = 0.0f;
+    for (uint32_t i = 0; i + 1 < nf; ++i)
+        eval_segment(sc, cfg, fn[i].mat, fn[i].prob, dist3(fn[i].p, fn[i + 1].p), &total, E);
+    eval_segment(sc, cfg, fn[nf - 1].mat, fn[nf - 1].prob, len, &total, E);
+    for (uint32_t j = nb - 1; j >= 1; --j)
+        eval_segment(sc, cfg, bn[j].mat, bn[j].prob, dist3(bn[j].p, bn[j - 1].p), &total, E);
+    float delay = total / cfg->sound_speed;       /* :419 */
+    /* AddEnergyAtDelay, COMP.h:87-91 */
+    float fb = floorf((delay * 1000.0f) / cfg->bin_ms);
+    int32_t bin;
+    if (!(fb >= 0.0f)) bin = 0;
+    else if (fb >= (float)(cfg->n_bins - 1)) bin = (int32_t)cfg->n_bins - 1;  /* late energy clamps */
+    else bin = (int32_t)fb;
+    for (uint32_t b = 0; b < cfg->n_bands; ++b) {
+        float e = E[b];
+        e = (e < cfg->energy_clamp) ? e : cfg->energy_clamp;   /* :410, NaN -> clamp */
+        e = e * cfg->energy_gain;                               /* :413 */
+        if (weight != 1.0f) e = e * weight;
+        uint64_t q = (uint64_t)(e * 4294967296.0f);             /* Q32.32, truncation */
+        hist_src[(uint64_t)b * cfg->n_bins + (uint32_t)bin] += q;
+        if (dbg) dbg->energy[b] = e;
+    }
+    if (dbg) { dbg->connected = 1; dbg->bin = bin; dbg->delay_s = delay; dbg->total_dist = total; }
+}
+
+/* all prefix connections.  Is_NaiveConnections (SUB.cpp:508-535) connects every forward prefix path
+ * with every backward prefix path through ConnectSubpaths; its MIS weights are unfinished (hard-coded pdf, SUB.cpp:537-597).
+ * Here: every (s, t), 1 <= s <= nf, 1 <= t <= nb, is connected with the visibility rule of SUB.cpp:252-257, evaluated
+ * exactly like the endpoint connection, and weighted 1 / (s + t - 1) = one over the number of (s', t') strategies that
+ * build a path of the same number of nodes.  (nf, nb) is the reference's connection, (1, 1) the direct path. */
+static void connect_all(const fso_scene* sc, const fso_config* cfg, const pnode* fn, uint32_t nf, const pnode* bn, uint32_t nb,
+                        uint64_t* hist_src, fso_stats* st, ocount* cnt)
+{
+    for (uint32_t s = 1; s <= nf; ++s)
+        for (uint32_t t = 1; t <= nb; ++t) {
+            const pnode* F = &fn[s - 1];
+            const pnode* Bn = &bn[t - 1];
+            float dl[3] = {Bn->p[0] - F->p[0], Bn->p[1] - F->p[1], Bn->p[2] - F->p[2]};
+            float len = sqrtf(dot3(dl, dl));
+            float tmax = len - cfg->eps_connect;
+            if (tmax > 0.0f) {
+                float inv = 1.0f / len;
+                float dir[3] = {dl[0] * inv, dl[1] * inv, dl[2] * inv};
+                st->shadow_rays++;
+                if (any_hit_cnt(sc, F->p, dir, tmax, cnt)) continue;
+            }
+            st->connected++;
+            splat_path(sc, cfg, fn, s, bn, t, len, 1.0f / (float)(s + t - 1u), hist_src, NULL);
+        }
+}
+
 static void trace_one(const fso_scene* sc, const fso_config* cfg, const float* src, const float* lis,
                       uint64_t g, uint32_t max_depth, uint64_t seed, pnode* fn, pnode* bn,
                       uint64_t* hist_src, fso_stats* st, ocount* cnt, fso_path_dbg* dbg)
@@ -618,6 +677,10 @@ static void trace_one(const fso_scene* sc, const fso_config* cfg, const float* s
     uint32_t nb = gen_subpath(sc, cfg, lis, g, 1u, max_depth, seed, bn, &rays, cnt);
     st->ext_rays += rays;
     st->paths++;
+    if (cfg->reserved[1] & FSO_FLAG_CONNECT_ALL) {           /* fs_config.flags lives in reserved[1] */
+        connect_all(sc, cfg, fn, nf, bn, nb, hist_src, st, cnt);
+        return;
+    }
     /* ConnectSubpaths, SUB.cpp:235-277: one visibility test between the two LAST nodes */
     const pnode* F = &fn[nf - 1];
     const pnode* Bn = &bn[nb - 1];
@@ -638,31 +701,7 @@ static void trace_one(const fso_scene* sc, const fso_config* cfg, const float* s
     }
     if (occluded) return;
     st->connected++;
-    /* EvaluatePath over F nodes ++ reverse(B nodes), SUB.cpp:259-267, 360-420 */
-    float E[FSO_MAX_BANDS];
-    for (uint32_t b = 0; b < cfg->n_bands; ++b) E[b] = 1.0f;
-    float total = 0.0f;
-    for (uint32_t i = 0; i + 1 < nf; ++i)
-        eval_segment(sc, cfg, fn[i].mat, fn[i].prob, dist3(fn[i].p, fn[i + 1].p), &total, E);
-    eval_segment(sc, cfg, F->mat, F->prob, len, &total, E);
-    for (uint32_t j = nb - 1; j >= 1; --j)
-        eval_segment(sc, cfg, bn[j].mat, bn[j].prob, dist3(bn[j].p, bn[j - 1].p), &total, E);
-    float delay = total / cfg->sound_speed;       /* :419 */
-    /* AddEnergyAtDelay, COMP.h:87-91 */
-    float fb = floorf((delay * 1000.0f) / cfg->bin_ms);
-    int32_t bin;
-    if (!(fb >= 0.0f)) bin = 0;
-    else if (fb >= (float)(cfg->n_bins - 1)) bin = (int32_t)cfg->n_bins - 1;  /* late energy clamps */
-    else bin = (int32_t)fb;
-    for (uint32_t b = 0; b < cfg->n_bands; ++b) {
-        float e = E[b];
-        e = (e < cfg->energy_clamp) ? e : cfg->energy_clamp;   /* :410, NaN -> clamp */
-        e = e * cfg->energy_gain;                               /* :413 */
-        uint64_t q = (uint64_t)(e * 4294967296.0f);             /* Q32.32, truncation */
-        hist_src[(uint64_t)b * cfg->n_bins + (uint32_t)bin] += q;
-        if (dbg) dbg->energy[b] = e;
-    }
-    if (dbg) { dbg->connected = 1; dbg->bin = bin; dbg->delay_s = delay; dbg->total_dist = total; }
+    splat_path(sc, cfg, fn, nf, bn, nb, len, 1.0f, hist_src, dbg);
 }
 
 typedef struct {

@@ -52,8 +52,9 @@ typedef struct fso_config {
     uint32_t conv_block;       /* 1024 (Config/DefaultEngine.ini:15) */
     uint32_t conv_clamp;       /* 1 = clamp output to +-1 (REV.cpp:162-168) */
     float    conv_wet;         /* MixAlpha = 1 (REV.cpp:161) */
-    uint32_t reserved[3];
+    uint32_t reserved[3];      /* fs_config: max_batch_paths, flags, device; the oracle reads flags & FSO_FLAG_CONNECT_ALL */
 } fso_config;
+#define FSO_FLAG_CONNECT_ALL 64u   /* all prefix connections, weight 1/(s+t-1) */
 
 typedef struct fso_stats {
     uint64_t paths;            /* path pairs processed */

@@ -139,6 +139,9 @@ def ref_lib():
     return _ref
 
 
+FLAG_CONNECT_ALL = 64
+
+
 def default_config(**over):
     cfg = Config()
     lib().fso_default_config(C.byref(cfg))
@@ -146,6 +149,8 @@ def default_config(**over):
         if k == "air_absorption":
             for i, a in enumerate(v):
                 cfg.air_absorption[i] = a
+        elif k == "flags":                                   # fs_config.flags lives in reserved[1]
+            cfg.reserved[1] = int(v)
         else:
             setattr(cfg, k, v)
     return cfg

@@ -243,3 +243,24 @@ def test_batch_lanes_and_batch_splits_are_bit_exact(fs, oracle, shoebox):
         assert np.array_equal(h, ho), "env=%r over=%r" % (env, over)
         assert np.array_equal(h2, ho)
         assert [st["ext_rays"], st["shadow_rays"], st["connected"]] == [so["ext_rays"], so["shadow_rays"], so["connected"]]
+
+
+def test_connect_all_prefixes_bit_exact(fs, oracle, shoebox, room):
+    """FS_FLAG_CONNECT_ALL: every prefix pair connected, weight 1 / (s + t - 1); bit-exact against
+    the oracle, through both connection-ray kernels, with batch splits, and for the counters"""
+    from frequensee import capi
+    ALL = capi.FLAG_CONNECT_ALL
+    for sc, n, depth, use_bvh in ((shoebox, 4096, 8, False), (room, 1500, 16, True), (shoebox, 777, 0, False), (shoebox, 300, 33, False)):
+        S = oracle.Scene(sc.verts, sc.tri_mat, sc.absorption, use_bvh=use_bvh)
+        ho, so = S.trace(oracle.default_config(flags=oracle.FLAG_CONNECT_ALL), sc.sources[:1], sc.listener, n, depth, 13, n_threads=16)
+        for env, over in (({}, {}), ({"FS_TUNE_TQ": 0}, {}), ({}, {"max_batch_paths": 500}), ({}, {"flags": ALL | capi.FLAG_COUNT_VISITS})):
+            with _env(**env):
+                ctx = _ctx(fs, sc, **dict({"flags": ALL}, **over))
+            with ctx:
+                h = ctx.trace(sc.sources[:1], sc.listener, n, depth, 13)
+                st = ctx.stats()
+            assert np.array_equal(h, ho), "n=%d depth=%d env=%r over=%r" % (n, depth, env, over)
+            assert [st["ext_rays"], st["shadow_rays"], st["connected"]] == [so["ext_rays"], so["shadow_rays"], so["connected"]]
+    with _ctx(fs, shoebox, flags=ALL) as ctx:
+        with pytest.raises(fs.FrequenSeeError):
+            ctx.trace(shoebox.sources, shoebox.listener, 64, 64, 1)              # depth > 63 does not fit the (s, t) ids

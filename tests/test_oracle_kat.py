@@ -258,3 +258,30 @@ def test_per_band_ir_single_bin_kat(oracle):
     for c in range(cfg.n_channels):
         assert np.allclose(ir[c], exp * car[c, 5], rtol=1e-6, atol=1e-9)
     assert np.count_nonzero(ir[0, :4800]) == 0 and np.count_nonzero(ir[0, 4896:]) == 0
+
+
+def test_connect_all_prefixes_kats(oracle):
+    """SURVEY 8f rank 1 (FLAG_CONNECT_ALL): every prefix pair (s, t) is connected, weight 1 / (s + t - 1)"""
+    from frequensee import scenes
+    ALL = oracle.FLAG_CONNECT_ALL
+    # free field: every ray misses, both subpaths are their node 0 -> only (1, 1): identical to the endpoint mode
+    e = np.zeros((0, 3, 3), np.float32)
+    S0 = oracle.Scene(e, np.zeros(0, np.uint32), np.full((1, 8), 0.5, np.float32), use_bvh=False)
+    a, _ = S0.trace(oracle.default_config(), [[1, 2, 3]], [4, 6, 3], 64, 8, 7)
+    b, sb = S0.trace(oracle.default_config(flags=ALL), [[1, 2, 3]], [4, 6, 3], 64, 8, 7)
+    assert np.array_equal(a, b) and sb["connected"] == 64
+    # depth 0: no extension at all -> the deterministic direct path, once per pair
+    sc = scenes.shoebox()
+    S = oracle.Scene(sc.verts, sc.tri_mat, sc.absorption, use_bvh=False)
+    d0, _ = S.trace(oracle.default_config(), sc.sources, sc.listener, 256, 0, 3)
+    d0a, _ = S.trace(oracle.default_config(flags=ALL), sc.sources, sc.listener, 256, 0, 3)
+    assert np.array_equal(d0, d0a) and np.count_nonzero(d0) == 8
+    # the direct path is in every pair's set of connections: its bin holds at least N times the direct energy
+    h, st = S.trace(oracle.default_config(flags=ALL), sc.sources, sc.listener, 256, 6, 3, n_threads=4)
+    k = int(np.flatnonzero(d0[0, 0])[0])
+    assert h[0, 0, k] >= d0[0, 0, k] and st["connected"] > 256 and st["shadow_rays"] >= st["connected"]
+    # order / thread / shard invariance (integer sums)
+    h1, _ = S.trace(oracle.default_config(flags=ALL), sc.sources, sc.listener, 256, 6, 3, n_threads=1)
+    ha, _ = S.trace(oracle.default_config(flags=ALL), sc.sources, sc.listener, 256, 6, 3, g_first=0, g_count=100)
+    hb, _ = S.trace(oracle.default_config(flags=ALL), sc.sources, sc.listener, 256, 6, 3, g_first=100, g_count=156)
+    assert np.array_equal(h, h1) and np.array_equal(h, ha + hb)
