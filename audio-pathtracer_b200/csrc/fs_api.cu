@@ -135,6 +135,7 @@ void fs_destroy(fs_ctx* ctx)
     cudaDeviceSynchronize();
     fs_conv_teardown(ctx);
     cudaFree(ctx->d_carriers); cudaFree(ctx->d_amp_bands); cudaFree(ctx->d_amp_all);
+    cudaFree(ctx->lis_rec); cudaFree(ctx->lis_end);
     fs_wave_free(&ctx->wb);
     for (int l = 0; l < FS_MAX_LANES - 1; ++l) {
         fs_wave_free(&ctx->lanes[l].wb);
@@ -330,6 +331,8 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
     uint32_t cap_cfg = ctx->cfg.max_batch_paths;
     uint32_t n_lanes = ctx->tune_streams;
     if ((ctx->cfg.flags & FS_FLAG_TIME_KERNELS) || d_dbg) n_lanes = 1;
+    if ((ctx->cfg.flags & FS_FLAG_SHARE_LISTENER) && (ctx->cfg.flags & (FS_FLAG_FUSED_EXTEND | FS_FLAG_BRUTE_FORCE)))
+        return fail(ctx, FS_ERR_INVALID, "FS_FLAG_SHARE_LISTENER needs the wavefront path");
     if (ctx->cfg.flags & FS_FLAG_CONNECT_ALL) {
         // up to (depth+1)^2 connection rays per pair: keep a batch's ray queue near 2^24 entries; ids are pair << 12 | s << 6 | t
         if (max_depth > 63) return fail(ctx, FS_ERR_INVALID, "FS_FLAG_CONNECT_ALL: max_depth <= 63");
@@ -358,6 +361,25 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     ctx->kev_used = 0; ctx->tev_used = 0; ctx->stats.extend_launches = 0;
     CK(fs_wave_reset_counters(ctx));
+    // FS_FLAG_SHARE_LISTENER with more than one source's worth of work: trace the n_paths listener subpaths once, now, and
+    // let every source batch copy them in (smaller jobs just use the shared keying and trace them in place)
+    if ((ctx->cfg.flags & FS_FLAG_SHARE_LISTENER) && !(ctx->cfg.flags & FS_FLAG_CONNECT_ALL) && !d_dbg && n_sources > 1 &&
+        g_count > n_paths && max_depth > 0 && !(ctx->cfg.flags & (FS_FLAG_FUSED_EXTEND | FS_FLAG_BRUTE_FORCE))) {
+        if (ctx->lis_cache_n < n_paths || ctx->lis_cache_depth < max_depth) {
+            cudaFree(ctx->lis_rec); cudaFree(ctx->lis_end); ctx->lis_rec = ctx->lis_end = nullptr; ctx->lis_cache_n = 0;
+            CK(cudaMalloc(&ctx->lis_rec, sizeof(float4) * (size_t)n_paths * (max_depth + 1ull)));
+            CK(cudaMalloc(&ctx->lis_end, sizeof(float4) * (size_t)n_paths));
+            ctx->lis_cache_n = n_paths; ctx->lis_cache_depth = max_depth;
+        }
+        tp.lis_rec = ctx->lis_rec; tp.lis_end = ctx->lis_end;
+        tp.lis_mode = 1;
+        for (uint64_t i0 = 0; i0 < n_paths; i0 += cap) {
+            tp.g_first = i0;
+            tp.batch = (uint32_t)(n_paths - i0 < cap ? n_paths - i0 : cap);
+            CK(fs_wave_trace_batch(ctx, tp, d_hist, nullptr));
+        }
+        tp.lis_mode = 2;
+    }
     if (n_lanes > 1) {
         CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
         for (uint32_t l = 1; l < n_lanes; ++l) CK(cudaStreamWaitEvent(ctx->lanes[l - 1].stream, ctx->ev_fork, 0));

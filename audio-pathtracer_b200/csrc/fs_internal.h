@@ -62,6 +62,11 @@ struct fs_trace_params {
     const float* src_pos;       // device [S][3]
     float lis[3];
     uint32_t flags;
+    // FS_FLAG_SHARE_LISTENER: 0 = both subpaths traced; 1 = listener pass (only side 1 is traced, then stored in the cache);
+    // 2 = source pass (only side 0 is traced, side 1 is loaded from the cache before the connection)
+    uint32_t lis_mode;
+    float4* lis_rec;            // cache [max_depth+1][n_paths]: node records of listener subpath i
+    float4* lis_end;            // cache [n_paths]: (end.xyz, bits(n_nodes))
 };
 
 struct fs_wave_buffers {
@@ -113,6 +118,7 @@ struct fs_ctx {
     // extra batch lanes: while one batch's traversal launch drains its slowest rays, the other lane's kernels fill the SMs
     struct lane_t { cudaStream_t stream; fs_wave_buffers wb; cudaEvent_t done; } lanes[FS_MAX_LANES - 1];
     cudaEvent_t ev_fork; uint32_t tune_streams;
+    float4 *lis_rec, *lis_end; uint64_t lis_cache_n; uint32_t lis_cache_depth;   // FS_FLAG_SHARE_LISTENER cache
     unsigned long long* d_hist; uint32_t hist_sources;   // [S][B][K]
     uint64_t hist_n_paths;
     fs_dev_counters* d_counters;

@@ -487,6 +487,7 @@ k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_d
             uint32_t nodes = 1;
             if (k == 0) {                         // node 0 (SUB.cpp:287-291)
                 sp_id = j;
+                if (tp.lis_mode && (sp_id & 1u) == tp.lis_mode - 1u) cont = false;   // shared listener: this side is not traced in this pass
                 if (sp_id & 1u) pos = fs_mk(tp.lis[0], tp.lis[1], tp.lis[2]);
                 else {
                     const uint64_t g0 = tp.g_first + (sp_id >> 1);
@@ -524,7 +525,8 @@ k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_d
                 }
             }
             if (cont) {
-                const uint64_t g = tp.g_first + (sp_id >> 1);
+                uint64_t g = tp.g_first + (sp_id >> 1);
+                if ((tp.flags & FS_FLAG_SHARE_LISTENER) && (sp_id & 1u)) g %= tp.n_paths;   // listener stream keyed by the path index only
                 uint32_t r[4];
                 fs_philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), k, sp_id & 1u, tp.seed_lo, tp.seed_hi, r);
                 const float u0 = fs_u01(r[0]), u1 = fs_u01(r[1]), u2 = fs_u01(r[2]);
@@ -1363,6 +1365,36 @@ k_connect_all_gen(const fs_trace_params tp, const fs_wave_buffers wb, fs_dev_cou
     if (lane_id() == 0 && n_shadow) atomicAdd(&dc->shadow_rays, n_shadow);
 }
 
+// FS_FLAG_SHARE_LISTENER: the listener subpaths of a call are traced once (lis_mode 1), kept as [D+1][n_paths] records +
+// end points, and copied into the side-1 slots of every source batch (lis_mode 2) before its connection stage
+__global__ void k_lis_store(const fs_trace_params tp, const fs_wave_buffers wb, fs_dev_counters* __restrict__ dc)
+{
+    const uint32_t stride = 2u * wb.cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long ext = 0;
+        for (uint32_t k = 0; k < tp.max_depth; ++k) ext += wb.q_count[k];
+        atomicAdd(&dc->ext_rays, ext);
+    }
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < tp.batch; p += gridDim.x * blockDim.x) {
+        const uint64_t i = tp.g_first + p;
+        const float4 e = wb.end_pos[2u * p + 1u];
+        tp.lis_end[i] = e;
+        const uint32_t n = __float_as_uint(e.w);
+        for (uint32_t k = 1; k < n; ++k) tp.lis_rec[(size_t)k * tp.n_paths + i] = wb.rec[(size_t)k * stride + 2u * p + 1u];
+    }
+}
+__global__ void k_lis_load(const fs_trace_params tp, const fs_wave_buffers wb)
+{
+    const uint32_t stride = 2u * wb.cap;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < tp.batch; p += gridDim.x * blockDim.x) {
+        const uint64_t i = (tp.g_first + p) % tp.n_paths;
+        const float4 e = tp.lis_end[i];
+        wb.end_pos[2u * p + 1u] = e;
+        const uint32_t n = __float_as_uint(e.w);
+        for (uint32_t k = 1; k < n; ++k) wb.rec[(size_t)k * stride + 2u * p + 1u] = tp.lis_rec[(size_t)k * tp.n_paths + i];
+    }
+}
+
 // max_depth == 0: no ray is ever extended, both subpaths consist of node 0 only
 __global__ void k_init_ends(const fs_trace_params tp, const fs_wave_buffers wb)
 {
@@ -1642,6 +1674,13 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
     uint32_t grid_cg = (tp.batch + WF_THREADS - 1) / WF_THREADS;
     if (grid_cg > (uint32_t)ctx->sm_count * 8u) grid_cg = (uint32_t)ctx->sm_count * 8u;
     if (!grid_cg) grid_cg = 1;
+    if (tp.lis_mode == 1) {                       // listener pass: keep the subpaths, no connection
+        k_lis_store<<<grid_cg, WF_THREADS, 0, st>>>(tp, wb, ctx->d_counters);
+        ++ctx->stats.kernel_launches;
+        if (timing) { cudaEventRecord(ev[2], st); cudaEventRecord(ev[3], st); }
+        return cudaGetLastError();
+    }
+    if (tp.lis_mode == 2) { k_lis_load<<<grid_cg, WF_THREADS, 0, st>>>(tp, wb); ++ctx->stats.kernel_launches; }
     const bool all = (tp.flags & FS_FLAG_CONNECT_ALL) != 0;        // every prefix pair (s, t) instead of the two end points
     if (all) k_connect_all_gen<<<grid_cg, WF_THREADS, 0, st>>>(tp, wb, ctx->d_counters);
     else k_connect_gen<<<grid_cg, WF_THREADS, 0, st>>>(tp, wb, ctx->d_counters, d_dbg);

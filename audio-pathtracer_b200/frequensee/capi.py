@@ -17,6 +17,7 @@ FS_OK = 0
 FS_ERR_INVALID, FS_ERR_CUDA, FS_ERR_NOMEM, FS_ERR_STATE, FS_ERR_OVERFLOW = -1, -2, -3, -4, -5
 FLAG_COUNT_VISITS, FLAG_NO_SPLAT_AGG, FLAG_SMEM_TREELET, FLAG_BRUTE_FORCE, FLAG_TIME_KERNELS, FLAG_FUSED_EXTEND = 1, 2, 4, 8, 16, 32
 FLAG_CONNECT_ALL = 64
+FLAG_SHARE_LISTENER = 128
 
 # every symbol include/frequensee.h declares (tests/test_abi.py checks the library exports them all)
 ABI_SYMBOLS = [

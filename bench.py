@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--sources", type=int, default=1,
                     help="emitters (BASELINE configs[3]: 64 in the mine tunnels); --paths stays the path pairs per GPU per step, "
                          "split evenly over the sources")
+    ap.add_argument("--share-listener", action="store_true",
+                    help="FS_FLAG_SHARE_LISTENER: listener subpaths keyed by the path index, traced once per update and shared "
+                         "by all sources (SURVEY 8f rank 4; different random numbers than the default mode)")
     ap.add_argument("--cpu-sample-paths", type=int, default=1 << 19)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -57,6 +60,7 @@ def config_dict(args, n):
     return {"workload": wl, "scene": "%s (seeded procedural)" % args.scene, "paths_per_gpu_per_step": args.paths,
             "max_depth": args.depth, "bands": 8, "bins": 1000, "sources": args.sources, "rr_prob": 0.9,
             "parallelism": "path-range sharding x%d, replicated BVH, one int64 reduce" % n,
+            "share_listener": bool(args.share_listener),
             "l2": "no explicit flush: per-step wavefront state+records (~0.6 GB) exceed the 126 MB L2; "
                   "the ~11 MB BVH is L2-resident by design, as in steady-state 60 Hz refresh"}
 
@@ -145,7 +149,7 @@ def cpu_oracle_rate(args, n_paths, threads, repeats=1, seed=SEED0):
     sc = scenes.by_name(args.scene)
     sc.sources = sc.sources[:args.sources]
     S = po.Scene(sc.verts, sc.tri_mat, sc.absorption, use_bvh=True)
-    cfg = po.default_config()
+    cfg = po.default_config(flags=po.FLAG_SHARE_LISTENER) if args.share_listener else po.default_config()
     times = []
     for r in range(repeats):
         t0 = time.perf_counter()
@@ -209,7 +213,8 @@ def run_b200(args):
     NS_ = len(sc.sources)
     if P * N % NS_:
         raise SystemExit("--paths x --gpus must be a multiple of --sources")
-    ctx = fs.Context(device=local)                          # production configuration: no per-kernel events, batch lanes on
+    base_flags = capi.FLAG_SHARE_LISTENER if args.share_listener else 0
+    ctx = fs.Context(device=local, flags=base_flags)        # production configuration: no per-kernel events, batch lanes on
     ctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
     stream = torch.cuda.Stream()                            # a real (non-NULL) stream: the C-ABI treats NULL as "own stream"
     torch.cuda.set_stream(stream)
@@ -262,7 +267,7 @@ def run_b200(args):
     # per-kernel-class device time: the same steps (same seeds) re-run on a second context with FS_FLAG_TIME_KERNELS,
     # i.e. CUDA events on the launching stream around every stage and every k_trace_closest launch.  That context runs
     # its batches on ONE lane, so each kernel is timed alone (in the headline run two batch lanes overlap their kernels).
-    tctx = fs.Context(device=local, flags=capi.FLAG_TIME_KERNELS)
+    tctx = fs.Context(device=local, flags=capi.FLAG_TIME_KERNELS | base_flags)
     tctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
     tctx.set_stream(stream.cuda_stream)
     per = []
@@ -280,7 +285,7 @@ def run_b200(args):
     connected = float(np.mean([s["connected"] for s in per]))
 
     # algorithmic bytes: visit counts of the same rays from the instrumented build of the same kernels
-    cctx = fs.Context(device=local, flags=capi.FLAG_COUNT_VISITS)
+    cctx = fs.Context(device=local, flags=capi.FLAG_COUNT_VISITS | base_flags)
     cctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
     cnt = []
     for k in range(min(K, 2)):

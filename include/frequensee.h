@@ -56,6 +56,10 @@ typedef enum fs_status {
                                        unfinished Is_NaiveConnections, SUB.cpp:508-535), each connected path evaluated like the
                                        endpoint connection and weighted 1 / (s + t - 1); (1, 1) is the deterministic direct path.
                                        Up to (depth+1)^2 connection rays per pair: batches shrink to ~2^24 / (depth+1)^2 pairs */
+#define FS_FLAG_SHARE_LISTENER 128u  /* the listener subpath of pair (source, i) is keyed by i only, so all
+                                       sources of a multi-emitter update share one set of listener subpaths, traced once per
+                                       fs_trace call (the reference regenerates it per source, SUB.cpp:215-230: different
+                                       random numbers, hence a separate mode).  Nearly halves the rays of BASELINE configs[3] */
 #define FS_FLAG_FUSED_EXTEND  32u   /* A/B: fused RR+sample+traverse+shade kernel per bounce instead of the
                                        split shade/trace wavefront with per-lane ray replacement */
 

@@ -668,13 +668,17 @@ static void connect_all(const fso_scene* sc, const fso_config* cfg, const pnode*
 }
 
 static void trace_one(const fso_scene* sc, const fso_config* cfg, const float* src, const float* lis,
-                      uint64_t g, uint32_t max_depth, uint64_t seed, pnode* fn, pnode* bn,
+                      uint64_t g, uint64_t n_paths, uint32_t max_depth, uint64_t seed, pnode* fn, pnode* bn,
                       uint64_t* hist_src, fso_stats* st, ocount* cnt, fso_path_dbg* dbg)
 {
     uint64_t rays = 0;
     /* GenerateFullPaths, SUB.cpp:215-230: forward from the source, backward from the listener */
     uint32_t nf = gen_subpath(sc, cfg, src, g, 0u, max_depth, seed, fn, &rays, cnt);
-    uint32_t nb = gen_subpath(sc, cfg, lis, g, 1u, max_depth, seed, bn, &rays, cnt);
+    /* with FSO_FLAG_SHARE_LISTENER the listener subpath of pair (source, i) depends on i only (its
+     * Philox stream is keyed by i = g mod n_paths), so the sources of a multi-emitter update share it.  The reference
+     * regenerates it per (source, i) (SUB.cpp:215-230): a separate mode because the results differ. */
+    const uint64_t gl = (cfg->reserved[1] & FSO_FLAG_SHARE_LISTENER) ? g % n_paths : g;
+    uint32_t nb = gen_subpath(sc, cfg, lis, gl, 1u, max_depth, seed, bn, &rays, cnt);
     st->ext_rays += rays;
     st->paths++;
     if (cfg->reserved[1] & FSO_FLAG_CONNECT_ALL) {           /* fs_config.flags lives in reserved[1] */
@@ -727,7 +731,7 @@ static void* worker_main(void* arg)
         for (uint64_t i = lo; i < hi; ++i) {
             uint64_t g = w->g_first + i;
             uint32_t s = (uint32_t)(g / w->n_paths);
-            trace_one(w->sc, cfg, w->src_pos + 3 * s, w->lis_pos, g, w->max_depth, w->seed, fn, bn,
+            trace_one(w->sc, cfg, w->src_pos + 3 * s, w->lis_pos, g, w->n_paths, w->max_depth, w->seed, fn, bn,
                       w->h + (uint64_t)s * cfg->n_bands * cfg->n_bins, &w->st, &w->cnt,
                       w->dbg ? w->dbg + i : NULL);
         }

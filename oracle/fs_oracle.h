@@ -54,6 +54,7 @@ typedef struct fso_config {
     float    conv_wet;         /* MixAlpha = 1 (REV.cpp:161) */
     uint32_t reserved[3];      /* fs_config: max_batch_paths, flags, device; the oracle reads flags & FSO_FLAG_CONNECT_ALL */
 } fso_config;
+#define FSO_FLAG_SHARE_LISTENER 128u /* listener subpath keyed by the path index only: shared by all sources */
 #define FSO_FLAG_CONNECT_ALL 64u   /* all prefix connections, weight 1/(s+t-1) */
 
 typedef struct fso_stats {

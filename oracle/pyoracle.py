@@ -140,6 +140,7 @@ def ref_lib():
 
 
 FLAG_CONNECT_ALL = 64
+FLAG_SHARE_LISTENER = 128
 
 
 def default_config(**over):

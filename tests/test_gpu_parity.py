@@ -264,3 +264,36 @@ def test_connect_all_prefixes_bit_exact(fs, oracle, shoebox, room):
     with _ctx(fs, shoebox, flags=ALL) as ctx:
         with pytest.raises(fs.FrequenSeeError):
             ctx.trace(shoebox.sources, shoebox.listener, 64, 64, 1)              # depth > 63 does not fit the (s, t) ids
+
+
+def test_shared_listener_subpaths_bit_exact(fs, oracle, shoebox, room):
+    """FS_FLAG_SHARE_LISTENER (SURVEY 8f rank 4): listener subpaths keyed by the path index only and traced once per call;
+    same integers as the oracle (which regenerates them per source with the same keying), fewer rays"""
+    from frequensee import capi
+    SH = capi.FLAG_SHARE_LISTENER
+    srcs = np.array([[1.5, 1.2, 1.0], [3.0, 2.0, 1.5], [5.5, 4.0, 2.0], [2.0, 4.2, 0.8]], np.float32)
+    S = oracle.Scene(shoebox.verts, shoebox.tri_mat, shoebox.absorption, use_bvh=False)
+    cfgo = oracle.default_config(flags=oracle.FLAG_SHARE_LISTENER)
+    n = 3000
+    ho, so = S.trace(cfgo, srcs, shoebox.listener, n, 8, 17, n_threads=16)
+    h_plain, _ = S.trace(oracle.default_config(), srcs, shoebox.listener, n, 8, 17, n_threads=16)
+    assert np.array_equal(ho[0], h_plain[0]) and not np.array_equal(ho[1], h_plain[1])       # source 0 keeps its stream
+    for over in ({}, {"max_batch_paths": 700}, {"flags": SH | capi.FLAG_COUNT_VISITS}):
+        with _ctx(fs, shoebox, **dict({"flags": SH}, **over)) as ctx:
+            h = ctx.trace(srcs, shoebox.listener, n, 8, 17)
+            st = ctx.stats()
+            assert np.array_equal(h, ho), "over=%r" % (over,)
+            assert st["connected"] == so["connected"] and st["shadow_rays"] == so["shadow_rays"]
+            assert st["ext_rays"] < 0.7 * so["ext_rays"]                                      # 4 + 1 subpaths per index instead of 8
+            # shards: a range inside one source (traced in place) and ranges across sources (cache) sum to the whole
+            parts = np.zeros_like(ho)
+            for g0, gc in ((0, 1000), (1000, 5500), (6500, 4 * n - 6500)):
+                parts += ctx.trace_range(srcs, shoebox.listener, n, g0, gc, 8, 17)
+            assert np.array_equal(parts, ho)
+            h1 = ctx.trace(srcs[:1], shoebox.listener, n, 8, 17)                             # one source: nothing to share
+            assert np.array_equal(h1[0], ho[0])
+    Sr = oracle.Scene(room.verts, room.tri_mat, room.absorption, use_bvh=True)
+    rs = np.array([room.sources[0], room.sources[0] + np.float32([0.7, 0.4, 0.1])], np.float32)
+    hr, sr = Sr.trace(cfgo, rs, room.listener, 2048, 16, 3, n_threads=16)
+    with _ctx(fs, room, flags=SH) as ctx:
+        assert np.array_equal(ctx.trace(rs, room.listener, 2048, 16, 3), hr)
