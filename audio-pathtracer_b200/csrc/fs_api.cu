@@ -244,6 +244,27 @@ static void apply_l2_policy(fs_ctx* ctx)
     if (getenv("FS_VERBOSE")) fprintf(stderr, "[frequensee] L2 persisting window: %.1f MB of wide nodes (device max %d MB)\n", want / 1048576.0, max_persist >> 20);
 }
 
+int fs_scene_set_materials_ex(fs_ctx* ctx, const float* absorption, const float* transmission, const float* scattering,
+                              const float* thickness_cm, uint32_t n_materials, uint32_t n_bands)
+{
+    int rc = fs_scene_set_materials(ctx, absorption, n_materials, n_bands);
+    if (rc != FS_OK) return rc;
+    const size_t n = (size_t)n_materials * n_bands;
+    for (int which = 0; which < 2; ++which) {
+        const float* v = which ? scattering : transmission;
+        if (!v) continue;
+        for (size_t i = 0; i < n; ++i)
+            if (!(v[i] >= 0.0f && v[i] <= 1.0f)) return fail(ctx, FS_ERR_INVALID, which ? "scattering must be in [0,1]" : "transmission must be in [0,1]");
+    }
+    if (thickness_cm)
+        for (uint32_t m = 0; m < n_materials; ++m)
+            if (!(thickness_cm[m] >= 0.0f)) return fail(ctx, FS_ERR_INVALID, "thickness must be >= 0");
+    ctx->mat_transmission.assign(transmission ? transmission : nullptr, transmission ? transmission + n : nullptr);
+    ctx->mat_scattering.assign(scattering ? scattering : nullptr, scattering ? scattering + n : nullptr);
+    ctx->mat_thickness_cm.assign(thickness_cm ? thickness_cm : nullptr, thickness_cm ? thickness_cm + n_materials : nullptr);
+    return FS_OK;
+}
+
 int fs_scene_commit(fs_ctx* ctx)
 {
     if (!ctx) return FS_ERR_INVALID;

@@ -111,6 +111,7 @@ struct fs_ctx {
     // scene
     float* d_verts; uint32_t* d_tri_mat; uint64_t n_tris;
     float* d_refl_over_pi; uint32_t n_mats;
+    std::vector<float> mat_transmission, mat_scattering, mat_thickness_cm;   // carried, unused by the tracer (as in the reference)
     bool mats_set, tris_set, committed;
     fs_bvh_device bvh;
     // trace

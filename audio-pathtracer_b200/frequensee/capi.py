@@ -22,7 +22,7 @@ FLAG_SHARE_LISTENER = 128
 # every symbol include/frequensee.h declares (tests/test_abi.py checks the library exports them all)
 ABI_SYMBOLS = [
     "fs_default_config", "fs_create", "fs_destroy", "fs_last_error", "fs_set_stream", "fs_synchronize",
-    "fs_scene_set_triangles", "fs_scene_set_materials", "fs_scene_commit",
+    "fs_scene_set_triangles", "fs_scene_set_materials", "fs_scene_set_materials_ex", "fs_scene_commit",
     "fs_trace", "fs_trace_range_device", "fs_trace_range", "fs_trace_debug",
     "fs_debug_closest_hits", "fs_debug_any_hits",
     "fs_build_ir", "fs_build_ir_to", "fs_build_ir_all", "fs_build_ir_bands", "fs_build_ir_from_energy", "fs_set_histogram", "fs_set_histogram_device",
@@ -99,6 +99,7 @@ def load():
     L.fs_synchronize.argtypes = [vp]
     L.fs_scene_set_triangles.argtypes = [vp, vp, vp, u64]
     L.fs_scene_set_materials.argtypes = [vp, vp, u32, u32]
+    L.fs_scene_set_materials_ex.argtypes = [vp, vp, vp, vp, vp, u32, u32]
     L.fs_scene_commit.argtypes = [vp]
     L.fs_trace.argtypes = [vp, vp, u32, vp, u64, u32, u64, vp]
     L.fs_trace_range_device.argtypes = [vp, vp, u32, vp, u64, u64, u64, u32, u64, vp, i32]

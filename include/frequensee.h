@@ -144,6 +144,11 @@ int         fs_synchronize(fs_ctx* ctx);
  * verts: [T][3][3] float32 metres; tri_material: [T]; absorption: [M][B] in [0,1]. */
 int fs_scene_set_triangles(fs_ctx* ctx, const float* verts, const uint32_t* tri_material, uint64_t n_tris);
 int fs_scene_set_materials(fs_ctx* ctx, const float* absorption, uint32_t n_materials, uint32_t n_bands);
+/* the whole UAcousticMaterial asset (MAT.h:16-34).  Transmission [M][B], Scattering [M][B] and ThicknessCm [M] are validated
+ * ([0,1]; thickness >= 0) and kept with the context, but -- exactly like the reference's tracers -- not used by the path
+ * tracer.  Any of the three may be NULL. */
+int fs_scene_set_materials_ex(fs_ctx* ctx, const float* absorption, const float* transmission, const float* scattering,
+                              const float* thickness_cm, uint32_t n_materials, uint32_t n_bands);
 /* builds the BVH on the device (LBVH: Morton codes, radix sort, Karras topology, bottom-up fit) */
 int fs_scene_commit(fs_ctx* ctx);
 

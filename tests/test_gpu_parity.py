@@ -297,3 +297,19 @@ def test_shared_listener_subpaths_bit_exact(fs, oracle, shoebox, room):
     hr, sr = Sr.trace(cfgo, rs, room.listener, 2048, 16, 3, n_threads=16)
     with _ctx(fs, room, flags=SH) as ctx:
         assert np.array_equal(ctx.trace(rs, room.listener, 2048, 16, 3), hr)
+
+
+def test_full_material_schema_is_carried_but_unused(fs, oracle, shoebox):
+    """MAT.h:16-34: Transmission / Scattering / ThicknessCm travel through the ABI, are validated, and -- as in the
+    reference's tracers -- do not change the result"""
+    import ctypes as C
+    M, B = shoebox.absorption.shape
+    with _ctx(fs, shoebox) as ctx:
+        h0 = ctx.trace(shoebox.sources, shoebox.listener, 2048, 8, 4)
+        ab = np.ascontiguousarray(shoebox.absorption, np.float32)
+        tr = np.full((M, B), 0.3, np.float32); scat = np.full((M, B), 0.7, np.float32); th = np.full(M, 2.5, np.float32)
+        assert ctx.L.fs_scene_set_materials_ex(ctx.h, ab.ctypes.data, tr.ctypes.data, scat.ctypes.data, th.ctypes.data, M, B) == 0
+        assert ctx.L.fs_scene_commit(ctx.h) == 0
+        assert np.array_equal(ctx.trace(shoebox.sources, shoebox.listener, 2048, 8, 4), h0)
+        tr[1, 2] = 1.5
+        assert ctx.L.fs_scene_set_materials_ex(ctx.h, ab.ctypes.data, tr.ctypes.data, None, None, M, B) != 0
