@@ -63,7 +63,7 @@ def tobytes(val, unit):
 for r in rr[2:]:
     traffic.append(tobytes(r[ix["dram__bytes_read.sum"]], rr[1][ix["dram__bytes_read.sum"]]) +
                    tobytes(r[ix["dram__bytes_write.sum"]], rr[1][ix["dram__bytes_write.sum"]]))
-json.dump({"kernel": "k_trace_closest", "dram_bytes_per_launch": sum(traffic) / len(traffic), "launches": len(traffic),
+json.dump({"kernel": "k_trace_q", "dram_bytes_per_launch": sum(traffic) / len(traffic), "launches": len(traffic),
            "source": os.path.basename(rep)}, open(os.path.join(ROOT, "profiles", tag + "_traffic.json"), "w"))
 open(out_md, "w").write("\n".join(lines) + "\n")
 print("\n".join(lines[:40]))
