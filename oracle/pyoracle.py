@@ -204,7 +204,10 @@ class Scene:
             self.h = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:                 # interpreter shutdown: the module globals may already be gone
+            pass
 
     def closest_hit(self, o, d):
         t = C.c_float()
