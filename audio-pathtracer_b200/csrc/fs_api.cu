@@ -327,6 +327,17 @@ static int ensure_hist(fs_ctx* ctx, uint32_t n_sources)
     return FS_OK;
 }
 
+// the listener cache is [max_depth + 2][n_paths] float4; without room for it the shared keying still holds, the listener
+// subpaths are then simply traced in place by every batch
+static bool lis_cache_fits(fs_ctx* ctx, uint64_t n_paths, uint32_t max_depth)
+{
+    if (ctx->lis_cache_n >= n_paths && ctx->lis_cache_depth >= max_depth) return true;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    const double need = 16.0 * (double)n_paths * (double)(max_depth + 2u);
+    return need < 0.25 * (double)free_b;
+}
+
 static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, const float lis_pos[3],
                         uint64_t n_paths, uint64_t g_first, uint64_t g_count, uint32_t max_depth, uint64_t seed,
                         unsigned long long* d_hist, fs_path_dbg* d_dbg)
@@ -385,7 +396,8 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
     // FS_FLAG_SHARE_LISTENER with more than one source's worth of work: trace the n_paths listener subpaths once, now, and
     // let every source batch copy them in (smaller jobs just use the shared keying and trace them in place)
     if ((ctx->cfg.flags & FS_FLAG_SHARE_LISTENER) && !(ctx->cfg.flags & FS_FLAG_CONNECT_ALL) && !d_dbg && n_sources > 1 &&
-        g_count > n_paths && max_depth > 0 && !(ctx->cfg.flags & (FS_FLAG_FUSED_EXTEND | FS_FLAG_BRUTE_FORCE))) {
+        g_count > n_paths && max_depth > 0 && !(ctx->cfg.flags & (FS_FLAG_FUSED_EXTEND | FS_FLAG_BRUTE_FORCE)) &&
+        lis_cache_fits(ctx, n_paths, max_depth)) {
         if (ctx->lis_cache_n < n_paths || ctx->lis_cache_depth < max_depth) {
             cudaFree(ctx->lis_rec); cudaFree(ctx->lis_end); ctx->lis_rec = ctx->lis_end = nullptr; ctx->lis_cache_n = 0;
             CK(cudaMalloc(&ctx->lis_rec, sizeof(float4) * (size_t)n_paths * (max_depth + 1ull)));

@@ -1053,10 +1053,10 @@ k_trace_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* 
             for (uint32_t base = 0; base < total; base += 32) {
                 const uint32_t idx = base + lane;
                 const uint32_t e = idx < total ? squeue[idx] : TQ_INVALID;
-                const uint32_t owner = e & 31u;
-                const float ox = __shfl_sync(FULLM, s.o.x, owner), oy = __shfl_sync(FULLM, s.o.y, owner), oz = __shfl_sync(FULLM, s.o.z, owner);
-                const float dx = __shfl_sync(FULLM, s.d.x, owner), dy = __shfl_sync(FULLM, s.d.y, owner), dz = __shfl_sync(FULLM, s.d.z, owner);
-                const float bto = __shfl_sync(FULLM, bt, owner);
+                const uint32_t eo = e & 31u;                       // lane that owns the entry's ray
+                const float ox = __shfl_sync(FULLM, s.o.x, eo), oy = __shfl_sync(FULLM, s.o.y, eo), oz = __shfl_sync(FULLM, s.o.z, eo);
+                const float dx = __shfl_sync(FULLM, s.d.x, eo), dy = __shfl_sync(FULLM, s.d.y, eo), dz = __shfl_sync(FULLM, s.d.z, eo);
+                const float bto = __shfl_sync(FULLM, bt, eo);
                 if (e != TQ_INVALID) {
                     const uint32_t tri = e >> 5;
                     const float4* tq = bv.tris + (size_t)tri * 4;
@@ -1067,11 +1067,11 @@ k_trace_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* 
                     const bool hit = fs_intersect_tri(fs_mk(ox, oy, oz), fs_mk(dx, dy, dz), fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z),
                                                       fs_mk(c.x, c.y, c.z), t);
                     if (ANY) {
-                        if (hit && t < bto) *(volatile unsigned long long*)(wkey + owner) = 0ull;      // occluded: any store wins
+                        if (hit && t < bto) *(volatile unsigned long long*)(wkey + eo) = 0ull;      // occluded: any store wins
                     } else if (hit && t <= bto) {
                         // merge into the owner's best: min over (t, ORIGINAL triangle id); ids are fetched only on a tie
                         const unsigned long long mine = ((unsigned long long)__float_as_uint(t) << 32) | tri;
-                        unsigned long long old = *(volatile unsigned long long*)(wkey + owner);
+                        unsigned long long old = *(volatile unsigned long long*)(wkey + eo);
                         for (;;) {
                             const float told = __uint_as_float((uint32_t)(old >> 32));
                             bool better = t < told;
@@ -1081,7 +1081,7 @@ k_trace_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* 
                                          __float_as_uint(fs_ldg4(tq + 3).x) < __float_as_uint(fs_ldg4(bv.tris + (size_t)otri * 4 + 3).x);
                             }
                             if (!better) break;
-                            const unsigned long long prev = atomicCAS(wkey + owner, old, mine);
+                            const unsigned long long prev = atomicCAS(wkey + eo, old, mine);
                             if (prev == old) break;
                             old = prev;
                         }
