@@ -935,6 +935,9 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
 #ifndef FS_PREFETCH_TRIS
 #define FS_PREFETCH_TRIS 0
 #endif
+#ifndef FS_TRI_TEX
+#define FS_TRI_TEX 0
+#endif
 // ANY = false: closest hit of extension rays -> hits[j] = (t, triangle).
 // ANY = true : connection rays (F.xyz, tmax) (dir.xyz, path id): any triangle closer than tmax occludes; the paths that
 //              stay visible are appended to conn_queue.  Same node phase and queue; the "best key" of a lane degenerates
@@ -1060,7 +1063,15 @@ k_trace_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* 
                 if (e != TQ_INVALID) {
                     const uint32_t tri = e >> 5;
                     const float4* tq = bv.tris + (size_t)tri * 4;
+#if FS_TRI_TEX
+                    // one of the three triangle quarters through the texture data pipe (as for the nodes)
+                    const bool ttex = TEX >= 2 && bv.tris_tex;
+                    const float4 a = ttex ? tex1Dfetch<float4>((cudaTextureObject_t)bv.tris_tex, (int)(tri * 4u)) : fs_ldg4(tq);
+                    const float4 b = (FS_TRI_TEX >= 2 && ttex) ? tex1Dfetch<float4>((cudaTextureObject_t)bv.tris_tex, (int)(tri * 4u + 1u)) : fs_ldg4(tq + 1);
+                    const float4 c = fs_ldg4(tq + 2);
+#else
                     const float4 a = fs_ldg4(tq), b = fs_ldg4(tq + 1), c = fs_ldg4(tq + 2);
+#endif
                     if (COUNT) vc.tris++;
                     squeue[idx] = TQ_INVALID;
                     float t;
