@@ -458,10 +458,13 @@ __device__ __forceinline__ void leaf_range(int leafnode, uint32_t& tc, uint32_t&
     te = tc + (payload & 7u) + 1u;
 }
 
-#ifndef FS_SHADE_MINBLOCKS
-#define FS_SHADE_MINBLOCKS 6
+#ifndef FS_SG_THREADS
+#define FS_SG_THREADS 256
 #endif
-__global__ void __launch_bounds__(WF_THREADS, FS_SHADE_MINBLOCKS)
+#ifndef FS_SHADE_MINBLOCKS
+#define FS_SHADE_MINBLOCKS (1536 / FS_SG_THREADS)
+#endif
+__global__ void __launch_bounds__(FS_SG_THREADS, FS_SHADE_MINBLOCKS)
 k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_dev_counters* __restrict__ dc)
 {
     const uint32_t lane = lane_id();
@@ -474,7 +477,7 @@ k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_d
     const uint32_t stride = 2u * wb.cap;             // rec[k][sp_id]: one plane per node index (writes of a bounce stay semi-coalesced)
     // One queue-slot atomic per CTA tile, not per warp: ncu (r1i) had 43 % of this kernel's stall samples on the return
     // of the per-warp atomicAdd -- 10^5 same-address atomics per launch run at about one per nanosecond.
-    __shared__ uint32_t s_cnt[WF_THREADS / 32], s_base;
+    __shared__ uint32_t s_cnt[FS_SG_THREADS / 32], s_base;
     const uint32_t warp = threadIdx.x >> 5;
     for (uint32_t tile = blockIdx.x * blockDim.x; tile < count_in; tile += gridDim.x * blockDim.x) {
         const uint32_t j = tile + threadIdx.x;
@@ -545,7 +548,7 @@ k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_d
         if (threadIdx.x == 0) {
             uint32_t tot = 0;
 #pragma unroll
-            for (int w = 0; w < WF_THREADS / 32; ++w) { const uint32_t c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+            for (int w = 0; w < FS_SG_THREADS / 32; ++w) { const uint32_t c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
             s_base = tot ? atomicAdd(&wb.q_count[k], tot) : 0u;      // ext_rays = sum of the queue lengths (k_connect_gen)
         }
         __syncthreads();
@@ -1636,8 +1639,8 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
     ++ctx->stats.kernel_launches;
     const uint32_t D = tp.max_depth;
     const uint32_t n_sub = 2u * tp.batch;
-    uint32_t grid_sh = (n_sub + WF_THREADS - 1) / WF_THREADS;
-    if (grid_sh > (uint32_t)ctx->sm_count * 8u) grid_sh = (uint32_t)ctx->sm_count * 8u;
+    uint32_t grid_sh = (n_sub + FS_SG_THREADS - 1) / FS_SG_THREADS;
+    if (grid_sh > (uint32_t)ctx->sm_count * (2048u / FS_SG_THREADS)) grid_sh = (uint32_t)ctx->sm_count * (2048u / FS_SG_THREADS);
     const bool use_tq = ctx->tune_tq && tp.bv.wnodes != nullptr && ctx->bvh.max_leaf == 1;    // queue entries are single triangles
     uint32_t grid_tr = (uint32_t)(ctx->sm_count * (use_tq ? occ_tq : occ_tr));
     const uint32_t ctas_needed = (n_sub + TR_THREADS - 1) / TR_THREADS;
@@ -1648,7 +1651,7 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
         ++ctx->stats.kernel_launches;
     } else {
         for (uint32_t k = 0; k <= D; ++k) {
-            k_shade_gen<<<grid_sh, WF_THREADS, 0, st>>>(tp, wb, k, ctx->d_counters);
+            k_shade_gen<<<grid_sh, FS_SG_THREADS, 0, st>>>(tp, wb, k, ctx->d_counters);
             ++ctx->stats.kernel_launches;
             if (k == D) break;
             const bool wide = tp.bv.wnodes != nullptr;
