@@ -84,6 +84,8 @@ int fs_create(const fs_config* cfg, fs_ctx** out)
     if (const char* e14 = getenv("FS_TUNE_STREAMS")) { int v = atoi(e14); if (v >= 1 && v <= FS_MAX_LANES) ctx->tune_streams = (uint32_t)v; } ctx->tune_tq = 2;      // 0: phased kernels, 1: queue kernel for extension rays only, 2: also for connection rays
     ctx->tune_tq_node_min = 10; ctx->tune_tq_flush = 24;
     if (const char* e11 = getenv("FS_TUNE_TQ")) ctx->tune_tq = (uint32_t)atoi(e11);
+    ctx->tune_mega = 0;          // EXPERIMENTAL: one persistent launch per batch for the extension stage (k_path_q)
+    if (const char* e15 = getenv("FS_TUNE_MEGA")) ctx->tune_mega = (uint32_t)atoi(e15);
     if (const char* e12 = getenv("FS_TUNE_TQ_NODE_MIN")) ctx->tune_tq_node_min = (uint32_t)atoi(e12);
     if (const char* e13 = getenv("FS_TUNE_TQ_FLUSH")) ctx->tune_tq_flush = (uint32_t)atoi(e13);
     if (ctx->tune_tq_flush < 1) ctx->tune_tq_flush = 1;

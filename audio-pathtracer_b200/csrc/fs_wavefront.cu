@@ -1178,6 +1178,288 @@ k_trace_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* 
     if (COUNT) flush_counters(dc, vc, ANY);
 }
 
+// =============================================================================================
+// k_path_q (EXPERIMENTAL, FS_TUNE_MEGA=1): ONE persistent launch per batch for the whole extension stage.
+//
+// The per-bounce pipeline pays a fixed cost per bounce -- the drain of the traversal launch (the slowest ray) plus the
+// latency floor of k_shade_gen -- about 90 us x 16 bounces = 29 % of a room update.  Here a retired ray is not written
+// out as a hit record: it goes to a per-warp SHADE QUEUE in shared memory, and when 24 have gathered the warp shades
+// them converged (lane i takes entry i: node record, Russian roulette, next direction -- the arithmetic of
+// k_shade_gen), appends the successor rays to a global RAY LOG and publishes each with an epoch flag.  Idle lanes of any
+// warp take tickets (atomicAdd on the log head) and start a ray as soon as its flag shows the current epoch.  Rays of
+// bounce k+1 therefore start while the long rays of bounce k are still walking; there is one drain per batch.
+// Termination: `done` counts shaded rays, `tail` appended ones; a parent's successor is appended before the parent is
+// counted done, so done == tail (done read first) means nothing is in flight and nothing can be appended any more.
+// Every wait is bounded (a poll budget turns a protocol error into FS_ERR_OVERFLOW instead of a hang).
+// =============================================================================================
+struct pq_globals { uint32_t tail, head, done, error; };
+#define PQ_NO_TICKET 0xffffffffu
+#define PQ_SQ_CAP 64
+#define PQ_SHADE_MIN 24u
+#define PQ_SMEM (FS_SSTACK * TR_THREADS * sizeof(int) + TR_THREADS * sizeof(unsigned long long) + \
+                 TQ_WARPS * FS_TQ_CAP * sizeof(uint32_t) + TQ_WARPS * sizeof(uint32_t) + 2 * TR_THREADS * sizeof(uint32_t) + \
+                 TQ_WARPS * PQ_SQ_CAP * 10 * sizeof(uint32_t))
+
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ float4 ld_cg_f4(const float4* p)
+{
+    float4 r;
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+// bounce-0 rays (written by k_shade_gen(0) into the ping-pong queue) become the first entries of the ray log
+__global__ void k_pq_seed(const fs_wave_buffers wb, float4* __restrict__ log_o, float4* __restrict__ log_d,
+                          uint32_t* __restrict__ log_flag, uint32_t epoch, pq_globals* __restrict__ g)
+{
+    const uint32_t n = wb.q_count[0];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        log_o[i] = wb.st_pos[0][i];                 // (pos, bits(sp_id)): bounce index 0 in the upper bits
+        log_d[i] = wb.st_nrm[0][i];
+        log_flag[i] = epoch;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { g->tail = n; g->head = 0u; g->done = 0u; g->error = 0u; }
+}
+// the total number of extension rays, where k_connect_gen looks for it
+__global__ void k_pq_finish(const fs_wave_buffers wb, const pq_globals* __restrict__ g, uint32_t max_depth, fs_dev_counters* dc)
+{
+    wb.q_count[0] = g->tail;
+    for (uint32_t k = 1; k < max_depth; ++k) wb.q_count[k] = 0u;
+    if (g->error) dc->overflow = 0x100u | g->error;
+}
+
+#ifndef FS_PQ_MINBLOCKS
+#define FS_PQ_MINBLOCKS 4      // 62 registers, 32 warps/SM (3: 72 registers is slower, 5: spills and no L1 left)
+#endif
+template <int TEX>
+__global__ void __launch_bounds__(TR_THREADS, FS_PQ_MINBLOCKS)
+k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict__ log_o, float4* __restrict__ log_d,
+         uint32_t* __restrict__ log_flag, const uint32_t epoch, const uint32_t log_cap, pq_globals* __restrict__ g,
+         const uint32_t REFILL_MIN, const uint32_t NODE_MIN, const uint32_t FLUSH_MIN)
+{
+    const fs_bvh_view& bv = tp.bv;
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    extern __shared__ __align__(8) unsigned char smem_raw[];
+    int* const sstack = reinterpret_cast<int*>(smem_raw);
+    unsigned long long* const skey = reinterpret_cast<unsigned long long*>(sstack + FS_SSTACK * TR_THREADS);
+    uint32_t* const w32 = reinterpret_cast<uint32_t*>(skey + TR_THREADS);
+    uint32_t* const squeue = w32 + warp * FS_TQ_CAP;
+    uint32_t* const sqcount = w32 + TQ_WARPS * FS_TQ_CAP + warp;
+    uint32_t* const sspk = w32 + TQ_WARPS * FS_TQ_CAP + TQ_WARPS;                     // [T] sp_id | bounce << 22 of the lane's ray
+    float* const spdf = reinterpret_cast<float*>(sspk + TR_THREADS);                 // [T] pdf the ray was sampled with
+    uint32_t* const shq = reinterpret_cast<uint32_t*>(spdf + TR_THREADS) + warp * (PQ_SQ_CAP * 10);   // shade queue, 10 planes
+    unsigned long long* const mykey = skey + threadIdx.x;
+    unsigned long long* const wkey = skey + (threadIdx.x & ~31u);
+    int lstack[FS_STACK_SIZE - FS_SSTACK];
+    tr_stack<false> stack; stack.sh = sstack + threadIdx.x; stack.loc = lstack;
+    const unsigned long long KEY_NONE = ((unsigned long long)0x7f800000u << 32) | 0xffffffffull;
+    if (lane == 0) *sqcount = 0u;
+    *mykey = KEY_NONE;
+    __syncwarp();
+    tr_state s;
+    s.node = TR_SENT; s.leaf = 0; s.sp = 0; s.tc = 0; s.te = 0;
+    s.o = fs_mk(0.f, 0.f, 0.f); s.d = s.o; s.idx = s.idy = s.idz = s.oodx = s.oody = s.oodz = 0.f;
+    bool running = false;
+    uint32_t ticket = PQ_NO_TICKET;
+    uint32_t* const ovf_p = &g->error;                 // stack overflow lands in the same word (value 1)
+    float bt = __int_as_float(0x7f800000);
+    uint32_t qn = 0, sn = 0, polls = 0;
+    const uint32_t stride = 2u * wb.cap;
+    for (;;) {
+        // ---- idle lanes take tickets for the next entries of the ray log (one atomic per warp)
+        const bool need = !running && ticket == PQ_NO_TICKET;
+        const uint32_t m_need = __ballot_sync(FULLM, need);
+        const uint32_t m_run0 = __ballot_sync(FULLM, running);
+        if ((uint32_t)__popc(m_need) >= REFILL_MIN || (m_need && m_run0 == 0u)) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&g->head, (uint32_t)__popc(m_need));
+            base = __shfl_sync(FULLM, base, 0);
+            if (need) ticket = base + (uint32_t)__popc(m_need & lt);
+        }
+        // ---- a ticket becomes a ray once its log entry is published
+        if (!running && ticket != PQ_NO_TICKET && ticket < log_cap && ld_cg_u32(log_flag + ticket) == epoch) {
+            __threadfence();
+            const float4 a = ld_cg_f4(log_o + ticket), b = ld_cg_f4(log_d + ticket);
+            tr_init<true>(s, bv, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z));
+            bt = __int_as_float(0x7f800000); *mykey = KEY_NONE;
+            sspk[threadIdx.x] = __float_as_uint(a.w); spdf[threadIdx.x] = b.w;
+            running = true; ticket = PQ_NO_TICKET;
+        }
+        const uint32_t m_run = __ballot_sync(FULLM, running);
+        if (m_run == 0u && sn == 0u) {                // nothing to walk, nothing to shade: finished, or wait for rays
+            const uint32_t dn = ld_cg_u32(&g->done);
+            const uint32_t tl = ld_cg_u32(&g->tail);
+            if (dn == tl || ld_cg_u32(&g->error)) break;
+            if (++polls > (1u << 21)) { if (lane == 0) atomicMax(&g->error, 3u); break; }
+            __nanosleep(256);
+            continue;
+        }
+        if (m_run) {
+            // ---- node phase (as k_trace_q)
+            for (;;) {
+                const bool can = running && s.node >= 0 && s.node != TR_SENT;
+                const uint32_t m_can = __ballot_sync(FULLM, can);
+                if (m_can == 0u || qn >= FLUSH_MIN) break;
+                if (NODE_MIN && qn && (uint32_t)__popc(m_can) < NODE_MIN) break;
+                uint32_t nl = 0;
+                if (can) {
+                    const float INF = __int_as_float(0x7f800000);
+                    float k0, k1, k2, k3; int v0, v1, v2, v3;
+                    wide_children<2, TEX>(bv, s, bt, k0, k1, k2, k3, v0, v1, v2, v3);
+                    const bool l0 = k0 != INF && v0 < 0, l1 = k1 != INF && v1 < 0, l2 = k2 != INF && v2 < 0, l3 = k3 != INF && v3 < 0;
+                    nl = (uint32_t)l0 + (uint32_t)l1 + (uint32_t)l2 + (uint32_t)l3;
+                    if (nl) {
+                        uint32_t* q = squeue + atomicAdd(sqcount, nl);
+                        const uint32_t lm4 = lane - 4u;
+                        if (l0) *q = (uint32_t)v0 * 0xfffffffcu + lm4;
+                        q += l0;
+                        if (l1) *q = (uint32_t)v1 * 0xfffffffcu + lm4;
+                        q += l1;
+                        if (l2) *q = (uint32_t)v2 * 0xfffffffcu + lm4;
+                        q += l2;
+                        if (l3) *q = (uint32_t)v3 * 0xfffffffcu + lm4;
+                    }
+                    k0 = l0 ? INF : k0; k1 = l1 ? INF : k1; k2 = l2 ? INF : k2; k3 = l3 ? INF : k3;
+                    FS_CSWAP(k0, v0, k1, v1) FS_CSWAP(k2, v2, k3, v3) FS_CSWAP(k0, v0, k2, v2) FS_CSWAP(k1, v1, k3, v3) FS_CSWAP(k1, v1, k2, v2)
+                    if (k1 != INF) stack.push3(s.sp, k2 != INF, k3 != INF, v1, k1, v2, k2, v3, k3, ovf_p);
+                    s.node = (k0 != INF) ? v0 : stack.pop(s.sp, 0.f);
+                }
+                qn += __reduce_add_sync(FULLM, nl);
+            }
+            // ---- triangle phase
+            __syncwarp();
+            const uint32_t total = qn;
+            for (uint32_t base = 0; base < total; base += 32) {
+                const uint32_t idx = base + lane;
+                const uint32_t e = idx < total ? squeue[idx] : TQ_INVALID;
+                const uint32_t eo = e & 31u;
+                const float ox = __shfl_sync(FULLM, s.o.x, eo), oy = __shfl_sync(FULLM, s.o.y, eo), oz = __shfl_sync(FULLM, s.o.z, eo);
+                const float dx = __shfl_sync(FULLM, s.d.x, eo), dy = __shfl_sync(FULLM, s.d.y, eo), dz = __shfl_sync(FULLM, s.d.z, eo);
+                const float bto = __shfl_sync(FULLM, bt, eo);
+                if (e != TQ_INVALID) {
+                    const uint32_t tri = e >> 5;
+                    const float4* tq = bv.tris + (size_t)tri * 4;
+                    const float4 a = fs_ldg4(tq), b = fs_ldg4(tq + 1), c = fs_ldg4(tq + 2);
+                    float t;
+                    if (fs_intersect_tri(fs_mk(ox, oy, oz), fs_mk(dx, dy, dz), fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z), fs_mk(c.x, c.y, c.z), t)
+                        && t <= bto) {
+                        const unsigned long long mine = ((unsigned long long)__float_as_uint(t) << 32) | tri;
+                        unsigned long long old = *(volatile unsigned long long*)(wkey + eo);
+                        for (;;) {
+                            const float told = __uint_as_float((uint32_t)(old >> 32));
+                            bool better = t < told;
+                            if (t == told) {
+                                const uint32_t otri = (uint32_t)old;
+                                better = otri == 0xffffffffu ||
+                                         __float_as_uint(fs_ldg4(tq + 3).x) < __float_as_uint(fs_ldg4(bv.tris + (size_t)otri * 4 + 3).x);
+                            }
+                            if (!better) break;
+                            const unsigned long long prev = atomicCAS(wkey + eo, old, mine);
+                            if (prev == old) break;
+                            old = prev;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) *sqcount = 0u;
+            qn = 0u;
+            const unsigned long long kk = *(volatile unsigned long long*)mykey;
+            bt = __uint_as_float((uint32_t)(kk >> 32));
+            __syncwarp();
+            // ---- retire: the finished ray goes to the warp's shade queue
+            const bool fin = running && s.node == TR_SENT;
+            const uint32_t m_fin = __ballot_sync(FULLM, fin);
+            if (fin) {
+                const uint32_t q = sn + (uint32_t)__popc(m_fin & lt);
+                shq[0 * PQ_SQ_CAP + q] = sspk[threadIdx.x];
+                shq[1 * PQ_SQ_CAP + q] = __float_as_uint(bt);
+                shq[2 * PQ_SQ_CAP + q] = (uint32_t)kk;
+                shq[3 * PQ_SQ_CAP + q] = __float_as_uint(s.o.x); shq[4 * PQ_SQ_CAP + q] = __float_as_uint(s.o.y); shq[5 * PQ_SQ_CAP + q] = __float_as_uint(s.o.z);
+                shq[6 * PQ_SQ_CAP + q] = __float_as_uint(s.d.x); shq[7 * PQ_SQ_CAP + q] = __float_as_uint(s.d.y); shq[8 * PQ_SQ_CAP + q] = __float_as_uint(s.d.z);
+                shq[9 * PQ_SQ_CAP + q] = __float_as_uint(spdf[threadIdx.x]);
+                running = false;
+            }
+            sn += (uint32_t)__popc(m_fin);
+        }
+        // ---- shading phase: converged, lane i shades entry i (the arithmetic of k_shade_gen for node k = bounce + 1)
+        if (sn >= PQ_SHADE_MIN || (sn && !__any_sync(FULLM, running))) {
+            __syncwarp();
+            for (uint32_t base = 0; base < sn; base += 32) {
+                const uint32_t qi = base + lane;
+                bool emit = false;
+                fs_vec3 pos = fs_mk(0.f, 0.f, 0.f), dir = pos;
+                float prob = 1.0f; uint32_t spk_out = 0;
+                if (qi < sn) {
+                    const uint32_t spk = shq[0 * PQ_SQ_CAP + qi];
+                    const uint32_t sp_id = spk & 0x3fffffu, k = (spk >> 22) + 1u;
+                    const float t = __uint_as_float(shq[1 * PQ_SQ_CAP + qi]);
+                    const int tri = (int)shq[2 * PQ_SQ_CAP + qi];
+                    const fs_vec3 o = fs_mk(__uint_as_float(shq[3 * PQ_SQ_CAP + qi]), __uint_as_float(shq[4 * PQ_SQ_CAP + qi]), __uint_as_float(shq[5 * PQ_SQ_CAP + qi]));
+                    const fs_vec3 d = fs_mk(__uint_as_float(shq[6 * PQ_SQ_CAP + qi]), __uint_as_float(shq[7 * PQ_SQ_CAP + qi]), __uint_as_float(shq[8 * PQ_SQ_CAP + qi]));
+                    const float pdf_in = __uint_as_float(shq[9 * PQ_SQ_CAP + qi]);
+                    fs_vec3 nrm = fs_mk(0.f, 0.f, 0.f);
+                    bool cont = true;
+                    uint32_t nodes = k;
+                    if (tri < 0) {                    // miss: the subpath ends at its current node
+                        wb.end_pos[sp_id] = make_float4(o.x, o.y, o.z, __uint_as_float(k));
+                        cont = false;
+                    } else {                          // SUB.cpp:343-348
+                        const float4 nm = fs_ldg4(bv.tri_nm + tri);
+                        fs_vec3 fn = fs_mk(nm.x, nm.y, nm.z);
+                        if (fs_dot(fn, d) > 0.0f) { fn.x = -fn.x; fn.y = -fn.y; fn.z = -fn.z; }
+                        pos.x = fmaf(tp.eps_offset, fn.x, fmaf(t, d.x, o.x));
+                        pos.y = fmaf(tp.eps_offset, fn.y, fmaf(t, d.y, o.y));
+                        pos.z = fmaf(tp.eps_offset, fn.z, fmaf(t, d.z, o.z));
+                        const fs_vec3 dl = fs_sub(pos, o);
+                        const float seg = sqrtf(fs_dot(dl, dl));
+                        wb.rec[(size_t)k * stride + sp_id] = make_float4(seg, nm.w, pdf_in, fs_pow(pdf_in, tp.ep.pdf_exponent));
+                        nrm = fn;
+                        nodes = k + 1u;
+                        if (k >= tp.max_depth) {
+                            wb.end_pos[sp_id] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(nodes));
+                            cont = false;
+                        }
+                    }
+                    if (cont) {
+                        uint64_t gg = tp.g_first + (sp_id >> 1);
+                        if ((tp.flags & FS_FLAG_SHARE_LISTENER) && (sp_id & 1u)) gg %= tp.n_paths;
+                        uint32_t r[4];
+                        fs_philox4x32_10((uint32_t)gg, (uint32_t)(gg >> 32), k, sp_id & 1u, tp.seed_lo, tp.seed_hi, r);
+                        const float u0 = fs_u01(r[0]), u1 = fs_u01(r[1]), u2 = fs_u01(r[2]);
+                        if (u0 < tp.rr_prob) {        // SUB.cpp:301-302
+                            float ct; dir = fs_sample_cos_hemisphere(nrm, u1, u2, ct); prob = (ct * FS_INV_PI) * tp.rr_prob;
+                            emit = true; spk_out = sp_id | (k << 22);
+                        } else {
+                            wb.end_pos[sp_id] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(nodes));
+                        }
+                    }
+                }
+                const uint32_t m_emit = __ballot_sync(FULLM, emit);
+                if (m_emit) {
+                    uint32_t slot = 0;
+                    if (lane == 0) slot = atomicAdd(&g->tail, (uint32_t)__popc(m_emit));
+                    slot = __shfl_sync(FULLM, slot, 0);
+                    if (emit) {
+                        const uint32_t w = slot + (uint32_t)__popc(m_emit & lt);
+                        if (w < log_cap) {
+                            log_d[w] = make_float4(dir.x, dir.y, dir.z, prob);
+                            log_o[w] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(spk_out));
+                            __threadfence();
+                            *(volatile uint32_t*)(log_flag + w) = epoch;
+                        } else atomicMax(&g->error, 2u);        // the log is sized for the worst case: cannot happen
+                    }
+                }
+            }
+            __syncwarp();
+            __threadfence();
+            if (lane == 0) atomicAdd(&g->done, sn);            // after the successors were appended
+            sn = 0u;
+        }
+    }
+}
+
 // connection rays: (F.xyz, tmax) (dir.xyz, path id); unoccluded paths are appended to conn_queue
 template <bool COUNT, int TEX, bool WIDE>
 __global__ void __launch_bounds__(TR_THREADS, FS_TR_MINBLOCKS)
@@ -1536,6 +1818,18 @@ cudaError_t fs_wave_alloc(fs_ctx* ctx, uint32_t cap, uint32_t max_depth)
         if ((e = cudaMalloc(&wb->all_d, sizeof(float4) * wb->all_cap)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&wb->all_conn, 4ull * wb->all_cap)) != cudaSuccess) return e;
     }
+    if (ctx->tune_mega && max_depth >= 1 && cap <= (1u << 21) && !(ctx->cfg.flags & FS_FLAG_CONNECT_ALL)) {
+        const uint64_t lc = (uint64_t)n2 * max_depth;                  // every subpath traces at most max_depth rays
+        if (lc < 0xffffffffull) {
+            wb->log_cap = (uint32_t)lc;
+            if ((e = cudaMalloc(&wb->log_o, sizeof(float4) * lc)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&wb->log_d, sizeof(float4) * lc)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&wb->log_flag, 4ull * lc)) != cudaSuccess) return e;
+            if ((e = cudaMemset(wb->log_flag, 0, 4ull * lc)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&wb->pq, 16)) != cudaSuccess) return e;
+            wb->pq_epoch = 0;
+        }
+    }
     wb->cap = cap; wb->depth_cap = max_depth;
     return cudaSuccess;
 }
@@ -1546,6 +1840,7 @@ void fs_wave_free(fs_wave_buffers* wb)
     cudaFree(wb->rec); cudaFree(wb->end_pos); cudaFree(wb->conn_queue); cudaFree(wb->conn_len);
     cudaFree(wb->q_count); cudaFree(wb->q_cursor); cudaFree(wb->hit);
     cudaFree(wb->npos); cudaFree(wb->all_o); cudaFree(wb->all_d); cudaFree(wb->all_conn);
+    cudaFree(wb->log_o); cudaFree(wb->log_d); cudaFree(wb->log_flag); cudaFree(wb->pq);
     memset(wb, 0, sizeof(*wb));
 }
 
@@ -1649,6 +1944,24 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
     if (D == 0) {
         k_init_ends<<<(n_sub + 255u) / 256u, 256, 0, st>>>(tp, wb);
         ++ctx->stats.kernel_launches;
+    } else if (!COUNT && !timing && use_tq && wb.log_o && ctx->tune_mega && (uint64_t)n_sub * D <= wb.log_cap) {
+        // EXPERIMENTAL: bounce 0 by k_shade_gen, every later bounce inside ONE persistent launch (k_path_q)
+        static int occ_pq = 0;
+        if (!occ_pq) occ_pq = resident_ctas(k_path_q<2>, TR_THREADS, PQ_SMEM);
+        fs_wave_buffers* wbm = const_cast<fs_wave_buffers*>(&wb);
+        const uint32_t epoch = ++wbm->pq_epoch;
+        pq_globals* g = (pq_globals*)wb.pq;
+        k_shade_gen<<<grid_sh, FS_SG_THREADS, 0, st>>>(tp, wb, 0, ctx->d_counters);
+        k_pq_seed<<<ctx->sm_count * 4, 256, 0, st>>>(wb, wb.log_o, wb.log_d, wb.log_flag, epoch, g);
+        const bool texq = tp.bv.wnodes_tex && ctx->tune_tex >= 2;
+        const uint32_t grid_pq = (uint32_t)(ctx->sm_count * occ_pq);
+        if (texq) k_path_q<2><<<grid_pq, TR_THREADS, PQ_SMEM, st>>>(tp, wb, wb.log_o, wb.log_d, wb.log_flag, epoch, wb.log_cap, g,
+                                                                  ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush);
+        else k_path_q<0><<<grid_pq, TR_THREADS, PQ_SMEM, st>>>(tp, wb, wb.log_o, wb.log_d, wb.log_flag, epoch, wb.log_cap, g,
+                                                             ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush);
+        k_pq_finish<<<1, 1, 0, st>>>(wb, g, D, ctx->d_counters);
+        ctx->stats.kernel_launches += 4;
+        ctx->stats.extend_launches += 1;
     } else {
         for (uint32_t k = 0; k <= D; ++k) {
             k_shade_gen<<<grid_sh, FS_SG_THREADS, 0, st>>>(tp, wb, k, ctx->d_counters);

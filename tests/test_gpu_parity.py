@@ -213,7 +213,7 @@ def test_every_traversal_kernel_and_bvh_layout_gives_the_same_histogram(fs, orac
     BVH2 float nodes, LBVH with multi-triangle leaves: the closest hit does not depend on the structure"""
     S = oracle.Scene(room.verts, room.tri_mat, room.absorption, use_bvh=True)
     ho, so = S.trace(oracle.default_config(), room.sources, room.listener, 8192, 16, 1, n_threads=16)
-    for env in ({}, {"FS_TUNE_TQ": 0}, {"FS_TUNE_TQ": 1}, {"FS_TUNE_COLLAPSE": 0}, {"FS_TUNE_PLOC_R": 3}, {"FS_TUNE_ROTATE": 3}, {"FS_TUNE_COLLAPSE": 3}, {"FS_TUNE_TQ": 0, "FS_TUNE_COLLAPSE": 2},
+    for env in ({}, {"FS_TUNE_TQ": 0}, {"FS_TUNE_TQ": 1}, {"FS_TUNE_COLLAPSE": 0}, {"FS_TUNE_PLOC_R": 3}, {"FS_TUNE_ROTATE": 3}, {"FS_TUNE_MEGA": 1}, {"FS_TUNE_MEGA": 1, "FS_TUNE_TEX": 0}, {"FS_TUNE_COLLAPSE": 3}, {"FS_TUNE_TQ": 0, "FS_TUNE_COLLAPSE": 2},
                 {"FS_TUNE_WIDE": 0}, {"FS_TUNE_BUILDER": 0}, {"FS_TUNE_BUILDER": 0, "FS_TUNE_LEAF_MAX": 1},
                 {"FS_TUNE_TQ_FLUSH": 1}, {"FS_TUNE_TQ_FLUSH": 32, "FS_TUNE_TQ_NODE_MIN": 0}, {"FS_TUNE_REFILL": 1},
                 {"FS_TUNE_L2PIN": 8}):
@@ -233,7 +233,8 @@ def test_batch_lanes_and_batch_splits_are_bit_exact(fs, oracle, shoebox):
     S = oracle.Scene(shoebox.verts, shoebox.tri_mat, shoebox.absorption, use_bvh=False)
     ho, so = S.trace(oracle.default_config(), shoebox.sources, shoebox.listener, n, 8, 77, n_threads=16)
     for env, over in (({}, {}), ({"FS_TUNE_STREAMS": 1}, {}), ({"FS_TUNE_STREAMS": 3}, {"max_batch_paths": 70001}),
-                      ({"FS_TUNE_STREAMS": 4}, {}), ({"FS_TUNE_STREAMS": 2}, {"max_batch_paths": 1 << 16})):
+                      ({"FS_TUNE_STREAMS": 4}, {}), ({"FS_TUNE_STREAMS": 2}, {"max_batch_paths": 1 << 16}),
+                      ({"FS_TUNE_MEGA": 1}, {}), ({"FS_TUNE_MEGA": 1, "FS_TUNE_STREAMS": 1}, {"max_batch_paths": 100000})):
         with _env(**env):
             ctx = _ctx(fs, shoebox, **over)
         with ctx:
