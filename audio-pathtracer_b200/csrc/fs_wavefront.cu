@@ -1194,8 +1194,10 @@ k_trace_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* 
 // =============================================================================================
 struct pq_globals { uint32_t tail, head, done, error; };
 #define PQ_NO_TICKET 0xffffffffu
-#define PQ_SQ_CAP 64
+#ifndef PQ_SHADE_MIN
 #define PQ_SHADE_MIN 24u
+#endif
+#define PQ_SQ_CAP (PQ_SHADE_MIN + 32u)         // at most SHADE_MIN - 1 entries wait when up to 32 lanes retire
 #define PQ_SMEM (FS_SSTACK * TR_THREADS * sizeof(int) + TR_THREADS * sizeof(unsigned long long) + \
                  TQ_WARPS * FS_TQ_CAP * sizeof(uint32_t) + TQ_WARPS * sizeof(uint32_t) + 2 * TR_THREADS * sizeof(uint32_t) + \
                  TQ_WARPS * PQ_SQ_CAP * 10 * sizeof(uint32_t))
