@@ -1,6 +1,6 @@
 /*
- * fs_oracle.c -- CPU oracle (plain C99).  See fs_oracle.h: TEST INFRASTRUCTURE ONLY,
- * "parity unpinned" by the reference's own tests; pinned by analytic KATs + oracle/_ref.
+ * fs_oracle.c -- CPU oracle (plain C99).  See fs_oracle.h: TEST INFRASTRUCTURE ONLY; pinned by the reference's own
+ * function bodies compiled into oracle/_ref (tests/test_oracle_ref_ue.py) and by analytic KATs.
  *
  * Build: gcc -O2 -std=c99 -ffp-contract=off -fno-fast-math [-mfma] -pthread -fPIC -shared
  *
@@ -608,6 +608,34 @@ static inline void eval_segment(const fso_scene* sc, const fso_config* cfg, int3
     }
 }
 
+/* AddEnergyAtDelay, COMP.h:87-91: BinIndex = Clamp(FloorToInt(DelaySeconds * 1000 / BinSizeMs), 0, Num - 1) */
+int32_t fso_bin_index(const fso_config* cfg, float delay_s)
+{
+    float fb = floorf((delay_s * 1000.0f) / cfg->bin_ms);
+    if (!(fb >= 0.0f)) return 0;
+    if (fb >= (float)(cfg->n_bins - 1)) return (int32_t)cfg->n_bins - 1;      /* late energy clamps into the last bin */
+    return (int32_t)fb;
+}
+
+/* EvaluatePath (SUB.cpp:360-420) on an explicit node list, exactly the reference's loop over consecutive node pairs
+ * i -> i + 1 with node i's material and probability; pos [n][3] metres, mat[i] < 0 = no material.  Returns the delay and
+ * the clamped, gained energy per band.  (splat_path below is the same walk over F ++ reverse(B) without building the list.) */
+void fso_evaluate_nodes(const fso_scene* sc, const fso_config* cfg, const float* pos, const int32_t* mat, const float* prob,
+                        uint32_t n, float* delay_out, float* energy_out)
+{
+    float E[FSO_MAX_BANDS];
+    for (uint32_t b = 0; b < cfg->n_bands; ++b) E[b] = 1.0f;
+    float total = 0.0f;
+    for (uint32_t i = 0; i + 1 < n; ++i)
+        eval_segment(sc, cfg, mat[i], prob[i], dist3(pos + 3 * i, pos + 3 * (i + 1)), &total, E);
+    *delay_out = total / cfg->sound_speed;
+    for (uint32_t b = 0; b < cfg->n_bands; ++b) {
+        float e = E[b];
+        e = (e < cfg->energy_clamp) ? e : cfg->energy_clamp;
+        energy_out[b] = e * cfg->energy_gain;
+    }
+}
+
 /* EvaluatePath over F[0..nf) ++ reverse(B[0..nb)) (SUB.cpp:259-267, 360-420), then AddEnergyAtDelay (COMP.h:87-91).
  * `len` = length of the connecting segment F[nf-1] -> B[nb-1]; `weight` multiplies the clamped, gained energy
  * (1 for the reference's endpoint connection). */
@@ -623,12 +651,7 @@ static void splat_path(const fso_scene* sc, const fso_config* cfg, const pnode* 
     for (uint32_t j = nb - 1; j >= 1; --j)
         eval_segment(sc, cfg, bn[j].mat, bn[j].prob, dist3(bn[j].p, bn[j - 1].p), &total, E);
     float delay = total / cfg->sound_speed;       /* :419 */
-    /* AddEnergyAtDelay, COMP.h:87-91 */
-    float fb = floorf((delay * 1000.0f) / cfg->bin_ms);
-    int32_t bin;
-    if (!(fb >= 0.0f)) bin = 0;
-    else if (fb >= (float)(cfg->n_bins - 1)) bin = (int32_t)cfg->n_bins - 1;  /* late energy clamps */
-    else bin = (int32_t)fb;
+    const int32_t bin = fso_bin_index(cfg, delay);
     for (uint32_t b = 0; b < cfg->n_bands; ++b) {
         float e = E[b];
         e = (e < cfg->energy_clamp) ? e : cfg->energy_clamp;   /* :410, NaN -> clamp */

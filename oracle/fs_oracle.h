@@ -5,14 +5,24 @@
  * link or call this.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs use it, and only as the checker / the timed CPU baseline.
  *
- * PARITY STATUS: "parity unpinned" by the reference's own tests -- the reference
- * (henreedev/audio-pathtracer) ships no tests, golden vectors or fixtures for this path
- * (SURVEY.md section 4), its BDPT code cannot be compiled without Unreal Engine 5.4, and its
- * RNG is libc rand().  This file is therefore a *restatement* of the reference's algorithm
- * (every function cites the reference file:line it follows, with the KEEP/FIX/PARAM
- * dispositions of SURVEY.md section 8a) pinned by analytic known-answer tests
- * (tests/test_oracle_kat.py) and -- for the FFT/convolution stage, where the reference's
- * vendored KissFFT does compile -- by oracle/_ref (tests/test_oracle_ref_kissfft.py).
+ * PARITY STATUS: pinned by the reference's own code.  The reference (henreedev/audio-pathtracer) ships no tests, golden
+ * vectors or fixtures for this path and its plugin cannot be built without Unreal Engine 5.4, but the
+ * function bodies on the path are plain C++ over a handful of engine types.  oracle/Makefile therefore compiles, from the
+ * sources where they lie under /root/reference (nothing is copied into this repo):
+ *   oracle/_ref/libref_ue_bodies.so  the UNMODIFIED bodies of UpdateSource, GenerateFullPaths, ConnectSubpaths, GeneratePath,
+ *                                    EvaluatePath (SUB.cpp:128-420), FlushEnergyBuffer / AddEnergyAtDelay (COMP.h:76-91),
+ *                                    ReconstructImpulseResponse (COMP.cpp:320-380), the reverb plugin's Initialize and
+ *                                    ConvolveFFT (REV.cpp:74-102, 172-213), FCircularAudioBuffer (CIRC.cpp) and KissFFT,
+ *                                    against the engine stand-in oracle/ue_shim/CoreMinimal.h (oracle/ref_ue_bodies.cpp,
+ *                                    oracle/extract_ue_bodies.py)
+ *   oracle/_ref/libref_kissfft.so    the reference's KissFFT + a restated driver of its convolution scheme
+ * and tests/test_oracle_ref_ue.py runs this file against them with the reference's constants: same rays traced, same
+ * per-path node counts / connections / delays / gains, histogram within 2e-5 (float vs double rounding), bin index exact,
+ * ReconstructImpulseResponse BIT-EXACT.  What stands in for the engine (the absent third-party dependency): the scene query
+ * (UWorld::LineTraceSingleByObjectType) and the random numbers (FMath::FRand / VRand / VRandCone -> Philox) -- that is where the
+ * REPLACE / FIX dispositions of SURVEY.md section 8a enter.  The remaining dispositions (metres instead of "/ 1000", B bands,
+ * 48 samples per bin, Q32.32 integers, miss terminates, max_depth) are parameters of this file whose reference values the pin
+ * tests use; analytic known-answer tests (tests/test_oracle_kat.py) cover the rest.
  *
  * Reference aliases: SUB.cpp = Plugins/FrequenSee/Source/FrequenSee/Private/AudioRayTracingSubsystem.cpp
  *                    COMP.h/.cpp = .../FrequenSeeAudioComponent.{h,cpp}
@@ -114,6 +124,12 @@ int fso_trace(const fso_scene* sc, const fso_config* cfg, const float* src_pos, 
               const float lis_pos[3], uint64_t n_paths, uint64_t g_first, uint64_t g_count,
               uint32_t max_depth, uint64_t seed, uint64_t* hist, fso_stats* stats,
               fso_path_dbg* dbg, int n_threads);
+
+/* EvaluatePath (SUB.cpp:360-420) on an explicit node list; AddEnergyAtDelay's bin index (COMP.h:87-91).  Exposed so that
+ * tests can pin them one to one against the reference's own bodies (oracle/_ref/libref_ue_bodies.so). */
+void fso_evaluate_nodes(const fso_scene* sc, const fso_config* cfg, const float* pos, const int32_t* mat, const float* prob,
+                        uint32_t n, float* delay_out, float* energy_out);
+int32_t fso_bin_index(const fso_config* cfg, float delay_s);
 
 /* ---- IR (COMP.cpp:320-380) ---- */
 /* hist: [B][K] for one source; ir_out: [C][sample_rate] */

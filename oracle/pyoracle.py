@@ -100,6 +100,10 @@ def lib():
         L.fso_trace.argtypes = [C.c_void_p, C.POINTER(Config), C.c_void_p, C.c_uint32, C.c_void_p,
                                 C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64,
                                 C.c_void_p, C.POINTER(Stats), C.c_void_p, C.c_int]
+        L.fso_evaluate_nodes.argtypes = [C.c_void_p, C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, fp, C.c_void_p]
+        L.fso_evaluate_nodes.restype = None
+        L.fso_bin_index.argtypes = [C.POINTER(Config), C.c_float]
+        L.fso_bin_index.restype = C.c_int32
         L.fso_build_ir.argtypes = [C.POINTER(Config), C.c_void_p, C.c_uint64, C.c_void_p]
         L.fso_build_ir_from_energy.argtypes = [C.POINTER(Config), C.c_void_p, C.c_void_p]
         L.fso_band_carriers.argtypes = [C.POINTER(Config), C.c_uint64, C.c_void_p]
@@ -236,6 +240,21 @@ class Scene:
         return (hist, st.as_dict(), dbg) if debug else (hist, st.as_dict())
 
 
+def evaluate_nodes(scene, cfg, pos, mat, prob):
+    """EvaluatePath (SUB.cpp:360-420) on an explicit node list -> (delay_s, energy[B])"""
+    pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+    mat = np.ascontiguousarray(mat, dtype=np.int32)
+    prob = np.ascontiguousarray(prob, dtype=np.float32)
+    d = C.c_float()
+    e = np.zeros(cfg.n_bands, np.float32)
+    lib().fso_evaluate_nodes(scene.h, C.byref(cfg), pos.ctypes.data, mat.ctypes.data, prob.ctypes.data, len(pos), C.byref(d), e.ctypes.data)
+    return d.value, e
+
+
+def bin_index(cfg, delay_s):
+    return int(lib().fso_bin_index(C.byref(cfg), float(delay_s)))
+
+
 def build_ir(cfg, hist, n_paths):
     hist = np.ascontiguousarray(hist, dtype=np.uint64)
     out = np.zeros((cfg.n_channels, cfg.sample_rate), dtype=np.float32)
@@ -324,3 +343,155 @@ def kiss_fftr(x):
     out = np.zeros((len(x) // 2 + 1, 2), dtype=np.float32)
     R.ref_kiss_fftr(len(x), x.ctypes.data, out.ctypes.data)
     return out[:, 0] + 1j * out[:, 1]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# oracle/_ref/libref_ue_bodies.so: the REFERENCE's own UpdateSource / GenerateFullPaths / ConnectSubpaths / GeneratePath /
+# EvaluatePath / AddEnergyAtDelay / ReconstructImpulseResponse / ConvolveFFT / FCircularAudioBuffer, compiled from
+# /root/reference against oracle/ue_shim (see oracle/ref_ue_bodies.cpp).  Used to pin fs_oracle.c.
+# ---------------------------------------------------------------------------------------------------------------------
+_ue = None
+
+UE_PATH_REC = np.dtype([("n_src_nodes", np.uint32), ("n_lis_nodes", np.uint32), ("connected", np.uint32), ("pad", np.uint32),
+                        ("delay_s", np.float32), ("gain", np.float32), ("src_end", np.float64, (3,)), ("lis_end", np.float64, (3,))])
+
+
+def ref_ue_lib():
+    """None when oracle/_ref/libref_ue_bodies.so was never built (reference tree absent and no prebuilt copy)"""
+    global _ue
+    if _ue is None:
+        p = os.path.join(HERE, "_ref", "libref_ue_bodies.so")
+        if not os.path.exists(p):
+            if os.path.isdir("/root/reference"):
+                subprocess.check_call(["make", "-C", HERE, "-s", "ref_ue"], stdout=subprocess.DEVNULL)
+            if not os.path.exists(p):
+                return None
+        U = C.CDLL(p)
+        vp = C.c_void_p
+        U.ref_ue_world_create.restype = vp
+        U.ref_ue_world_create.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint32, C.c_double]
+        U.ref_ue_world_destroy.argtypes = [vp]
+        U.ref_ue_world_destroy.restype = None
+        U.ref_ue_update_source.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, vp, vp, C.POINTER(C.c_uint64)]
+        U.ref_ue_paths.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_int, vp]
+        U.ref_ue_evaluate_path.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        U.ref_ue_add_energy.argtypes = [vp, vp, C.c_int, vp]
+        U.ref_ue_reconstruct_ir.argtypes = [vp, vp]
+        U.ref_ue_conv_create.restype = vp
+        U.ref_ue_conv_create.argtypes = [C.c_int, C.c_int]
+        U.ref_ue_conv_destroy.argtypes = [vp]
+        U.ref_ue_conv_destroy.restype = None
+        U.ref_ue_conv_fft_size.argtypes = [vp]
+        U.ref_ue_conv_set_ir.argtypes = [vp, vp]
+        U.ref_ue_conv_set_ir.restype = None
+        U.ref_ue_conv_process.argtypes = [vp, vp, vp, C.c_int]
+        U.ref_ue_conv_process.restype = None
+        _ue = U
+    return _ue
+
+
+# the reference's compile-time constants as an oracle configuration (SURVEY.md appendix A): one band, Absorption[2] used as
+# reflectivity, distances in units of 1000 world units, "NodeDistance < 1" skip, air 0.05, offsets 0.1 world units
+UE_UNIT = 1000.0          # world units per metre in the pin tests, so that EvaluatePath's "/ 1000" yields metres
+
+
+def ue_pin_config(**over):
+    kw = dict(n_bands=1, n_bins=1000, bin_ms=1.0, rr_prob=0.9, eps_offset=0.1 / UE_UNIT, eps_connect=0.1 / UE_UNIT, min_seg=1.0,
+              sound_speed=343.0, pdf_exponent=0.1, energy_clamp=1.0, energy_gain=10.0, air_absorption=[0.05] * MAX_BANDS)
+    kw.update(over)
+    return default_config(**kw)
+
+
+class RefUEWorld:
+    """a triangle scene inside the engine stand-in; value2[m] = Absorption[2].Value of material m (used as reflectivity)"""
+
+    def __init__(self, verts, tri_mat, value2, unit=UE_UNIT):
+        self.U = ref_ue_lib()
+        if self.U is None:
+            raise RuntimeError("oracle/_ref/libref_ue_bodies.so not built")
+        v = np.ascontiguousarray(verts, np.float32).reshape(-1, 3, 3)
+        m = np.ascontiguousarray(tri_mat, np.uint32)
+        a = np.ascontiguousarray(value2, np.float32)
+        self.unit = unit
+        self.h = self.U.ref_ue_world_create(v.ctypes.data, m.ctypes.data, len(v), a.ctypes.data, len(a), unit)
+
+    def update_source(self, src, lis, seed, g_first=0):
+        """the reference's UpdateSource, whole and unmodified: (EnergyBuffer[1000], ImpulseBuffer[2][48000], line traces)"""
+        s, l = np.ascontiguousarray(src, np.float32).reshape(3), np.ascontiguousarray(lis, np.float32).reshape(3)
+        e = np.zeros(1000, np.float32); ir = np.zeros((2, 48000), np.float32); n = C.c_uint64()
+        rc = self.U.ref_ue_update_source(self.h, s.ctypes.data, l.ctypes.data, seed, g_first, e.ctypes.data, ir.ctypes.data, C.byref(n))
+        assert rc == 0
+        return e, ir, n.value
+
+    def paths(self, src, lis, seed, n, g_first=0):
+        s, l = np.ascontiguousarray(src, np.float32).reshape(3), np.ascontiguousarray(lis, np.float32).reshape(3)
+        rec = np.zeros(n, UE_PATH_REC)
+        rc = self.U.ref_ue_paths(self.h, s.ctypes.data, l.ctypes.data, seed, g_first, n, rec.ctypes.data)
+        assert rc == 0, rc
+        return rec
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.U.ref_ue_world_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ref_ue_evaluate_path(pos_units, value2, prob):
+    U = ref_ue_lib()
+    p = np.ascontiguousarray(pos_units, np.float64).reshape(-1, 3)
+    a = np.ascontiguousarray(value2, np.float32); q = np.ascontiguousarray(prob, np.float32)
+    d, g = C.c_float(), C.c_float()
+    U.ref_ue_evaluate_path(p.ctypes.data, a.ctypes.data, q.ctypes.data, len(p), C.byref(d), C.byref(g))
+    return d.value, g.value
+
+
+def ref_ue_add_energy(delays, energies):
+    U = ref_ue_lib()
+    d = np.ascontiguousarray(delays, np.float32); e = np.ascontiguousarray(energies, np.float32)
+    out = np.zeros(1000, np.float32)
+    U.ref_ue_add_energy(d.ctypes.data, e.ctypes.data, len(d), out.ctypes.data)
+    return out
+
+
+def ref_ue_reconstruct_ir(energy):
+    """-> (ir[2][48000], the NumSamplesPerBin the reference computes)"""
+    U = ref_ue_lib()
+    e = np.ascontiguousarray(energy, np.float32)
+    ir = np.zeros((2, 48000), np.float32)
+    spb = U.ref_ue_reconstruct_ir(e.ctypes.data, ir.ctypes.data)
+    return ir, spb
+
+
+class RefUEConv:
+    """the reference's reverb: its Initialize + ConvolveFFT bodies, its FCircularAudioBuffer and its KissFFT"""
+
+    def __init__(self, sample_rate=48000, frame=1024):
+        self.U = ref_ue_lib()
+        if self.U is None:
+            raise RuntimeError("oracle/_ref/libref_ue_bodies.so not built")
+        self.h = self.U.ref_ue_conv_create(sample_rate, frame)
+
+    @property
+    def fft_size(self):
+        return self.U.ref_ue_conv_fft_size(self.h)
+
+    def set_ir(self, ir):
+        ir = np.ascontiguousarray(ir, np.float32)
+        self.U.ref_ue_conv_set_ir(self.h, ir.ctypes.data)
+
+    def process(self, block, clamp=True):
+        block = np.ascontiguousarray(block, np.float32)
+        out = np.zeros_like(block)
+        self.U.ref_ue_conv_process(self.h, block.ctypes.data, out.ctypes.data, int(clamp))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.U.ref_ue_conv_destroy(self.h)
+            self.h = None
