@@ -8,7 +8,8 @@
 #include <new>
 #include <vector>
 
-static thread_local std::string g_create_err;
+// last failure message of the CALLING THREAD (the game thread and the audio thread use one context concurrently)
+static thread_local std::string g_err;
 
 #define CK(call)                                                                              \
     do {                                                                                      \
@@ -18,14 +19,17 @@ static thread_local std::string g_create_err;
 
 static int fail(fs_ctx* ctx, int code, const char* msg)
 {
-    if (ctx) ctx->err = msg; else g_create_err = msg;
+    (void)ctx;
+    g_err = msg;
     return code;
 }
 static int fail_cuda(fs_ctx* ctx, cudaError_t e, const char* what)
 {
     char buf[512];
     snprintf(buf, sizeof(buf), "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
-    if (ctx) ctx->err = buf; else g_create_err = buf;
+    (void)ctx;
+    g_err = buf;
+    (void)cudaGetLastError();
     return e == cudaErrorMemoryAllocation ? FS_ERR_NOMEM : FS_ERR_CUDA;
 }
 
@@ -50,7 +54,7 @@ void fs_default_config(fs_config* c)
     c->max_batch_paths = 0; c->flags = 0; c->device = -1;
 }
 
-const char* fs_last_error(const fs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+const char* fs_last_error(const fs_ctx* ctx) { (void)ctx; return g_err.c_str(); }
 
 int fs_create(const fs_config* cfg, fs_ctx** out)
 {
@@ -64,6 +68,17 @@ int fs_create(const fs_config* cfg, fs_ctx** out)
     if (cfg->conv_block < 32 || cfg->conv_block > 2048 || (cfg->conv_block & (cfg->conv_block - 1)))
         return fail(nullptr, FS_ERR_INVALID, "conv_block must be a power of two in 32..2048");
     if (cfg->sample_rate < cfg->conv_block) return fail(nullptr, FS_ERR_INVALID, "sample_rate < conv_block");
+    if ((uint32_t)((double)cfg->bin_ms * 1e-3 * cfg->sample_rate + 0.5) < 1u)
+        return fail(nullptr, FS_ERR_INVALID, "bin_ms * sample_rate / 1000 must be at least one sample");
+    if (!(cfg->ir_lowpass > 0.0f) || cfg->ir_lowpass > 1.0f) return fail(nullptr, FS_ERR_INVALID, "ir_lowpass must be in (0,1]");
+    // warm-up window of the per-sample low-pass evaluation: (1 - a)^W <= 1e-12, a multiple of 32 taps
+    uint32_t ir_window = 32;
+    if (cfg->ir_lowpass < 1.0f) {
+        const double w = ceil(log(1e-12) / log(1.0 - (double)cfg->ir_lowpass));
+        if (!(w <= 8192.0)) return fail(nullptr, FS_ERR_INVALID, "ir_lowpass too small (needs a warm-up window above 8192 samples)");
+        ir_window = ((uint32_t)w + 31u) & ~31u;
+        if (ir_window < 32u) ir_window = 32u;
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -80,6 +95,8 @@ int fs_create(const fs_config* cfg, fs_ctx** out)
     ctx->cfg = *cfg;
     if (ctx->cfg.max_batch_paths == 0) ctx->cfg.max_batch_paths = 1u << 21;
     ctx->device = dev;
+    ctx->ir_window = ir_window;
+    ctx->launches.store(0);
     ctx->tune_refill = 4; ctx->tune_leaf_max = FS_LEAF_MAX; ctx->tune_tex = 2; ctx->tune_builder = 1; ctx->tune_wide = 1; ctx->tune_node_min = 14; ctx->tune_tri_min = 4; ctx->tune_collapse = 1; ctx->tune_l2pin_mb = 0; ctx->tune_streams = 2;
     if (const char* e14 = getenv("FS_TUNE_STREAMS")) { int v = atoi(e14); if (v >= 1 && v <= FS_MAX_LANES) ctx->tune_streams = (uint32_t)v; } ctx->tune_tq = 2;      // 0: phased kernels, 1: queue kernel for extension rays only, 2: also for connection rays
     ctx->tune_tq_node_min = 10; ctx->tune_tq_flush = 24;
@@ -112,15 +129,20 @@ int fs_create(const fs_config* cfg, fs_ctx** out)
         ctx->sm_count = prop.multiProcessorCount;
         if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaStreamCreate"); break; }
         ctx->stream = ctx->own_stream;
-        if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaEventCreate"); break; }
+        if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+            (e = cudaEventCreate(&ctx->ev_ir0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_ir1)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaEventCreate"); break; }
         if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaEventCreate"); break; }
-        for (int l = 0; l < FS_MAX_LANES - 1 && e == cudaSuccess; ++l) {
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_overflow, cudaEventDisableTiming)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaEventCreate"); break; }
+        if ((e = cudaMallocHost(&ctx->h_overflow, sizeof(uint32_t))) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaMallocHost"); break; }
+        *ctx->h_overflow = 0u;
+        for (int l = 1; l < FS_MAX_LANES && e == cudaSuccess; ++l) {          // lane 0 runs on the context stream itself
             if ((e = cudaStreamCreateWithFlags(&ctx->lanes[l].stream, cudaStreamNonBlocking)) != cudaSuccess) break;
             e = cudaEventCreateWithFlags(&ctx->lanes[l].done, cudaEventDisableTiming);
         }
         if (e != cudaSuccess) { rc = fail_cuda(nullptr, e, "batch lanes"); break; }
         if ((e = cudaMalloc(&ctx->d_counters, sizeof(fs_dev_counters))) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaMalloc counters"); break; }
-        if ((e = cudaMemset(ctx->d_counters, 0, sizeof(fs_dev_counters))) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaMemset"); break; }
+        if ((e = cudaMemsetAsync(ctx->d_counters, 0, sizeof(fs_dev_counters), ctx->own_stream)) != cudaSuccess ||
+            (e = cudaStreamSynchronize(ctx->own_stream)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaMemset"); break; }
         if ((e = cudaMalloc(&ctx->d_amp, sizeof(float) * cfg->n_bins)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaMalloc amp"); break; }
         if ((e = cudaMalloc(&ctx->d_energy, sizeof(float) * cfg->n_bins)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaMalloc energy"); break; }
         if ((e = fs_conv_setup(ctx)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "fs_conv_setup"); break; }
@@ -138,13 +160,15 @@ void fs_destroy(fs_ctx* ctx)
     fs_conv_teardown(ctx);
     cudaFree(ctx->d_carriers); cudaFree(ctx->d_amp_bands); cudaFree(ctx->d_amp_all);
     cudaFree(ctx->lis_rec); cudaFree(ctx->lis_end);
-    fs_wave_free(&ctx->wb);
-    for (int l = 0; l < FS_MAX_LANES - 1; ++l) {
+    for (int l = 0; l < FS_MAX_LANES; ++l) {
         fs_wave_free(&ctx->lanes[l].wb);
-        if (ctx->lanes[l].stream) cudaStreamDestroy(ctx->lanes[l].stream);
+        if (l && ctx->lanes[l].stream) cudaStreamDestroy(ctx->lanes[l].stream);
         if (ctx->lanes[l].done) cudaEventDestroy(ctx->lanes[l].done);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_overflow) cudaEventDestroy(ctx->ev_overflow);
+    if (ctx->h_overflow) cudaFreeHost(ctx->h_overflow);
+    cudaFree(ctx->d_mat_ext);
     fs_bvh_free(&ctx->bvh);
     cudaFree(ctx->d_verts); cudaFree(ctx->d_tri_mat); cudaFree(ctx->d_refl_over_pi);
     cudaFree(ctx->d_hist); cudaFree(ctx->d_counters); cudaFree(ctx->d_src_pos); cudaFree(ctx->d_dbg);
@@ -153,11 +177,29 @@ void fs_destroy(fs_ctx* ctx)
     for (cudaEvent_t e : ctx->tev) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_ir0) cudaEventDestroy(ctx->ev_ir0);
+    if (ctx->ev_ir1) cudaEventDestroy(ctx->ev_ir1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
 
 static void apply_l2_policy(fs_ctx* ctx);
+
+// Traversal-stack overflow of an earlier trace (fs_dev_counters::overflow, copied to pinned memory by one 4-byte async
+// copy after every fs_trace*).  wait = false: look only if the copy has landed (never blocks); the flag stays on the
+// device until the host has seen it, so it cannot be lost between two asynchronous traces.
+static int check_overflow(fs_ctx* ctx, bool wait)
+{
+    if (!ctx->overflow_pending) return FS_OK;
+    if (wait) { CK(cudaEventSynchronize(ctx->ev_overflow)); }
+    else if (cudaEventQuery(ctx->ev_overflow) != cudaSuccess) { (void)cudaGetLastError(); return FS_OK; }
+    ctx->overflow_pending = false;
+    if (*ctx->h_overflow) {
+        *ctx->h_overflow = 0u;
+        return fail(ctx, FS_ERR_OVERFLOW, "BVH traversal stack overflow in the last trace (tree deeper than FS_STACK_SIZE): its histogram is incomplete");
+    }
+    return FS_OK;
+}
 
 int fs_set_stream(fs_ctx* ctx, void* cuda_stream)
 {
@@ -172,7 +214,7 @@ int fs_synchronize(fs_ctx* ctx)
     if (!ctx) return FS_ERR_INVALID;
     dev_guard g(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream));
-    return FS_OK;
+    return check_overflow(ctx, true);
 }
 
 // ---- scene -----------------------------------------------------------------------------------
@@ -215,7 +257,8 @@ int fs_scene_set_materials(fs_ctx* ctx, const float* absorption, uint32_t n_mate
     }
     cudaFree(ctx->d_refl_over_pi); ctx->d_refl_over_pi = nullptr;
     CK(cudaMalloc(&ctx->d_refl_over_pi, sizeof(float) * r.size()));
-    CK(cudaMemcpy(ctx->d_refl_over_pi, r.data(), sizeof(float) * r.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(ctx->d_refl_over_pi, r.data(), sizeof(float) * r.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     ctx->n_mats = n_materials; ctx->mats_set = true; ctx->committed = false;
     return FS_OK;
 }
@@ -275,13 +318,16 @@ int fs_scene_commit(fs_ctx* ctx)
     if (ctx->n_tris) {
         // validate material ids on the host copy-back of the id array (one-time, commit only)
         std::vector<uint32_t> m(ctx->n_tris);
-        CK(cudaMemcpy(m.data(), ctx->d_tri_mat, sizeof(uint32_t) * ctx->n_tris, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpyAsync(m.data(), ctx->d_tri_mat, sizeof(uint32_t) * ctx->n_tris, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
         for (uint64_t i = 0; i < ctx->n_tris; ++i)
             if (m[i] >= ctx->n_mats) return fail(ctx, FS_ERR_INVALID, "triangle material id out of range");
     }
-    CK(fs_bvh_build(ctx->stream, ctx->d_verts, ctx->d_tri_mat, ctx->n_tris, &ctx->bvh, &ctx->stats.kernel_launches,
+    uint64_t bvh_launches = 0;
+    CK(fs_bvh_build(ctx->stream, ctx->d_verts, ctx->d_tri_mat, ctx->n_tris, &ctx->bvh, &bvh_launches,
                     ctx->tune_leaf_max, ctx->tune_builder, ctx->tune_collapse));
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->launches.fetch_add(bvh_launches);
     ctx->stats.bvh_nodes = ctx->bvh.n_inner;
     if (getenv("FS_VERBOSE")) fprintf(stderr, "[frequensee] BVH: %u triangles, %u BVH2 nodes, %u reachable 4-wide nodes (%.1f MB)\n",
                                       ctx->bvh.n_tris, ctx->bvh.n_inner, ctx->bvh.n_wide, ctx->bvh.n_wide * 64.0 / 1e6);
@@ -316,13 +362,12 @@ static void fill_params(fs_ctx* ctx, fs_trace_params* tp, const float lis[3], ui
     tp->src_pos = ctx->d_src_pos;
     if (lis) { tp->lis[0] = lis[0]; tp->lis[1] = lis[1]; tp->lis[2] = lis[2]; }
     tp->flags = c.flags;
-    tp->cap = ctx->wb.cap;
 }
 
 static int ensure_hist(fs_ctx* ctx, uint32_t n_sources)
 {
     if (ctx->d_hist && ctx->hist_sources >= n_sources) return FS_OK;
-    cudaFree(ctx->d_hist); ctx->d_hist = nullptr;
+    cudaFree(ctx->d_hist); ctx->d_hist = nullptr; ctx->hist_sources = 0; ctx->hist_cur_sources = 0;
     const size_t n = (size_t)n_sources * ctx->cfg.n_bands * ctx->cfg.n_bins;
     CK(cudaMalloc(&ctx->d_hist, 8 * n));
     ctx->hist_sources = n_sources;
@@ -350,6 +395,11 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
     if (max_depth > 1024) return fail(ctx, FS_ERR_INVALID, "fs_trace: max_depth > 1024");
     if (g_first + g_count > (uint64_t)n_sources * n_paths) return fail(ctx, FS_ERR_INVALID, "fs_trace: work range exceeds n_sources * n_paths");
     if ((uint64_t)n_sources * ctx->cfg.n_bins >= 0xffffffffull) return fail(ctx, FS_ERR_INVALID, "fs_trace: n_sources * n_bins too large");
+    // an overflow of the PREVIOUS trace that nobody has looked at yet: report it now if its flag has landed; if it is
+    // still in flight the device flag is left set (reset_ovf = 0) so that this call's copy carries it
+    int rc_ovf = check_overflow(ctx, false);
+    if (rc_ovf) return rc_ovf;
+    const int reset_ovf = ctx->overflow_pending ? 0 : 1;
     if (ctx->src_cap < n_sources) {
         cudaFree(ctx->d_src_pos); ctx->d_src_pos = nullptr;
         CK(cudaMalloc(&ctx->d_src_pos, sizeof(float) * 3 * n_sources));
@@ -378,23 +428,19 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
         if (cap_cfg > lim) cap_cfg = lim;
         n_lanes = 1;
     }
+    if (ctx->tune_mega && !(ctx->cfg.flags & (FS_FLAG_COUNT_VISITS | FS_FLAG_TIME_KERNELS))) n_lanes = 1;   // the persistent per-batch kernel owns the whole GPU
     while (n_lanes > 1 && g_count / n_lanes < (1u << 17)) --n_lanes;            // small jobs: not worth a second set of launches
     uint64_t n_batches = g_count ? (g_count + cap_cfg - 1) / cap_cfg : 1;
     if (n_batches < n_lanes) n_batches = n_lanes;
     if (n_batches % n_lanes) n_batches += n_lanes - n_batches % n_lanes;
     const uint32_t cap = (uint32_t)(g_count ? (g_count + n_batches - 1) / n_batches : 1);
-    CK(fs_wave_alloc(ctx, cap, max_depth));
-    for (uint32_t l = 1; l < n_lanes; ++l) {
-        std::swap(ctx->wb, ctx->lanes[l - 1].wb);
-        cudaError_t ea = fs_wave_alloc(ctx, cap, max_depth);
-        std::swap(ctx->wb, ctx->lanes[l - 1].wb);
-        CK(ea);
-    }
+    ctx->lanes[0].stream = ctx->stream;                       // lane 0 = the caller's stream; nothing else is rebound
+    for (uint32_t l = 0; l < n_lanes; ++l) CK(fs_wave_alloc(ctx, &ctx->lanes[l], cap, max_depth));
     fs_trace_params tp;
     fill_params(ctx, &tp, lis_pos, n_paths, max_depth, seed);
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     ctx->kev_used = 0; ctx->tev_used = 0; ctx->stats.extend_launches = 0;
-    CK(fs_wave_reset_counters(ctx));
+    CK(fs_wave_reset_counters(ctx, reset_ovf));
     // FS_FLAG_SHARE_LISTENER with more than one source's worth of work: trace the n_paths listener subpaths once, now, and
     // let every source batch copy them in (smaller jobs just use the shared keying and trace them in place)
     if ((ctx->cfg.flags & FS_FLAG_SHARE_LISTENER) && !(ctx->cfg.flags & FS_FLAG_CONNECT_ALL) && !d_dbg && n_sources > 1 &&
@@ -411,13 +457,13 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
         for (uint64_t i0 = 0; i0 < n_paths; i0 += cap) {
             tp.g_first = i0;
             tp.batch = (uint32_t)(n_paths - i0 < cap ? n_paths - i0 : cap);
-            CK(fs_wave_trace_batch(ctx, tp, d_hist, nullptr));
+            CK(fs_wave_trace_batch(ctx, &ctx->lanes[0], tp, d_hist, nullptr));
         }
         tp.lis_mode = 2;
     }
     if (n_lanes > 1) {
         CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-        for (uint32_t l = 1; l < n_lanes; ++l) CK(cudaStreamWaitEvent(ctx->lanes[l - 1].stream, ctx->ev_fork, 0));
+        for (uint32_t l = 1; l < n_lanes; ++l) CK(cudaStreamWaitEvent(ctx->lanes[l].stream, ctx->ev_fork, 0));
     }
     uint32_t b = 0;
     for (uint64_t done = 0; done < g_count; ++b) {
@@ -426,27 +472,24 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
         tp.g_first = g_first + done;
         tp.batch = (uint32_t)nb;
         const uint32_t l = b % n_lanes;
-        cudaError_t eb;
-        if (l == 0) eb = fs_wave_trace_batch(ctx, tp, d_hist, d_dbg ? d_dbg + done : nullptr);
-        else {                                       // run the batch with the lane's stream and buffers swapped in
-            cudaStream_t main_stream = ctx->stream;
-            std::swap(ctx->wb, ctx->lanes[l - 1].wb); ctx->stream = ctx->lanes[l - 1].stream;
-            eb = fs_wave_trace_batch(ctx, tp, d_hist, nullptr);
-            std::swap(ctx->wb, ctx->lanes[l - 1].wb); ctx->stream = main_stream;
-        }
-        CK(eb);
+        CK(fs_wave_trace_batch(ctx, &ctx->lanes[l], tp, d_hist, (d_dbg && l == 0) ? d_dbg + done : nullptr));
         done += nb;
     }
     for (uint32_t l = 1; l < n_lanes; ++l) {
-        CK(cudaEventRecord(ctx->lanes[l - 1].done, ctx->lanes[l - 1].stream));
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->lanes[l - 1].done, 0));
+        CK(cudaEventRecord(ctx->lanes[l].done, ctx->lanes[l].stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->lanes[l].done, 0));
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    // one 4-byte copy of the overflow flag on every return path (the async ones included)
+    CK(cudaMemcpyAsync(ctx->h_overflow, &ctx->d_counters->overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_overflow, ctx->stream));
+    ctx->overflow_pending = true;
     ctx->timed = true;
     ctx->stats.paths = g_count;
     return FS_OK;
 }
 
+// synchronises the context stream and fills the host-side statistics of the last trace
 static int finish_stats(fs_ctx* ctx)
 {
     fs_dev_counters h;
@@ -484,8 +527,12 @@ static int finish_stats(fs_ctx* ctx)
         if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.last_trace_ms = ms;
         else (void)cudaGetLastError();
     }
-    if (h.overflow) return fail(ctx, FS_ERR_OVERFLOW, "BVH traversal stack overflow (tree deeper than FS_STACK_SIZE)");
-    return FS_OK;
+    if (ctx->ir_timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev_ir0, ctx->ev_ir1) == cudaSuccess) ctx->stats.last_ir_ms = ms;
+        else (void)cudaGetLastError();
+    }
+    return check_overflow(ctx, true);
 }
 
 int fs_trace(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, const float lis_pos[3], uint64_t n_paths,
@@ -501,7 +548,7 @@ int fs_trace(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, const float 
     rc = trace_common(ctx, src_pos, n_sources, lis_pos, n_paths, 0, (uint64_t)n_sources * n_paths, max_depth, seed,
                       ctx->d_hist, nullptr);
     if (rc) return rc;
-    ctx->hist_n_paths = n_paths;
+    ctx->hist_n_paths = n_paths; ctx->hist_cur_sources = n_sources;
     if (hist_out) {
         CK(cudaMemcpyAsync(hist_out, ctx->d_hist, 8 * hn, cudaMemcpyDeviceToHost, ctx->stream));
         return finish_stats(ctx);
@@ -534,7 +581,7 @@ int fs_trace_range(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, const 
     CK(cudaMemcpyAsync(ctx->d_hist, hist_inout, 8 * hn, cudaMemcpyHostToDevice, ctx->stream));
     rc = trace_common(ctx, src_pos, n_sources, lis_pos, n_paths, g_first, g_count, max_depth, seed, ctx->d_hist, nullptr);
     if (rc) return rc;
-    ctx->hist_n_paths = n_paths;
+    ctx->hist_n_paths = n_paths; ctx->hist_cur_sources = n_sources;
     CK(cudaMemcpyAsync(hist_inout, ctx->d_hist, 8 * hn, cudaMemcpyDeviceToHost, ctx->stream));
     return finish_stats(ctx);
 }
@@ -548,7 +595,7 @@ int fs_trace_debug(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, const 
     int rc = ensure_hist(ctx, n_sources);
     if (rc) return rc;
     if (ctx->dbg_cap < g_count) {
-        cudaFree(ctx->d_dbg); ctx->d_dbg = nullptr;
+        cudaFree(ctx->d_dbg); ctx->d_dbg = nullptr; ctx->dbg_cap = 0;
         CK(cudaMalloc(&ctx->d_dbg, sizeof(fs_path_dbg) * g_count));
         ctx->dbg_cap = g_count;
     }
@@ -556,6 +603,7 @@ int fs_trace_debug(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, const 
     CK(cudaMemsetAsync(ctx->d_hist, 0, 8 * hn, ctx->stream));
     rc = trace_common(ctx, src_pos, n_sources, lis_pos, n_paths, g_first, g_count, max_depth, seed, ctx->d_hist, ctx->d_dbg);
     if (rc) return rc;
+    ctx->hist_n_paths = n_paths; ctx->hist_cur_sources = n_sources;
     CK(cudaMemcpyAsync(dbg_out, ctx->d_dbg, sizeof(fs_path_dbg) * g_count, cudaMemcpyDeviceToHost, ctx->stream));
     return finish_stats(ctx);
 }
@@ -570,28 +618,30 @@ static int debug_rays(fs_ctx* ctx, const float* rays, const float* tmax, uint64_
     float *d_rays = nullptr, *d_tmax = nullptr, *d_t = nullptr; uint32_t* d_tri = nullptr; uint8_t* d_hit = nullptr;
     int rc = FS_OK;
     cudaError_t e = cudaSuccess;
+    cudaStream_t st = ctx->stream;
     fs_trace_params tp;
     fill_params(ctx, &tp, nullptr, 1, 1, 0);
     do {
         if ((e = cudaMalloc(&d_rays, sizeof(float) * 6 * n)) != cudaSuccess) break;
-        if ((e = cudaMemcpy(d_rays, rays, sizeof(float) * 6 * n, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(d_rays, rays, sizeof(float) * 6 * n, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
         if (out_hit) {
             if ((e = cudaMalloc(&d_tmax, sizeof(float) * n)) != cudaSuccess) break;
-            if ((e = cudaMemcpy(d_tmax, tmax, sizeof(float) * n, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+            if ((e = cudaMemcpyAsync(d_tmax, tmax, sizeof(float) * n, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
             if ((e = cudaMalloc(&d_hit, n)) != cudaSuccess) break;
         } else {
             if ((e = cudaMalloc(&d_t, sizeof(float) * n)) != cudaSuccess) break;
             if ((e = cudaMalloc(&d_tri, sizeof(uint32_t) * n)) != cudaSuccess) break;
         }
-        if ((e = fs_wave_reset_counters(ctx)) != cudaSuccess) break;
+        if ((e = fs_wave_reset_counters(ctx, 1)) != cudaSuccess) break;
         if ((e = fs_wave_debug_rays(ctx, tp, d_rays, d_tmax, n, d_t, d_tri, d_hit)) != cudaSuccess) break;
-        if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) break;
-        if (out_hit) { if ((e = cudaMemcpy(out_hit, d_hit, n, cudaMemcpyDeviceToHost)) != cudaSuccess) break; }
+        if (out_hit) { if ((e = cudaMemcpyAsync(out_hit, d_hit, n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break; }
         else {
-            if ((e = cudaMemcpy(out_t, d_t, sizeof(float) * n, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
-            if ((e = cudaMemcpy(out_tri, d_tri, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+            if ((e = cudaMemcpyAsync(out_t, d_t, sizeof(float) * n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+            if ((e = cudaMemcpyAsync(out_tri, d_tri, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
         }
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
     } while (0);
+    if (e != cudaSuccess) cudaStreamSynchronize(st);
     cudaFree(d_rays); cudaFree(d_tmax); cudaFree(d_t); cudaFree(d_tri); cudaFree(d_hit);
     if (e != cudaSuccess) rc = fail_cuda(ctx, e, "fs_debug rays");
     return rc;
@@ -619,7 +669,7 @@ int fs_set_histogram(fs_ctx* ctx, const uint64_t* hist, uint32_t n_sources, uint
     const size_t hn = (size_t)n_sources * ctx->cfg.n_bands * ctx->cfg.n_bins;
     CK(cudaMemcpyAsync(ctx->d_hist, hist, 8 * hn, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->hist_n_paths = n_paths;
+    ctx->hist_n_paths = n_paths; ctx->hist_cur_sources = n_sources;
     return FS_OK;
 }
 
@@ -632,57 +682,88 @@ int fs_set_histogram_device(fs_ctx* ctx, const void* d_hist, uint32_t n_sources,
     if (rc) return rc;
     const size_t hn = (size_t)n_sources * ctx->cfg.n_bands * ctx->cfg.n_bins;
     CK(cudaMemcpyAsync(ctx->d_hist, d_hist, 8 * hn, cudaMemcpyDeviceToDevice, ctx->stream));
-    ctx->hist_n_paths = n_paths;
+    ctx->hist_n_paths = n_paths; ctx->hist_cur_sources = n_sources;
+    return FS_OK;
+}
+
+int fs_get_histogram_sources(fs_ctx* ctx, uint32_t* n_sources_out)
+{
+    if (!ctx || !n_sources_out) return FS_ERR_INVALID;
+    *n_sources_out = ctx->d_hist ? ctx->hist_cur_sources : 0u;
     return FS_OK;
 }
 
 int fs_get_histogram(fs_ctx* ctx, uint64_t* hist_out)
 {
     if (!ctx) return FS_ERR_INVALID;
-    if (!hist_out || !ctx->d_hist) return fail(ctx, FS_ERR_STATE, "fs_get_histogram: no histogram");
+    if (!hist_out || !ctx->d_hist || ctx->hist_cur_sources == 0) return fail(ctx, FS_ERR_STATE, "fs_get_histogram: no histogram");
     dev_guard g(ctx->device);
-    const size_t hn = (size_t)ctx->hist_sources * ctx->cfg.n_bands * ctx->cfg.n_bins;
+    // the sources of the LAST trace / fs_set_histogram (not the high-water mark of the allocation)
+    const size_t hn = (size_t)ctx->hist_cur_sources * ctx->cfg.n_bands * ctx->cfg.n_bins;
     CK(cudaMemcpyAsync(hist_out, ctx->d_hist, 8 * hn, cudaMemcpyDeviceToHost, ctx->stream));
     return finish_stats(ctx);
+}
+
+// the per-source convolver slot (it also holds the device IR): created on first use, under conv_mu
+static int ensure_conv_source(fs_ctx* ctx, uint32_t source)
+{
+    if (source >= FS_MAX_SOURCES) return fail(ctx, FS_ERR_INVALID, "source id too large (< 4096)");
+    std::lock_guard<std::mutex> lk(ctx->conv_mu);
+    if (ctx->conv[source] && ctx->conv[source]->ir) return FS_OK;
+    cudaError_t e = fs_conv_source_alloc(ctx, source, false);
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "fs_conv_source_alloc");
+    return FS_OK;
+}
+
+static int ensure_pin_ir(fs_ctx* ctx, size_t n_floats)
+{
+    if (ctx->pin_ir_cap >= n_floats) return FS_OK;
+    if (ctx->h_pin_ir) cudaFreeHost(ctx->h_pin_ir);
+    ctx->h_pin_ir = nullptr; ctx->pin_ir_cap = 0;
+    CK(cudaMallocHost(&ctx->h_pin_ir, sizeof(float) * n_floats));
+    ctx->pin_ir_cap = n_floats;
+    return FS_OK;
 }
 
 static int ir_common(fs_ctx* ctx, uint32_t hist_source, uint32_t source, const float* energy, float* ir_out,
                      bool per_band = false, uint64_t noise_seed = 0)
 {
     const fs_config& c = ctx->cfg;
-    if (source >= ctx->conv_cap || !ctx->conv[source].ir) {
-        // the IR lives in the convolver's per-source state; create it on first use
-        cudaError_t e = fs_conv_source_alloc(ctx, source);
-        if (e != cudaSuccess) return fail_cuda(ctx, e, "fs_conv_source_alloc");
-    }
-    fs_conv_source& s = ctx->conv[source];
-    cudaEvent_t a, b;
-    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-    CK(cudaEventRecord(a, ctx->stream));
+    int rc = check_overflow(ctx, false);            // never build an IR from a histogram known to be incomplete
+    if (rc) return rc;
+    if ((rc = ensure_conv_source(ctx, source)) != FS_OK) return rc;
+    fs_conv_source* s = ctx->conv[source];
+    CK(cudaEventRecord(ctx->ev_ir0, ctx->stream));
     const float* d_energy = nullptr;
     if (energy) {
         CK(cudaMemcpyAsync(ctx->d_energy, energy, sizeof(float) * c.n_bins, cudaMemcpyHostToDevice, ctx->stream));
         d_energy = ctx->d_energy;
     }
     const unsigned long long* hsrc = ctx->d_hist ? ctx->d_hist + (size_t)hist_source * c.n_bands * c.n_bins : nullptr;
-    if (per_band) CK(fs_ir_build_bands(ctx, hsrc, ctx->hist_n_paths, noise_seed, s.ir));
-    else CK(fs_ir_build(ctx, hsrc, ctx->hist_n_paths, d_energy, s.ir));
+    if (per_band) CK(fs_ir_build_bands(ctx, hsrc, ctx->hist_n_paths, noise_seed, s->ir));
+    else CK(fs_ir_build(ctx, hsrc, ctx->hist_n_paths, d_energy, s->ir));
     { std::lock_guard<std::mutex> lk(ctx->conv_mu); CK(fs_conv_update_ir(ctx, source, ctx->stream)); }
-    CK(cudaEventRecord(b, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_ir1, ctx->stream));
+    ctx->ir_timed = true;
     if (ir_out) {
-        CK(cudaMemcpyAsync(ir_out, s.ir, sizeof(float) * c.n_channels * c.sample_rate, cudaMemcpyDeviceToHost, ctx->stream));
+        const size_t n = (size_t)c.n_channels * c.sample_rate;
+        if ((rc = ensure_pin_ir(ctx, n)) != FS_OK) return rc;
+        CK(cudaMemcpyAsync(ctx->h_pin_ir, s->ir, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        memcpy(ir_out, ctx->h_pin_ir, sizeof(float) * n);
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) ctx->stats.last_ir_ms = ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev_ir0, ctx->ev_ir1) == cudaSuccess) ctx->stats.last_ir_ms = ms;
+        return check_overflow(ctx, true);
     }
-    cudaEventDestroy(a); cudaEventDestroy(b);
     return FS_OK;
 }
+
+static bool have_hist(const fs_ctx* ctx, uint32_t source) { return ctx->d_hist && source < ctx->hist_cur_sources && ctx->hist_n_paths; }
 
 int fs_build_ir(fs_ctx* ctx, uint32_t source, float* ir_out)
 {
     if (!ctx) return FS_ERR_INVALID;
-    if (!ctx->d_hist || source >= ctx->hist_sources || ctx->hist_n_paths == 0)
+    if (!have_hist(ctx, source))
         return fail(ctx, FS_ERR_STATE, "fs_build_ir: no histogram for this source (call fs_trace or fs_set_histogram)");
     dev_guard g(ctx->device);
     return ir_common(ctx, source, source, nullptr, ir_out);
@@ -691,9 +772,8 @@ int fs_build_ir(fs_ctx* ctx, uint32_t source, float* ir_out)
 int fs_build_ir_to(fs_ctx* ctx, uint32_t hist_source, uint32_t conv_source, float* ir_out)
 {
     if (!ctx) return FS_ERR_INVALID;
-    if (!ctx->d_hist || hist_source >= ctx->hist_sources || ctx->hist_n_paths == 0)
+    if (!have_hist(ctx, hist_source))
         return fail(ctx, FS_ERR_STATE, "fs_build_ir_to: no histogram for this source (call fs_trace or fs_set_histogram)");
-    if (conv_source >= 4096) return fail(ctx, FS_ERR_INVALID, "source id too large");
     dev_guard g(ctx->device);
     return ir_common(ctx, hist_source, conv_source, nullptr, ir_out);
 }
@@ -701,45 +781,45 @@ int fs_build_ir_to(fs_ctx* ctx, uint32_t hist_source, uint32_t conv_source, floa
 int fs_build_ir_all(fs_ctx* ctx, uint32_t n_sources, float* ir_out)
 {
     if (!ctx) return FS_ERR_INVALID;
-    if (!ctx->d_hist || n_sources == 0 || n_sources > ctx->hist_sources || ctx->hist_n_paths == 0)
+    if (n_sources == 0 || !have_hist(ctx, n_sources - 1))
         return fail(ctx, FS_ERR_STATE, "fs_build_ir_all: no histogram for these sources (call fs_trace or fs_set_histogram)");
-    if (n_sources > 4096) return fail(ctx, FS_ERR_INVALID, "source id too large");
+    if (n_sources > FS_MAX_SOURCES) return fail(ctx, FS_ERR_INVALID, "source id too large (< 4096)");
     dev_guard g(ctx->device);
     const fs_config& c = ctx->cfg;
+    int rc = check_overflow(ctx, false);
+    if (rc) return rc;
     for (uint32_t s = 0; s < n_sources; ++s)
-        if (s >= ctx->conv_cap || !ctx->conv[s].ir) {
-            cudaError_t e = fs_conv_source_alloc(ctx, s);
-            if (e != cudaSuccess) return fail_cuda(ctx, e, "fs_conv_source_alloc");
-        }
-    cudaEvent_t a, b;
-    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-    CK(cudaEventRecord(a, ctx->stream));
+        if ((rc = ensure_conv_source(ctx, s)) != FS_OK) return rc;
+    CK(cudaEventRecord(ctx->ev_ir0, ctx->stream));
     for (uint32_t s0 = 0; s0 < n_sources; s0 += FS_PTR_TABLE) {
         const uint32_t n = n_sources - s0 < FS_PTR_TABLE ? n_sources - s0 : FS_PTR_TABLE;
         fs_ptr_table tab;
-        for (uint32_t i = 0; i < n; ++i) { tab.p[i] = ctx->conv[s0 + i].ir; tab.q[i] = nullptr; }
+        for (uint32_t i = 0; i < n; ++i) { tab.p[i] = ctx->conv[s0 + i]->ir; tab.q[i] = nullptr; }
         CK(fs_ir_build_multi(ctx, ctx->d_hist, s0, n, ctx->hist_n_paths, tab));
         { std::lock_guard<std::mutex> lk(ctx->conv_mu); CK(fs_conv_update_ir_multi(ctx, s0, n, ctx->stream)); }
     }
-    CK(cudaEventRecord(b, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_ir1, ctx->stream));
+    ctx->ir_timed = true;
     if (ir_out) {
+        // all IRs leave through one pinned staging buffer (a pageable destination would be staged 64 KB at a time)
         const size_t per = (size_t)c.n_channels * c.sample_rate;
+        if ((rc = ensure_pin_ir(ctx, per * n_sources)) != FS_OK) return rc;
         for (uint32_t s = 0; s < n_sources; ++s)
-            CK(cudaMemcpyAsync(ir_out + s * per, ctx->conv[s].ir, sizeof(float) * per, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->h_pin_ir + s * per, ctx->conv[s]->ir, sizeof(float) * per, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        memcpy(ir_out, ctx->h_pin_ir, sizeof(float) * per * n_sources);
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) ctx->stats.last_ir_ms = ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev_ir0, ctx->ev_ir1) == cudaSuccess) ctx->stats.last_ir_ms = ms;
+        return check_overflow(ctx, true);
     }
-    cudaEventDestroy(a); cudaEventDestroy(b);
     return FS_OK;
 }
 
 int fs_build_ir_bands(fs_ctx* ctx, uint32_t hist_source, uint32_t conv_source, uint64_t noise_seed, float* ir_out)
 {
     if (!ctx) return FS_ERR_INVALID;
-    if (!ctx->d_hist || hist_source >= ctx->hist_sources || ctx->hist_n_paths == 0)
+    if (!have_hist(ctx, hist_source))
         return fail(ctx, FS_ERR_STATE, "fs_build_ir_bands: no histogram for this source (call fs_trace or fs_set_histogram)");
-    if (conv_source >= 4096) return fail(ctx, FS_ERR_INVALID, "source id too large");
     dev_guard g(ctx->device);
     return ir_common(ctx, hist_source, conv_source, nullptr, ir_out, true, noise_seed);
 }
@@ -757,52 +837,57 @@ int fs_set_ir(fs_ctx* ctx, uint32_t source, const float* ir)
     if (!ctx) return FS_ERR_INVALID;
     if (!ir) return fail(ctx, FS_ERR_INVALID, "fs_set_ir: null ir");
     dev_guard g(ctx->device);
-    if (source >= ctx->conv_cap || !ctx->conv[source].ir) {
-        cudaError_t e = fs_conv_source_alloc(ctx, source);
-        if (e != cudaSuccess) return fail_cuda(ctx, e, "fs_conv_source_alloc");
-    }
-    fs_conv_source& s = ctx->conv[source];
+    int rc = ensure_conv_source(ctx, source);
+    if (rc) return rc;
+    fs_conv_source* s = ctx->conv[source];
     const fs_config& c = ctx->cfg;
-    CK(cudaMemcpyAsync(s.ir, ir, sizeof(float) * c.n_channels * c.sample_rate, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(s->ir, ir, sizeof(float) * c.n_channels * c.sample_rate, cudaMemcpyHostToDevice, ctx->stream));
     { std::lock_guard<std::mutex> lk(ctx->conv_mu); CK(fs_conv_update_ir(ctx, source, ctx->stream)); }
     CK(cudaStreamSynchronize(ctx->stream));
     return FS_OK;
 }
 
-// ---- convolution --------------------------------------------------------------------------------
+// ---- convolution (the audio thread; everything on conv_stream under conv_mu) --------------------------------------
 int fs_conv_init_source(fs_ctx* ctx, uint32_t source)
 {
     if (!ctx) return FS_ERR_INVALID;
-    if (source >= 4096) return fail(ctx, FS_ERR_INVALID, "source id too large");
+    if (source >= FS_MAX_SOURCES) return fail(ctx, FS_ERR_INVALID, "source id too large (< 4096)");
     dev_guard g(ctx->device);
     std::lock_guard<std::mutex> lk(ctx->conv_mu);
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(fs_conv_source_alloc(ctx, source));
+    CK(fs_conv_source_alloc(ctx, source, true));
     return FS_OK;
 }
 
 int fs_conv_release_source(fs_ctx* ctx, uint32_t source)
 {
     if (!ctx) return FS_ERR_INVALID;
+    if (source >= FS_MAX_SOURCES) return fail(ctx, FS_ERR_INVALID, "source id too large (< 4096)");
     dev_guard g(ctx->device);
     std::lock_guard<std::mutex> lk(ctx->conv_mu);
-    CK(cudaStreamSynchronize(ctx->stream));
-    fs_conv_source_free(ctx, source);            // Source.ClearBuffers(), REV.cpp:112-116
+    // Source.ClearBuffers(), REV.cpp:112-116: the history goes, the slot (and its IR, which the game thread may be
+    // rebuilding right now on its own stream) stays until fs_destroy
+    if (ctx->conv[source]) ctx->conv[source]->active = false;
     return FS_OK;
 }
 
-int fs_conv_process_many(fs_ctx* ctx, uint32_t source, const float* in, float* out, uint32_t frames, uint32_t n_blocks)
+static int conv_process(fs_ctx* ctx, const uint32_t* sources, uint32_t n_src, const float* in, float* out, uint32_t frames,
+                        uint32_t n_blocks)
 {
     if (!ctx) return FS_ERR_INVALID;
-    if (!in || !out) return fail(ctx, FS_ERR_INVALID, "fs_conv_process: null buffer");
+    if (!in || !out || !sources) return fail(ctx, FS_ERR_INVALID, "fs_conv_process: null buffer");
     if (frames != ctx->cfg.conv_block) return fail(ctx, FS_ERR_INVALID, "fs_conv_process: frames must equal conv_block");
-    if (n_blocks == 0) return FS_OK;
+    if (n_blocks == 0 || n_src == 0) return FS_OK;
     dev_guard g(ctx->device);
     std::lock_guard<std::mutex> lk(ctx->conv_mu);
-    if (source >= ctx->conv_cap || !ctx->conv[source].active)
-        return fail(ctx, FS_ERR_STATE, "fs_conv_process: source not initialised (fs_conv_init_source)");
+    for (uint32_t i = 0; i < n_src; ++i) {
+        if (sources[i] >= FS_MAX_SOURCES || !ctx->conv[sources[i]] || !ctx->conv[sources[i]]->active)
+            return fail(ctx, FS_ERR_STATE, "fs_conv_process: source not initialised (fs_conv_init_source)");
+        for (uint32_t j = 0; j < i; ++j)
+            if (sources[j] == sources[i]) return fail(ctx, FS_ERR_INVALID, "fs_conv_process_multi: duplicate source id");
+    }
     const fs_config& c = ctx->cfg;
-    const size_t n = (size_t)n_blocks * frames * c.n_channels;
+    const size_t n = (size_t)n_src * n_blocks * frames * c.n_channels;
+    cudaStream_t st = ctx->conv_stream;
     if (ctx->conv_io_cap < n) {
         cudaFree(ctx->d_conv_in); cudaFree(ctx->d_conv_out); ctx->d_conv_in = ctx->d_conv_out = nullptr;
         if (ctx->h_pin_in) cudaFreeHost(ctx->h_pin_in);
@@ -812,20 +897,30 @@ int fs_conv_process_many(fs_ctx* ctx, uint32_t source, const float* in, float* o
         CK(cudaMalloc(&ctx->d_conv_out, sizeof(float) * n));
         CK(cudaMallocHost(&ctx->h_pin_in, sizeof(float) * n));
         CK(cudaMallocHost(&ctx->h_pin_out, sizeof(float) * n));
-        ctx->conv_io_cap = (uint32_t)n;
+        ctx->conv_io_cap = n;
     }
     memcpy(ctx->h_pin_in, in, sizeof(float) * n);
-    CK(cudaMemcpyAsync(ctx->d_conv_in, ctx->h_pin_in, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(fs_conv_run(ctx, source, ctx->d_conv_in, ctx->d_conv_out, n_blocks, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_pin_out, ctx->d_conv_out, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_conv_in, ctx->h_pin_in, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    CK(fs_conv_run(ctx, sources, n_src, ctx->d_conv_in, ctx->d_conv_out, n_blocks, st));
+    CK(cudaMemcpyAsync(ctx->h_pin_out, ctx->d_conv_out, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     memcpy(out, ctx->h_pin_out, sizeof(float) * n);
     return FS_OK;
 }
 
+int fs_conv_process_many(fs_ctx* ctx, uint32_t source, const float* in, float* out, uint32_t frames, uint32_t n_blocks)
+{
+    return conv_process(ctx, &source, 1, in, out, frames, n_blocks);
+}
+
 int fs_conv_process(fs_ctx* ctx, uint32_t source, const float* in, float* out, uint32_t frames)
 {
-    return fs_conv_process_many(ctx, source, in, out, frames, 1);
+    return conv_process(ctx, &source, 1, in, out, frames, 1);
+}
+
+int fs_conv_process_multi(fs_ctx* ctx, const uint32_t* sources, uint32_t n_sources, const float* in, float* out, uint32_t frames)
+{
+    return conv_process(ctx, sources, n_sources, in, out, frames, 1);
 }
 
 int fs_debug_rfft(fs_ctx* ctx, const float* in, uint32_t n, float* out_ri)
@@ -835,12 +930,13 @@ int fs_debug_rfft(fs_ctx* ctx, const float* in, uint32_t n, float* out_ri)
     dev_guard g(ctx->device);
     float* d_in = nullptr; float2* d_out = nullptr;
     CK(cudaMalloc(&d_in, sizeof(float) * n));
-    CK(cudaMalloc(&d_out, sizeof(float2) * (n / 2 + 1)));
-    CK(cudaMemcpy(d_in, in, sizeof(float) * n, cudaMemcpyHostToDevice));
-    CK(fs_conv_rfft(ctx, d_in, n, d_out, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemcpy(out_ri, d_out, sizeof(float2) * (n / 2 + 1), cudaMemcpyDeviceToHost));
+    cudaError_t e = cudaMalloc(&d_out, sizeof(float2) * (n / 2 + 1));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, in, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = fs_conv_rfft(ctx, d_in, n, d_out, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_ri, d_out, sizeof(float2) * (n / 2 + 1), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess || e2 != cudaSuccess) return fail_cuda(ctx, e != cudaSuccess ? e : e2, "fs_debug_rfft");
     return FS_OK;
 }
 
@@ -850,6 +946,7 @@ int fs_get_stats(fs_ctx* ctx, fs_stats* out)
     dev_guard g(ctx->device);
     int rc = finish_stats(ctx);
     *out = ctx->stats;
+    out->kernel_launches = ctx->launches.load();
     return rc;
 }
 

@@ -95,43 +95,55 @@ struct fs_conv_source {
     float2* H[2];               // double-buffered IR partition spectra [P][C][NF]
     float* prev;                // [C][Bk] previous input block
     float* ir;                  // [C][sample_rate] device IR of this source
-    std::atomic<int> h_published;   // which H buffer the audio thread uses
-    int h_valid;
+    // IR hand-off (game thread -> audio thread), all under fs_ctx::conv_mu: `pub` is the buffer the convolver reads;
+    // `pending` (or -1) was written by the last IR update and becomes `pub` at the first callback that finds its
+    // h_ready event complete -- the audio thread never waits for a trace that is still running
+    int pub, pending;
+    cudaEvent_t h_ready[2];
     uint32_t head;              // FDL head slot
 };
 
 #define FS_MAX_LANES 4
+#define FS_MAX_SOURCES 4096
 #define FS_PTR_TABLE 64
 struct fs_ptr_table { void* p[FS_PTR_TABLE]; void* q[FS_PTR_TABLE]; };   // per-source device pointers passed by value
+
+// one batch lane: a stream and its own wavefront buffers.  Lane 0 runs on the context stream itself.
+struct fs_lane { cudaStream_t stream; fs_wave_buffers wb; cudaEvent_t done; };
 
 struct fs_ctx {
     fs_config cfg;
     int device;
     cudaStream_t own_stream, stream;
-    cudaStream_t conv_stream;
-    std::string err;
+    cudaStream_t conv_stream;   // the audio thread's stream: fs_conv_process* never queues behind a trace
     // scene
     float* d_verts; uint32_t* d_tri_mat; uint64_t n_tris;
     float* d_refl_over_pi; uint32_t n_mats;
-    std::vector<float> mat_transmission, mat_scattering, mat_thickness_cm;   // carried, unused by the tracer (as in the reference)
+    float* d_mat_ext;           // [M][FS_MAT_EXT_STRIDE]: transmission / scattering per band + thickness (FS_FLAG_MATERIAL_MODEL)
+    std::vector<float> mat_transmission, mat_scattering, mat_thickness_cm;
     bool mats_set, tris_set, committed;
     fs_bvh_device bvh;
-    // trace
-    fs_wave_buffers wb;
-    // extra batch lanes: while one batch's traversal launch drains its slowest rays, the other lane's kernels fill the SMs
-    struct lane_t { cudaStream_t stream; fs_wave_buffers wb; cudaEvent_t done; } lanes[FS_MAX_LANES - 1];
+    // trace: batches alternate between lanes -- while one batch's traversal launch drains its slowest rays, the other
+    // lane's kernels fill the SMs
+    fs_lane lanes[FS_MAX_LANES];
     cudaEvent_t ev_fork; uint32_t tune_streams;
     float4 *lis_rec, *lis_end; uint64_t lis_cache_n; uint32_t lis_cache_depth;   // FS_FLAG_SHARE_LISTENER cache
-    unsigned long long* d_hist; uint32_t hist_sources;   // [S][B][K]
+    unsigned long long* d_hist; uint32_t hist_sources;   // [S][B][K]; hist_sources = allocated, hist_cur_sources = valid
+    uint32_t hist_cur_sources;
     uint64_t hist_n_paths;
     fs_dev_counters* d_counters;
+    // traversal-stack overflow of the last trace: one 4-byte async copy into pinned memory after every fs_trace*, looked at
+    // by the next call that can (sticky until reported)
+    uint32_t* h_overflow; cudaEvent_t ev_overflow; bool overflow_pending;
     float* d_src_pos; uint32_t src_cap;
     fs_path_dbg* d_dbg; uint64_t dbg_cap;
-    fs_stats stats;
-    cudaEvent_t ev0, ev1; bool timed;
+    fs_stats stats;                      // game-thread fields only; kernel launches are counted in `launches`
+    std::atomic<uint64_t> launches;
+    cudaEvent_t ev0, ev1, ev_ir0, ev_ir1; bool timed, ir_timed;
     std::vector<cudaEvent_t> kev; size_t kev_used;   // FS_FLAG_TIME_KERNELS: 4 events per batch
     std::vector<cudaEvent_t> tev; size_t tev_used;   //   + one (begin, end) pair per k_trace_closest launch
     int sm_count;
+    int occ[16];                         // resident CTAs per SM of the persistent kernels (per context = per device)
     uint32_t tune_refill, tune_leaf_max, tune_tex, tune_builder, tune_wide, tune_node_min, tune_tri_min, tune_collapse, tune_l2pin_mb, tune_tq, tune_tq_node_min, tune_tq_flush, tune_mega;      // experiment knobs (env FS_TUNE_REFILL / FS_TUNE_LEAF_MAX)
     // IR / conv
     float* d_energy;            // [K] scratch
@@ -139,19 +151,22 @@ struct fs_ctx {
     float* d_amp_all; uint32_t amp_all_cap;   // [FS_PTR_TABLE][K]: multi-source IR build
     float* d_carriers; float* d_amp_bands; uint64_t carrier_seed;   // per-band IR synthesis: [C][B][fs] noise carriers, [B][K]
     float2* d_twiddle;          // [conv fft size / 2]
-    uint32_t fft_n, n_part, n_freq;
-    fs_conv_source* conv; uint32_t conv_cap;
-    float *d_conv_in, *d_conv_out; uint32_t conv_io_cap;   // device staging [blocks][frames][C]
+    uint32_t fft_n, n_part, n_freq, ir_window;
+    // per-source convolver state: FS_MAX_SOURCES stable slots (never reallocated: the audio thread may hold one while the
+    // game thread creates another); creation, release and the IR hand-off fields are guarded by conv_mu
+    std::vector<fs_conv_source*> conv;
+    float *d_conv_in, *d_conv_out; size_t conv_io_cap;   // device staging [sources][blocks][frames][C]
     float *h_pin_in, *h_pin_out;
+    float* h_pin_ir; size_t pin_ir_cap;  // pinned staging for IR read-back (fs_build_ir_all: one copy for all sources)
     std::mutex conv_mu;
 };
 
 // fs_wavefront.cu
-cudaError_t fs_wave_alloc(fs_ctx* ctx, uint32_t cap, uint32_t max_depth);
+cudaError_t fs_wave_alloc(fs_ctx* ctx, fs_lane* lane, uint32_t cap, uint32_t max_depth);
 void fs_wave_free(fs_wave_buffers* wb);
-cudaError_t fs_wave_trace_batch(fs_ctx* ctx, const fs_trace_params& tp, unsigned long long* d_hist,
+cudaError_t fs_wave_trace_batch(fs_ctx* ctx, fs_lane* lane, const fs_trace_params& tp, unsigned long long* d_hist,
                                 fs_path_dbg* d_dbg);
-cudaError_t fs_wave_reset_counters(fs_ctx* ctx);
+cudaError_t fs_wave_reset_counters(fs_ctx* ctx, int reset_overflow);
 cudaError_t fs_wave_debug_rays(fs_ctx* ctx, const fs_trace_params& tp, const float* d_rays, const float* d_tmax,
                                uint64_t n, float* d_t, uint32_t* d_tri, uint8_t* d_hit);
 
@@ -167,9 +182,11 @@ cudaError_t fs_ir_build(fs_ctx* ctx, const unsigned long long* d_hist_src, uint6
 // fs_conv.cu
 cudaError_t fs_conv_setup(fs_ctx* ctx);
 void fs_conv_teardown(fs_ctx* ctx);
-cudaError_t fs_conv_source_alloc(fs_ctx* ctx, uint32_t source);
+// all three: conv_mu held by the caller
+cudaError_t fs_conv_source_alloc(fs_ctx* ctx, uint32_t source, bool reset_history);
 void fs_conv_source_free(fs_ctx* ctx, uint32_t source);
 cudaError_t fs_conv_update_ir(fs_ctx* ctx, uint32_t source, cudaStream_t st);
-cudaError_t fs_conv_run(fs_ctx* ctx, uint32_t source, const float* d_in, float* d_out, uint32_t n_blocks,
+// n_src sources x n_blocks callbacks in ONE launch (grid = sources x channels); d_in / d_out: [n_src][n_blocks][Bk][C]
+cudaError_t fs_conv_run(fs_ctx* ctx, const uint32_t* sources, uint32_t n_src, const float* d_in, float* d_out, uint32_t n_blocks,
                         cudaStream_t st);
 cudaError_t fs_conv_rfft(fs_ctx* ctx, const float* d_in, uint32_t n, float2* d_out, cudaStream_t st);

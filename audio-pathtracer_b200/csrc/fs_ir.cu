@@ -7,7 +7,7 @@
 //   k_ir     : sample j of bin k: (1-w) a_{k-1} + w a_k, w = j/48 (COMP.cpp:347-363; FIX: 48
 //              samples per bin, the reference's ceil(0.001f*48000.f) is 49); one-pole low-pass
 //              y_i = 0.25 x_i + 0.75 y_{i-1}, y_0 = x_0 (COMP.cpp:366-375) evaluated per output
-//              sample over a 128-tap warm-up window (0.75^128 ~ 1e-16, below float resolution);
+//              sample over a warm-up window of W taps, (1 - a)^W <= 1e-12 (a = 0.25: W = 128; fs_ctx::ir_window);
 //              output = filtered, un-normalised (COMP.cpp:377-378); every channel gets the same
 //              mono IR (COMP.cpp:327-330).
 // Algorithmic bytes per update: read B*K*8, write C*sample_rate*4.
@@ -46,14 +46,12 @@ __device__ __forceinline__ float raw_sample(const float* __restrict__ amp, uint3
     return (1.0f - w) * pe + w * e;
 }
 
-constexpr int IR_WINDOW = 128;
-
 // One CTA = IR_TILE consecutive samples.  The raw (ramp) samples of the tile and of the IR_WINDOW samples before it are
-// computed once into shared memory (one integer + one float division each), then every thread runs its 128-tap low-pass
+// computed once into shared memory (one integer + one float division each), then every thread runs its W-tap low-pass
 // recurrence from shared memory -- same operations in the same order as evaluating raw_sample() per tap, 8x faster.
 constexpr int IR_TILE = 256;
 __device__ __forceinline__ void ir_tile(const float* __restrict__ amp, uint32_t n_bins, uint32_t spb, uint32_t n_samples,
-                                        uint32_t n_channels, float a, float* __restrict__ ir, float* sraw)
+                                        uint32_t n_channels, float a, float* __restrict__ ir, float* sraw, const uint32_t IR_WINDOW)
 {
     const uint32_t t0 = blockIdx.x * IR_TILE;
     const uint32_t first = t0 >= (uint32_t)IR_WINDOW ? t0 - IR_WINDOW : 0u;      // first sample held in sraw
@@ -71,10 +69,10 @@ __device__ __forceinline__ void ir_tile(const float* __restrict__ amp, uint32_t 
 
 __global__ void __launch_bounds__(IR_TILE)
 k_ir(const float* __restrict__ amp, uint32_t n_bins, uint32_t spb, uint32_t n_samples,
-     uint32_t n_channels, float a, float* __restrict__ ir)
+     uint32_t n_channels, float a, float* __restrict__ ir, uint32_t win)
 {
-    __shared__ float sraw[IR_TILE + IR_WINDOW];
-    ir_tile(amp, n_bins, spb, n_samples, n_channels, a, ir, sraw);
+    extern __shared__ float sraw[];                        // [IR_TILE + win]
+    ir_tile(amp, n_bins, spb, n_samples, n_channels, a, ir, sraw, win);
 }
 
 // ---- per-band synthesis: band envelopes x band-limited noise carriers ------------------------
@@ -125,11 +123,11 @@ __global__ void k_energy_multi(const unsigned long long* __restrict__ hist, uint
 
 __global__ void __launch_bounds__(IR_TILE)
 k_ir_multi(const float* __restrict__ amp, uint32_t n_bins, uint32_t spb, uint32_t n_samples,
-           uint32_t n_channels, float a, fs_ptr_table tab)
+           uint32_t n_channels, float a, fs_ptr_table tab, uint32_t win)
 {
-    __shared__ float sraw[IR_TILE + IR_WINDOW];
+    extern __shared__ float sraw[];                        // [IR_TILE + win]
     const uint32_t src = blockIdx.y;
-    ir_tile(amp + (size_t)src * n_bins, n_bins, spb, n_samples, n_channels, a, (float*)tab.p[src], sraw);
+    ir_tile(amp + (size_t)src * n_bins, n_bins, spb, n_samples, n_channels, a, (float*)tab.p[src], sraw, win);
 }
 
 }  // namespace
@@ -149,9 +147,9 @@ cudaError_t fs_ir_build_multi(fs_ctx* ctx, const unsigned long long* d_hist, uin
     const double inv_scale = n_paths ? 1.0 / (double)n_paths : 0.0;
     k_energy_multi<<<dim3((c.n_bins + 255) / 256, n), 256, 0, ctx->stream>>>(d_hist + (size_t)s0 * c.n_bands * c.n_bins, c.n_bands,
                                                                             c.n_bins, inv_scale, c.ir_threshold, ctx->d_amp_all);
-    k_ir_multi<<<dim3((c.sample_rate + IR_TILE - 1) / IR_TILE, n), IR_TILE, 0, ctx->stream>>>(ctx->d_amp_all, c.n_bins, spb, c.sample_rate,
-                                                                             c.n_channels, c.ir_lowpass, d_ir);
-    ctx->stats.kernel_launches += 2;
+    k_ir_multi<<<dim3((c.sample_rate + IR_TILE - 1) / IR_TILE, n), IR_TILE, sizeof(float) * (IR_TILE + ctx->ir_window), ctx->stream>>>(
+        ctx->d_amp_all, c.n_bins, spb, c.sample_rate, c.n_channels, c.ir_lowpass, d_ir, ctx->ir_window);
+    ctx->launches.fetch_add(2);
     return cudaGetLastError();
 }
 
@@ -211,7 +209,7 @@ cudaError_t fs_ir_build_bands(fs_ctx* ctx, const unsigned long long* d_hist_src,
                                                               ctx->d_amp_bands);
     k_ir_bands<<<(c.sample_rate + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_amp_bands, ctx->d_carriers, c.n_bands, c.n_bins, spb,
                                                                       c.sample_rate, c.n_channels, d_ir_out);
-    ctx->stats.kernel_launches += 2;
+    ctx->launches.fetch_add(2);
     return cudaGetLastError();
 }
 
@@ -223,8 +221,8 @@ cudaError_t fs_ir_build(fs_ctx* ctx, const unsigned long long* d_hist_src, uint6
     const double inv_scale = n_paths ? 1.0 / (double)n_paths : 0.0;
     k_energy<<<(c.n_bins + 255) / 256, 256, 0, ctx->stream>>>(d_hist_src, c.n_bands, c.n_bins, inv_scale,
                                                               d_energy_in, c.ir_threshold, ctx->d_amp);
-    k_ir<<<(c.sample_rate + IR_TILE - 1) / IR_TILE, IR_TILE, 0, ctx->stream>>>(ctx->d_amp, c.n_bins, spb, c.sample_rate,
-                                                                c.n_channels, c.ir_lowpass, d_ir_out);
-    ctx->stats.kernel_launches += 2;
+    k_ir<<<(c.sample_rate + IR_TILE - 1) / IR_TILE, IR_TILE, sizeof(float) * (IR_TILE + ctx->ir_window), ctx->stream>>>(
+        ctx->d_amp, c.n_bins, spb, c.sample_rate, c.n_channels, c.ir_lowpass, d_ir_out, ctx->ir_window);
+    ctx->launches.fetch_add(2);
     return cudaGetLastError();
 }

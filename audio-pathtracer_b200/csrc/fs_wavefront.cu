@@ -1708,6 +1708,8 @@ __global__ void k_init_ends(const fs_trace_params tp, const fs_wave_buffers wb)
     wb.end_pos[sp] = make_float4(x, y, z, __uint_as_float(1u));
 }
 
+// reset_dc: bit 0 = the per-call counters, bit 1 = the overflow flag too (left alone while the host has not yet seen the
+// flag of the previous call)
 __global__ void k_reset_queues(uint32_t* q_count, uint32_t* q_cursor, uint32_t n, fs_dev_counters* dc, int reset_dc)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1715,7 +1717,8 @@ __global__ void k_reset_queues(uint32_t* q_count, uint32_t* q_cursor, uint32_t n
     if (reset_dc && i == 0) {
         dc->ext_rays = 0; dc->shadow_rays = 0; dc->connected = 0; dc->node_visits = 0; dc->tri_tests = 0;
         dc->shadow_node_visits = 0; dc->shadow_tri_tests = 0;
-        dc->overflow = 0; dc->max_steps = 0;
+        if (reset_dc & 2) dc->overflow = 0;
+        dc->max_steps = 0;
         for (int b = 0; b < 16; ++b) dc->steps_hist[b] = 0;
     }
 }
@@ -1792,9 +1795,9 @@ int pick_mode(const fs_trace_params& tp)
 
 }  // namespace
 
-cudaError_t fs_wave_alloc(fs_ctx* ctx, uint32_t cap, uint32_t max_depth)
+cudaError_t fs_wave_alloc(fs_ctx* ctx, fs_lane* lane, uint32_t cap, uint32_t max_depth)
 {
-    fs_wave_buffers* wb = &ctx->wb;
+    fs_wave_buffers* wb = &lane->wb;
     if (wb->cap >= cap && wb->depth_cap >= max_depth && wb->rec) return cudaSuccess;
     if (cap < wb->cap) cap = wb->cap;
     if (max_depth < wb->depth_cap) max_depth = wb->depth_cap;
@@ -1827,7 +1830,8 @@ cudaError_t fs_wave_alloc(fs_ctx* ctx, uint32_t cap, uint32_t max_depth)
             if ((e = cudaMalloc(&wb->log_o, sizeof(float4) * lc)) != cudaSuccess) return e;
             if ((e = cudaMalloc(&wb->log_d, sizeof(float4) * lc)) != cudaSuccess) return e;
             if ((e = cudaMalloc(&wb->log_flag, 4ull * lc)) != cudaSuccess) return e;
-            if ((e = cudaMemset(wb->log_flag, 0, 4ull * lc)) != cudaSuccess) return e;
+            if ((e = cudaMemsetAsync(wb->log_flag, 0, 4ull * lc, lane->stream)) != cudaSuccess) return e;
+            if ((e = cudaStreamSynchronize(lane->stream)) != cudaSuccess) return e;
             if ((e = cudaMalloc(&wb->pq, 16)) != cudaSuccess) return e;
             wb->pq_epoch = 0;
         }
@@ -1847,15 +1851,15 @@ void fs_wave_free(fs_wave_buffers* wb)
 }
 
 template <bool COUNT, int MODE>
-static cudaError_t launch_batch(fs_ctx* ctx, const fs_trace_params& tp, unsigned long long* d_hist,
+static cudaError_t launch_batch(fs_ctx* ctx, fs_lane* lane, const fs_trace_params& tp, unsigned long long* d_hist,
                                 fs_path_dbg* d_dbg)
 {
-    cudaStream_t st = ctx->stream;
-    const fs_wave_buffers& wb = ctx->wb;
+    cudaStream_t st = lane->stream;
+    const fs_wave_buffers& wb = lane->wb;
     const size_t smem = (MODE == MODE_TOP) ? (size_t)tp.n_top * 64 : 0;
-    static int occ_ext = 0, occ_con = 0;
-    if (!occ_ext) occ_ext = resident_ctas(k_extend<COUNT, MODE>, WF_THREADS, smem);
-    if (!occ_con) occ_con = resident_ctas(k_connect<COUNT, MODE>, WF_THREADS, smem);
+    // occupancy depends on the instantiation (COUNT, MODE) and on the treelet size: queried per call, it is a host-only lookup
+    const int occ_ext = resident_ctas(k_extend<COUNT, MODE>, WF_THREADS, smem);
+    const int occ_con = resident_ctas(k_connect<COUNT, MODE>, WF_THREADS, smem);
     if (smem > 48 * 1024) {
         cudaFuncSetAttribute(k_extend<COUNT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_connect<COUNT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1873,7 +1877,7 @@ static cudaError_t launch_batch(fs_ctx* ctx, const fs_trace_params& tp, unsigned
     }
     const uint32_t nq = tp.max_depth + 4;
     k_reset_queues<<<(nq + 63) / 64, 64, 0, st>>>(wb.q_count, wb.q_cursor, nq, ctx->d_counters, 0);
-    ++ctx->stats.kernel_launches;
+    ctx->launches.fetch_add(1);
     // persistent grids: SMs x resident CTAs, capped by the work available
     const uint32_t warps_needed = (2u * tp.batch + 31u) / 32u;
     uint32_t grid_ext = (uint32_t)(ctx->sm_count * occ_ext);
@@ -1882,11 +1886,11 @@ static cudaError_t launch_batch(fs_ctx* ctx, const fs_trace_params& tp, unsigned
     if (timing) cudaEventRecord(ev[0], st);
     if (tp.max_depth == 0) {
         k_init_ends<<<(2u * tp.batch + 255u) / 256u, 256, 0, st>>>(tp, wb);
-        ++ctx->stats.kernel_launches;
+        ctx->launches.fetch_add(1);
     }
     for (uint32_t k = 0; k < tp.max_depth; ++k) {
         k_extend<COUNT, MODE><<<grid_ext, WF_THREADS, smem, st>>>(tp, wb, k, (int)(k & 1u), ctx->d_counters);
-        ++ctx->stats.kernel_launches;
+        ctx->launches.fetch_add(1);
         ++ctx->stats.extend_launches;
     }
     if (timing) cudaEventRecord(ev[1], st);
@@ -1894,13 +1898,13 @@ static cudaError_t launch_batch(fs_ctx* ctx, const fs_trace_params& tp, unsigned
     uint32_t ctas_con = ((tp.batch + 31u) / 32u + WF_THREADS / 32 - 1) / (WF_THREADS / 32);
     if (grid_con > ctas_con) grid_con = ctas_con ? ctas_con : 1;
     k_connect<COUNT, MODE><<<grid_con, WF_THREADS, smem, st>>>(tp, wb, ctx->d_counters, d_dbg);
-    ++ctx->stats.kernel_launches;
+    ctx->launches.fetch_add(1);
     if (timing) cudaEventRecord(ev[2], st);
     uint32_t grid_ev = (uint32_t)ctx->sm_count * 8u;
     const uint32_t ctas_ev = (tp.batch / 4u + WF_THREADS / 32 - 1) / (WF_THREADS / 32) + 1;
     if (grid_ev > ctas_ev) grid_ev = ctas_ev;
     k_eval<false><<<grid_ev, WF_THREADS, 0, st>>>(tp, wb, d_hist, ctx->d_counters, d_dbg);
-    ++ctx->stats.kernel_launches;
+    ctx->launches.fetch_add(1);
     if (timing) cudaEventRecord(ev[3], st);
     return cudaGetLastError();
 }
@@ -1911,15 +1915,17 @@ static cudaError_t launch_batch(fs_ctx* ctx, const fs_trace_params& tp, unsigned
 // trace_any eval
 // ---------------------------------------------------------------------------------------------
 template <bool COUNT>
-static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, unsigned long long* d_hist,
+static cudaError_t launch_batch_split(fs_ctx* ctx, fs_lane* lane, const fs_trace_params& tp, unsigned long long* d_hist,
                                       fs_path_dbg* d_dbg)
 {
-    cudaStream_t st = ctx->stream;
-    const fs_wave_buffers& wb = ctx->wb;
-    static int occ_tr = 0, occ_any = 0, occ_tq = 0;
-    if (!occ_tr) occ_tr = resident_ctas(k_trace_closest<COUNT, 2, true>, TR_THREADS, TR_SMEM_CLOSEST);
-    if (!occ_tq) occ_tq = resident_ctas(k_trace_q<COUNT, 2, false>, TR_THREADS, TR_SMEM_TQ);
-    if (!occ_any) occ_any = resident_ctas(k_trace_any<COUNT, 2, true>, TR_THREADS, TR_SMEM_ANY);
+    cudaStream_t st = lane->stream;
+    fs_wave_buffers& wb = lane->wb;
+    // resident CTAs per SM of the persistent kernels: cached per context (= per device) and per instantiation
+    int* occ = ctx->occ + (COUNT ? 4 : 0);
+    if (!occ[0]) occ[0] = resident_ctas(k_trace_closest<COUNT, 2, true>, TR_THREADS, TR_SMEM_CLOSEST);
+    if (!occ[1]) occ[1] = resident_ctas(k_trace_q<COUNT, 2, false>, TR_THREADS, TR_SMEM_TQ);
+    if (!occ[2]) occ[2] = resident_ctas(k_trace_any<COUNT, 2, true>, TR_THREADS, TR_SMEM_ANY);
+    const int occ_tr = occ[0], occ_tq = occ[1], occ_any = occ[2];
     const bool timing = (tp.flags & FS_FLAG_TIME_KERNELS) != 0;
     cudaEvent_t* ev = nullptr;
     if (timing) {
@@ -1933,7 +1939,7 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
     }
     const uint32_t nq = tp.max_depth + 4;
     k_reset_queues<<<(nq + 63) / 64, 64, 0, st>>>(wb.q_count, wb.q_cursor, nq, ctx->d_counters, 0);
-    ++ctx->stats.kernel_launches;
+    ctx->launches.fetch_add(1);
     const uint32_t D = tp.max_depth;
     const uint32_t n_sub = 2u * tp.batch;
     uint32_t grid_sh = (n_sub + FS_SG_THREADS - 1) / FS_SG_THREADS;
@@ -1945,29 +1951,29 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
     if (timing) cudaEventRecord(ev[0], st);
     if (D == 0) {
         k_init_ends<<<(n_sub + 255u) / 256u, 256, 0, st>>>(tp, wb);
-        ++ctx->stats.kernel_launches;
+        ctx->launches.fetch_add(1);
     } else if (!COUNT && !timing && use_tq && wb.log_o && ctx->tune_mega && (uint64_t)n_sub * D <= wb.log_cap) {
         // EXPERIMENTAL: bounce 0 by k_shade_gen, every later bounce inside ONE persistent launch (k_path_q)
-        static int occ_pq = 0;
-        if (!occ_pq) occ_pq = resident_ctas(k_path_q<2>, TR_THREADS, PQ_SMEM);
-        fs_wave_buffers* wbm = const_cast<fs_wave_buffers*>(&wb);
-        const uint32_t epoch = ++wbm->pq_epoch;
+        // the flag/ticket protocol needs every CTA of the grid resident: occupancy of the instantiation that is launched
+        const bool texq = tp.bv.wnodes_tex && ctx->tune_tex >= 2;
+        int& occ_pq = ctx->occ[texq ? 8 : 9];
+        if (!occ_pq) occ_pq = texq ? resident_ctas(k_path_q<2>, TR_THREADS, PQ_SMEM) : resident_ctas(k_path_q<0>, TR_THREADS, PQ_SMEM);
+        const uint32_t epoch = ++wb.pq_epoch;
         pq_globals* g = (pq_globals*)wb.pq;
         k_shade_gen<<<grid_sh, FS_SG_THREADS, 0, st>>>(tp, wb, 0, ctx->d_counters);
         k_pq_seed<<<ctx->sm_count * 4, 256, 0, st>>>(wb, wb.log_o, wb.log_d, wb.log_flag, epoch, g);
-        const bool texq = tp.bv.wnodes_tex && ctx->tune_tex >= 2;
         const uint32_t grid_pq = (uint32_t)(ctx->sm_count * occ_pq);
         if (texq) k_path_q<2><<<grid_pq, TR_THREADS, PQ_SMEM, st>>>(tp, wb, wb.log_o, wb.log_d, wb.log_flag, epoch, wb.log_cap, g,
                                                                   ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush);
         else k_path_q<0><<<grid_pq, TR_THREADS, PQ_SMEM, st>>>(tp, wb, wb.log_o, wb.log_d, wb.log_flag, epoch, wb.log_cap, g,
                                                              ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush);
         k_pq_finish<<<1, 1, 0, st>>>(wb, g, D, ctx->d_counters);
-        ctx->stats.kernel_launches += 4;
+        ctx->launches.fetch_add(4);
         ctx->stats.extend_launches += 1;
     } else {
         for (uint32_t k = 0; k <= D; ++k) {
             k_shade_gen<<<grid_sh, FS_SG_THREADS, 0, st>>>(tp, wb, k, ctx->d_counters);
-            ++ctx->stats.kernel_launches;
+            ctx->launches.fetch_add(1);
             if (k == D) break;
             const bool wide = tp.bv.wnodes != nullptr;
             const int texm = (wide ? tp.bv.wnodes_tex : tp.bv.nodes_tex) ? (int)ctx->tune_tex : 0;
@@ -1995,7 +2001,7 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
 #undef FS_LAUNCH_TQ
 #undef FS_LAUNCH_TRACE
             if (timing) cudaEventRecord(te[1], st);
-            ++ctx->stats.kernel_launches;
+            ctx->launches.fetch_add(1);
             ++ctx->stats.extend_launches;
         }
     }
@@ -2005,11 +2011,11 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
     if (!grid_cg) grid_cg = 1;
     if (tp.lis_mode == 1) {                       // listener pass: keep the subpaths, no connection
         k_lis_store<<<grid_cg, WF_THREADS, 0, st>>>(tp, wb, ctx->d_counters);
-        ++ctx->stats.kernel_launches;
+        ctx->launches.fetch_add(1);
         if (timing) { cudaEventRecord(ev[2], st); cudaEventRecord(ev[3], st); }
         return cudaGetLastError();
     }
-    if (tp.lis_mode == 2) { k_lis_load<<<grid_cg, WF_THREADS, 0, st>>>(tp, wb); ++ctx->stats.kernel_launches; }
+    if (tp.lis_mode == 2) { k_lis_load<<<grid_cg, WF_THREADS, 0, st>>>(tp, wb); ctx->launches.fetch_add(1); }
     const bool all = (tp.flags & FS_FLAG_CONNECT_ALL) != 0;        // every prefix pair (s, t) instead of the two end points
     if (all) k_connect_all_gen<<<grid_cg, WF_THREADS, 0, st>>>(tp, wb, ctx->d_counters);
     else k_connect_gen<<<grid_cg, WF_THREADS, 0, st>>>(tp, wb, ctx->d_counters, d_dbg);
@@ -2035,40 +2041,40 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, const fs_trace_params& tp, un
 #undef FS_LAUNCH_ANYQ
 #undef FS_LAUNCH_ANY
     }
-    ctx->stats.kernel_launches += 2;
+    ctx->launches.fetch_add(2);
     if (timing) cudaEventRecord(ev[2], st);
     uint32_t grid_ev = (uint32_t)ctx->sm_count * 8u;
     const uint32_t ctas_ev = (tp.batch / 4u + WF_THREADS / 32 - 1) / (WF_THREADS / 32) + 1;   // 4 paths per warp
     if (!all && grid_ev > ctas_ev) grid_ev = ctas_ev;
     if (all) k_eval<true><<<grid_ev, WF_THREADS, 0, st>>>(tp, wb, d_hist, ctx->d_counters, nullptr);
     else k_eval<false><<<grid_ev, WF_THREADS, 0, st>>>(tp, wb, d_hist, ctx->d_counters, d_dbg);
-    ++ctx->stats.kernel_launches;
+    ctx->launches.fetch_add(1);
     if (timing) cudaEventRecord(ev[3], st);
     return cudaGetLastError();
 }
 
-cudaError_t fs_wave_trace_batch(fs_ctx* ctx, const fs_trace_params& tp, unsigned long long* d_hist,
+cudaError_t fs_wave_trace_batch(fs_ctx* ctx, fs_lane* lane, const fs_trace_params& tp, unsigned long long* d_hist,
                                 fs_path_dbg* d_dbg)
 {
     const bool count = (tp.flags & FS_FLAG_COUNT_VISITS) != 0;
     if (!(tp.flags & (FS_FLAG_FUSED_EXTEND | FS_FLAG_BRUTE_FORCE)))
-        return count ? launch_batch_split<true>(ctx, tp, d_hist, d_dbg) : launch_batch_split<false>(ctx, tp, d_hist, d_dbg);
+        return count ? launch_batch_split<true>(ctx, lane, tp, d_hist, d_dbg) : launch_batch_split<false>(ctx, lane, tp, d_hist, d_dbg);
     switch (pick_mode(tp)) {
-    case MODE_BRUTE: return launch_batch<false, MODE_BRUTE>(ctx, tp, d_hist, d_dbg);
+    case MODE_BRUTE: return launch_batch<false, MODE_BRUTE>(ctx, lane, tp, d_hist, d_dbg);
     case MODE_TOP:
-        return count ? launch_batch<true, MODE_TOP>(ctx, tp, d_hist, d_dbg)
-                     : launch_batch<false, MODE_TOP>(ctx, tp, d_hist, d_dbg);
+        return count ? launch_batch<true, MODE_TOP>(ctx, lane, tp, d_hist, d_dbg)
+                     : launch_batch<false, MODE_TOP>(ctx, lane, tp, d_hist, d_dbg);
     default:
-        return count ? launch_batch<true, MODE_BVH>(ctx, tp, d_hist, d_dbg)
-                     : launch_batch<false, MODE_BVH>(ctx, tp, d_hist, d_dbg);
+        return count ? launch_batch<true, MODE_BVH>(ctx, lane, tp, d_hist, d_dbg)
+                     : launch_batch<false, MODE_BVH>(ctx, lane, tp, d_hist, d_dbg);
     }
 }
 
 // reset of the per-call device counters (first batch of a trace call)
-cudaError_t fs_wave_reset_counters(fs_ctx* ctx)
+cudaError_t fs_wave_reset_counters(fs_ctx* ctx, int reset_overflow)
 {
-    k_reset_queues<<<1, 64, 0, ctx->stream>>>(ctx->wb.q_count, ctx->wb.q_cursor, 0, ctx->d_counters, 1);
-    ++ctx->stats.kernel_launches;
+    k_reset_queues<<<1, 64, 0, ctx->stream>>>(nullptr, nullptr, 0, ctx->d_counters, reset_overflow ? 3 : 1);
+    ctx->launches.fetch_add(1);
     return cudaGetLastError();
 }
 
@@ -2110,7 +2116,7 @@ cudaError_t fs_wave_debug_rays(fs_ctx* ctx, const fs_trace_params& tp, const flo
 #undef FS_DBG_CL
             k_dbg_unpack_closest<<<g, 256, 0, st>>>(tp.bv, hits, n, d_t, d_tri);
         }
-        ctx->stats.kernel_launches += 3;
+        ctx->launches.fetch_add(3);
         e = cudaStreamSynchronize(st);
         cudaFree(ro); cudaFree(rd); cudaFree(hits); cudaFree(conn); cudaFree(misc);
         return e != cudaSuccess ? e : cudaGetLastError();
@@ -2124,6 +2130,6 @@ cudaError_t fs_wave_debug_rays(fs_ctx* ctx, const fs_trace_params& tp, const flo
         if (smem > 48 * 1024) cudaFuncSetAttribute(k_debug_rays<MODE_TOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_debug_rays<MODE_TOP><<<grid, WF_THREADS, smem, st>>>(tp, d_rays, d_tmax, n, d_t, d_tri, d_hit, ctx->d_counters);
     } else k_debug_rays<MODE_BVH><<<grid, WF_THREADS, 0, st>>>(tp, d_rays, d_tmax, n, d_t, d_tri, d_hit, ctx->d_counters);
-    ++ctx->stats.kernel_launches;
+    ctx->launches.fetch_add(1);
     return cudaGetLastError();
 }

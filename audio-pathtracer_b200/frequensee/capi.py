@@ -26,8 +26,8 @@ ABI_SYMBOLS = [
     "fs_trace", "fs_trace_range_device", "fs_trace_range", "fs_trace_debug",
     "fs_debug_closest_hits", "fs_debug_any_hits",
     "fs_build_ir", "fs_build_ir_to", "fs_build_ir_all", "fs_build_ir_bands", "fs_build_ir_from_energy", "fs_set_histogram", "fs_set_histogram_device",
-    "fs_get_histogram", "fs_set_ir", "fs_load_float_array", "fs_save_float_array",
-    "fs_conv_init_source", "fs_conv_release_source", "fs_conv_process", "fs_conv_process_many",
+    "fs_get_histogram", "fs_get_histogram_sources", "fs_set_ir", "fs_load_float_array", "fs_save_float_array",
+    "fs_conv_init_source", "fs_conv_release_source", "fs_conv_process", "fs_conv_process_many", "fs_conv_process_multi",
     "fs_debug_rfft", "fs_get_stats",
 ]
 
@@ -113,6 +113,7 @@ def load():
     L.fs_set_histogram.argtypes = [vp, vp, u32, u64]
     L.fs_set_histogram_device.argtypes = [vp, vp, u32, u64]
     L.fs_get_histogram.argtypes = [vp, vp]
+    L.fs_get_histogram_sources.argtypes = [vp, C.POINTER(u32)]
     L.fs_set_ir.argtypes = [vp, u32, vp]
     L.fs_build_ir_bands.argtypes = [vp, u32, u32, u64, vp]
     L.fs_build_ir_all.argtypes = [vp, u32, vp]
@@ -122,6 +123,7 @@ def load():
     L.fs_conv_release_source.argtypes = [vp, u32]
     L.fs_conv_process.argtypes = [vp, u32, vp, vp, u32]
     L.fs_conv_process_many.argtypes = [vp, u32, vp, vp, u32, u32]
+    L.fs_conv_process_multi.argtypes = [vp, vp, u32, vp, vp, u32]
     L.fs_debug_rfft.argtypes = [vp, vp, u32, vp]
     L.fs_get_stats.argtypes = [vp, C.POINTER(Stats)]
     for n in ABI_SYMBOLS:
@@ -263,7 +265,9 @@ class Context:
         self._ck(self.L.fs_set_histogram_device(self.h, C.c_void_p(d_ptr), n_sources, n_paths))
 
     def get_histogram(self):
-        hist = np.zeros((self.n_sources, self.cfg.n_bands, self.cfg.n_bins), dtype=np.uint64)
+        n = C.c_uint32(0)
+        self._ck(self.L.fs_get_histogram_sources(self.h, C.byref(n)))
+        hist = np.zeros((n.value, self.cfg.n_bands, self.cfg.n_bins), dtype=np.uint64)
         self._ck(self.L.fs_get_histogram(self.h, hist.ctypes.data))
         return hist
 
@@ -322,6 +326,16 @@ class Context:
         out = np.zeros_like(blocks)
         self._ck(self.L.fs_conv_process_many(self.h, source, blocks.ctypes.data, out.ctypes.data,
                                              blocks.shape[1], blocks.shape[0]))
+        return out
+
+    def conv_process_multi(self, blocks, sources):
+        """blocks: [n_sources][frames][C], one callback of every listed source in one launch"""
+        blocks = np.ascontiguousarray(blocks, dtype=np.float32)
+        src = np.ascontiguousarray(sources, dtype=np.uint32)
+        assert blocks.shape[0] == len(src)
+        out = np.zeros_like(blocks)
+        self._ck(self.L.fs_conv_process_multi(self.h, src.ctypes.data, len(src), blocks.ctypes.data, out.ctypes.data,
+                                              blocks.shape[1]))
         return out
 
     def rfft(self, x):

@@ -51,13 +51,20 @@ def parse():
                          "by all sources (SURVEY 8f rank 4; different random numbers than the default mode)")
     ap.add_argument("--cpu-sample-paths", type=int, default=1 << 19)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: --paths is the TOTAL per step, cut into N shards (default: weak, --paths per GPU)")
+    ap.add_argument("--north-star", choices=["auto", "on", "off"], default="auto",
+                    help="after the headline measurement also time BASELINE north_star's point (concert hall ~5 M triangles, "
+                         "10 485 760 path pairs, depth 32, sharded over the N GPUs) and report it under 'north_star'; auto = at N = 8")
+    ap.add_argument("--north-star-steps", type=int, default=5)
     return ap.parse_args()
 
 
 def config_dict(args, n):
     wl = WORKLOAD if (args.scene == "furnished_room" and args.paths == 1 << 20 and args.depth == 16 and args.sources == 1) else \
         "%s_%d_paths_depth%d_8bands%s" % (args.scene, args.paths, args.depth, "_%dsources" % args.sources if args.sources > 1 else "")
-    return {"workload": wl, "scene": "%s (seeded procedural)" % args.scene, "paths_per_gpu_per_step": args.paths,
+    return {"workload": wl, "scene": "%s (seeded procedural)" % args.scene,
+            "paths_per_gpu_per_step": (args.paths // n) if args.strong else args.paths,
             "max_depth": args.depth, "bands": 8, "bins": 1000, "sources": args.sources, "rr_prob": 0.9,
             "parallelism": "path-range sharding x%d, replicated BVH, one int64 reduce" % n,
             "share_listener": bool(args.share_listener),
@@ -113,22 +120,6 @@ class Clocks:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def traffic_from_profiles(args):
-    """dram__bytes_read.sum + dram__bytes_write.sum per k_trace_closest launch from the committed ncu --set full
-    capture of this workload (profiles/*_traffic.json); None for workloads that were not captured"""
-    if not (args.scene == "furnished_room" and args.paths == 1 << 20 and args.depth == 16):
-        return None
-    best = None
-    pdir = os.path.join(ROOT, "profiles")
-    for f in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
-        if f.endswith("_traffic.json"):
-            try:
-                best = float(json.load(open(os.path.join(pdir, f)))["dram_bytes_per_launch"])
-            except Exception:
-                pass
-    return best
-
-
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -158,6 +149,7 @@ def cpu_oracle_rate(args, n_paths, threads, repeats=1, seed=SEED0):
         for si in range(len(sc.sources)):
             po.build_ir(cfg, h[si], per_source)
         times.append(time.perf_counter() - t0)
+    st["hist"] = h                                           # of the last repeat (seed + repeats - 1): bench parity check
     return times, st
 
 
@@ -187,12 +179,167 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------
+def profile_counters(args):
+    """per-launch ncu counters of the traversal kernel on this workload from the committed `ncu --set full` capture
+    (profiles/*_traffic.json: dram bytes, lts throughput, thread instructions); {} for workloads that were not captured"""
+    out = {}
+    pdir = os.path.join(ROOT, "profiles")
+    want = "hall" if args.scene == "concert_hall" else ("room" if args.scene == "furnished_room" else None)
+    for f in sorted(os.listdir(pdir)) if (want and os.path.isdir(pdir)) else []:
+        if f.endswith("_traffic.json"):
+            try:
+                j = json.load(open(os.path.join(pdir, f)))
+            except Exception:
+                continue
+            if j.get("scene", "room") == want:
+                out = j
+    return out
+
+
+class Workload:
+    """one scene + job size on this rank: contexts, the device step and every measurement taken of it"""
+
+    def __init__(self, env, scene, paths_total_or_per_gpu, depth, n_sources, share_listener, strong):
+        import frequensee as fs
+        from frequensee import scenes, capi
+        from frequensee.distributed import shard_range
+        self.env, self.fs, self.capi = env, fs, capi
+        torch = env["torch"]
+        N, rank, local = env["N"], env["rank"], env["local"]
+        sc = scenes.by_name(scene)
+        sc.sources = sc.sources[:n_sources]
+        self.sc, self.D, self.NS = sc, depth, len(sc.sources)
+        self.P_total = paths_total_or_per_gpu if strong else paths_total_or_per_gpu * N     # path pairs per step, whole job
+        if self.P_total % self.NS:
+            raise SystemExit("--paths x --gpus must be a multiple of --sources")
+        self.base_flags = capi.FLAG_SHARE_LISTENER if share_listener else 0
+        self.ctx = fs.Context(device=local, flags=self.base_flags)   # production configuration: no per-kernel events, batch lanes on
+        self.ctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
+        self.ctx.set_stream(env["stream"].cuda_stream)
+        self.B, self.Kb = self.ctx.cfg.n_bands, self.ctx.cfg.n_bins
+        self.d_hist = torch.zeros((self.NS, self.B, self.Kb), dtype=torch.int64, device="cuda")
+        self.n_global = self.P_total // self.NS                  # per-source path count of the whole job
+        self.g_first, self.g_count = shard_range(self.n_global * self.NS, rank, N)   # contiguous range of g = source * n + i
+
+    def step_device(self, seed):
+        env, ctx, sc = self.env, self.ctx, self.sc
+        ctx.trace_range_device(sc.sources, sc.listener, self.n_global, self.g_first, self.g_count, self.D, seed,
+                               self.d_hist.data_ptr(), True)
+        if env["N"] > 1:
+            env["dist"].reduce(self.d_hist, dst=0, op=env["dist"].ReduceOp.SUM)
+        if env["rank"] == 0:
+            ctx.set_histogram_device(self.d_hist.data_ptr(), self.NS, self.n_global)
+            if self.NS == 1:
+                ctx.build_ir(0, want_ir=False)
+            else:
+                ctx.build_ir_all(self.NS, want_ir=False)
+
+    def time_device(self, K, W, seed0=SEED0):
+        """W warm-up steps, then K steps between a barrier + synchronize on both sides; CUDA events; max over ranks"""
+        env = self.env
+        torch = env["torch"]
+        for w in range(W):
+            self.step_device(seed0 - 1 - w)
+        env["barrier"]()
+        launches0 = self.ctx.stats()["kernel_launches"]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with Clocks(env["local"]) as clk:
+            env["barrier"]()
+            e0.record(env["stream"])
+            for k in range(K):
+                self.step_device(seed0 + k)
+            e1.record(env["stream"])
+            env["barrier"]()
+            dev_ms = e0.elapsed_time(e1)
+        launches = self.ctx.stats()["kernel_launches"] - launches0
+        t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+        if env["N"] > 1:
+            env["dist"].all_reduce(t, op=env["dist"].ReduceOp.MAX)
+        return float(t.item()), int(launches), clk.summary()
+
+    def stage_times(self, n_steps, seed0=SEED0):
+        """per-kernel-class device time: the same steps (same seeds) re-run on a second context with FS_FLAG_TIME_KERNELS,
+        i.e. CUDA events on the launching stream around every stage and every k_trace_q launch.  That context runs its
+        batches on ONE lane, so each kernel is timed alone (in the headline run two batch lanes overlap their kernels)."""
+        torch = self.env["torch"]
+        tctx = self.fs.Context(device=self.env["local"], flags=self.capi.FLAG_TIME_KERNELS | self.base_flags)
+        tctx.set_scene(self.sc.verts, self.sc.tri_mat, self.sc.absorption)
+        tctx.set_stream(self.env["stream"].cuda_stream)
+        per = []
+        for k in range(-1, n_steps):
+            tctx.trace_range_device(self.sc.sources, self.sc.listener, self.n_global, self.g_first, self.g_count, self.D,
+                                    seed0 + k, self.d_hist.data_ptr(), True)
+            torch.cuda.synchronize()
+            if k >= 0:
+                per.append(tctx.stats())
+        tctx.close()
+        m = lambda key: float(np.mean([s[key] for s in per]))       # noqa: E731
+        return {"extend_ms": m("extend_ms"), "connect_ms": m("connect_ms"), "trace_ms": m("trace_ms"), "eval_ms": m("eval_ms"),
+                "extend_launches": per[0]["extend_launches"], "rays": m("ext_rays") + m("shadow_rays"),
+                "ext_rays": m("ext_rays"), "connected": m("connected")}
+
+    def visit_counts(self, n_steps, seed0=SEED0):
+        """algorithmic bytes: visit counts of the same rays from the instrumented build of the same kernels"""
+        cctx = self.fs.Context(device=self.env["local"], flags=self.capi.FLAG_COUNT_VISITS | self.base_flags)
+        cctx.set_scene(self.sc.verts, self.sc.tri_mat, self.sc.absorption)
+        cnt = []
+        for k in range(n_steps):
+            cctx.trace_range(self.sc.sources, self.sc.listener, self.n_global, self.g_first, self.g_count, self.D, seed0 + k)
+            cnt.append(cctx.stats())
+        cctx.close()
+        en = float(np.mean([c["node_visits"] - c["shadow_node_visits"] for c in cnt]))
+        et = float(np.mean([c["tri_tests"] - c["shadow_tri_tests"] for c in cnt]))
+        er = float(np.mean([c["ext_rays"] for c in cnt]))
+        return en, et, er
+
+    def roofline(self, args_like, st, clocks):
+        """bytes_ray = 64 * n_node (one 4-wide node) + 48 * n_tri (v0, e1, e2) + 32 (ray record read) + 8 (hit
+        write), n_node / n_tri measured; achieved = bytes / CUDA-event time of the traversal launches; peak = measured HBM copy
+        bandwidth.  `bound` names the resource that actually limits the kernel on this scene (ncu evidence under profiles/)."""
+        en, et, er = self.visit_counts(2)
+        ext_bytes = 64.0 * en + 48.0 * et + 40.0 * er
+        peak, peak_src = measured_peak()
+        trc_ms, nl = st["trace_ms"], max(st["extend_launches"], 1)
+        achieved = ext_bytes / (trc_ms * 1e-3) / 1e9 if trc_ms > 0 else None
+        bvh_mb = (self.sc.n_tris * 0.5 * 64 + self.sc.n_tris * 64) / 1e6      # reachable 4-wide nodes (~T/2 x 64 B) + triangles (64 B)
+        in_l2 = bvh_mb < 100
+        prof = profile_counters(args_like)
+        r = {"bound": "issue" if in_l2 else "hbm",
+             "binding_resource": ("issue slots / ALU pipe: the %.0f MB of nodes + triangles are L2/L1-resident (DRAM traffic is a few % of "
+                                  "the algorithmic bytes), the kernel is limited by instruction issue at ~2/3 lane occupancy" % bvh_mb) if in_l2
+                                 else ("memory latency / L2+HBM fetch of the %.0f MB of nodes + triangles (larger than the 126 MB L2): "
+                                       "a third of the stall samples wait for the node fetch" % bvh_mb),
+             "kernel": "k_trace_q<closest> (persistent 4-wide BVH closest-hit traversal, warp-shared triangle queue), %d launches "
+                       "per step on the one-lane timing context" % st["extend_launches"],
+             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+             "traffic": prof.get("dram_bytes_per_launch"), "peak_source": peak_src,
+             "bytes_per_launch": ext_bytes / nl, "ms_per_launch": trc_ms / nl,
+             "nodes_per_ray": en / er, "tris_per_ray": et / er,
+             "note": "achieved = ALGORITHMIC fetch bytes (SURVEY.md 8d) / kernel time, normalised by the measured HBM copy peak as "
+                     "prescribed; with an L2-resident BVH it is served by L2/L1, so frac is not a distance to a physical limit -- "
+                     "l2_frac and inst below are"}
+        # L2-relative figure and instruction roofline (ncu counters of the committed capture of this scene, per launch)
+        if prof.get("lts_throughput_pct") is not None:
+            r["l2_frac"] = prof["lts_throughput_pct"] / 100.0
+        if prof.get("thread_inst_per_step") and prof.get("launches") == st["extend_launches"]:
+            # the capture covers one step of this workload on one lane: thread-level instructions per extension ray
+            tipr = prof["thread_inst_per_step"] / er
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            peak_inst = 148 * 4 * 32 * sm_mhz * 1e6                       # thread-instructions/s: SMs x schedulers x lanes x clock
+            ach_inst = tipr * er / (trc_ms * 1e-3) if trc_ms > 0 else None
+            r["inst"] = {"thread_inst_per_ray": tipr, "achieved": ach_inst, "peak": peak_inst,
+                         "unit": "thread-inst/s", "frac": (ach_inst / peak_inst) if ach_inst else None,
+                         "active_lanes_per_inst": prof.get("active_lanes_per_inst"),
+                         "source": prof.get("source")}
+        return r
+
+    def close(self):
+        self.ctx.close()
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    import frequensee as fs
-    from frequensee import scenes, capi
-    from frequensee.distributed import shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -207,116 +354,48 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N, K, W = world, args.steps, args.warmup
-    P, D = args.paths, args.depth
-    sc = scenes.by_name(args.scene)
-    sc.sources = sc.sources[:args.sources]
-    NS_ = len(sc.sources)
-    if P * N % NS_:
-        raise SystemExit("--paths x --gpus must be a multiple of --sources")
-    base_flags = capi.FLAG_SHARE_LISTENER if args.share_listener else 0
-    ctx = fs.Context(device=local, flags=base_flags)        # production configuration: no per-kernel events, batch lanes on
-    ctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
     stream = torch.cuda.Stream()                            # a real (non-NULL) stream: the C-ABI treats NULL as "own stream"
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
-    ctx.set_stream(stream.cuda_stream)
-    B, Kb = ctx.cfg.n_bands, ctx.cfg.n_bins
-    d_hist = torch.zeros((NS_, B, Kb), dtype=torch.int64, device="cuda")
-    n_global = P * N // NS_                                 # per-source path count of the whole job
-    g_first, g_count = shard_range(n_global * NS_, rank, N) # contiguous range of the global index g = source * n + i
-
-    def step_device(seed):
-        ctx.trace_range_device(sc.sources, sc.listener, n_global, g_first, g_count, D, seed, d_hist.data_ptr(), True)
-        if N > 1:
-            dist.reduce(d_hist, dst=0, op=dist.ReduceOp.SUM)
-        if rank == 0:
-            ctx.set_histogram_device(d_hist.data_ptr(), NS_, n_global)
-            if NS_ == 1:
-                ctx.build_ir(0, want_ir=False)
-            else:
-                ctx.build_ir_all(NS_, want_ir=False)
 
     def barrier():
         if N > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for w in range(W):
-        step_device(SEED0 - 1 - w)
-    barrier()
-    launches0 = ctx.stats()["kernel_launches"]
-    ext_ms, con_ms, evl_ms, ext_launches = 0.0, 0.0, 0.0, 0
-    rays = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with Clocks(local) as clk:
-        barrier()
-        e0.record(stream)
-        for k in range(K):
-            step_device(SEED0 + k)
-        e1.record(stream)
-        barrier()
-        dev_ms = e0.elapsed_time(e1)
-    st = ctx.stats()                                        # kernel-class times of the LAST timed step
-    launches = st["kernel_launches"] - launches0
-    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    env = {"torch": torch, "dist": dist, "N": N, "rank": rank, "local": local, "stream": stream, "barrier": barrier}
+    wl = Workload(env, args.scene, args.paths, args.depth, args.sources, args.share_listener, args.strong)
+    sc, ctx, D, NS_, B, Kb = wl.sc, wl.ctx, wl.D, wl.NS, wl.B, wl.Kb
+    P_total = wl.P_total
+    dev_ms, launches, clocks = wl.time_device(K, W)
+    value = P_total * K / (dev_ms * 1e-3)
+    st = wl.stage_times(min(K, 5))
+    roofline = wl.roofline(args, st, clocks)
+
+    # ---- parity inside the driver-run line ---------------------------------------------------------------------------
+    # N > 1: the NCCL-reduced histogram of the N shards == rank 0's own single-GPU trace of the same global range
+    # (one step's worth of one GPU: wl.P_total / N pairs in total, cut into N shards).  Outside the timed region.
+    parity = {}
+    from frequensee.distributed import shard_range
+    n_chk = max(NS_, (P_total // N) // NS_ * NS_) // NS_   # per-source path count of the check job
     if N > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
-    value = P * N * K / (dev_ms * 1e-3)
-
-    # per-kernel-class device time: the same steps (same seeds) re-run on a second context with FS_FLAG_TIME_KERNELS,
-    # i.e. CUDA events on the launching stream around every stage and every k_trace_closest launch.  That context runs
-    # its batches on ONE lane, so each kernel is timed alone (in the headline run two batch lanes overlap their kernels).
-    tctx = fs.Context(device=local, flags=capi.FLAG_TIME_KERNELS | base_flags)
-    tctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
-    tctx.set_stream(stream.cuda_stream)
-    per = []
-    for k in range(-1, min(K, 5)):
-        tctx.trace_range_device(sc.sources, sc.listener, n_global, g_first, g_count, D, SEED0 + k, d_hist.data_ptr(), True)
+        gf, gc = shard_range(n_chk * NS_, rank, N)
+        ctx.trace_range_device(sc.sources, sc.listener, n_chk, gf, gc, D, SEED0 + 77, wl.d_hist.data_ptr(), True)
+        dist.reduce(wl.d_hist, dst=0, op=dist.ReduceOp.SUM)
         torch.cuda.synchronize()
-        if k >= 0:
-            per.append(tctx.stats())
-    tctx.close()
-    ext_ms = float(np.mean([s["extend_ms"] for s in per])); con_ms = float(np.mean([s["connect_ms"] for s in per]))
-    trc_ms = float(np.mean([s["trace_ms"] for s in per]))
-    evl_ms = float(np.mean([s["eval_ms"] for s in per])); ext_launches = per[0]["extend_launches"]
-    rays = float(np.mean([s["ext_rays"] + s["shadow_rays"] for s in per]))
-    ext_rays = float(np.mean([s["ext_rays"] for s in per]))
-    connected = float(np.mean([s["connected"] for s in per]))
-
-    # algorithmic bytes: visit counts of the same rays from the instrumented build of the same kernels
-    cctx = fs.Context(device=local, flags=capi.FLAG_COUNT_VISITS | base_flags)
-    cctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
-    cnt = []
-    for k in range(min(K, 2)):
-        cctx.trace_range(sc.sources, sc.listener, n_global, g_first, g_count, D, SEED0 + k)
-        cnt.append(cctx.stats())
-    cctx.close()
-    en = float(np.mean([c["node_visits"] - c["shadow_node_visits"] for c in cnt]))
-    et = float(np.mean([c["tri_tests"] - c["shadow_tri_tests"] for c in cnt]))
-    er = float(np.mean([c["ext_rays"] for c in cnt]))
-    # SURVEY.md 8(d) per-ray figure with this build's record sizes:
-    # bytes_ray = 64 * n_node (BVH2 node, both child boxes) + 48 * n_tri (v0,e1,e2) + 32 (ray record read) + 8 (hit write)
-    ext_bytes = 64.0 * en + 48.0 * et + 40.0 * er
-    peak, peak_src = measured_peak()
-    achieved = ext_bytes / (trc_ms * 1e-3) / 1e9 if trc_ms > 0 else None
-    ext_ms_all = ext_ms
-    ext_ms = trc_ms
-    bvh_mb = (sc.n_tris * 0.5 * 64 + sc.n_tris * 64) / 1e6          # reachable 4-wide nodes (~T/2 x 64 B) + triangles (64 B)
-    roofline = {"bound": "hbm", "kernel": "k_trace_closest_q (persistent 4-wide BVH closest-hit traversal, warp-shared triangle "
-                                          "queue), %d launches per step on the one-lane timing context" % ext_launches,
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": traffic_from_profiles(args), "peak_source": peak_src,
-                "bytes_per_launch": ext_bytes / max(ext_launches, 1), "ms_per_launch": ext_ms / max(ext_launches, 1),
-                "nodes_per_ray": en / er, "tris_per_ray": et / er,
-                "note": ("nodes + triangles (~%.0f MB) are L2-resident: achieved is algorithmic fetch bandwidth, served mostly "
-                         "by L2/L1, normalised by the measured HBM copy peak as SURVEY.md 8(d) prescribes" % bvh_mb) if bvh_mb < 100
-                        else ("nodes + triangles (~%.0f MB) exceed the 126 MB L2: algorithmic fetch bandwidth against the "
-                              "measured HBM copy peak; n_node / n_tri counted by the instrumented build of the same kernel" % bvh_mb)}
+        if rank == 0:
+            reduced = wl.d_hist.clone()
+            ctx.trace_range_device(sc.sources, sc.listener, n_chk, 0, n_chk * NS_, D, SEED0 + 77, wl.d_hist.data_ptr(), True)
+            torch.cuda.synchronize()
+            parity["nccl_reduce_bit_exact"] = bool(torch.equal(reduced, wl.d_hist))
+            parity["nccl_reduce_check"] = "%d path pairs x %d sources, %d shards reduced over NCCL vs one GPU" % (n_chk, NS_, N)
+        barrier()
 
     # e2e: the public C-ABI call with host buffers in and out, copies inside the timed region
     ctx.set_stream(None)
     e2e = None
+    g_first, g_count, n_global = wl.g_first, wl.g_count, wl.n_global
+    d_hist = wl.d_hist
     if rank == 0 or N > 1:
         def step_host(seed):
             if N == 1:
@@ -343,28 +422,60 @@ def run_b200(args):
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
         wall = float(tw.item())
         hb = NS_ * B * Kb * 8
-        e2e = {"value": P * N * K / wall, "unit": UNIT, "h2d_bytes_per_step": int(sc.sources.nbytes + sc.listener.nbytes),
+        e2e = {"value": P_total * K / wall, "unit": UNIT, "h2d_bytes_per_step": int(sc.sources.nbytes + sc.listener.nbytes),
                "d2h_bytes_per_step": int(hb + NS_ * ctx.cfg.n_channels * ctx.cfg.sample_rate * 4), "ms_per_step": 1e3 * wall / K}
-    cpu = None
+    cpu = cpu1 = None
     if rank == 0 and N == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         times, so = cpu_oracle_rate(args, args.cpu_sample_paths, threads, repeats=1)
         cpu = {"value": args.cpu_sample_paths / times[0], "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "%d path pairs of the same workload (oracle/fs_oracle.c, pthreads, %d threads), %.2f s"
                          % (args.cpu_sample_paths, threads, times[0])}
+        # the same sample on the GPU through the C-ABI: the integers must be the oracle's (the oracle only as the checker)
+        per_src = max(1, args.cpu_sample_paths // NS_)
+        hg = ctx.trace(sc.sources, sc.listener, per_src, D, SEED0)
+        parity["oracle_bit_exact"] = bool(np.array_equal(hg, so["hist"]))
+        parity["oracle_check"] = "%d path pairs of this workload, GPU histogram == CPU oracle histogram" % (per_src * NS_)
+        # one host thread: what the reference has, its whole update runs on the game thread (SUB.cpp:55-85)
+        n1 = max(NS_, min(args.cpu_sample_paths, 1 << 15))
+        t1, _ = cpu_oracle_rate(args, n1, 1, repeats=1)
+        cpu1 = {"value": n1 / t1[0], "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": "%d path pairs of the same workload on ONE host thread, %.2f s" % (n1, t1[0])}
+    wl.close()
+
+    # ---- BASELINE north_star's point, in the same driver-run line -------------------------------------------------------
+    north = None
+    want_ns = args.north_star == "on" or (args.north_star == "auto" and N == 8 and args.scene == "furnished_room" and not args.strong)
+    if want_ns:
+        NS_PAIRS = 10 * (1 << 20)                                            # 10 485 760 >= 10 M bidirectional path pairs
+        hall = Workload(env, "concert_hall", NS_PAIRS, 32, 1, False, strong=True)
+        h_ms, h_launches, h_clocks = hall.time_device(args.north_star_steps, 2, seed0=SEED0 + 500)
+        hst = hall.stage_times(2, seed0=SEED0 + 500)
+        class _A: scene = "concert_hall"; paths = NS_PAIRS // N; depth = 32     # noqa: E701
+        hroof = hall.roofline(_A, hst, h_clocks)
+        if rank == 0:
+            per = h_ms / args.north_star_steps
+            north = {"workload": "concert_hall_%d_tris_%d_pairs_depth32_8bands" % (hall.sc.n_tris, NS_PAIRS), "n_gpus": N,
+                     "ms_per_ir_update": per, "target_ms": 16.0, "paths_per_s": NS_PAIRS / (per * 1e-3),
+                     "mrays_per_s": hst["rays"] * N / (per * 1e-3) / 1e6, "steps": args.north_star_steps, "warmup": 2,
+                     "roofline_frac": hroof["frac"], "roofline": hroof, "clocks": h_clocks, "gpu_launches": h_launches,
+                     "stage_ms_rank0_one_lane": {"trace_closest": hst["trace_ms"], "shade_gen": hst["extend_ms"] - hst["trace_ms"],
+                                                 "connect": hst["connect_ms"], "eval_splat": hst["eval_ms"]}}
+        hall.close()
     if rank == 0:
+        ext_ms_all, trc_ms = st["extend_ms"], st["trace_ms"]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": K, "warmup": W,
-                "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
                 "dtype": "f32 + u64 Q32.32", "data": "synthetic", "config": config_dict(args, N),
-                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu,
-                "mrays_per_s": rays * N / (dev_ms / K * 1e-3) / 1e6, "ms_per_ir_update": dev_ms / K,
-                "stage_ms": {"trace_closest": trc_ms, "shade_gen": ext_ms_all - trc_ms, "connect": con_ms, "eval_splat": evl_ms},
-                "rays_per_step_per_gpu": rays, "ext_rays_per_step_per_gpu": ext_rays, "connected_per_step_per_gpu": connected,
-                "triangles": int(sc.n_tris)}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_1thread": cpu1, "parity": parity, "north_star": north,
+                "mrays_per_s": st["rays"] * N / (dev_ms / K * 1e-3) / 1e6,
+                "ms_per_ir_update": dev_ms / K,
+                "stage_ms": {"trace_closest": trc_ms, "shade_gen": ext_ms_all - trc_ms, "connect": st["connect_ms"], "eval_splat": st["eval_ms"]},
+                "rays_per_step_per_gpu": st["rays"], "ext_rays_per_step_per_gpu": st["ext_rays"],
+                "connected_per_step_per_gpu": st["connected"], "triangles": int(sc.n_tris)}
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()
-    ctx.close()
     if N > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -12,16 +12,23 @@
  *   GEO.h, MAT.h = Public/AcousticGeometryComponent.h, Public/AcousticMaterial.h
  *
  * Error convention: every function returns fs_status (0 = OK, negative = error);
- * fs_last_error(ctx) returns a human-readable message for the last failure on that context.
+ * fs_last_error(ctx) returns a human-readable message for the last failure ON THE CALLING THREAD
+ * (thread-local: the game thread and the audio thread use one context concurrently).
  * Nothing throws across this boundary.  There is NO CPU fallback: if no CUDA device is usable
  * fs_create fails with FS_ERR_CUDA.
  *
- * Threading: fs_scene_*, fs_trace*, fs_build_ir* from one thread at a time per context (the
- * reference's game thread, SUB.cpp:55); fs_conv_process may be called from another thread (the
- * reference's audio render thread, REV.cpp:118); the IR hand-off between them is a
- * double-buffered set of partition spectra published with an atomic index swap at a block
- * boundary (the reference shares ImpulseBuffer with no synchronisation, COMP.cpp:378 vs
- * REV.cpp:136).
+ * Threading: fs_scene_*, fs_trace*, fs_build_ir*, fs_set_*, fs_get_* from one thread at a time
+ * per context (the reference's game thread, SUB.cpp:55).  fs_conv_init_source /
+ * fs_conv_release_source / fs_conv_process* may be called concurrently from other threads (the
+ * reference's audio render thread and its source workers, REV.cpp:118): they run on a stream of
+ * their own and never queue behind a trace.  The IR hand-off between the two is a
+ * double-buffered set of partition spectra: an IR update writes the unpublished buffer on the
+ * game thread's stream, and the convolver adopts it at the first callback (block boundary)
+ * that finds the update complete -- a callback never waits for an update that is still being
+ * computed, it keeps the previous IR (the reference shares ImpulseBuffer with no
+ * synchronisation, COMP.cpp:378 vs REV.cpp:136).  An update is guaranteed to be in effect for
+ * callbacks issued after a host-synchronising call of the game thread has returned
+ * (fs_build_ir* with ir_out, fs_set_ir, fs_synchronize).
  *
  * Ownership: the caller owns every host buffer passed in or out; the library copies at call
  * time and retains nothing.  Device memory is owned by the context.
@@ -43,7 +50,10 @@ typedef enum fs_status {
     FS_ERR_CUDA = -2,         /* CUDA runtime failure (message has the CUDA error string) */
     FS_ERR_NOMEM = -3,
     FS_ERR_STATE = -4,        /* e.g. fs_trace before fs_scene_commit */
-    FS_ERR_OVERFLOW = -5      /* traversal stack overflow (BVH deeper than the kernel supports) */
+    FS_ERR_OVERFLOW = -5      /* traversal stack overflow (BVH deeper than the kernel supports): the histogram of that trace is
+                                 incomplete.  Reported by the trace call itself when it returns host data, otherwise by the
+                                 next call on the context that can see the flag (fs_build_ir*, fs_trace*, fs_synchronize,
+                                 fs_get_*) */
 } fs_status;
 
 /* flags for fs_config.flags */
@@ -206,7 +216,10 @@ int fs_build_ir_from_energy(fs_ctx* ctx, uint32_t source, const float* energy /*
 /* install an already reduced histogram (host [S][B][K]) and its path count, e.g. after an NCCL reduce */
 int fs_set_histogram(fs_ctx* ctx, const uint64_t* hist, uint32_t n_sources, uint64_t n_paths);
 int fs_set_histogram_device(fs_ctx* ctx, const void* d_hist, uint32_t n_sources, uint64_t n_paths);
+/* copies the histogram of the LAST fs_trace* / fs_set_histogram*: [S][B][K] with S = the source count of that call, which
+ * fs_get_histogram_sources returns (size the buffer with it) */
 int fs_get_histogram(fs_ctx* ctx, uint64_t* hist_out /*[S][B][K]*/);
+int fs_get_histogram_sources(fs_ctx* ctx, uint32_t* n_sources_out);
 /* install an external IR (host [C][sample_rate]) for `source`, e.g. a loaded saved_ir.txt
  * (COMP.cpp:454-490) */
 int fs_set_ir(fs_ctx* ctx, uint32_t source, const float* ir);
@@ -228,6 +241,11 @@ int fs_conv_init_source(fs_ctx* ctx, uint32_t source);
 int fs_conv_release_source(fs_ctx* ctx, uint32_t source);
 int fs_conv_process(fs_ctx* ctx, uint32_t source, const float* in_interleaved, float* out_interleaved,
                     uint32_t frames);
+/* multi-emitter callback (BASELINE configs[3]: 64 sources): one block of every listed source in ONE kernel launch
+ * (grid = sources x channels) instead of n_sources serial calls.  sources: n_sources distinct initialised ids;
+ * in / out: host [n_sources][frames][C] interleaved, in the order of `sources`. */
+int fs_conv_process_multi(fs_ctx* ctx, const uint32_t* sources, uint32_t n_sources, const float* in_interleaved,
+                          float* out_interleaved, uint32_t frames);
 /* offline form: n_blocks consecutive callbacks in one call (config 3 bench); host buffers */
 int fs_conv_process_many(fs_ctx* ctx, uint32_t source, const float* in_interleaved,
                          float* out_interleaved, uint32_t frames_per_block, uint32_t n_blocks);

@@ -100,6 +100,12 @@ def test_config5_concert_hall(fs, oracle):
         h = ctx.trace(sc.sources, sc.listener, 2048, 32, 5)
         st = ctx.stats()
         assert np.array_equal(h, ho) and st["ext_rays"] == so["ext_rays"] and st["connected"] == so["connected"]
+        # 2^17 pairs, depth 32 (a tenth of one GPU's share of the north-star update) bit for bit against the oracle
+        import os
+        ho, so = S.trace(oracle.default_config(), sc.sources, sc.listener, 1 << 17, 32, 6, n_threads=os.cpu_count() or 8)
+        h = ctx.trace(sc.sources, sc.listener, 1 << 17, 32, 6)
+        st = ctx.stats()
+        assert np.array_equal(h, ho) and st["ext_rays"] == so["ext_rays"] and st["connected"] == so["connected"]
         del S
         N = 1 << 22
         full = ctx.trace(sc.sources, sc.listener, N, 32, 55)

@@ -133,6 +133,31 @@ def test_full_size_config2_linearity(fs, room):
     assert int(full.sum(axis=2).max()) <= 10 * 2 ** 32 * st["connected"]
 
 
+def test_full_size_config2_bit_exact_vs_oracle(fs, oracle, room):
+    """BASELINE config 2 at FULL size -- 2^20 path pairs, depth 16, 8 bands, the default two-lane batching, i.e. exactly what
+    bench.py times -- bit for bit against the CPU oracle on all host threads (queue wrap, batch split and lane overlap at
+    full occupancy are what the small cases cannot exercise)"""
+    N = 1 << 20
+    S = oracle.Scene(room.verts, room.tri_mat, room.absorption, use_bvh=True)
+    ho, so = S.trace(oracle.default_config(), room.sources, room.listener, N, 16, 1000, n_threads=os.cpu_count() or 8)
+    with _ctx(fs, room) as ctx:
+        h = ctx.trace(room.sources, room.listener, N, 16, 1000)
+        st = ctx.stats()
+        assert np.array_equal(h, ho)
+        assert [st["ext_rays"], st["shadow_rays"], st["connected"]] == [so["ext_rays"], so["shadow_rays"], so["connected"]]
+        # the shard form the multi-GPU path uses: 8 device-resident shards summed == the whole job
+        from frequensee.distributed import shard_range
+        acc = np.zeros_like(h)
+        for r in range(8):
+            lo, cnt = shard_range(N, r, 8)
+            ctx.trace_range(room.sources, room.listener, N, lo, cnt, 16, 1000, hist=acc)
+        assert np.array_equal(acc, ho)
+    with _env(FS_TUNE_MEGA=1):
+        ctx = _ctx(fs, room)
+    with ctx:                                                           # the persistent per-batch kernel at full size
+        assert np.array_equal(ctx.trace(room.sources, room.listener, N, 16, 1000), ho)
+
+
 def test_edge_cases(fs, oracle, shoebox):
     empty_v, empty_m = np.zeros((0, 3, 3), np.float32), np.zeros(0, np.uint32)
     ab = np.full((1, 8), 0.5, np.float32)

@@ -1,8 +1,14 @@
 """Turns gpurun_out/{launches_*.csv, prof_*.ncu-rep} into the committed summaries under profiles/.
-usage: python tools/summarize_profiles.py <launches.csv> <prof.ncu-rep> <tag>"""
+usage: python tools/summarize_profiles.py <launches.csv> <prof.ncu-rep> <tag> [scene=room|hall] [launches_per_step=16]
+
+<tag>_traffic.json (read by bench.py's roofline block) holds, for the closest-hit instance of k_trace_q over the LAST complete
+step that was captured: mean DRAM bytes per launch, time-weighted lts__throughput, and the thread-level / warp-level
+instruction totals of that step (bench.py divides them by the extension rays it measures)."""
 import csv, collections, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 launches, rep, tag = sys.argv[1], sys.argv[2], sys.argv[3]
+scene = sys.argv[4] if len(sys.argv) > 4 else "room"
+per_step = int(sys.argv[5]) if len(sys.argv) > 5 else 16
 out_md = os.path.join(ROOT, "profiles", tag + "_summary.md")
 lines = ["# ncu summary `%s`" % tag, "",
          "Command: `python bench.py --steps 2 --warmup 1 --no-cpu-baseline` (furnished room, 2^20 path pairs, depth 16).",
@@ -53,17 +59,29 @@ want = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_
 lines += ["", "## `ncu --set full` of the dominant kernel (k_trace_closest), %d launches captured" % (len(rr) - 2), ""]
 lines.append("| metric | " + " | ".join("launch %d" % i for i in range(len(rr) - 2)) + " | unit |")
 lines.append("|---|" + "---:|" * (len(rr) - 2) + "---|")
-traffic = []
 for w in want:
     if w in ix:
         lines.append("| %s | %s | %s |" % (w, " | ".join(r[ix[w]] for r in rr[2:]), rr[1][ix[w]]))
 def tobytes(val, unit):
     m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    return float(val) * m.get(unit, 1)
-for r in rr[2:]:
-    traffic.append(tobytes(r[ix["dram__bytes_read.sum"]], rr[1][ix["dram__bytes_read.sum"]]) +
-                   tobytes(r[ix["dram__bytes_write.sum"]], rr[1][ix["dram__bytes_write.sum"]]))
-json.dump({"kernel": "k_trace_q", "dram_bytes_per_launch": sum(traffic) / len(traffic), "launches": len(traffic),
+    return float(val.replace(",", "")) * m.get(unit, 1)
+def num(r, k):
+    return float(r[ix[k]].replace(",", ""))
+# the closest-hit instance only (template arguments <COUNT, TEX, ANY = false>), last complete step
+closest = [r for r in rr[2:] if "k_trace_q" in r[ix["Kernel Name"]] and not r[ix["Kernel Name"]].rstrip().endswith("true>") and "(bool)1>" not in r[ix["Kernel Name"]].replace(" ", "")[-9:]]
+if not closest:
+    closest = rr[2:]
+step_rows = closest[-per_step:] if len(closest) >= per_step else closest
+dur = [num(r, "gpu__time_duration.sum") for r in step_rows]
+dram = [tobytes(r[ix["dram__bytes_read.sum"]], rr[1][ix["dram__bytes_read.sum"]]) + tobytes(r[ix["dram__bytes_write.sum"]], rr[1][ix["dram__bytes_write.sum"]]) for r in step_rows]
+lts = [num(r, "lts__throughput.avg.pct_of_peak_sustained_elapsed") for r in step_rows]
+tinst = [num(r, "smsp__inst_executed.sum") * num(r, "smsp__thread_inst_executed_per_inst_executed.ratio") for r in step_rows]
+winst = [num(r, "smsp__inst_executed.sum") for r in step_rows]
+json.dump({"kernel": "k_trace_q<closest>", "scene": scene, "launches": len(step_rows), "launches_per_step": per_step,
+           "dram_bytes_per_launch": sum(dram) / len(dram),
+           "lts_throughput_pct": sum(l * d for l, d in zip(lts, dur)) / sum(dur),
+           "thread_inst_per_step": sum(tinst), "warp_inst_per_step": sum(winst),
+           "active_lanes_per_inst": sum(tinst) / sum(winst),
            "source": os.path.basename(rep)}, open(os.path.join(ROOT, "profiles", tag + "_traffic.json"), "w"))
 open(out_md, "w").write("\n".join(lines) + "\n")
 print("\n".join(lines[:40]))
