@@ -133,6 +133,7 @@ int fs_create(const fs_config* cfg, fs_ctx** out)
             (e = cudaEventCreate(&ctx->ev_ir0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_ir1)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaEventCreate"); break; }
         if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaEventCreate"); break; }
         if ((e = cudaEventCreateWithFlags(&ctx->ev_overflow, cudaEventDisableTiming)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaEventCreate"); break; }
+        if ((e = cudaEventCreate(&ctx->ev_c0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_c1)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaEventCreate"); break; }
         if ((e = cudaMallocHost(&ctx->h_overflow, sizeof(uint32_t))) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaMallocHost"); break; }
         *ctx->h_overflow = 0u;
         for (int l = 1; l < FS_MAX_LANES && e == cudaSuccess; ++l) {          // lane 0 runs on the context stream itself
@@ -167,6 +168,8 @@ void fs_destroy(fs_ctx* ctx)
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_overflow) cudaEventDestroy(ctx->ev_overflow);
+    if (ctx->ev_c0) cudaEventDestroy(ctx->ev_c0);
+    if (ctx->ev_c1) cudaEventDestroy(ctx->ev_c1);
     if (ctx->h_overflow) cudaFreeHost(ctx->h_overflow);
     cudaFree(ctx->d_mat_ext);
     fs_bvh_free(&ctx->bvh);
@@ -901,9 +904,12 @@ static int conv_process(fs_ctx* ctx, const uint32_t* sources, uint32_t n_src, co
     }
     memcpy(ctx->h_pin_in, in, sizeof(float) * n);
     CK(cudaMemcpyAsync(ctx->d_conv_in, ctx->h_pin_in, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev_c0, st));
     CK(fs_conv_run(ctx, sources, n_src, ctx->d_conv_in, ctx->d_conv_out, n_blocks, st));
+    CK(cudaEventRecord(ctx->ev_c1, st));
     CK(cudaMemcpyAsync(ctx->h_pin_out, ctx->d_conv_out, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (cudaEventElapsedTime(&ctx->last_conv_ms, ctx->ev_c0, ctx->ev_c1) != cudaSuccess) (void)cudaGetLastError();
     memcpy(out, ctx->h_pin_out, sizeof(float) * n);
     return FS_OK;
 }
@@ -947,6 +953,7 @@ int fs_get_stats(fs_ctx* ctx, fs_stats* out)
     int rc = finish_stats(ctx);
     *out = ctx->stats;
     out->kernel_launches = ctx->launches.load();
+    { std::lock_guard<std::mutex> lk(ctx->conv_mu); out->last_conv_ms = ctx->last_conv_ms; }
     return rc;
 }
 

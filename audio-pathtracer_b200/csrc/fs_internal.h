@@ -157,6 +157,7 @@ struct fs_ctx {
     std::vector<fs_conv_source*> conv;
     float *d_conv_in, *d_conv_out; size_t conv_io_cap;   // device staging [sources][blocks][frames][C]
     float *h_pin_in, *h_pin_out;
+    cudaEvent_t ev_c0, ev_c1; float last_conv_ms;        // device time of the last callback's k_conv_blocks (under conv_mu)
     float* h_pin_ir; size_t pin_ir_cap;  // pinned staging for IR read-back (fs_build_ir_all: one copy for all sources)
     std::mutex conv_mu;
 };

@@ -305,7 +305,7 @@ class Workload:
         in_l2 = bvh_mb < 100
         prof = profile_counters(args_like)
         r = {"bound": "issue" if in_l2 else "hbm",
-             "binding_resource": ("issue slots / ALU pipe: the %.0f MB of nodes + triangles are L2/L1-resident (DRAM traffic is a few % of "
+             "binding_resource": ("issue slots / ALU pipe: the %.0f MB of nodes + triangles are L2/L1-resident (DRAM traffic is a few %% of "
                                   "the algorithmic bytes), the kernel is limited by instruction issue at ~2/3 lane occupancy" % bvh_mb) if in_l2
                                  else ("memory latency / L2+HBM fetch of the %.0f MB of nodes + triangles (larger than the 126 MB L2): "
                                        "a third of the stall samples wait for the node fetch" % bvh_mb),

@@ -122,6 +122,8 @@ typedef struct fs_stats {
     float    eval_ms;          /*   "   k_eval (evaluate + splat) */
     uint32_t extend_launches;  /* closest-hit traversal launches (k_trace_closest / k_extend) in the last trace */
     float    trace_ms;         /* only with FS_FLAG_TIME_KERNELS: sum over the k_trace_closest launches alone */
+    float    last_conv_ms;     /* device time of the k_conv_blocks launch(es) of the last fs_conv_process* call (CUDA events on the
+                                  convolver's stream) */
 } fs_stats;
 
 /* per-path debug record, same layout as fso_path_dbg in oracle/fs_oracle.h */

@@ -8,8 +8,8 @@ TOL = 1e-5
 
 
 def _rel(a, b):
-    return float(np.linalg.norm(np.asarray(a, np.float64) - np.asarray(b, np.float64)) /
-                 max(np.linalg.norm(np.asarray(b, np.float64)), 1e-30))
+    dt = np.complex128 if (np.iscomplexobj(a) or np.iscomplexobj(b)) else np.float64
+    return float(np.linalg.norm(np.asarray(a, dt) - np.asarray(b, dt)) / max(np.linalg.norm(np.asarray(b, dt)), 1e-30))
 
 
 def test_ir_from_trace_matches_oracle(fs, oracle):

@@ -7,6 +7,9 @@ Prints one JSON line:
   ms_per_block_callback  fs_conv_process, host buffers in and out, one 1024-frame block per call (wall clock)
   ms_per_block_stream    fs_conv_process_many over all 469 blocks (wall clock / blocks)
   rel_l2_vs_direct       against the double-precision direct-form convolution with the IR held fixed (tolerance 1e-5)
+  multi_emitter          fs_conv_process_multi: one callback of 64 sources in ONE launch (grid = sources x channels), device time
+                         (CUDA events on the convolver's stream) and wall clock, with the `roofline` block of SURVEY.md 8(d):
+                         algorithmic bytes = S * C * [(P+1)(Bk+1) * 16 + 2 Bk * 8] per callback against the measured HBM peak
   cpu_reference          the reference's own scheme (3 x 65 536-point KissFFT per channel per callback, REV.cpp:172-213)
                          from oracle/_ref on one host thread, when that library was built
 The oracle is used here only as the checker / CPU baseline (tools/, not the product)."""
@@ -67,6 +70,43 @@ def main():
         t0 = time.perf_counter()
         y = ctx.conv_process_many(x.reshape(NB, BLK, 2), 0).reshape(-1, 2)
         out["ms_per_block_stream"] = 1e3 * (time.perf_counter() - t0) / NB
+        out["ms_per_block_device"] = ctx.stats()["last_conv_ms"] / NB
+    # --- multi-emitter callback (BASELINE configs[3]: 64 sources), every source with its own IR and history
+    S = 64
+    with fs.Context(conv_clamp=0) as ctx:
+        c = ctx.cfg
+        P = (c.sample_rate + c.conv_block - 1) // c.conv_block
+        irs = (rng.normal(size=(S, 2, 48000)) * np.exp(-np.arange(48000) / 7000.0) * 0.02).astype(np.float32)
+        ids = np.arange(S, dtype=np.uint32)
+        for i in range(S):
+            ctx.conv_init_source(i); ctx.set_ir(irs[i], i)
+        xb = rng.uniform(-0.5, 0.5, size=(S, BLK, 2)).astype(np.float32)
+        dev, wall = [], []
+        for it in range(60):
+            t0 = time.perf_counter()
+            ctx.conv_process_multi(xb, ids)
+            wall.append(1e3 * (time.perf_counter() - t0))
+            dev.append(ctx.stats()["last_conv_ms"])
+        t_serial = []
+        for it in range(5):
+            t0 = time.perf_counter()
+            for i in range(S):
+                ctx.conv_process(xb[i], i)
+            t_serial.append(1e3 * (time.perf_counter() - t0))
+        bytes_cb = S * c.n_channels * ((P + 1) * (BLK + 1) * 16 + 2 * BLK * 8)
+        peak = 6545.9
+        try:
+            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            pass
+        d = float(np.median(dev[10:]))
+        out["multi_emitter"] = {"sources": S, "ms_per_callback_device": d, "ms_per_callback_wall": float(np.median(wall[10:])),
+                                "ms_per_callback_wall_p99": float(np.percentile(wall[10:], 99)),
+                                "ms_64_serial_calls_wall": float(np.median(t_serial)),
+                                "roofline": {"bound": "hbm", "kernel": "k_conv_blocks (grid = 64 sources x 2 channels, radix-4 Stockham FFT, 47-partition spectral MAC)",
+                                             "achieved": bytes_cb / (d * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                             "frac": bytes_cb / (d * 1e-3) / 1e9 / peak, "bytes_per_launch": bytes_cb,
+                                             "note": "64 x (FDL + H) = 99 MB per callback: partly L2-resident between callbacks"}}
     num = den = 0.0
     n_chk = 96000                                                    # first 2 s: direct form in double is O(n * taps)
     for c in range(2):
