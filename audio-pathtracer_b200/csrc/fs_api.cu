@@ -103,6 +103,9 @@ int fs_create(const fs_config* cfg, fs_ctx** out)
     if (const char* e11 = getenv("FS_TUNE_TQ")) ctx->tune_tq = (uint32_t)atoi(e11);
     ctx->tune_mega = 0;          // EXPERIMENTAL: one persistent launch per batch for the extension stage (k_path_q)
     if (const char* e15 = getenv("FS_TUNE_MEGA")) ctx->tune_mega = (uint32_t)atoi(e15);
+    ctx->tune_mega_from = 0; ctx->tune_mega_lanes = 1;   // first bounce inside the persistent kernel; batch lanes with it
+    if (const char* e16 = getenv("FS_TUNE_MEGA_FROM")) ctx->tune_mega_from = (uint32_t)atoi(e16);
+    if (const char* e17 = getenv("FS_TUNE_MEGA_LANES")) { int v = atoi(e17); if (v >= 1 && v <= FS_MAX_LANES) ctx->tune_mega_lanes = (uint32_t)v; }
     if (const char* e12 = getenv("FS_TUNE_TQ_NODE_MIN")) ctx->tune_tq_node_min = (uint32_t)atoi(e12);
     if (const char* e13 = getenv("FS_TUNE_TQ_FLUSH")) ctx->tune_tq_flush = (uint32_t)atoi(e13);
     if (ctx->tune_tq_flush < 1) ctx->tune_tq_flush = 1;
@@ -171,7 +174,7 @@ void fs_destroy(fs_ctx* ctx)
     if (ctx->ev_c0) cudaEventDestroy(ctx->ev_c0);
     if (ctx->ev_c1) cudaEventDestroy(ctx->ev_c1);
     if (ctx->h_overflow) cudaFreeHost(ctx->h_overflow);
-    cudaFree(ctx->d_mat_ext);
+    cudaFree(ctx->d_bsdf_tab); cudaFree(ctx->d_lobes);
     fs_bvh_free(&ctx->bvh);
     cudaFree(ctx->d_verts); cudaFree(ctx->d_tri_mat); cudaFree(ctx->d_refl_over_pi);
     cudaFree(ctx->d_hist); cudaFree(ctx->d_counters); cudaFree(ctx->d_src_pos); cudaFree(ctx->d_dbg);
@@ -251,6 +254,8 @@ int fs_scene_set_materials(fs_ctx* ctx, const float* absorption, uint32_t n_mate
     if (n_bands != ctx->cfg.n_bands) return fail(ctx, FS_ERR_INVALID, "n_bands differs from fs_config.n_bands");
     dev_guard g(ctx->device);
     std::vector<float> r((size_t)n_materials * n_bands);
+    ctx->mat_absorption.assign(absorption, absorption + r.size());
+    ctx->mat_transmission.clear(); ctx->mat_scattering.clear(); ctx->mat_thickness_cm.clear();
     for (size_t i = 0; i < r.size(); ++i) {
         float a = absorption[i];
         if (!(a >= 0.0f && a <= 1.0f)) return fail(ctx, FS_ERR_INVALID, "absorption must be in [0,1]");
@@ -310,6 +315,52 @@ int fs_scene_set_materials_ex(fs_ctx* ctx, const float* absorption, const float*
     ctx->mat_transmission.assign(transmission ? transmission : nullptr, transmission ? transmission + n : nullptr);
     ctx->mat_scattering.assign(scattering ? scattering : nullptr, scattering ? scattering + n : nullptr);
     ctx->mat_thickness_cm.assign(thickness_cm ? thickness_cm : nullptr, thickness_cm ? thickness_cm + n_materials : nullptr);
+    ctx->committed = false;
+    return FS_OK;
+}
+
+// FS_FLAG_MATERIAL_MODEL: per (event, material, band) energy factors and per material lobe thresholds.
+// Plain float arithmetic in exactly the order of oracle/fs_oracle.c fso_scene_set_material_model (the tables must be
+// bit-identical on both sides); fs_pow is the shared polynomial of fs_math.cuh.
+static int build_material_model(fs_ctx* ctx)
+{
+    const uint32_t M = ctx->n_mats, B = ctx->cfg.n_bands;
+    std::vector<float> tab((size_t)3 * M * B, 0.0f);
+    std::vector<float4> lobes(M);
+    const float* tr = ctx->mat_transmission.empty() ? nullptr : ctx->mat_transmission.data();
+    const float* sc = ctx->mat_scattering.empty() ? nullptr : ctx->mat_scattering.data();
+    const float* th = ctx->mat_thickness_cm.empty() ? nullptr : ctx->mat_thickness_cm.data();
+    for (uint32_t m = 0; m < M; ++m) {
+        float sum_r = 0.0f, sum_t = 0.0f, sum_s = 0.0f;
+        const float thick = th ? th[m] : 2.5f;
+        const float ex = thick / 2.5f;
+        for (uint32_t b = 0; b < B; ++b) {
+            const float a = ctx->mat_absorption[(size_t)m * B + b];
+            const float refl = 1.0f - a;
+            float tau = tr ? tr[(size_t)m * B + b] : 0.0f;
+            if (refl + tau > 1.0f) tau = 1.0f - refl;                      // MaterialAcousticProcessor.cpp:59-60
+            const float sig = sc ? sc[(size_t)m * B + b] : 1.0f;
+            float tau_eff = 0.0f;
+            if (tau > 0.0f) tau_eff = (ex == 1.0f) ? tau : fs_pow(tau, ex);
+            tab[((size_t)0 * M + m) * B + b] = (refl * sig) / FS_PI;
+            tab[((size_t)1 * M + m) * B + b] = refl * (1.0f - sig);
+            tab[((size_t)2 * M + m) * B + b] = tau_eff;
+            sum_r += refl; sum_t += tau; sum_s += sig;
+        }
+        const float mr = sum_r / (float)B, mt = sum_t / (float)B, ms = sum_s / (float)B;
+        const float tot = mr + mt;
+        const float t1 = (tot > 0.0f) ? mt / tot : 0.0f;
+        const float ps = (1.0f - t1) * (1.0f - ms);
+        const float t2 = t1 + ps;
+        const float pd = 1.0f - t2;
+        lobes[m] = make_float4(t1, t2, ps, pd);
+    }
+    cudaFree(ctx->d_bsdf_tab); cudaFree(ctx->d_lobes); ctx->d_bsdf_tab = nullptr; ctx->d_lobes = nullptr;
+    CK(cudaMalloc(&ctx->d_bsdf_tab, sizeof(float) * tab.size()));
+    CK(cudaMalloc(&ctx->d_lobes, sizeof(float4) * lobes.size()));
+    CK(cudaMemcpyAsync(ctx->d_bsdf_tab, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_lobes, lobes.data(), sizeof(float4) * lobes.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return FS_OK;
 }
 
@@ -325,6 +376,10 @@ int fs_scene_commit(fs_ctx* ctx)
         CK(cudaStreamSynchronize(ctx->stream));
         for (uint64_t i = 0; i < ctx->n_tris; ++i)
             if (m[i] >= ctx->n_mats) return fail(ctx, FS_ERR_INVALID, "triangle material id out of range");
+    }
+    if (ctx->cfg.flags & FS_FLAG_MATERIAL_MODEL) {
+        int rc = build_material_model(ctx);
+        if (rc) return rc;
     }
     uint64_t bvh_launches = 0;
     CK(fs_bvh_build(ctx->stream, ctx->d_verts, ctx->d_tri_mat, ctx->n_tris, &ctx->bvh, &bvh_launches,
@@ -354,7 +409,9 @@ static void fill_params(fs_ctx* ctx, fs_trace_params* tp, const float lis[3], ui
     tp->bv.nodes = ctx->bvh.nodes; tp->bv.tris = ctx->bvh.tris; tp->bv.tri_orig = ctx->bvh.tri_orig;
     tp->bv.tri_mat = ctx->bvh.tri_mat; tp->bv.tri_nm = ctx->bvh.tri_nm; tp->bv.n_tris = ctx->bvh.n_tris; tp->bv.n_inner = ctx->bvh.n_inner;
     tp->top = ctx->bvh.top_nodes; tp->n_top = ctx->bvh.n_top;
-    tp->refl_over_pi = ctx->d_refl_over_pi; tp->n_mats = ctx->n_mats;
+    const bool model = (c.flags & FS_FLAG_MATERIAL_MODEL) && ctx->d_lobes;
+    tp->refl_over_pi = model ? ctx->d_bsdf_tab : ctx->d_refl_over_pi; tp->n_mats = ctx->n_mats;
+    tp->lobes = model ? ctx->d_lobes : nullptr;
     tp->ep.min_seg = c.min_seg; tp->ep.pdf_exponent = c.pdf_exponent; tp->ep.n_bands = c.n_bands;
     for (int b = 0; b < FS_MAX_BANDS; ++b) tp->ep.air[b] = c.air_absorption[b];
     tp->n_bins = c.n_bins; tp->bin_ms = c.bin_ms; tp->rr_prob = c.rr_prob; tp->eps_offset = c.eps_offset;
@@ -420,6 +477,8 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
     if ((ctx->cfg.flags & FS_FLAG_TIME_KERNELS) || d_dbg) n_lanes = 1;
     if ((ctx->cfg.flags & FS_FLAG_SHARE_LISTENER) && (ctx->cfg.flags & (FS_FLAG_FUSED_EXTEND | FS_FLAG_BRUTE_FORCE)))
         return fail(ctx, FS_ERR_INVALID, "FS_FLAG_SHARE_LISTENER needs the wavefront path");
+    if ((ctx->cfg.flags & FS_FLAG_MATERIAL_MODEL) && (ctx->cfg.flags & (FS_FLAG_FUSED_EXTEND | FS_FLAG_BRUTE_FORCE)))
+        return fail(ctx, FS_ERR_INVALID, "FS_FLAG_MATERIAL_MODEL needs the wavefront path");
     if (ctx->cfg.flags & FS_FLAG_CONNECT_ALL) {
         // up to (depth+1)^2 connection rays per pair: keep a batch's ray queue near 2^24 entries; ids are pair << 12 | s << 6 | t
         if (max_depth > 63) return fail(ctx, FS_ERR_INVALID, "FS_FLAG_CONNECT_ALL: max_depth <= 63");
@@ -431,13 +490,15 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
         if (cap_cfg > lim) cap_cfg = lim;
         n_lanes = 1;
     }
-    if (ctx->tune_mega && !(ctx->cfg.flags & (FS_FLAG_COUNT_VISITS | FS_FLAG_TIME_KERNELS))) n_lanes = 1;   // the persistent per-batch kernel owns the whole GPU
+    if (ctx->tune_mega && !(ctx->cfg.flags & (FS_FLAG_COUNT_VISITS | FS_FLAG_TIME_KERNELS)) && n_lanes > ctx->tune_mega_lanes)
+        n_lanes = ctx->tune_mega_lanes;                       // lanes that run a persistent per-batch kernel share the SMs
     while (n_lanes > 1 && g_count / n_lanes < (1u << 17)) --n_lanes;            // small jobs: not worth a second set of launches
     uint64_t n_batches = g_count ? (g_count + cap_cfg - 1) / cap_cfg : 1;
     if (n_batches < n_lanes) n_batches = n_lanes;
     if (n_batches % n_lanes) n_batches += n_lanes - n_batches % n_lanes;
     const uint32_t cap = (uint32_t)(g_count ? (g_count + n_batches - 1) / n_batches : 1);
     ctx->lanes[0].stream = ctx->stream;                       // lane 0 = the caller's stream; nothing else is rebound
+    ctx->cur_lanes = n_lanes;
     for (uint32_t l = 0; l < n_lanes; ++l) CK(fs_wave_alloc(ctx, &ctx->lanes[l], cap, max_depth));
     fs_trace_params tp;
     fill_params(ctx, &tp, lis_pos, n_paths, max_depth, seed);

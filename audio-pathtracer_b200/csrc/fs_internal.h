@@ -48,7 +48,8 @@ struct fs_trace_params {
     fs_bvh_view bv;
     const float4* top;          // global copy of the treelet (staged to smem by each CTA)
     uint32_t n_top;
-    const float* refl_over_pi;  // [M][B]
+    const float* refl_over_pi;  // [E][M][B] factor per (event, material, band); E = 1 (reflectivity / pi) without the material model, else 3
+    const float4* lobes;        // [M] (t1, t2, P_spec, P_diff) event thresholds / probabilities; null without FS_FLAG_MATERIAL_MODEL
     uint32_t n_mats;
     fs_eval_params ep;
     uint32_t n_bins;
@@ -119,7 +120,8 @@ struct fs_ctx {
     // scene
     float* d_verts; uint32_t* d_tri_mat; uint64_t n_tris;
     float* d_refl_over_pi; uint32_t n_mats;
-    float* d_mat_ext;           // [M][FS_MAT_EXT_STRIDE]: transmission / scattering per band + thickness (FS_FLAG_MATERIAL_MODEL)
+    float* d_bsdf_tab; float4* d_lobes;   // FS_FLAG_MATERIAL_MODEL: [3][M][B] diffuse / specular / transmitted factors, [M] lobe thresholds
+    std::vector<float> mat_absorption;
     std::vector<float> mat_transmission, mat_scattering, mat_thickness_cm;
     bool mats_set, tris_set, committed;
     fs_bvh_device bvh;
@@ -144,7 +146,7 @@ struct fs_ctx {
     std::vector<cudaEvent_t> tev; size_t tev_used;   //   + one (begin, end) pair per k_trace_closest launch
     int sm_count;
     int occ[16];                         // resident CTAs per SM of the persistent kernels (per context = per device)
-    uint32_t tune_refill, tune_leaf_max, tune_tex, tune_builder, tune_wide, tune_node_min, tune_tri_min, tune_collapse, tune_l2pin_mb, tune_tq, tune_tq_node_min, tune_tq_flush, tune_mega;      // experiment knobs (env FS_TUNE_REFILL / FS_TUNE_LEAF_MAX)
+    uint32_t tune_refill, tune_leaf_max, tune_tex, tune_builder, tune_wide, tune_node_min, tune_tri_min, tune_collapse, tune_l2pin_mb, tune_tq, tune_tq_node_min, tune_tq_flush, tune_mega, tune_mega_from, tune_mega_lanes, cur_lanes;      // experiment knobs (env FS_TUNE_REFILL / FS_TUNE_LEAF_MAX)
     // IR / conv
     float* d_energy;            // [K] scratch
     float* d_amp;               // [K]

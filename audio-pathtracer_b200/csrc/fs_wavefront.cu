@@ -368,7 +368,11 @@ k_eval(const fs_trace_params tp, const fs_wave_buffers wb, unsigned long long* _
                     if (i0 + u < nf) {
                         total += r[u].x;                  // ScaledDistance += NodeDistance, SUB.cpp:374
                         eval_seg_band(tp.ep, bs, P, r[u].x, air_b, E);
-                        bs = __ldg(tp.refl_over_pi + (size_t)__float_as_uint(r[u].y) * NBr + b);
+                        // factor of node i0 + u for the segment that leaves it: the lobe the walk took there (top byte; always
+                        // the diffuse one without the material model), the diffuse lobe where the prefix is cut for a connection
+                        const uint32_t mw = __float_as_uint(r[u].y);
+                        const uint32_t evn = (ALL && i0 + u == nf - 1u) ? 0u : (mw >> 24);
+                        bs = __ldg(tp.refl_over_pi + ((size_t)evn * tp.n_mats + (mw & 0x00ffffffu)) * NBr + b);
                         P = r[u].w;
                     }
                 }
@@ -383,7 +387,9 @@ k_eval(const fs_trace_params tp, const fs_wave_buffers wb, unsigned long long* _
                 for (int u = 0; u < 4; ++u) {
                     if (i0 - u >= 1) {
                         total += r[u].x;
-                        eval_seg_band(tp.ep, __ldg(tp.refl_over_pi + (size_t)__float_as_uint(r[u].y) * NBr + b), r[u].w, r[u].x, air_b, E);
+                        const uint32_t mw = __float_as_uint(r[u].y);
+                        const uint32_t evn = (ALL && i0 - u == (int)nb - 1) ? 0u : (mw >> 24);
+                        eval_seg_band(tp.ep, __ldg(tp.refl_over_pi + ((size_t)evn * tp.n_mats + (mw & 0x00ffffffu)) * NBr + b), r[u].w, r[u].x, air_b, E);
                     }
                 }
             }
@@ -458,6 +464,49 @@ __device__ __forceinline__ void leaf_range(int leafnode, uint32_t& tc, uint32_t&
     te = tc + (payload & 7u) + 1u;
 }
 
+// Russian roulette + direction of bounce k of subpath (g, side) at a node with normal nrm reached along d_in (GeneratePath,
+// SUB.cpp:301-318).  Returns false when the walk ends here.  ev = the lobe taken (FS_EV_*), org = origin of the new ray.
+// Without FS_FLAG_MATERIAL_MODEL every surface event is the cosine lobe (ev = 0, org = pos) -- the reference's model.
+// With it the fourth word of the bounce's Philox block picks pass-through / mirror / cosine lobe by the
+// per-material thresholds of tp.lobes (built in fs_scene_commit; same arithmetic as oracle/fs_oracle.c gen_subpath).
+#define FS_EV_DIFFUSE 0u
+#define FS_EV_SPECULAR 1u
+#define FS_EV_TRANSMIT 2u
+__device__ __forceinline__ bool choose_direction(const fs_trace_params& tp, uint32_t k, uint64_t g, uint32_t side, fs_vec3 nrm,
+                                                 fs_vec3 d_in, uint32_t mat, fs_vec3 pos, fs_vec3& dir, float& prob, uint32_t& ev,
+                                                 fs_vec3& org)
+{
+    uint32_t r[4];
+    fs_philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), k, side, tp.seed_lo, tp.seed_hi, r);
+    const float u0 = fs_u01(r[0]), u1 = fs_u01(r[1]), u2 = fs_u01(r[2]);
+    ev = FS_EV_DIFFUSE; org = pos;
+    if (!(u0 < tp.rr_prob)) return false;                   // SUB.cpp:301-302
+    if (k == 0) { dir = fs_sample_sphere(u1, u2); prob = FS_INV_4PI * tp.rr_prob; return true; }     // SUB.cpp:306-311
+    if (tp.lobes) {
+        const float4 lb = __ldg(tp.lobes + mat);            // (t1, t2, P_spec, P_diff)
+        const float u3 = fs_u01(r[3]);
+        if (u3 < lb.x) {                                    // pass through (COMP.cpp:271-275): continue from the far side
+            ev = FS_EV_TRANSMIT; dir = d_in; prob = tp.rr_prob * lb.x;
+            const float e2 = -2.0f * tp.eps_offset;
+            org = fs_mk(fmaf(e2, nrm.x, pos.x), fmaf(e2, nrm.y, pos.y), fmaf(e2, nrm.z, pos.z));
+            return true;
+        }
+        if (u3 < lb.y) {                                    // mirror (GetReflectionVector, COMP.cpp:186)
+            ev = FS_EV_SPECULAR;
+            const float sdn = -2.0f * fs_dot(d_in, nrm);
+            dir = fs_mk(fmaf(sdn, nrm.x, d_in.x), fmaf(sdn, nrm.y, d_in.y), fmaf(sdn, nrm.z, d_in.z));
+            prob = tp.rr_prob * lb.z;
+            return true;
+        }
+        float ct; dir = fs_sample_cos_hemisphere(nrm, u1, u2, ct);
+        prob = ((ct * FS_INV_PI) * tp.rr_prob) * lb.w;
+        return true;
+    }
+    float ct; dir = fs_sample_cos_hemisphere(nrm, u1, u2, ct);      // SUB.cpp:312-318 (FIX: true cosine lobe)
+    prob = (ct * FS_INV_PI) * tp.rr_prob;
+    return true;
+}
+
 #ifndef FS_SG_THREADS
 #define FS_SG_THREADS 256
 #endif
@@ -485,9 +534,10 @@ k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_d
         fs_vec3 pos = fs_mk(0.f, 0.f, 0.f), dir = fs_mk(0.f, 0.f, 0.f);
         uint32_t sp_id = 0; float prob = 1.0f;
         if (j < count_in) {
-            fs_vec3 nrm = fs_mk(0.f, 0.f, 0.f);
-            bool cont = true;
-            uint32_t nodes = 1;
+            fs_vec3 nrm = fs_mk(0.f, 0.f, 0.f), din = fs_mk(0.f, 0.f, 0.f);
+            bool cont = true, hit = false;
+            uint32_t nodes = 1, mat = 0;
+            float seg = 0.f, pdf_in = 1.f;
             if (k == 0) {                         // node 0 (SUB.cpp:287-291)
                 sp_id = j;
                 if (tp.lis_mode && (sp_id & 1u) == tp.lis_mode - 1u) cont = false;   // shared listener: this side is not traced in this pass
@@ -503,8 +553,16 @@ k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_d
                 sp_id = __float_as_uint(a.w);
                 const fs_vec3 o = fs_mk(a.x, a.y, a.z), d = fs_mk(b.x, b.y, b.z);
                 const int tri = __float_as_int(h.y);
-                if (tri < 0) {                    // miss: FIX -> the subpath ends at its current node
-                    wb.end_pos[sp_id] = make_float4(o.x, o.y, o.z, __uint_as_float(k));
+                if (tri < 0) {                    // miss: FIX -> the subpath ends at the node the ray left
+                    if (!tp.lobes) wb.end_pos[sp_id] = make_float4(o.x, o.y, o.z, __uint_as_float(k));
+                    else if (k >= 2u) {
+                        // material model: end_pos already holds that node (written when the ray was emitted: after a
+                        // pass-through the ray origin is not the node); as an end node it connects through its diffuse lobe
+                        float4* rp = wb.rec + (size_t)(k - 1u) * stride + sp_id;
+                        float4 rv = *rp;
+                        rv.y = __uint_as_float(__float_as_uint(rv.y) & 0x00ffffffu);
+                        *rp = rv;
+                    }
                     cont = false;
                 } else {                          // SUB.cpp:343-348
                     const float t = h.x;
@@ -515,32 +573,29 @@ k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_d
                     pos.y = fmaf(tp.eps_offset, fn.y, fmaf(t, d.y, o.y));
                     pos.z = fmaf(tp.eps_offset, fn.z, fmaf(t, d.z, o.z));
                     const fs_vec3 dl = fs_sub(pos, o);
-                    const float seg = sqrtf(fs_dot(dl, dl));
-                    const uint32_t mat = __float_as_uint(nm.w);
-                    wb.rec[(size_t)k * stride + sp_id] = make_float4(seg, __uint_as_float(mat), b.w, fs_pow(b.w, tp.ep.pdf_exponent));
+                    seg = sqrtf(fs_dot(dl, dl));
+                    mat = __float_as_uint(nm.w);
+                    pdf_in = b.w;
                     if (wb.npos) wb.npos[(size_t)k * stride + sp_id] = make_float4(pos.x, pos.y, pos.z, 0.0f);
-                    nrm = fn;
+                    nrm = fn; din = d;
                     nodes = k + 1;
-                    if (k >= tp.max_depth) {      // PARAM: ray budget per subpath exhausted
-                        wb.end_pos[sp_id] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(nodes));
-                        cont = false;
-                    }
+                    hit = true;
+                    if (k >= tp.max_depth) cont = false;      // PARAM: ray budget per subpath exhausted
                 }
             }
+            uint32_t ev = FS_EV_DIFFUSE;
+            fs_vec3 org = pos;
             if (cont) {
                 uint64_t g = tp.g_first + (sp_id >> 1);
                 if ((tp.flags & FS_FLAG_SHARE_LISTENER) && (sp_id & 1u)) g %= tp.n_paths;   // listener stream keyed by the path index only
-                uint32_t r[4];
-                fs_philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), k, sp_id & 1u, tp.seed_lo, tp.seed_hi, r);
-                const float u0 = fs_u01(r[0]), u1 = fs_u01(r[1]), u2 = fs_u01(r[2]);
-                if (u0 < tp.rr_prob) {            // SUB.cpp:301-302
-                    if (k == 0) { dir = fs_sample_sphere(u1, u2); prob = FS_INV_4PI * tp.rr_prob; }
-                    else { float ct; dir = fs_sample_cos_hemisphere(nrm, u1, u2, ct); prob = (ct * FS_INV_PI) * tp.rr_prob; }
-                    emit = true;
-                } else {
-                    wb.end_pos[sp_id] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(nodes));
-                }
+                emit = choose_direction(tp, k, g, sp_id & 1u, nrm, din, mat, pos, dir, prob, ev, org);
             }
+            // node record of node k: the lobe the walk takes here rides in the top byte of the material word
+            if (hit) wb.rec[(size_t)k * stride + sp_id] = make_float4(seg, __uint_as_float(mat | (ev << 24)), pdf_in, fs_pow(pdf_in, tp.ep.pdf_exponent));
+            // the walk ends at this node -- or, with the material model, may end here if the ray just emitted misses
+            const bool at_node = (k == 0) ? !(tp.lis_mode && (sp_id & 1u) == tp.lis_mode - 1u) : hit;
+            if (at_node && (!emit || tp.lobes)) wb.end_pos[sp_id] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(nodes));
+            pos = org;                            // the ray starts at the node, or beyond its surface after a pass-through
         }
         const uint32_t m = __ballot_sync(FULLM, emit);
         if (lane == 0) s_cnt[warp] = (uint32_t)__popc(m);
@@ -1211,22 +1266,27 @@ __device__ __forceinline__ float4 ld_cg_f4(const float4* p)
 }
 
 // bounce-0 rays (written by k_shade_gen(0) into the ping-pong queue) become the first entries of the ray log
+// the rays of bounce k0 (written by k_shade_gen(k0) into the ping-pong queue) become the first entries of the ray log
 __global__ void k_pq_seed(const fs_wave_buffers wb, float4* __restrict__ log_o, float4* __restrict__ log_d,
-                          uint32_t* __restrict__ log_flag, uint32_t epoch, pq_globals* __restrict__ g)
+                          uint32_t* __restrict__ log_flag, uint32_t epoch, pq_globals* __restrict__ g, uint32_t k0)
 {
-    const uint32_t n = wb.q_count[0];
+    const uint32_t n = wb.q_count[k0];
+    const float4* __restrict__ so = wb.st_pos[k0 & 1u];
+    const float4* __restrict__ sd = wb.st_nrm[k0 & 1u];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        log_o[i] = wb.st_pos[0][i];                 // (pos, bits(sp_id)): bounce index 0 in the upper bits
-        log_d[i] = wb.st_nrm[0][i];
+        float4 a = so[i];                           // (pos, bits(sp_id)): the bounce index goes into the upper bits
+        a.w = __uint_as_float(__float_as_uint(a.w) | (k0 << 22));
+        log_o[i] = a;
+        log_d[i] = sd[i];
         log_flag[i] = epoch;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { g->tail = n; g->head = 0u; g->done = 0u; g->error = 0u; }
 }
-// the total number of extension rays, where k_connect_gen looks for it
-__global__ void k_pq_finish(const fs_wave_buffers wb, const pq_globals* __restrict__ g, uint32_t max_depth, fs_dev_counters* dc)
+// the number of extension rays of bounces >= k0, where k_connect_gen looks for it
+__global__ void k_pq_finish(const fs_wave_buffers wb, const pq_globals* __restrict__ g, uint32_t max_depth, fs_dev_counters* dc, uint32_t k0)
 {
-    wb.q_count[0] = g->tail;
-    for (uint32_t k = 1; k < max_depth; ++k) wb.q_count[k] = 0u;
+    wb.q_count[k0] = g->tail;
+    for (uint32_t k = k0 + 1u; k < max_depth; ++k) wb.q_count[k] = 0u;
     if (g->error) dc->overflow = 0x100u | g->error;
 }
 
@@ -1402,10 +1462,17 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
                     const fs_vec3 d = fs_mk(__uint_as_float(shq[6 * PQ_SQ_CAP + qi]), __uint_as_float(shq[7 * PQ_SQ_CAP + qi]), __uint_as_float(shq[8 * PQ_SQ_CAP + qi]));
                     const float pdf_in = __uint_as_float(shq[9 * PQ_SQ_CAP + qi]);
                     fs_vec3 nrm = fs_mk(0.f, 0.f, 0.f);
-                    bool cont = true;
-                    uint32_t nodes = k;
-                    if (tri < 0) {                    // miss: the subpath ends at its current node
-                        wb.end_pos[sp_id] = make_float4(o.x, o.y, o.z, __uint_as_float(k));
+                    bool cont = true, hit = false;
+                    uint32_t nodes = k, mat = 0;
+                    float seg = 0.f;
+                    if (tri < 0) {                    // miss: the subpath ends at the node the ray left
+                        if (!tp.lobes) wb.end_pos[sp_id] = make_float4(o.x, o.y, o.z, __uint_as_float(k));
+                        else if (k >= 2u) {           // material model: see k_shade_gen
+                            float4* rp = wb.rec + (size_t)(k - 1u) * stride + sp_id;
+                            float4 rv = *rp;
+                            rv.y = __uint_as_float(__float_as_uint(rv.y) & 0x00ffffffu);
+                            *rp = rv;
+                        }
                         cont = false;
                     } else {                          // SUB.cpp:343-348
                         const float4 nm = fs_ldg4(bv.tri_nm + tri);
@@ -1415,28 +1482,26 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
                         pos.y = fmaf(tp.eps_offset, fn.y, fmaf(t, d.y, o.y));
                         pos.z = fmaf(tp.eps_offset, fn.z, fmaf(t, d.z, o.z));
                         const fs_vec3 dl = fs_sub(pos, o);
-                        const float seg = sqrtf(fs_dot(dl, dl));
-                        wb.rec[(size_t)k * stride + sp_id] = make_float4(seg, nm.w, pdf_in, fs_pow(pdf_in, tp.ep.pdf_exponent));
+                        seg = sqrtf(fs_dot(dl, dl));
+                        mat = __float_as_uint(nm.w);
                         nrm = fn;
                         nodes = k + 1u;
-                        if (k >= tp.max_depth) {
-                            wb.end_pos[sp_id] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(nodes));
-                            cont = false;
-                        }
+                        hit = true;
+                        if (k >= tp.max_depth) cont = false;
                     }
+                    uint32_t ev = FS_EV_DIFFUSE;
+                    fs_vec3 org = pos;
                     if (cont) {
                         uint64_t gg = tp.g_first + (sp_id >> 1);
                         if ((tp.flags & FS_FLAG_SHARE_LISTENER) && (sp_id & 1u)) gg %= tp.n_paths;
-                        uint32_t r[4];
-                        fs_philox4x32_10((uint32_t)gg, (uint32_t)(gg >> 32), k, sp_id & 1u, tp.seed_lo, tp.seed_hi, r);
-                        const float u0 = fs_u01(r[0]), u1 = fs_u01(r[1]), u2 = fs_u01(r[2]);
-                        if (u0 < tp.rr_prob) {        // SUB.cpp:301-302
-                            float ct; dir = fs_sample_cos_hemisphere(nrm, u1, u2, ct); prob = (ct * FS_INV_PI) * tp.rr_prob;
-                            emit = true; spk_out = sp_id | (k << 22);
-                        } else {
-                            wb.end_pos[sp_id] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(nodes));
-                        }
+                        emit = choose_direction(tp, k, gg, sp_id & 1u, nrm, d, mat, pos, dir, prob, ev, org);
+                        spk_out = sp_id | (k << 22);
                     }
+                    if (hit) {
+                        wb.rec[(size_t)k * stride + sp_id] = make_float4(seg, __uint_as_float(mat | (ev << 24)), pdf_in, fs_pow(pdf_in, tp.ep.pdf_exponent));
+                        if (!emit || tp.lobes) wb.end_pos[sp_id] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(nodes));
+                    }
+                    pos = org;
                 }
                 const uint32_t m_emit = __ballot_sync(FULLM, emit);
                 if (m_emit) {
@@ -1952,29 +2017,37 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, fs_lane* lane, const fs_trace
     if (D == 0) {
         k_init_ends<<<(n_sub + 255u) / 256u, 256, 0, st>>>(tp, wb);
         ctx->launches.fetch_add(1);
-    } else if (!COUNT && !timing && use_tq && wb.log_o && ctx->tune_mega && (uint64_t)n_sub * D <= wb.log_cap) {
-        // EXPERIMENTAL: bounce 0 by k_shade_gen, every later bounce inside ONE persistent launch (k_path_q)
-        // the flag/ticket protocol needs every CTA of the grid resident: occupancy of the instantiation that is launched
-        const bool texq = tp.bv.wnodes_tex && ctx->tune_tex >= 2;
-        int& occ_pq = ctx->occ[texq ? 8 : 9];
-        if (!occ_pq) occ_pq = texq ? resident_ctas(k_path_q<2>, TR_THREADS, PQ_SMEM) : resident_ctas(k_path_q<0>, TR_THREADS, PQ_SMEM);
-        const uint32_t epoch = ++wb.pq_epoch;
-        pq_globals* g = (pq_globals*)wb.pq;
-        k_shade_gen<<<grid_sh, FS_SG_THREADS, 0, st>>>(tp, wb, 0, ctx->d_counters);
-        k_pq_seed<<<ctx->sm_count * 4, 256, 0, st>>>(wb, wb.log_o, wb.log_d, wb.log_flag, epoch, g);
-        const uint32_t grid_pq = (uint32_t)(ctx->sm_count * occ_pq);
-        if (texq) k_path_q<2><<<grid_pq, TR_THREADS, PQ_SMEM, st>>>(tp, wb, wb.log_o, wb.log_d, wb.log_flag, epoch, wb.log_cap, g,
-                                                                  ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush);
-        else k_path_q<0><<<grid_pq, TR_THREADS, PQ_SMEM, st>>>(tp, wb, wb.log_o, wb.log_d, wb.log_flag, epoch, wb.log_cap, g,
-                                                             ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush);
-        k_pq_finish<<<1, 1, 0, st>>>(wb, g, D, ctx->d_counters);
-        ctx->launches.fetch_add(4);
-        ctx->stats.extend_launches += 1;
     } else {
+        // Bounces 0 .. k0-1 run as one k_shade_gen + k_trace_q pair each.  With the persistent per-batch kernel enabled
+        // (FS_TUNE_MEGA), every bounce from k0 on runs inside ONE k_path_q launch: those are the bounces where few rays are
+        // left and the fixed cost of a launch pair (the drain of its slowest rays + the latency floor of k_shade_gen)
+        // outweighs the work.  The timing / counting contexts keep the per-bounce pipeline for every bounce.
+        const bool mega = !COUNT && !timing && use_tq && wb.log_o && ctx->tune_mega && (uint64_t)n_sub * D <= wb.log_cap;
+        const uint32_t k0 = mega ? (ctx->tune_mega_from < D ? ctx->tune_mega_from : D) : D;
         for (uint32_t k = 0; k <= D; ++k) {
             k_shade_gen<<<grid_sh, FS_SG_THREADS, 0, st>>>(tp, wb, k, ctx->d_counters);
             ctx->launches.fetch_add(1);
             if (k == D) break;
+            if (k == k0) {
+                // the flag / ticket protocol does not need the whole grid resident (any resident warp can take any ray);
+                // with several batch lanes each lane's persistent grid gets its share of the SMs
+                const bool texq = tp.bv.wnodes_tex && ctx->tune_tex >= 2;
+                int& occ_pq = ctx->occ[texq ? 8 : 9];
+                if (!occ_pq) occ_pq = texq ? resident_ctas(k_path_q<2>, TR_THREADS, PQ_SMEM) : resident_ctas(k_path_q<0>, TR_THREADS, PQ_SMEM);
+                const uint32_t epoch = ++wb.pq_epoch;
+                pq_globals* g = (pq_globals*)wb.pq;
+                k_pq_seed<<<ctx->sm_count * 4, 256, 0, st>>>(wb, wb.log_o, wb.log_d, wb.log_flag, epoch, g, k0);
+                uint32_t grid_pq = (uint32_t)(ctx->sm_count * occ_pq) / (ctx->cur_lanes ? ctx->cur_lanes : 1u);
+                if (grid_pq > ctas_needed) grid_pq = ctas_needed ? ctas_needed : 1;
+                if (texq) k_path_q<2><<<grid_pq, TR_THREADS, PQ_SMEM, st>>>(tp, wb, wb.log_o, wb.log_d, wb.log_flag, epoch, wb.log_cap, g,
+                                                                          ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush);
+                else k_path_q<0><<<grid_pq, TR_THREADS, PQ_SMEM, st>>>(tp, wb, wb.log_o, wb.log_d, wb.log_flag, epoch, wb.log_cap, g,
+                                                                     ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush);
+                k_pq_finish<<<1, 1, 0, st>>>(wb, g, D, ctx->d_counters, k0);
+                ctx->launches.fetch_add(3);
+                ctx->stats.extend_launches += 1;
+                break;
+            }
             const bool wide = tp.bv.wnodes != nullptr;
             const int texm = (wide ? tp.bv.wnodes_tex : tp.bv.nodes_tex) ? (int)ctx->tune_tex : 0;
             cudaEvent_t* te = nullptr;

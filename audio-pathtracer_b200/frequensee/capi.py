@@ -18,6 +18,7 @@ FS_ERR_INVALID, FS_ERR_CUDA, FS_ERR_NOMEM, FS_ERR_STATE, FS_ERR_OVERFLOW = -1, -
 FLAG_COUNT_VISITS, FLAG_NO_SPLAT_AGG, FLAG_SMEM_TREELET, FLAG_BRUTE_FORCE, FLAG_TIME_KERNELS, FLAG_FUSED_EXTEND = 1, 2, 4, 8, 16, 32
 FLAG_CONNECT_ALL = 64
 FLAG_SHARE_LISTENER = 128
+FLAG_MATERIAL_MODEL = 256
 
 # every symbol include/frequensee.h declares (tests/test_abi.py checks the library exports them all)
 ABI_SYMBOLS = [
@@ -189,6 +190,17 @@ class Context:
         self._ck(self.L.fs_scene_set_triangles(self.h, verts.ctypes.data, tri_mat.ctypes.data, len(verts)))
         self._ck(self.L.fs_scene_set_materials(self.h, absorption.ctypes.data, absorption.shape[0],
                                                 absorption.shape[1]))
+        self._ck(self.L.fs_scene_commit(self.h))
+
+    def set_scene_ex(self, verts, tri_mat, absorption, transmission=None, scattering=None, thickness_cm=None):
+        """the whole UAcousticMaterial asset (MAT.h:16-34); used by the tracer only with FLAG_MATERIAL_MODEL"""
+        verts = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3, 3)
+        tri_mat = np.ascontiguousarray(tri_mat, dtype=np.uint32)
+        absorption = np.ascontiguousarray(absorption, dtype=np.float32)
+        opt = [None if a is None else np.ascontiguousarray(a, dtype=np.float32) for a in (transmission, scattering, thickness_cm)]
+        self._ck(self.L.fs_scene_set_triangles(self.h, verts.ctypes.data, tri_mat.ctypes.data, len(verts)))
+        self._ck(self.L.fs_scene_set_materials_ex(self.h, absorption.ctypes.data, *[a.ctypes.data if a is not None else None for a in opt],
+                                                   absorption.shape[0], absorption.shape[1]))
         self._ck(self.L.fs_scene_commit(self.h))
 
     def set_stream(self, stream_ptr):

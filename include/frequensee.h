@@ -70,6 +70,12 @@ typedef enum fs_status {
                                        sources of a multi-emitter update share one set of listener subpaths, traced once per
                                        fs_trace call (the reference regenerates it per source, SUB.cpp:215-230: different
                                        random numbers, hence a separate mode).  Nearly halves the rays of BASELINE configs[3] */
+#define FS_FLAG_MATERIAL_MODEL 256u /* the Transmission / Scattering / ThicknessCm fields of the material asset
+                                       (MAT.h:26-33, set with fs_scene_set_materials_ex) drive the walk: at a surface the ray passes
+                                       through (COMP.cpp:271-275), is mirrored (GetReflectionVector, COMP.cpp:186) or is scattered into
+                                       the cosine lobe, with the authors' own energy split (MaterialAcousticProcessor.cpp:50-66:
+                                       Refl = 1 - alpha, tau <= 1 - Refl, specular Refl (1 - sigma), diffuse Refl sigma, transmitted
+                                       tau ^ (ThicknessCm / 2.5)).  Off by default: the reference's tracers read Absorption only */
 #define FS_FLAG_FUSED_EXTEND  32u   /* A/B: fused RR+sample+traverse+shade kernel per bounce instead of the
                                        split shade/trace wavefront with per-lane ray replacement */
 
@@ -157,8 +163,9 @@ int         fs_synchronize(fs_ctx* ctx);
 int fs_scene_set_triangles(fs_ctx* ctx, const float* verts, const uint32_t* tri_material, uint64_t n_tris);
 int fs_scene_set_materials(fs_ctx* ctx, const float* absorption, uint32_t n_materials, uint32_t n_bands);
 /* the whole UAcousticMaterial asset (MAT.h:16-34).  Transmission [M][B], Scattering [M][B] and ThicknessCm [M] are validated
- * ([0,1]; thickness >= 0) and kept with the context, but -- exactly like the reference's tracers -- not used by the path
- * tracer.  Any of the three may be NULL. */
+ * ([0,1]; thickness >= 0) and kept with the context.  Exactly like the reference's tracers the path tracer ignores them
+ *  unless the context was created with FS_FLAG_MATERIAL_MODEL.  Any of the three may be
+ * NULL (0, 1, 2.5 cm: a purely diffuse surface -- with these defaults the model reproduces the default mode bit for bit). */
 int fs_scene_set_materials_ex(fs_ctx* ctx, const float* absorption, const float* transmission, const float* scattering,
                               const float* thickness_cm, uint32_t n_materials, uint32_t n_bands);
 /* builds the BVH on the device: Morton codes, radix sort, PLOC agglomeration (search radius chosen by surface-area cost),

@@ -248,6 +248,9 @@ struct fso_scene {
     float*    nrm;    /* [T][3] unit geometric normal */
     uint32_t* mat;    /* [T] */
     float*    refl_over_pi; /* [M][B]  (1-alpha)/pi */
+    float*    bsdf_tab;     /* FSO_FLAG_MATERIAL_MODEL: [3][M][B] diffuse / specular / transmitted factor per event */
+    float*    lobes;        /* [M][4] (t1, t2, P_spec, P_diff): event thresholds on u3 and event probabilities */
+    float*    absorption;   /* [M][B] copy of the input */
     int       use_bvh;
     onode*    nodes;
     uint32_t  n_nodes;
@@ -367,6 +370,8 @@ fso_scene* fso_scene_create(const float* verts, const uint32_t* tri_mat, uint64_
         sc->mat[t] = tri_mat ? tri_mat[t] : 0;
     }
     sc->refl_over_pi = (float*)malloc((size_t)(n_mats ? n_mats : 1) * n_bands * 4);
+    sc->absorption = (float*)malloc((size_t)(n_mats ? n_mats : 1) * n_bands * 4);
+    memcpy(sc->absorption, absorption, (size_t)n_mats * n_bands * 4);
     for (uint32_t m = 0; m < n_mats; ++m)
         for (uint32_t b = 0; b < n_bands; ++b)
             /* reference: Absorption[2].Value / PI used as reflectivity (SUB.cpp:381-386);
@@ -399,11 +404,54 @@ fso_scene* fso_scene_create(const float* verts, const uint32_t* tri_mat, uint64_
     return sc;
 }
 
+/* the rest of the UAcousticMaterial asset (MAT.h:26-33).  The model is the authors' own split of the
+ * reflected energy (MaterialAcousticProcessor.cpp:50-66): Refl = 1 - alpha, tau limited to 1 - Refl, specular gain
+ * Refl (1 - sigma), diffuse gain Refl sigma, transmitted gain tau; the mirror direction is the legacy tracer's
+ * GetReflectionVector (COMP.cpp:186), transmission its pass-through (COMP.cpp:271-275).  ThicknessCm scales the
+ * transmitted gain as a Beer-Lambert layer, the asset's default 2.5 cm being the reference thickness:
+ * tau_eff = tau ^ (ThicknessCm / 2.5).  The lobe a walk takes cannot depend on the band, so the choice uses band means.
+ * Every value is float arithmetic in this exact order -- the device tables (fs_api.cu) are built by the same sequence.
+ * transmission / scattering / thickness may be NULL (0, 1, 2.5 cm: a purely diffuse surface, which reproduces the
+ * reference model bit for bit). */
+int fso_scene_set_material_model(fso_scene* sc, const float* transmission, const float* scattering, const float* thickness_cm)
+{
+    const uint32_t M = sc->n_mats, B = sc->n_bands;
+    free(sc->bsdf_tab); free(sc->lobes);
+    sc->bsdf_tab = (float*)calloc((size_t)3 * (M ? M : 1) * B, 4);
+    sc->lobes = (float*)calloc((size_t)(M ? M : 1) * 4, 4);
+    for (uint32_t m = 0; m < M; ++m) {
+        float sum_r = 0.0f, sum_t = 0.0f, sum_s = 0.0f;
+        const float th = thickness_cm ? thickness_cm[m] : 2.5f;
+        const float ex = th / 2.5f;
+        for (uint32_t b = 0; b < B; ++b) {
+            const float a = sc->absorption[m * B + b];
+            const float refl = 1.0f - a;
+            float tau = transmission ? transmission[m * B + b] : 0.0f;
+            if (refl + tau > 1.0f) tau = 1.0f - refl;                      /* MaterialAcousticProcessor.cpp:59-60 */
+            const float sig = scattering ? scattering[m * B + b] : 1.0f;
+            float tau_eff = 0.0f;
+            if (tau > 0.0f) tau_eff = (ex == 1.0f) ? tau : fso_powf(tau, ex);
+            sc->bsdf_tab[((size_t)0 * M + m) * B + b] = (refl * sig) / FSO_PI;        /* diffuse: Refl sigma / pi */
+            sc->bsdf_tab[((size_t)1 * M + m) * B + b] = refl * (1.0f - sig);           /* specular: Refl (1 - sigma) */
+            sc->bsdf_tab[((size_t)2 * M + m) * B + b] = tau_eff;                       /* transmitted */
+            sum_r += refl; sum_t += tau; sum_s += sig;
+        }
+        const float mr = sum_r / (float)B, mt = sum_t / (float)B, ms = sum_s / (float)B;
+        const float tot = mr + mt;
+        const float t1 = (tot > 0.0f) ? mt / tot : 0.0f;                   /* P(transmit) */
+        const float ps = (1.0f - t1) * (1.0f - ms);                         /* P(specular) */
+        const float t2 = t1 + ps;
+        const float pd = 1.0f - t2;                                         /* P(diffuse) */
+        sc->lobes[4 * m + 0] = t1; sc->lobes[4 * m + 1] = t2; sc->lobes[4 * m + 2] = ps; sc->lobes[4 * m + 3] = pd;
+    }
+    return 0;
+}
+
 void fso_scene_destroy(fso_scene* sc)
 {
     if (!sc) return;
     free(sc->v0); free(sc->e1); free(sc->e2); free(sc->nrm); free(sc->mat);
-    free(sc->refl_over_pi); free(sc->nodes); free(sc->order);
+    free(sc->refl_over_pi); free(sc->bsdf_tab); free(sc->lobes); free(sc->absorption); free(sc->nodes); free(sc->order);
     free(sc);
 }
 
@@ -530,7 +578,10 @@ void fso_scene_stats(const fso_scene* sc, fso_stats* st) { *st = sc->counters; }
 /* ------------------------------------------------------------------------------------------
  * BDPT
  * ---------------------------------------------------------------------------------------- */
-typedef struct { float p[3]; float n[3]; int32_t mat; float prob; } pnode;
+typedef struct { float p[3]; float n[3]; int32_t mat; float prob; uint32_t ev; float ro[3]; } pnode;   /* ev: FSO_EV_* the walk took AT this node; ro: origin of the ray that left it (= p, or the far side of the surface after a pass-through) */
+#define FSO_EV_DIFFUSE 0u
+#define FSO_EV_SPECULAR 1u
+#define FSO_EV_TRANSMIT 2u
 
 /* GeneratePath, SUB.cpp:279-355.  Dispositions: Philox replaces FRand; miss
  * terminates the subpath (FIX; the reference keeps looping on duplicate nodes); max_depth
@@ -545,11 +596,15 @@ static uint32_t gen_subpath(const fso_scene* sc, const fso_config* cfg, const fl
     float prob = 1.0f;                            /* CurrentProbability = 1, SUB.cpp:291 */
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t nn = 0;
+    const int model = (cfg->reserved[1] & FSO_FLAG_MATERIAL_MODEL) && sc->lobes;
+    float din[3] = {0.0f, 0.0f, 0.0f};            /* direction the walk arrived with (mirror / pass-through events) */
     for (uint32_t k = 0;; ++k) {
         pnode* nd = &nodes[nn++];                 /* SUB.cpp:297-298: push node first */
         nd->p[0] = pos[0]; nd->p[1] = pos[1]; nd->p[2] = pos[2];
         nd->n[0] = nrm[0]; nd->n[1] = nrm[1]; nd->n[2] = nrm[2];
         nd->mat = mat; nd->prob = prob;
+        nd->ev = FSO_EV_DIFFUSE;                  /* a node the walk ends at can only be connected through its diffuse lobe */
+        nd->ro[0] = pos[0]; nd->ro[1] = pos[1]; nd->ro[2] = pos[2];
         if (k >= max_depth) break;
         uint32_t ctr[4] = {(uint32_t)g, (uint32_t)(g >> 32), k, side};
         uint32_t r[4];
@@ -560,22 +615,44 @@ static uint32_t gen_subpath(const fso_scene* sc, const fso_config* cfg, const fl
         if (k == 0) {                             /* CurrentNormal.IsNearlyZero(), SUB.cpp:306 */
             fso_sample_sphere(u1, u2, dir);
             newprob = FSO_INV_4PI * cfg->rr_prob; /* SUB.cpp:309-310 */
+        } else if (model) {
+            /* the lobe is chosen by the fourth word of the bounce's Philox block */
+            const float* lb = sc->lobes + 4 * (uint32_t)mat;
+            const float u3 = fso_u01(r[3]);
+            if (u3 < lb[0]) {                     /* pass through (COMP.cpp:271-275) */
+                nd->ev = FSO_EV_TRANSMIT;
+                dir[0] = din[0]; dir[1] = din[1]; dir[2] = din[2];
+                newprob = cfg->rr_prob * lb[0];
+            } else if (u3 < lb[1]) {              /* mirror (GetReflectionVector, COMP.cpp:186) */
+                nd->ev = FSO_EV_SPECULAR;
+                const float sdn = -2.0f * dot3(din, nrm);
+                dir[0] = fmaf(sdn, nrm[0], din[0]); dir[1] = fmaf(sdn, nrm[1], din[1]); dir[2] = fmaf(sdn, nrm[2], din[2]);
+                newprob = cfg->rr_prob * lb[2];
+            } else {
+                float ct;
+                fso_sample_cos_hemisphere(nrm, u1, u2, dir, &ct);
+                newprob = ((ct * FSO_INV_PI) * cfg->rr_prob) * lb[3];
+            }
         } else {
             float ct;
             fso_sample_cos_hemisphere(nrm, u1, u2, dir, &ct);
             newprob = (ct * FSO_INV_PI) * cfg->rr_prob;   /* SUB.cpp:315-317 */
         }
         (*rays)++;
+        float o[3] = {pos[0], pos[1], pos[2]};
+        if (nd->ev == FSO_EV_TRANSMIT)            /* continue from the far side of the surface: 2 x the offset along -n */
+            for (int a = 0; a < 3; ++a) { o[a] = fmaf(-2.0f * cfg->eps_offset, nrm[a], pos[a]); nd->ro[a] = o[a]; }
         float t; uint32_t tri;
-        if (!closest_hit_cnt(sc, pos, dir, &t, &tri, cnt)) break;   /* FIX: miss terminates */
+        if (!closest_hit_cnt(sc, o, dir, &t, &tri, cnt)) { nd->ev = FSO_EV_DIFFUSE; break; }   /* FIX: miss terminates */
         /* SUB.cpp:345-347: pos = ImpactPoint + 0.1 * ImpactNormal; normal; material */
         const float* tn = sc->nrm + 3 * (uint64_t)tri;
         float fn[3] = {tn[0], tn[1], tn[2]};
         if (dot3(fn, dir) > 0.0f) { fn[0] = -fn[0]; fn[1] = -fn[1]; fn[2] = -fn[2]; }
         for (int a = 0; a < 3; ++a) {
-            float hp = fmaf(t, dir[a], pos[a]);
+            float hp = fmaf(t, dir[a], o[a]);
             pos[a] = fmaf(cfg->eps_offset, fn[a], hp);
             nrm[a] = fn[a];
+            din[a] = dir[a];
         }
         mat = (int32_t)sc->mat[tri];
         prob = newprob;
@@ -590,15 +667,17 @@ static inline float dist3(const float a[3], const float b[3])
 }
 
 /* one segment of EvaluatePath, SUB.cpp:368-399 */
-static inline void eval_segment(const fso_scene* sc, const fso_config* cfg, int32_t mat, float prob,
-                                float d, float* total, float* E)
+static inline void eval_segment_ev(const fso_scene* sc, const fso_config* cfg, int32_t mat, uint32_t ev, float prob,
+                                   float d, float* total, float* E)
 {
+    const float* tab = ((cfg->reserved[1] & FSO_FLAG_MATERIAL_MODEL) && sc->bsdf_tab)
+                       ? sc->bsdf_tab + (size_t)ev * sc->n_mats * sc->n_bands : sc->refl_over_pi;
     *total += d;                                  /* ScaledDistance += NodeDistance, :374 */
     if (d < cfg->min_seg) return;                 /* :375-378 */
     float G = 1.0f / (FSO_FOUR_PI * (d * d));     /* :391 */
     float P = fso_powf(prob, cfg->pdf_exponent);  /* :398 */
     for (uint32_t b = 0; b < cfg->n_bands; ++b) {
-        float bs = (mat >= 0) ? sc->refl_over_pi[(uint32_t)mat * sc->n_bands + b] : 1.0f; /* :382-386 */
+        float bs = (mat >= 0) ? tab[(uint32_t)mat * sc->n_bands + b] : 1.0f; /* :382-386 */
         float e = E[b];
         e *= bs;                                  /* :392 */
         e *= G;                                   /* :393 */
@@ -606,6 +685,10 @@ static inline void eval_segment(const fso_scene* sc, const fso_config* cfg, int3
         e /= P;                                   /* :398 */
         E[b] = e;
     }
+}
+static inline void eval_segment(const fso_scene* sc, const fso_config* cfg, int32_t mat, float prob, float d, float* total, float* E)
+{
+    eval_segment_ev(sc, cfg, mat, FSO_EV_DIFFUSE, prob, d, total, E);
 }
 
 /* AddEnergyAtDelay, COMP.h:87-91: BinIndex = Clamp(FloorToInt(DelaySeconds * 1000 / BinSizeMs), 0, Num - 1) */
@@ -645,11 +728,13 @@ static void splat_path(const fso_scene* sc, const fso_config* cfg, const pnode* 
     float E[FSO_MAX_BANDS];
     for (uint32_t b = 0; b < cfg->n_bands; ++b) E[b] = 1.0f;
     float total = 0.0f;
+    /* the factor of a node is the one of the event the walk took there; where a subpath is cut (its last node, or the
+     * prefix end of an all-prefix connection) the connection leaves in an arbitrary direction: the diffuse lobe */
     for (uint32_t i = 0; i + 1 < nf; ++i)
-        eval_segment(sc, cfg, fn[i].mat, fn[i].prob, dist3(fn[i].p, fn[i + 1].p), &total, E);
-    eval_segment(sc, cfg, fn[nf - 1].mat, fn[nf - 1].prob, len, &total, E);
+        eval_segment_ev(sc, cfg, fn[i].mat, fn[i].ev, fn[i].prob, dist3(fn[i].ro, fn[i + 1].p), &total, E);
+    eval_segment_ev(sc, cfg, fn[nf - 1].mat, FSO_EV_DIFFUSE, fn[nf - 1].prob, len, &total, E);
     for (uint32_t j = nb - 1; j >= 1; --j)
-        eval_segment(sc, cfg, bn[j].mat, bn[j].prob, dist3(bn[j].p, bn[j - 1].p), &total, E);
+        eval_segment_ev(sc, cfg, bn[j].mat, (j == nb - 1) ? FSO_EV_DIFFUSE : bn[j].ev, bn[j].prob, dist3(bn[j - 1].ro, bn[j].p), &total, E);
     float delay = total / cfg->sound_speed;       /* :419 */
     const int32_t bin = fso_bin_index(cfg, delay);
     for (uint32_t b = 0; b < cfg->n_bands; ++b) {
@@ -729,6 +814,31 @@ static void trace_one(const fso_scene* sc, const fso_config* cfg, const float* s
     if (occluded) return;
     st->connected++;
     splat_path(sc, cfg, fn, nf, bn, nb, len, 1.0f, hist_src, dbg);
+}
+
+/* the node lists of ONE path pair (known-answer tests of the walk): per node 8 floats (p.xyz, ro.xyz, prob, bits: mat + 1 | ev << 24) */
+int fso_debug_path(const fso_scene* sc, const fso_config* cfg, const float* src, const float* lis, uint64_t g, uint64_t n_paths,
+                   uint32_t max_depth, uint64_t seed, float* f_nodes, uint32_t* nf_out, float* b_nodes, uint32_t* nb_out)
+{
+    pnode* fn = (pnode*)malloc(sizeof(pnode) * (max_depth + 2));
+    pnode* bn = (pnode*)malloc(sizeof(pnode) * (max_depth + 2));
+    uint64_t rays = 0;
+    const uint64_t gl = (cfg->reserved[1] & FSO_FLAG_SHARE_LISTENER) ? g % n_paths : g;
+    const uint32_t nf = gen_subpath(sc, cfg, src, g, 0u, max_depth, seed, fn, &rays, NULL);
+    const uint32_t nb = gen_subpath(sc, cfg, lis, gl, 1u, max_depth, seed, bn, &rays, NULL);
+    for (int side = 0; side < 2; ++side) {
+        const pnode* nd = side ? bn : fn;
+        float* out = side ? b_nodes : f_nodes;
+        const uint32_t n = side ? nb : nf;
+        for (uint32_t i = 0; i < n; ++i) {
+            for (int a = 0; a < 3; ++a) { out[8 * i + a] = nd[i].p[a]; out[8 * i + 3 + a] = nd[i].ro[a]; }
+            out[8 * i + 6] = nd[i].prob;
+            out[8 * i + 7] = u2f((uint32_t)(nd[i].mat + 1) | (nd[i].ev << 24));
+        }
+    }
+    *nf_out = nf; *nb_out = nb;
+    free(fn); free(bn);
+    return 0;
 }
 
 typedef struct {

@@ -65,6 +65,7 @@ typedef struct fso_config {
     uint32_t reserved[3];      /* fs_config: max_batch_paths, flags, device; the oracle reads flags & FSO_FLAG_CONNECT_ALL */
 } fso_config;
 #define FSO_FLAG_SHARE_LISTENER 128u /* listener subpath keyed by the path index only: shared by all sources */
+#define FSO_FLAG_MATERIAL_MODEL 256u /* transmission / scattering / thickness of the material asset drive the walk */
 #define FSO_FLAG_CONNECT_ALL 64u   /* all prefix connections, weight 1/(s+t-1) */
 
 typedef struct fso_stats {
@@ -111,6 +112,8 @@ int   fso_intersect_tri(const float o[3], const float d[3], const float v0[3], c
 fso_scene* fso_scene_create(const float* verts, const uint32_t* tri_mat, uint64_t n_tris,
                             const float* absorption, uint32_t n_mats, uint32_t n_bands, int use_bvh);
 void fso_scene_destroy(fso_scene* sc);
+/* SURVEY 8f rank 3 (FSO_FLAG_MATERIAL_MODEL): transmission [M][B], scattering [M][B], thickness_cm [M]; any may be NULL */
+int  fso_scene_set_material_model(fso_scene* sc, const float* transmission, const float* scattering, const float* thickness_cm);
 /* closest hit by lexicographic min of (t, tri_id); returns 1 on hit */
 int  fso_closest_hit(const fso_scene* sc, const float o[3], const float d[3], float* t, uint32_t* tri);
 int  fso_any_hit(const fso_scene* sc, const float o[3], const float d[3], float tmax);
@@ -125,6 +128,9 @@ int fso_trace(const fso_scene* sc, const fso_config* cfg, const float* src_pos, 
               uint32_t max_depth, uint64_t seed, uint64_t* hist, fso_stats* stats,
               fso_path_dbg* dbg, int n_threads);
 
+/* node lists of one path pair g: per node 8 floats (p.xyz, ray origin.xyz, prob, bits(mat + 1 | event << 24)); [max_depth + 1] each */
+int fso_debug_path(const fso_scene* sc, const fso_config* cfg, const float* src, const float* lis, uint64_t g, uint64_t n_paths,
+                   uint32_t max_depth, uint64_t seed, float* f_nodes, uint32_t* nf_out, float* b_nodes, uint32_t* nb_out);
 /* EvaluatePath (SUB.cpp:360-420) on an explicit node list; AddEnergyAtDelay's bin index (COMP.h:87-91).  Exposed so that
  * tests can pin them one to one against the reference's own bodies (oracle/_ref/libref_ue_bodies.so). */
 void fso_evaluate_nodes(const fso_scene* sc, const fso_config* cfg, const float* pos, const int32_t* mat, const float* prob,

@@ -100,6 +100,9 @@ def lib():
         L.fso_trace.argtypes = [C.c_void_p, C.POINTER(Config), C.c_void_p, C.c_uint32, C.c_void_p,
                                 C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64,
                                 C.c_void_p, C.POINTER(Stats), C.c_void_p, C.c_int]
+        L.fso_scene_set_material_model.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fso_debug_path.argtypes = [C.c_void_p, C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32,
+                                     C.c_uint64, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.POINTER(C.c_uint32)]
         L.fso_evaluate_nodes.argtypes = [C.c_void_p, C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, fp, C.c_void_p]
         L.fso_evaluate_nodes.restype = None
         L.fso_bin_index.argtypes = [C.POINTER(Config), C.c_float]
@@ -145,6 +148,7 @@ def ref_lib():
 
 FLAG_CONNECT_ALL = 64
 FLAG_SHARE_LISTENER = 128
+FLAG_MATERIAL_MODEL = 256
 
 
 def default_config(**over):
@@ -212,6 +216,32 @@ class Scene:
             self.close()
         except Exception:                 # interpreter shutdown: the module globals may already be gone
             pass
+
+    def set_material_model(self, transmission=None, scattering=None, thickness_cm=None):
+        """transmission [M][B], scattering [M][B], thickness_cm [M] (None = 0 / 1 / 2.5 cm)"""
+        def arr(a, shape):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, np.float32)
+            assert a.shape == shape, (a.shape, shape)
+            return a
+        self._tr, self._sc, self._th = arr(transmission, self.absorption.shape), arr(scattering, self.absorption.shape), arr(thickness_cm, (self.n_mats,))
+        p = lambda a: a.ctypes.data if a is not None else None      # noqa: E731
+        lib().fso_scene_set_material_model(self.h, p(self._tr), p(self._sc), p(self._th))
+
+    def debug_path(self, cfg, src, lis, g, n_paths, max_depth, seed):
+        """node lists of path pair g: two arrays [n][8] = (p.xyz, ray origin.xyz, prob, bits) and the decoded (mat, event)"""
+        s = np.ascontiguousarray(src, np.float32).reshape(3); l = np.ascontiguousarray(lis, np.float32).reshape(3)
+        F = np.zeros((max_depth + 2, 8), np.float32); B = np.zeros((max_depth + 2, 8), np.float32)
+        nf, nb = C.c_uint32(), C.c_uint32()
+        lib().fso_debug_path(self.h, C.byref(cfg), s.ctypes.data, l.ctypes.data, g, n_paths, max_depth, seed,
+                             F.ctypes.data, C.byref(nf), B.ctypes.data, C.byref(nb))
+        out = []
+        for a, n in ((F, nf.value), (B, nb.value)):
+            bits = a[:n, 7].view(np.uint32)
+            out.append({"p": a[:n, 0:3].copy(), "ro": a[:n, 3:6].copy(), "prob": a[:n, 6].copy(),
+                        "mat": (bits & 0xffffff).astype(np.int64) - 1, "ev": (bits >> 24).astype(np.int64)})
+        return out
 
     def closest_hit(self, o, d):
         t = C.c_float()
