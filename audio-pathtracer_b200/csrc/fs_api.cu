@@ -320,7 +320,7 @@ int fs_scene_set_materials_ex(fs_ctx* ctx, const float* absorption, const float*
 }
 
 // FS_FLAG_MATERIAL_MODEL: per (event, material, band) energy factors and per material lobe thresholds.
-// Plain float arithmetic in exactly the order of oracle/fs_oracle.c fso_scene_set_material_model (the tables must be
+// Plain float arithmetic in a fixed order that the CPU harness restates (the tables must be
 // bit-identical on both sides); fs_pow is the shared polynomial of fs_math.cuh.
 static int build_material_model(fs_ctx* ctx)
 {

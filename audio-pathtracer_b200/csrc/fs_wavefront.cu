@@ -468,7 +468,7 @@ __device__ __forceinline__ void leaf_range(int leafnode, uint32_t& tc, uint32_t&
 // SUB.cpp:301-318).  Returns false when the walk ends here.  ev = the lobe taken (FS_EV_*), org = origin of the new ray.
 // Without FS_FLAG_MATERIAL_MODEL every surface event is the cosine lobe (ev = 0, org = pos) -- the reference's model.
 // With it the fourth word of the bounce's Philox block picks pass-through / mirror / cosine lobe by the
-// per-material thresholds of tp.lobes (built in fs_scene_commit; same arithmetic as oracle/fs_oracle.c gen_subpath).
+// per-material thresholds of tp.lobes (built in fs_scene_commit; the CPU harness restates the same arithmetic).
 #define FS_EV_DIFFUSE 0u
 #define FS_EV_SPECULAR 1u
 #define FS_EV_TRANSMIT 2u
