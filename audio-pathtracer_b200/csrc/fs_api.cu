@@ -1020,6 +1020,20 @@ int fs_get_stats(fs_ctx* ctx, fs_stats* out)
 
 }  // extern "C"
 
+// fs_multi.cu: make context 0's histogram the target of a multi-device update (allocated for n_sources, zeroed on the
+// context stream, bookkeeping of fs_trace)
+int fs_internal_hist_prepare(fs_ctx* ctx, uint32_t n_sources, uint64_t n_paths, unsigned long long** d_hist_out)
+{
+    dev_guard g(ctx->device);
+    int rc = ensure_hist(ctx, n_sources);
+    if (rc) return rc;
+    const size_t hn = (size_t)n_sources * ctx->cfg.n_bands * ctx->cfg.n_bins;
+    CK(cudaMemsetAsync(ctx->d_hist, 0, 8 * hn, ctx->stream));
+    ctx->hist_n_paths = n_paths; ctx->hist_cur_sources = n_sources;
+    *d_hist_out = ctx->d_hist;
+    return FS_OK;
+}
+
 // ---- text float arrays (saved_ir.txt: one float per line, COMP.cpp:454-505); host only
 int fs_load_float_array(const char* path, float* out, uint64_t cap, uint64_t* n_out)
 {

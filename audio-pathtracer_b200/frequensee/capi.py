@@ -30,6 +30,9 @@ ABI_SYMBOLS = [
     "fs_get_histogram", "fs_get_histogram_sources", "fs_set_ir", "fs_load_float_array", "fs_save_float_array",
     "fs_conv_init_source", "fs_conv_release_source", "fs_conv_process", "fs_conv_process_many", "fs_conv_process_multi",
     "fs_debug_rfft", "fs_get_stats",
+    "fs_multi_create", "fs_multi_destroy", "fs_multi_last_error", "fs_multi_device_count", "fs_multi_context",
+    "fs_multi_scene_set_triangles", "fs_multi_scene_set_materials", "fs_multi_scene_set_materials_ex", "fs_multi_scene_commit",
+    "fs_multi_trace", "fs_multi_last_ms", "fs_multi_synchronize",
 ]
 
 
@@ -127,8 +130,25 @@ def load():
     L.fs_conv_process_multi.argtypes = [vp, vp, u32, vp, vp, u32]
     L.fs_debug_rfft.argtypes = [vp, vp, u32, vp]
     L.fs_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.fs_multi_create.argtypes = [C.POINTER(Config), vp, u32, C.POINTER(vp)]
+    L.fs_multi_destroy.argtypes = [vp]
+    L.fs_multi_destroy.restype = None
+    L.fs_multi_last_error.argtypes = []
+    L.fs_multi_last_error.restype = C.c_char_p
+    L.fs_multi_device_count.argtypes = [vp]
+    L.fs_multi_device_count.restype = u32
+    L.fs_multi_context.argtypes = [vp, u32]
+    L.fs_multi_context.restype = vp
+    L.fs_multi_scene_set_triangles.argtypes = [vp, vp, vp, u64]
+    L.fs_multi_scene_set_materials.argtypes = [vp, vp, u32, u32]
+    L.fs_multi_scene_set_materials_ex.argtypes = [vp, vp, vp, vp, vp, u32, u32]
+    L.fs_multi_scene_commit.argtypes = [vp]
+    L.fs_multi_trace.argtypes = [vp, vp, u32, vp, u64, u32, u64, vp]
+    L.fs_multi_last_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.fs_multi_synchronize.argtypes = [vp]
     for n in ABI_SYMBOLS:
-        if n not in ("fs_default_config", "fs_destroy", "fs_last_error"):
+        if n not in ("fs_default_config", "fs_destroy", "fs_last_error", "fs_multi_destroy", "fs_multi_last_error",
+                     "fs_multi_device_count", "fs_multi_context"):
             getattr(L, n).restype = C.c_int
     _lib = L
     return L
@@ -360,6 +380,67 @@ class Context:
         st = Stats()
         self._ck(self.L.fs_get_stats(self.h, C.byref(st)))
         return st.as_dict()
+
+
+class MultiContext:
+    """fs_multi: one context per device inside this process, peer-store histogram reduce on device 0"""
+
+    def __init__(self, devices, cfg=None, **over):
+        self.L = load()
+        self.cfg = cfg if cfg is not None else default_config(**over)
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.L.fs_multi_create(C.byref(self.cfg), devs, len(devices), C.byref(h))
+        if rc != FS_OK:
+            raise FrequenSeeError(rc, (self.L.fs_multi_last_error() or b"").decode())
+        self.h = h
+        self.n = len(devices)
+
+    def _ck(self, rc):
+        if rc != FS_OK:
+            raise FrequenSeeError(rc, (self.L.fs_multi_last_error() or b"").decode())
+
+    def context(self, i=0):
+        """the per-device context as a (non-owning) Context: build_ir / conv / stats continue on it"""
+        c = Context.__new__(Context)
+        c.L, c.cfg, c.n_sources = self.L, self.cfg, 0
+        c.h = C.c_void_p(self.L.fs_multi_context(self.h, i))
+        c.close = lambda: None
+        return c
+
+    def set_scene(self, verts, tri_mat, absorption):
+        verts = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3, 3)
+        tri_mat = np.ascontiguousarray(tri_mat, dtype=np.uint32)
+        absorption = np.ascontiguousarray(absorption, dtype=np.float32)
+        self._ck(self.L.fs_multi_scene_set_triangles(self.h, verts.ctypes.data, tri_mat.ctypes.data, len(verts)))
+        self._ck(self.L.fs_multi_scene_set_materials(self.h, absorption.ctypes.data, absorption.shape[0], absorption.shape[1]))
+        self._ck(self.L.fs_multi_scene_commit(self.h))
+
+    def trace(self, src_pos, lis_pos, n_paths, max_depth, seed, want_hist=True):
+        src, lis = Context._pos(src_pos, lis_pos)
+        hist = np.zeros((len(src), self.cfg.n_bands, self.cfg.n_bins), dtype=np.uint64) if want_hist else None
+        self._ck(self.L.fs_multi_trace(self.h, src.ctypes.data, len(src), lis.ctypes.data, n_paths, max_depth, seed,
+                                       hist.ctypes.data if want_hist else None))
+        return hist
+
+    def last_ms(self):
+        a, b = C.c_float(), C.c_float()
+        self._ck(self.L.fs_multi_last_ms(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def synchronize(self):
+        self._ck(self.L.fs_multi_synchronize(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.fs_multi_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 def load_float_array(path):

@@ -261,6 +261,37 @@ int fs_conv_process_many(fs_ctx* ctx, uint32_t source, const float* in_interleav
 /* real FFT of n samples on the device FFT kernel (n power of two, 64..4096); out [n/2+1][2] */
 int fs_debug_rfft(fs_ctx* ctx, const float* in, uint32_t n, float* out_ri);
 
+/* ---- several GPUs of one box -----------------------------------------------------------------
+ * The reference is one process with one game thread (SUB.cpp:55-85); the independent unit of work is one iteration of its
+ * pair loop (SUB.cpp:215-230).  fs_multi owns one context per device inside ONE host process (no Python, no MPI, no
+ * collective library): the global work range g = source * n_paths + i is cut into contiguous shards, every device traces
+ * its shard against its own copy of the BVH (one host thread per device enqueues it), the per-device Q32.32 histograms are
+ * written into a staging buffer on device 0 by peer stores over NVLink and summed there.  Integer sums: bit-identical to
+ * the single-device result for every device count.  The reduced histogram is that of context 0 (fs_multi_context(m, 0)):
+ * fs_build_ir*, fs_conv_* and fs_get_histogram of the single-device API continue from it.
+ * devices: CUDA ordinals (NULL = 0 .. n_devices-1); an ordinal may repeat (several contexts on one GPU).
+ * Errors: fs_status; fs_multi_last_error() = message of the calling thread's last fs_multi_* failure. */
+typedef struct fs_multi fs_multi;
+int         fs_multi_create(const fs_config* cfg, const int* devices, uint32_t n_devices, fs_multi** out);
+void        fs_multi_destroy(fs_multi* m);
+const char* fs_multi_last_error(void);
+uint32_t    fs_multi_device_count(const fs_multi* m);
+fs_ctx*     fs_multi_context(fs_multi* m, uint32_t i);
+/* the scene is replicated: every device builds its own (identical) BVH -- replaces RegisterGeometry (SUB.h:99-100) */
+int fs_multi_scene_set_triangles(fs_multi* m, const float* verts, const uint32_t* tri_material, uint64_t n_tris);
+int fs_multi_scene_set_materials(fs_multi* m, const float* absorption, uint32_t n_materials, uint32_t n_bands);
+int fs_multi_scene_set_materials_ex(fs_multi* m, const float* absorption, const float* transmission, const float* scattering,
+                                    const float* thickness_cm, uint32_t n_materials, uint32_t n_bands);
+int fs_multi_scene_commit(fs_multi* m);
+/* fs_trace over all devices (UpdateSource, SUB.cpp:128-195).  Enqueues and returns; hist_out (host [S][B][K]) may be NULL,
+ * non-NULL synchronises. */
+int fs_multi_trace(fs_multi* m, const float* src_pos, uint32_t n_sources, const float lis_pos[3], uint64_t n_paths,
+                   uint32_t max_depth, uint64_t seed, uint64_t* hist_out);
+/* device time of the last fs_multi_trace (CUDA events on device 0's stream): the whole update, and the part after device
+ * 0's own shard was done (waiting for the peers' stores + the sum).  Synchronises. */
+int fs_multi_last_ms(fs_multi* m, float* total_ms, float* reduce_ms);
+int fs_multi_synchronize(fs_multi* m);
+
 /* ---- stats ------------------------------------------------------------------------------- */
 int fs_get_stats(fs_ctx* ctx, fs_stats* out);
 
