@@ -479,7 +479,12 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
         return fail(ctx, FS_ERR_INVALID, "FS_FLAG_SHARE_LISTENER needs the wavefront path");
     if ((ctx->cfg.flags & FS_FLAG_MATERIAL_MODEL) && (ctx->cfg.flags & (FS_FLAG_FUSED_EXTEND | FS_FLAG_BRUTE_FORCE)))
         return fail(ctx, FS_ERR_INVALID, "FS_FLAG_MATERIAL_MODEL needs the wavefront path");
-    if (ctx->cfg.flags & FS_FLAG_CONNECT_ALL) {
+    if (ctx->cfg.flags & FS_FLAG_MIS) {
+        if (max_depth > 32) return fail(ctx, FS_ERR_INVALID, "FS_FLAG_MIS: max_depth <= 32");
+        if (ctx->cfg.flags & FS_FLAG_MATERIAL_MODEL) return fail(ctx, FS_ERR_INVALID, "FS_FLAG_MIS: diffuse surfaces only (not with FS_FLAG_MATERIAL_MODEL)");
+        if (ctx->cfg.flags & FS_FLAG_SHARE_LISTENER) return fail(ctx, FS_ERR_INVALID, "FS_FLAG_MIS: not with FS_FLAG_SHARE_LISTENER");
+    }
+    if (ctx->cfg.flags & (FS_FLAG_CONNECT_ALL | FS_FLAG_MIS)) {
         // up to (depth+1)^2 connection rays per pair: keep a batch's ray queue near 2^24 entries; ids are pair << 12 | s << 6 | t
         if (max_depth > 63) return fail(ctx, FS_ERR_INVALID, "FS_FLAG_CONNECT_ALL: max_depth <= 63");
         if (d_dbg) return fail(ctx, FS_ERR_INVALID, "FS_FLAG_CONNECT_ALL: no per-path debug records");

@@ -83,6 +83,7 @@ struct fs_wave_buffers {
     uint32_t cap, depth_cap;
     // FS_FLAG_CONNECT_ALL: node positions of every subpath and the (s, t) connection rays of a batch
     float4* npos;               // [max_depth+1][2*cap]: position of node k >= 1 of subpath sp_id
+    float4* nnrm;               // FS_FLAG_MIS: [max_depth+1][2*cap] surface normal (facing the arriving ray) at node k >= 1
     float4 *all_o, *all_d;      // [all_cap] connection rays (F.xyz, tmax) (dir.xyz, bits(pair << 12 | (s-1) << 6 | (t-1)))
     uint32_t* all_conn;         // [all_cap] ids of the visible connections
     uint64_t all_cap;

@@ -428,6 +428,121 @@ k_eval(const fs_trace_params tp, const fs_wave_buffers wb, unsigned long long* _
 }
 
 
+// ---------------------------------------------------------------------------------------------
+// k_eval_mis (FS_FLAG_MIS): every visible prefix connection (s, t) contributes f / sum_{s'} p_{s'} -- the
+// balance heuristic over all strategies that build a path of s + t vertices, for the physically based contribution
+//     f = 1/(4 pi) * prod_edges [cos_a cos_b / d^2 * exp(-air d)] * prod_interior [rho / pi]
+// with area-measure densities rr * D_a * cos_b / d^2 (D = 1/(4 pi) at the end points, cos_a / pi on surfaces).  This is what
+// the reference's unfinished getPdf / getExpectedWeight / MISEnergy aim at (SUB.cpp:537-597).  8 lanes per connection (one
+// band each); the geometry of the path is band independent and computed by all eight.  Same float operations in the same
+// order as the CPU harness.
+// ---------------------------------------------------------------------------------------------
+#define FS_MIS_MAXV 66
+__device__ __forceinline__ void mis_vertex(const fs_trace_params& tp, const fs_wave_buffers& wb, uint32_t sf, uint32_t sb, uint32_t s,
+                                           uint32_t k, uint32_t i, uint32_t stride, fs_vec3& P, fs_vec3& N)
+{
+    const uint32_t sp = (i < s) ? sf : sb;
+    const uint32_t node = (i < s) ? i : (k - 1u - i);
+    P = node_pos(tp, wb, sp, node, stride);
+    if (node == 0u) { N = fs_mk(0.f, 0.f, 0.f); return; }
+    const float4 nv = wb.nnrm[(size_t)node * stride + sp];
+    N = fs_mk(nv.x, nv.y, nv.z);
+}
+
+__global__ void __launch_bounds__(WF_THREADS)
+k_eval_mis(const fs_trace_params tp, const fs_wave_buffers wb, unsigned long long* __restrict__ hist, fs_dev_counters* __restrict__ dc)
+{
+    const uint32_t lane = lane_id();
+    const uint32_t sub = lane >> 3, b = lane & 7u;
+    const uint32_t qi = tp.max_depth + 1;
+    const uint32_t count = wb.q_count[qi];
+    const uint32_t stride = 2u * wb.cap;
+    const uint32_t NBr = tp.ep.n_bands;
+    const bool band_on = b < NBr;
+    const float air_b = band_on ? tp.ep.air[b] : 0.0f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&dc->connected, (unsigned long long)count);
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    float pf[FS_MIS_MAXV], pb[FS_MIS_MAXV], gg[FS_MIS_MAXV], dlen[FS_MIS_MAXV];
+    for (uint32_t base = warp_global * 4u; base < count; base += n_warps * 4u) {
+        const uint32_t j = base + sub;
+        bool valid = (j < count) && band_on;
+        unsigned long long q = 0ull;
+        uint32_t key = 0xffffffffu;
+        size_t hidx = 0;
+        if (valid) {
+            const uint32_t id = wb.all_conn[j];
+            const uint32_t p = id >> 12;
+            const uint32_t sf = 2u * p, sb = 2u * p + 1u;
+            const uint32_t s = ((id >> 6) & 63u) + 1u, t = (id & 63u) + 1u;
+            const uint32_t k = s + t;
+            float total = 0.0f;
+            bool ok = k <= (uint32_t)FS_MIS_MAXV;
+            fs_vec3 Pa, Na;
+            if (ok) mis_vertex(tp, wb, sf, sb, s, k, 0u, stride, Pa, Na);
+            for (uint32_t i = 0; ok && i + 1u < k; ++i) {
+                fs_vec3 Pb, Nb;
+                mis_vertex(tp, wb, sf, sb, s, k, i + 1u, stride, Pb, Nb);
+                const fs_vec3 dl = fs_sub(Pb, Pa);
+                const float d2 = fs_dot(dl, dl);
+                const float d = sqrtf(d2);
+                total += d;
+                if (d < tp.ep.min_seg) { ok = false; break; }
+                const float inv = 1.0f / d;
+                const fs_vec3 dir = fs_mk(dl.x * inv, dl.y * inv, dl.z * inv);
+                const float cp = (i == 0u) ? 1.0f : fabsf(fs_dot(Na, dir));
+                const float cm = (i + 2u == k) ? 1.0f : fabsf(fs_dot(Nb, dir));
+                const float rd2 = 1.0f / d2;
+                gg[i] = (cp * cm) * rd2;
+                if (!(gg[i] > 0.0f)) { ok = false; break; }
+                pf[i] = (tp.rr_prob * ((i == 0u) ? FS_INV_4PI : cp * FS_INV_PI)) * (cm * rd2);
+                pb[i] = (tp.rr_prob * ((i + 2u == k) ? FS_INV_4PI : cm * FS_INV_PI)) * (cp * rd2);
+                dlen[i] = d;
+                Pa = Pb; Na = Nb;
+            }
+            if (ok) {
+                float sum = 1.0f, r = 1.0f;
+                for (uint32_t sp = s; sp + 1u < k && sp <= tp.max_depth; ++sp) { r = r * (pf[sp - 1u] / pb[sp]); sum += r; }
+                r = 1.0f;
+                for (uint32_t sp = s; sp > 1u && k - sp <= tp.max_depth; --sp) { r = r * (pb[sp - 1u] / pf[sp - 2u]); sum += r; }
+                float val = FS_INV_4PI;
+                for (uint32_t i = 0; i + 1u < k; ++i) {
+                    val = val * gg[i];
+                    val = val * fs_exp(-air_b * dlen[i]);
+                    const uint32_t jv = i + 1u;
+                    if (jv + 1u < k) {
+                        const uint32_t sp = (jv < s) ? sf : sb;
+                        const uint32_t node = (jv < s) ? jv : (k - 1u - jv);
+                        const uint32_t mw = __float_as_uint(wb.rec[(size_t)node * stride + sp].y) & 0x00ffffffu;
+                        val = val * __ldg(tp.refl_over_pi + (size_t)mw * NBr + b);
+                        val = val / ((jv < s) ? pf[jv - 1u] : pb[jv]);
+                    }
+                }
+                float e = val / sum;
+                const float delay = total / tp.sound_speed;
+                const float fb = floorf((delay * 1000.0f) / tp.bin_ms);
+                uint32_t bin;
+                if (!(fb >= 0.0f)) bin = 0;
+                else if (fb >= (float)(tp.n_bins - 1)) bin = tp.n_bins - 1;
+                else bin = (uint32_t)fb;
+                const uint64_t g = tp.g_first + p;
+                const uint32_t src = (uint32_t)(g / tp.n_paths);
+                e = (e < tp.energy_clamp) ? e : tp.energy_clamp;
+                e = e * tp.energy_gain;
+                q = (unsigned long long)(e * 4294967296.0f);
+                hidx = ((size_t)src * NBr + b) * tp.n_bins + bin;
+                key = (src * tp.n_bins + bin) * 8u + b;
+            } else valid = false;
+        }
+        const uint32_t active = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const uint32_t peers = __match_any_sync(active, key);
+            if (peers != (1u << lane)) q = reduce_peers(peers, q);
+            if ((uint32_t)(__ffs(peers) - 1) == lane) atomicAdd(hist + hidx, q);
+        }
+    }
+}
+
 // =============================================================================================
 // Split wavefront (default path): shading/generation kernels with every lane busy, and PURE
 // traversal kernels with per-lane ray replacement.
@@ -577,6 +692,7 @@ k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_d
                     mat = __float_as_uint(nm.w);
                     pdf_in = b.w;
                     if (wb.npos) wb.npos[(size_t)k * stride + sp_id] = make_float4(pos.x, pos.y, pos.z, 0.0f);
+                    if (wb.nnrm) wb.nnrm[(size_t)k * stride + sp_id] = make_float4(fn.x, fn.y, fn.z, 0.0f);
                     nrm = fn; din = d;
                     nodes = k + 1;
                     hit = true;
@@ -1880,15 +1996,16 @@ cudaError_t fs_wave_alloc(fs_ctx* ctx, fs_lane* lane, uint32_t cap, uint32_t max
     if ((e = cudaMalloc(&wb->hit, sizeof(float2) * n2)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&wb->q_count, 4ull * (max_depth + 4))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&wb->q_cursor, 4ull * (max_depth + 4))) != cudaSuccess) return e;
-    if (ctx->cfg.flags & FS_FLAG_CONNECT_ALL) {
+    if (ctx->cfg.flags & (FS_FLAG_CONNECT_ALL | FS_FLAG_MIS)) {
         const uint64_t per = (uint64_t)(max_depth + 1) * (max_depth + 1);
         wb->all_cap = (uint64_t)cap * per;
         if ((e = cudaMalloc(&wb->npos, sizeof(float4) * n2 * (max_depth + 1ull))) != cudaSuccess) return e;
+        if ((ctx->cfg.flags & FS_FLAG_MIS) && (e = cudaMalloc(&wb->nnrm, sizeof(float4) * n2 * (max_depth + 1ull))) != cudaSuccess) return e;
         if ((e = cudaMalloc(&wb->all_o, sizeof(float4) * wb->all_cap)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&wb->all_d, sizeof(float4) * wb->all_cap)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&wb->all_conn, 4ull * wb->all_cap)) != cudaSuccess) return e;
     }
-    if (ctx->tune_mega && max_depth >= 1 && cap <= (1u << 21) && !(ctx->cfg.flags & FS_FLAG_CONNECT_ALL)) {
+    if (ctx->tune_mega && max_depth >= 1 && cap <= (1u << 21) && !(ctx->cfg.flags & (FS_FLAG_CONNECT_ALL | FS_FLAG_MIS))) {
         const uint64_t lc = (uint64_t)n2 * max_depth;                  // every subpath traces at most max_depth rays
         if (lc < 0xffffffffull) {
             wb->log_cap = (uint32_t)lc;
@@ -1910,7 +2027,7 @@ void fs_wave_free(fs_wave_buffers* wb)
     for (int i = 0; i < 2; ++i) { cudaFree(wb->st_pos[i]); cudaFree(wb->st_nrm[i]); }
     cudaFree(wb->rec); cudaFree(wb->end_pos); cudaFree(wb->conn_queue); cudaFree(wb->conn_len);
     cudaFree(wb->q_count); cudaFree(wb->q_cursor); cudaFree(wb->hit);
-    cudaFree(wb->npos); cudaFree(wb->all_o); cudaFree(wb->all_d); cudaFree(wb->all_conn);
+    cudaFree(wb->npos); cudaFree(wb->nnrm); cudaFree(wb->all_o); cudaFree(wb->all_d); cudaFree(wb->all_conn);
     cudaFree(wb->log_o); cudaFree(wb->log_d); cudaFree(wb->log_flag); cudaFree(wb->pq);
     memset(wb, 0, sizeof(*wb));
 }
@@ -2089,7 +2206,7 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, fs_lane* lane, const fs_trace
         return cudaGetLastError();
     }
     if (tp.lis_mode == 2) { k_lis_load<<<grid_cg, WF_THREADS, 0, st>>>(tp, wb); ctx->launches.fetch_add(1); }
-    const bool all = (tp.flags & FS_FLAG_CONNECT_ALL) != 0;        // every prefix pair (s, t) instead of the two end points
+    const bool all = (tp.flags & (FS_FLAG_CONNECT_ALL | FS_FLAG_MIS)) != 0;        // every prefix pair (s, t) instead of the two end points
     if (all) k_connect_all_gen<<<grid_cg, WF_THREADS, 0, st>>>(tp, wb, ctx->d_counters);
     else k_connect_gen<<<grid_cg, WF_THREADS, 0, st>>>(tp, wb, ctx->d_counters, d_dbg);
     uint32_t grid_any = (uint32_t)(ctx->sm_count * ((use_tq && ctx->tune_tq >= 2) ? occ_tq : occ_any));
@@ -2119,7 +2236,8 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, fs_lane* lane, const fs_trace
     uint32_t grid_ev = (uint32_t)ctx->sm_count * 8u;
     const uint32_t ctas_ev = (tp.batch / 4u + WF_THREADS / 32 - 1) / (WF_THREADS / 32) + 1;   // 4 paths per warp
     if (!all && grid_ev > ctas_ev) grid_ev = ctas_ev;
-    if (all) k_eval<true><<<grid_ev, WF_THREADS, 0, st>>>(tp, wb, d_hist, ctx->d_counters, nullptr);
+    if (tp.flags & FS_FLAG_MIS) k_eval_mis<<<grid_ev, WF_THREADS, 0, st>>>(tp, wb, d_hist, ctx->d_counters);
+    else if (all) k_eval<true><<<grid_ev, WF_THREADS, 0, st>>>(tp, wb, d_hist, ctx->d_counters, nullptr);
     else k_eval<false><<<grid_ev, WF_THREADS, 0, st>>>(tp, wb, d_hist, ctx->d_counters, d_dbg);
     ctx->launches.fetch_add(1);
     if (timing) cudaEventRecord(ev[3], st);

@@ -19,6 +19,7 @@ FLAG_COUNT_VISITS, FLAG_NO_SPLAT_AGG, FLAG_SMEM_TREELET, FLAG_BRUTE_FORCE, FLAG_
 FLAG_CONNECT_ALL = 64
 FLAG_SHARE_LISTENER = 128
 FLAG_MATERIAL_MODEL = 256
+FLAG_MIS = 512
 
 # every symbol include/frequensee.h declares (tests/test_abi.py checks the library exports them all)
 ABI_SYMBOLS = [

@@ -66,6 +66,14 @@ typedef enum fs_status {
                                        unfinished Is_NaiveConnections, SUB.cpp:508-535), each connected path evaluated like the
                                        endpoint connection and weighted 1 / (s + t - 1); (1, 1) is the deterministic direct path.
                                        Up to (depth+1)^2 connection rays per pair: batches shrink to ~2^24 / (depth+1)^2 pairs */
+#define FS_FLAG_MIS           512u   /* SURVEY 8f rank 1, second half: all prefix connections (as FS_FLAG_CONNECT_ALL) combined with the
+                                       BALANCE HEURISTIC -- what the reference's unfinished getPdf / getExpectedWeight / MISEnergy aim
+                                       at (SUB.cpp:537-597).  MIS needs one integrand for all strategies, which the reference's
+                                       per-segment product (no cosines, pdf^0.1) is not: this mode evaluates the physically based
+                                       contribution 1/(4 pi) prod_edges [cos cos / d^2 exp(-air d)] prod_vertices [rho / pi] and each
+                                       visible connection (s, t) contributes f / sum_s' p_s' (area-measure densities of the walks).
+                                       energy_clamp / energy_gain still apply (set 1e30 / 1 for physical units); pdf_exponent is unused;
+                                       max_depth <= 32; diffuse surfaces only */
 #define FS_FLAG_SHARE_LISTENER 128u  /* the listener subpath of pair (source, i) is keyed by i only, so all
                                        sources of a multi-emitter update share one set of listener subpaths, traced once per
                                        fs_trace call (the reference regenerates it per source, SUB.cpp:215-230: different

@@ -754,9 +754,89 @@ static void splat_path(const fso_scene* sc, const fso_config* cfg, const pnode* 
  * Here: every (s, t), 1 <= s <= nf, 1 <= t <= nb, is connected with the visibility rule of SUB.cpp:252-257, evaluated
  * exactly like the endpoint connection, and weighted 1 / (s + t - 1) = one over the number of (s', t') strategies that
  * build a path of the same number of nodes.  (nf, nb) is the reference's connection, (1, 1) the direct path. */
-static void connect_all(const fso_scene* sc, const fso_config* cfg, const pnode* fn, uint32_t nf, const pnode* bn, uint32_t nb,
-                        uint64_t* hist_src, fso_stats* st, ocount* cnt)
+/* SURVEY 8f rank 1, second half -- FSO_FLAG_MIS: all prefix connections combined with the BALANCE HEURISTIC (Veach), which is what
+ * the reference's unfinished getPdf / getExpectedWeight / MISEnergy aim at (SUB.cpp:537-597: hard-coded pdf 0.9, integer
+ * division).  Multiple importance sampling needs ONE integrand for all strategies, which the reference's per-segment product
+ * (no cosines, pdf^0.1) is not; this mode therefore evaluates the physically based contribution in area measure
+ *     f(x_0 .. x_{k-1}) = 1/(4 pi) * prod_edges [ cos_a cos_b / d^2 * exp(-air d) ] * prod_interior [ rho / pi ]
+ * (cosines at the point source / point listener = 1; for k = 2 this is the reference's direct-path value 1/(4 pi d^2)) and
+ * weights the sample of strategy (s, t) by p_{s,t} / sum_{s'} p_{s',k-s'}, i.e. contributes f / sum_{s'} p_{s'}.
+ * Densities in area measure: a vertex generated from x_a towards x_b has rr * D_a * cos_b / d^2 with D = 1/(4 pi) at the two
+ * end points (uniform sphere, SUB.cpp:308-310) and cos_a / pi on surfaces (cosine lobe, SUB.cpp:312-318 with the FIX of A3).
+ * Strategies that a walk of at most max_depth rays cannot produce have density zero.  Edges shorter than min_seg drop the
+ * sample (the reference's glitch guard, SUB.cpp:375-378).  Everything is float arithmetic in a fixed order: the CUDA kernel
+ * (k_eval_mis) executes the same sequence.  FSO_FLAG_MIS_T1 / _S1 (oracle only, tests): a single strategy family with weight
+ * one -- an independent unbiased estimator of the same integral. */
+#define FSO_MIS_MAXV 66
+static void mis_splat(const fso_scene* sc, const fso_config* cfg, const pnode* fn, uint32_t s, const pnode* bn, uint32_t t,
+                      uint32_t max_depth, uint64_t* hist_src)
 {
+    const uint32_t k = s + t;
+    if (k > FSO_MIS_MAXV) return;
+    float pf[FSO_MIS_MAXV], pb[FSO_MIS_MAXV], gg[FSO_MIS_MAXV], dlen[FSO_MIS_MAXV];
+    float total = 0.0f;
+    for (uint32_t i = 0; i + 1 < k; ++i) {
+        const pnode* a = (i < s) ? &fn[i] : &bn[k - 1u - i];
+        const pnode* b = (i + 1u < s) ? &fn[i + 1u] : &bn[k - 2u - i];
+        const float dl[3] = {b->p[0] - a->p[0], b->p[1] - a->p[1], b->p[2] - a->p[2]};
+        const float d2 = dot3(dl, dl);
+        const float d = sqrtf(d2);
+        total += d;
+        if (d < cfg->min_seg) return;
+        const float inv = 1.0f / d;
+        const float dir[3] = {dl[0] * inv, dl[1] * inv, dl[2] * inv};
+        const float cp = (i == 0u) ? 1.0f : fabsf(dot3(a->n, dir));
+        const float cm = (i + 2u == k) ? 1.0f : fabsf(dot3(b->n, dir));
+        const float rd2 = 1.0f / d2;
+        gg[i] = (cp * cm) * rd2;
+        if (!(gg[i] > 0.0f)) return;
+        pf[i] = (cfg->rr_prob * ((i == 0u) ? FSO_INV_4PI : cp * FSO_INV_PI)) * (cm * rd2);
+        pb[i] = (cfg->rr_prob * ((i + 2u == k) ? FSO_INV_4PI : cm * FSO_INV_PI)) * (cp * rd2);
+        dlen[i] = d;
+    }
+    /* sum over the strategies s' of p_{s'} / p_s; valid s': s' - 1 <= max_depth and k - s' - 1 <= max_depth */
+    float sum = 1.0f;
+    const uint32_t flags = cfg->reserved[1];
+    if (flags & (FSO_FLAG_MIS_T1 | FSO_FLAG_MIS_S1)) {
+        if ((flags & FSO_FLAG_MIS_T1) && t != 1u) return;
+        if ((flags & FSO_FLAG_MIS_S1) && s != 1u) return;
+    } else {
+        float r = 1.0f;
+        for (uint32_t sp = s; sp + 1u < k && sp <= max_depth; ++sp) {            /* s' = sp + 1 */
+            r = r * (pf[sp - 1u] / pb[sp]);
+            sum += r;
+        }
+        r = 1.0f;
+        for (uint32_t sp = s; sp > 1u && k - sp <= max_depth; --sp) {            /* s' = sp - 1: t' - 1 = k - sp */
+            r = r * (pb[sp - 1u] / pf[sp - 2u]);
+            sum += r;
+        }
+    }
+    const float delay = total / cfg->sound_speed;
+    const int32_t bin = fso_bin_index(cfg, delay);
+    for (uint32_t b = 0; b < cfg->n_bands; ++b) {
+        float val = FSO_INV_4PI;
+        for (uint32_t i = 0; i + 1 < k; ++i) {
+            val = val * gg[i];
+            val = val * fso_expf(-cfg->air_absorption[b] * dlen[i]);
+            const uint32_t j = i + 1u;
+            if (j + 1u < k) {                                                    /* interior vertex j */
+                const pnode* v = (j < s) ? &fn[j] : &bn[k - 1u - j];
+                val = val * sc->refl_over_pi[(uint32_t)v->mat * sc->n_bands + b];
+                val = val / ((j < s) ? pf[j - 1u] : pb[j]);
+            }
+        }
+        float e = val / sum;
+        e = (e < cfg->energy_clamp) ? e : cfg->energy_clamp;
+        e = e * cfg->energy_gain;
+        hist_src[(uint64_t)b * cfg->n_bins + (uint32_t)bin] += (uint64_t)(e * 4294967296.0f);
+    }
+}
+
+static void connect_all(const fso_scene* sc, const fso_config* cfg, const pnode* fn, uint32_t nf, const pnode* bn, uint32_t nb,
+                        uint32_t max_depth, uint64_t* hist_src, fso_stats* st, ocount* cnt)
+{
+    const int mis = (cfg->reserved[1] & FSO_FLAG_MIS) != 0;
     for (uint32_t s = 1; s <= nf; ++s)
         for (uint32_t t = 1; t <= nb; ++t) {
             const pnode* F = &fn[s - 1];
@@ -771,7 +851,8 @@ static void connect_all(const fso_scene* sc, const fso_config* cfg, const pnode*
                 if (any_hit_cnt(sc, F->p, dir, tmax, cnt)) continue;
             }
             st->connected++;
-            splat_path(sc, cfg, fn, s, bn, t, len, 1.0f / (float)(s + t - 1u), hist_src, NULL);
+            if (mis) mis_splat(sc, cfg, fn, s, bn, t, max_depth, hist_src);
+            else splat_path(sc, cfg, fn, s, bn, t, len, 1.0f / (float)(s + t - 1u), hist_src, NULL);
         }
 }
 
@@ -789,8 +870,8 @@ static void trace_one(const fso_scene* sc, const fso_config* cfg, const float* s
     uint32_t nb = gen_subpath(sc, cfg, lis, gl, 1u, max_depth, seed, bn, &rays, cnt);
     st->ext_rays += rays;
     st->paths++;
-    if (cfg->reserved[1] & FSO_FLAG_CONNECT_ALL) {           /* fs_config.flags lives in reserved[1] */
-        connect_all(sc, cfg, fn, nf, bn, nb, hist_src, st, cnt);
+    if (cfg->reserved[1] & (FSO_FLAG_CONNECT_ALL | FSO_FLAG_MIS)) {           /* fs_config.flags lives in reserved[1] */
+        connect_all(sc, cfg, fn, nf, bn, nb, max_depth, hist_src, st, cnt);
         return;
     }
     /* ConnectSubpaths, SUB.cpp:235-277: one visibility test between the two LAST nodes */

@@ -66,6 +66,9 @@ typedef struct fso_config {
 } fso_config;
 #define FSO_FLAG_SHARE_LISTENER 128u /* listener subpath keyed by the path index only: shared by all sources */
 #define FSO_FLAG_MATERIAL_MODEL 256u /* transmission / scattering / thickness of the material asset drive the walk */
+#define FSO_FLAG_MIS 512u             /* all prefix connections weighted by the balance heuristic over a physically based contribution */
+#define FSO_FLAG_MIS_T1 (1u << 20)    /* oracle only (tests): only the strategies t = 1, weight 1 -- an independent estimator of the same integral */
+#define FSO_FLAG_MIS_S1 (1u << 21)    /* oracle only (tests): only the strategies s = 1 */
 #define FSO_FLAG_CONNECT_ALL 64u   /* all prefix connections, weight 1/(s+t-1) */
 
 typedef struct fso_stats {
