@@ -1805,43 +1805,50 @@ k_connect_gen(const fs_trace_params tp, const fs_wave_buffers wb, fs_dev_counter
     }
 }
 
-// FS_FLAG_CONNECT_ALL: the connection ray of every prefix pair (s, t) of every path pair.  One thread per pair reserves
-// nf * nb queue slots; a pair closer than eps_connect is visible by definition and travels as a ray with tmax = 0 (no
-// triangle has t < 0), so every (s, t) has exactly one queue entry.
+// FS_FLAG_CONNECT_ALL / FS_FLAG_MIS: the connection ray of every prefix pair (s, t) of every path pair.  One WARP per path
+// pair: lane 0 reserves the pair's nf * nb queue slots, the 32 lanes build the (s, t) rays side by side (a pair has up to
+// (depth + 1)^2 of them; one thread per pair left 31 lanes idle behind the longest pair of the warp).  A pair closer than
+// eps_connect is visible by definition and travels as a ray with tmax = 0 (no triangle has t < 0), so every (s, t) has
+// exactly one queue entry.
 __global__ void __launch_bounds__(WF_THREADS)
 k_connect_all_gen(const fs_trace_params tp, const fs_wave_buffers wb, fs_dev_counters* __restrict__ dc)
 {
     const uint32_t qs = tp.max_depth + 2;
     const uint32_t stride = 2u * wb.cap;
+    const uint32_t lane = lane_id();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         unsigned long long ext = 0;
         for (uint32_t k = 0; k < tp.max_depth; ++k) ext += wb.q_count[k];
         atomicAdd(&dc->ext_rays, ext);
     }
     unsigned long long n_shadow = 0;
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < tp.batch; p += gridDim.x * blockDim.x) {
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t p = warp_global; p < tp.batch; p += n_warps) {
         const uint32_t nf = __float_as_uint(wb.end_pos[2u * p].w), nb = __float_as_uint(wb.end_pos[2u * p + 1u].w);
-        uint32_t o = atomicAdd(&wb.q_count[qs], nf * nb);
-        for (uint32_t s = 1; s <= nf; ++s) {
+        const uint32_t n = nf * nb;
+        uint32_t o = 0;
+        if (lane == 0) o = atomicAdd(&wb.q_count[qs], n);
+        o = __shfl_sync(0xffffffffu, o, 0);
+        for (uint32_t idx = lane; idx < n; idx += 32u) {
+            const uint32_t s = idx / nb + 1u, t = idx - (s - 1u) * nb + 1u;
             const fs_vec3 F = node_pos(tp, wb, 2u * p, s - 1u, stride);
-            for (uint32_t t = 1; t <= nb; ++t, ++o) {
-                const fs_vec3 B = node_pos(tp, wb, 2u * p + 1u, t - 1u, stride);
-                const fs_vec3 dl = fs_sub(B, F);
-                const float len = sqrtf(fs_dot(dl, dl));
-                float tmax = len - tp.eps_connect;                  // SUB.cpp:253
-                fs_vec3 dir = fs_mk(1.0f, 0.0f, 0.0f);
-                if (tmax > 0.0f) {
-                    const float inv = 1.0f / len;
-                    dir = fs_mk(dl.x * inv, dl.y * inv, dl.z * inv);
-                    ++n_shadow;
-                } else tmax = 0.0f;
-                wb.all_o[o] = make_float4(F.x, F.y, F.z, tmax);
-                wb.all_d[o] = make_float4(dir.x, dir.y, dir.z, __uint_as_float((p << 12) | ((s - 1u) << 6) | (t - 1u)));
-            }
+            const fs_vec3 B = node_pos(tp, wb, 2u * p + 1u, t - 1u, stride);
+            const fs_vec3 dl = fs_sub(B, F);
+            const float len = sqrtf(fs_dot(dl, dl));
+            float tmax = len - tp.eps_connect;                  // SUB.cpp:253
+            fs_vec3 dir = fs_mk(1.0f, 0.0f, 0.0f);
+            if (tmax > 0.0f) {
+                const float inv = 1.0f / len;
+                dir = fs_mk(dl.x * inv, dl.y * inv, dl.z * inv);
+                ++n_shadow;
+            } else tmax = 0.0f;
+            wb.all_o[o + idx] = make_float4(F.x, F.y, F.z, tmax);
+            wb.all_d[o + idx] = make_float4(dir.x, dir.y, dir.z, __uint_as_float((p << 12) | ((s - 1u) << 6) | (t - 1u)));
         }
     }
     for (int of = 16; of; of >>= 1) n_shadow += __shfl_xor_sync(0xffffffffu, n_shadow, of);
-    if (lane_id() == 0 && n_shadow) atomicAdd(&dc->shadow_rays, n_shadow);
+    if (lane == 0 && n_shadow) atomicAdd(&dc->shadow_rays, n_shadow);
 }
 
 // FS_FLAG_SHARE_LISTENER: the listener subpaths of a call are traced once (lis_mode 1), kept as [D+1][n_paths] records +
@@ -2207,7 +2214,11 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, fs_lane* lane, const fs_trace
     }
     if (tp.lis_mode == 2) { k_lis_load<<<grid_cg, WF_THREADS, 0, st>>>(tp, wb); ctx->launches.fetch_add(1); }
     const bool all = (tp.flags & (FS_FLAG_CONNECT_ALL | FS_FLAG_MIS)) != 0;        // every prefix pair (s, t) instead of the two end points
-    if (all) k_connect_all_gen<<<grid_cg, WF_THREADS, 0, st>>>(tp, wb, ctx->d_counters);
+    if (all) {
+        uint32_t grid_ca = (tp.batch + WF_THREADS / 32 - 1) / (WF_THREADS / 32);          // one warp per path pair
+        if (grid_ca > (uint32_t)ctx->sm_count * 8u) grid_ca = (uint32_t)ctx->sm_count * 8u;
+        k_connect_all_gen<<<grid_ca ? grid_ca : 1, WF_THREADS, 0, st>>>(tp, wb, ctx->d_counters);
+    }
     else k_connect_gen<<<grid_cg, WF_THREADS, 0, st>>>(tp, wb, ctx->d_counters, d_dbg);
     uint32_t grid_any = (uint32_t)(ctx->sm_count * ((use_tq && ctx->tune_tq >= 2) ? occ_tq : occ_any));
     const uint32_t ctas_any = (tp.batch + TR_THREADS - 1) / TR_THREADS;
