@@ -101,7 +101,7 @@ int fs_create(const fs_config* cfg, fs_ctx** out)
     if (const char* e14 = getenv("FS_TUNE_STREAMS")) { int v = atoi(e14); if (v >= 1 && v <= FS_MAX_LANES) ctx->tune_streams = (uint32_t)v; } ctx->tune_tq = 2;      // 0: phased kernels, 1: queue kernel for extension rays only, 2: also for connection rays
     ctx->tune_tq_node_min = 10; ctx->tune_tq_flush = 24;
     if (const char* e11 = getenv("FS_TUNE_TQ")) ctx->tune_tq = (uint32_t)atoi(e11);
-    ctx->tune_mega = 0;          // EXPERIMENTAL: one persistent launch per batch for the extension stage (k_path_q)
+    ctx->tune_mega = 2;          // one persistent launch per batch for the extension stage (k_path_q): 0 never, 1 always, 2 when it pays
     if (const char* e15 = getenv("FS_TUNE_MEGA")) ctx->tune_mega = (uint32_t)atoi(e15);
     ctx->tune_mega_from = 0; ctx->tune_mega_lanes = 1;   // first bounce inside the persistent kernel; batch lanes with it
     if (const char* e16 = getenv("FS_TUNE_MEGA_FROM")) ctx->tune_mega_from = (uint32_t)atoi(e16);
@@ -495,8 +495,15 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
         if (cap_cfg > lim) cap_cfg = lim;
         n_lanes = 1;
     }
-    if (ctx->tune_mega && !(ctx->cfg.flags & (FS_FLAG_COUNT_VISITS | FS_FLAG_TIME_KERNELS)) && n_lanes > ctx->tune_mega_lanes)
-        n_lanes = ctx->tune_mega_lanes;                       // lanes that run a persistent per-batch kernel share the SMs
+    // one persistent kernel per batch fills the GPU by itself: a job that will use it runs on one lane (same rule as in
+    // launch_batch_split: batches of >= 2^18 pairs on a scene of >= 4096 triangles, or FS_TUNE_MEGA=1)
+    {
+        const uint64_t nb1 = g_count ? (g_count + cap_cfg - 1) / cap_cfg : 1;
+        const uint64_t cap1 = g_count ? (g_count + nb1 - 1) / nb1 : 1;
+        const bool mega_job = !(ctx->cfg.flags & (FS_FLAG_COUNT_VISITS | FS_FLAG_CONNECT_ALL | FS_FLAG_MIS)) && max_depth >= 1 &&
+                              (ctx->tune_mega == 1u || (ctx->tune_mega == 2u && cap1 >= (1u << 18) && ctx->bvh.n_tris >= 4096u));
+        if (mega_job && n_lanes > ctx->tune_mega_lanes) n_lanes = ctx->tune_mega_lanes;
+    }
     while (n_lanes > 1 && g_count / n_lanes < (1u << 17)) --n_lanes;            // small jobs: not worth a second set of launches
     uint64_t n_batches = g_count ? (g_count + cap_cfg - 1) / cap_cfg : 1;
     if (n_batches < n_lanes) n_batches = n_lanes;
@@ -508,7 +515,7 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
     fs_trace_params tp;
     fill_params(ctx, &tp, lis_pos, n_paths, max_depth, seed);
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    ctx->kev_used = 0; ctx->tev_used = 0; ctx->stats.extend_launches = 0;
+    ctx->kev_used = 0; ctx->tev_used = 0; ctx->stats.extend_launches = 0; ctx->stats.persistent_launches = 0;
     CK(fs_wave_reset_counters(ctx, reset_ovf));
     // FS_FLAG_SHARE_LISTENER with more than one source's worth of work: trace the n_paths listener subpaths once, now, and
     // let every source batch copy them in (smaller jobs just use the shared keying and trace them in place)

@@ -1369,9 +1369,11 @@ struct pq_globals { uint32_t tail, head, done, error; };
 #define PQ_SHADE_MIN 24u
 #endif
 #define PQ_SQ_CAP (PQ_SHADE_MIN + 32u)         // at most SHADE_MIN - 1 entries wait when up to 32 lanes retire
+// shade queue entry = (ray-log index, t, triangle): the ray itself (origin, direction, subpath id, pdf) is re-read from the log
+// when the entry is shaded -- 3 instead of 10 words per entry keeps a CTA at 25 KB of shared memory
 #define PQ_SMEM (FS_SSTACK * TR_THREADS * sizeof(int) + TR_THREADS * sizeof(unsigned long long) + \
-                 TQ_WARPS * FS_TQ_CAP * sizeof(uint32_t) + TQ_WARPS * sizeof(uint32_t) + 2 * TR_THREADS * sizeof(uint32_t) + \
-                 TQ_WARPS * PQ_SQ_CAP * 10 * sizeof(uint32_t))
+                 TQ_WARPS * FS_TQ_CAP * sizeof(uint32_t) + TQ_WARPS * sizeof(uint32_t) + \
+                 TQ_WARPS * PQ_SQ_CAP * 3 * sizeof(uint32_t))
 
 __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 __device__ __forceinline__ float4 ld_cg_f4(const float4* p)
@@ -1424,9 +1426,8 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
     uint32_t* const w32 = reinterpret_cast<uint32_t*>(skey + TR_THREADS);
     uint32_t* const squeue = w32 + warp * FS_TQ_CAP;
     uint32_t* const sqcount = w32 + TQ_WARPS * FS_TQ_CAP + warp;
-    uint32_t* const sspk = w32 + TQ_WARPS * FS_TQ_CAP + TQ_WARPS;                     // [T] sp_id | bounce << 22 of the lane's ray
-    float* const spdf = reinterpret_cast<float*>(sspk + TR_THREADS);                 // [T] pdf the ray was sampled with
-    uint32_t* const shq = reinterpret_cast<uint32_t*>(spdf + TR_THREADS) + warp * (PQ_SQ_CAP * 10);   // shade queue, 10 planes
+    uint32_t* const shq = w32 + TQ_WARPS * FS_TQ_CAP + TQ_WARPS + warp * (PQ_SQ_CAP * 3);   // shade queue, 3 planes
+    uint32_t my_ray = 0;                                                              // ray-log index of the ray this lane walks
     unsigned long long* const mykey = skey + threadIdx.x;
     unsigned long long* const wkey = skey + (threadIdx.x & ~31u);
     int lstack[FS_STACK_SIZE - FS_SSTACK];
@@ -1461,7 +1462,7 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
             const float4 a = ld_cg_f4(log_o + ticket), b = ld_cg_f4(log_d + ticket);
             tr_init<true>(s, bv, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z));
             bt = __int_as_float(0x7f800000); *mykey = KEY_NONE;
-            sspk[threadIdx.x] = __float_as_uint(a.w); spdf[threadIdx.x] = b.w;
+            my_ray = ticket;
             running = true; ticket = PQ_NO_TICKET;
         }
         const uint32_t m_run = __ballot_sync(FULLM, running);
@@ -1551,12 +1552,9 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
             const uint32_t m_fin = __ballot_sync(FULLM, fin);
             if (fin) {
                 const uint32_t q = sn + (uint32_t)__popc(m_fin & lt);
-                shq[0 * PQ_SQ_CAP + q] = sspk[threadIdx.x];
+                shq[0 * PQ_SQ_CAP + q] = my_ray;
                 shq[1 * PQ_SQ_CAP + q] = __float_as_uint(bt);
                 shq[2 * PQ_SQ_CAP + q] = (uint32_t)kk;
-                shq[3 * PQ_SQ_CAP + q] = __float_as_uint(s.o.x); shq[4 * PQ_SQ_CAP + q] = __float_as_uint(s.o.y); shq[5 * PQ_SQ_CAP + q] = __float_as_uint(s.o.z);
-                shq[6 * PQ_SQ_CAP + q] = __float_as_uint(s.d.x); shq[7 * PQ_SQ_CAP + q] = __float_as_uint(s.d.y); shq[8 * PQ_SQ_CAP + q] = __float_as_uint(s.d.z);
-                shq[9 * PQ_SQ_CAP + q] = __float_as_uint(spdf[threadIdx.x]);
                 running = false;
             }
             sn += (uint32_t)__popc(m_fin);
@@ -1570,13 +1568,15 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
                 fs_vec3 pos = fs_mk(0.f, 0.f, 0.f), dir = pos;
                 float prob = 1.0f; uint32_t spk_out = 0;
                 if (qi < sn) {
-                    const uint32_t spk = shq[0 * PQ_SQ_CAP + qi];
+                    const uint32_t ri = shq[0 * PQ_SQ_CAP + qi];
+                    const float4 ra = ld_cg_f4(log_o + ri), rb = ld_cg_f4(log_d + ri);      // the ray, back from the log (L2)
+                    const uint32_t spk = __float_as_uint(ra.w);
                     const uint32_t sp_id = spk & 0x3fffffu, k = (spk >> 22) + 1u;
                     const float t = __uint_as_float(shq[1 * PQ_SQ_CAP + qi]);
                     const int tri = (int)shq[2 * PQ_SQ_CAP + qi];
-                    const fs_vec3 o = fs_mk(__uint_as_float(shq[3 * PQ_SQ_CAP + qi]), __uint_as_float(shq[4 * PQ_SQ_CAP + qi]), __uint_as_float(shq[5 * PQ_SQ_CAP + qi]));
-                    const fs_vec3 d = fs_mk(__uint_as_float(shq[6 * PQ_SQ_CAP + qi]), __uint_as_float(shq[7 * PQ_SQ_CAP + qi]), __uint_as_float(shq[8 * PQ_SQ_CAP + qi]));
-                    const float pdf_in = __uint_as_float(shq[9 * PQ_SQ_CAP + qi]);
+                    const fs_vec3 o = fs_mk(ra.x, ra.y, ra.z);
+                    const fs_vec3 d = fs_mk(rb.x, rb.y, rb.z);
+                    const float pdf_in = rb.w;
                     fs_vec3 nrm = fs_mk(0.f, 0.f, 0.f);
                     bool cont = true, hit = false;
                     uint32_t nodes = k, mat = 0;
@@ -2012,7 +2012,8 @@ cudaError_t fs_wave_alloc(fs_ctx* ctx, fs_lane* lane, uint32_t cap, uint32_t max
         if ((e = cudaMalloc(&wb->all_d, sizeof(float4) * wb->all_cap)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&wb->all_conn, 4ull * wb->all_cap)) != cudaSuccess) return e;
     }
-    if (ctx->tune_mega && max_depth >= 1 && cap <= (1u << 21) && !(ctx->cfg.flags & (FS_FLAG_CONNECT_ALL | FS_FLAG_MIS))) {
+    const bool mega_alloc = ctx->tune_mega == 1u || (ctx->tune_mega == 2u && cap >= (1u << 18) && ctx->bvh.n_tris >= 4096u);
+    if (mega_alloc && max_depth >= 1 && cap <= (1u << 21) && !(ctx->cfg.flags & (FS_FLAG_CONNECT_ALL | FS_FLAG_MIS | FS_FLAG_COUNT_VISITS))) {
         const uint64_t lc = (uint64_t)n2 * max_depth;                  // every subpath traces at most max_depth rays
         if (lc < 0xffffffffull) {
             wb->log_cap = (uint32_t)lc;
@@ -2146,7 +2147,11 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, fs_lane* lane, const fs_trace
         // (FS_TUNE_MEGA), every bounce from k0 on runs inside ONE k_path_q launch: those are the bounces where few rays are
         // left and the fixed cost of a launch pair (the drain of its slowest rays + the latency floor of k_shade_gen)
         // outweighs the work.  The timing / counting contexts keep the per-bounce pipeline for every bounce.
-        const bool mega = !COUNT && !timing && use_tq && wb.log_o && ctx->tune_mega && (uint64_t)n_sub * D <= wb.log_cap;
+        // FS_TUNE_MEGA: 0 = never, 1 = always, 2 (default) = when it pays: large batches on scenes where traversal dominates
+        // (measured, profiles/r2_experiments.md: room 2^20 pairs -5.7 %, hall -2.2 %; 2^16-pair jobs and the 12-triangle
+        // shoebox +16 ... +32 %: one long persistent launch has a longer tail than it saves, in-kernel shading at partial warps)
+        const bool mega_ok = ctx->tune_mega == 1u || (ctx->tune_mega == 2u && tp.batch >= (1u << 18) && tp.bv.n_tris >= 4096u);
+        const bool mega = !COUNT && use_tq && wb.log_o && mega_ok && (uint64_t)n_sub * D <= wb.log_cap;
         const uint32_t k0 = mega ? (ctx->tune_mega_from < D ? ctx->tune_mega_from : D) : D;
         for (uint32_t k = 0; k <= D; ++k) {
             k_shade_gen<<<grid_sh, FS_SG_THREADS, 0, st>>>(tp, wb, k, ctx->d_counters);
@@ -2163,10 +2168,23 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, fs_lane* lane, const fs_trace
                 k_pq_seed<<<ctx->sm_count * 4, 256, 0, st>>>(wb, wb.log_o, wb.log_d, wb.log_flag, epoch, g, k0);
                 uint32_t grid_pq = (uint32_t)(ctx->sm_count * occ_pq) / (ctx->cur_lanes ? ctx->cur_lanes : 1u);
                 if (grid_pq > ctas_needed) grid_pq = ctas_needed ? ctas_needed : 1;
+                cudaEvent_t* te = nullptr;
+                if (timing) {                              // the persistent launch is the "traversal launch" of this batch
+                    if (ctx->tev.size() < ctx->tev_used + 2) {
+                        size_t old = ctx->tev.size();
+                        ctx->tev.resize(ctx->tev_used + 2);
+                        for (size_t i = old; i < ctx->tev.size(); ++i) cudaEventCreate(&ctx->tev[i]);
+                    }
+                    te = &ctx->tev[ctx->tev_used];
+                    ctx->tev_used += 2;
+                    cudaEventRecord(te[0], st);
+                }
                 if (texq) k_path_q<2><<<grid_pq, TR_THREADS, PQ_SMEM, st>>>(tp, wb, wb.log_o, wb.log_d, wb.log_flag, epoch, wb.log_cap, g,
                                                                           ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush);
                 else k_path_q<0><<<grid_pq, TR_THREADS, PQ_SMEM, st>>>(tp, wb, wb.log_o, wb.log_d, wb.log_flag, epoch, wb.log_cap, g,
                                                                      ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush);
+                if (timing) cudaEventRecord(te[1], st);
+                ctx->stats.persistent_launches += 1;
                 k_pq_finish<<<1, 1, 0, st>>>(wb, g, D, ctx->d_counters, k0);
                 ctx->launches.fetch_add(3);
                 ctx->stats.extend_launches += 1;

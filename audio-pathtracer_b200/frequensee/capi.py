@@ -60,7 +60,8 @@ class Stats(C.Structure):
                 ("kernel_launches", C.c_uint64), ("bvh_nodes", C.c_uint64), ("bvh_max_leaf", C.c_uint64),
                 ("last_trace_ms", C.c_float), ("last_ir_ms", C.c_float),
                 ("extend_ms", C.c_float), ("connect_ms", C.c_float), ("eval_ms", C.c_float),
-                ("extend_launches", C.c_uint32), ("trace_ms", C.c_float), ("last_conv_ms", C.c_float)]
+                ("extend_launches", C.c_uint32), ("trace_ms", C.c_float), ("persistent_launches", C.c_uint32),
+                ("last_conv_ms", C.c_float)]
 
     def as_dict(self):
         return {k: (float(getattr(self, k)) if t is C.c_float else int(getattr(self, k)))

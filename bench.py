@@ -179,7 +179,7 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------
-def profile_counters(args):
+def profile_counters(args, kernel="k_trace_q"):
     """per-launch ncu counters of the traversal kernel on this workload from the committed `ncu --set full` capture
     (profiles/*_traffic.json: dram bytes, lts throughput, thread instructions); {} for workloads that were not captured"""
     out = {}
@@ -191,7 +191,7 @@ def profile_counters(args):
                 j = json.load(open(os.path.join(pdir, f)))
             except Exception:
                 continue
-            if j.get("scene", "room") == want:
+            if j.get("scene", "room") == want and j.get("kernel", "k_trace_q").startswith(kernel):
                 out = j
     return out
 
@@ -259,8 +259,8 @@ class Workload:
 
     def stage_times(self, n_steps, seed0=SEED0):
         """per-kernel-class device time: the same steps (same seeds) re-run on a second context with FS_FLAG_TIME_KERNELS,
-        i.e. CUDA events on the launching stream around every stage and every k_trace_q launch.  That context runs its
-        batches on ONE lane, so each kernel is timed alone (in the headline run two batch lanes overlap their kernels)."""
+        i.e. CUDA events on the launching stream around every stage and every traversal launch (k_trace_q per bounce, or the
+        one k_path_q of a batch).  That context runs its batches on ONE lane, so each kernel is timed alone."""
         torch = self.env["torch"]
         tctx = self.fs.Context(device=self.env["local"], flags=self.capi.FLAG_TIME_KERNELS | self.base_flags)
         tctx.set_scene(self.sc.verts, self.sc.tri_mat, self.sc.absorption)
@@ -275,7 +275,8 @@ class Workload:
         tctx.close()
         m = lambda key: float(np.mean([s[key] for s in per]))       # noqa: E731
         return {"extend_ms": m("extend_ms"), "connect_ms": m("connect_ms"), "trace_ms": m("trace_ms"), "eval_ms": m("eval_ms"),
-                "extend_launches": per[0]["extend_launches"], "rays": m("ext_rays") + m("shadow_rays"),
+                "extend_launches": per[0]["extend_launches"], "persistent": per[0].get("persistent_launches", 0),
+                "rays": m("ext_rays") + m("shadow_rays"),
                 "ext_rays": m("ext_rays"), "connected": m("connected")}
 
     def visit_counts(self, n_steps, seed0=SEED0):
@@ -303,14 +304,19 @@ class Workload:
         achieved = ext_bytes / (trc_ms * 1e-3) / 1e9 if trc_ms > 0 else None
         bvh_mb = (self.sc.n_tris * 0.5 * 64 + self.sc.n_tris * 64) / 1e6      # reachable 4-wide nodes (~T/2 x 64 B) + triangles (64 B)
         in_l2 = bvh_mb < 100
-        prof = profile_counters(args_like)
+        persistent = st.get("persistent", 0) > 0
+        prof = profile_counters(args_like, "k_path_q" if persistent else "k_trace_q")
+        kname = ("k_path_q (persistent per-batch kernel: every bounce of the batch -- 4-wide BVH closest-hit traversal with the "
+                 "warp-shared triangle queue AND in-kernel shading / ray generation -- in %d launch(es) per step; bytes counted "
+                 "are the traversal's only" % st["extend_launches"]) if persistent else \
+                ("k_trace_q<closest> (persistent 4-wide BVH closest-hit traversal, warp-shared triangle queue), %d launches "
+                 "per step on the one-lane timing context" % st["extend_launches"])
         r = {"bound": "issue" if in_l2 else "hbm",
              "binding_resource": ("issue slots / ALU pipe: the %.0f MB of nodes + triangles are L2/L1-resident (DRAM traffic is a few %% of "
                                   "the algorithmic bytes), the kernel is limited by instruction issue at ~2/3 lane occupancy" % bvh_mb) if in_l2
                                  else ("memory latency / L2+HBM fetch of the %.0f MB of nodes + triangles (larger than the 126 MB L2): "
                                        "a third of the stall samples wait for the node fetch" % bvh_mb),
-             "kernel": "k_trace_q<closest> (persistent 4-wide BVH closest-hit traversal, warp-shared triangle queue), %d launches "
-                       "per step on the one-lane timing context" % st["extend_launches"],
+             "kernel": kname,
              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
              "traffic": prof.get("dram_bytes_per_launch"), "peak_source": peak_src,
              "bytes_per_launch": ext_bytes / nl, "ms_per_launch": trc_ms / nl,
@@ -351,8 +357,10 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        host_group = dist.new_group(backend="gloo")        # host-side barrier (no kernel spinning on the idle GPUs)
     N, K, W = world, args.steps, args.warmup
     stream = torch.cuda.Stream()                            # a real (non-NULL) stream: the C-ABI treats NULL as "own stream"
     torch.cuda.set_stream(stream)
@@ -462,13 +470,47 @@ def run_b200(args):
                      "stage_ms_rank0_one_lane": {"trace_closest": hst["trace_ms"], "shade_gen": hst["extend_ms"] - hst["trace_ms"],
                                                  "connect": hst["connect_ms"], "eval_splat": hst["eval_ms"]}}
         hall.close()
+    # ---- the same update through the C-ABI's own multi-GPU path (fs_multi_*: one process, one context per device, peer-store
+    # reduce on device 0 -- no NCCL, no torch on the data path), run by rank 0 alone while the other ranks wait on the host
+    cabi_multi = None
+    if N > 1 and args.scene == "furnished_room" and not args.strong:
+        if rank == 0:
+            import frequensee as fs2
+            from frequensee import scenes as scenes2
+            try:
+                sc2 = scenes2.by_name(args.scene); sc2.sources = sc2.sources[:args.sources]
+                per_src = args.paths * N // len(sc2.sources)
+                # NCCL reduce of one histogram, alone (CUDA events), for comparison
+                with fs2.MultiContext(list(range(N))) as mc:
+                    mc.set_scene(sc2.verts, sc2.tri_mat, sc2.absorption)
+                    c0 = mc.context(0)
+                    for w in range(3):
+                        mc.trace(sc2.sources, sc2.listener, per_src, args.depth, SEED0 - 1 - w, want_hist=False)
+                        c0.build_ir(0, want_ir=False)
+                    mc.synchronize()
+                    t0 = time.perf_counter()
+                    for k in range(K):
+                        mc.trace(sc2.sources, sc2.listener, per_src, args.depth, SEED0 + k, want_hist=False)
+                        c0.build_ir(0, want_ir=False) if len(sc2.sources) == 1 else c0.build_ir_all(len(sc2.sources), want_ir=False)
+                    mc.synchronize()
+                    wall_m = time.perf_counter() - t0
+                    tot_ms, red_ms = mc.last_ms()
+                    hm = mc.trace(sc2.sources, sc2.listener, n_chk, args.depth, SEED0 + 77)
+                cabi_multi = {"ms_per_step": 1e3 * wall_m / K, "value": args.paths * N * K / wall_m, "unit": UNIT,
+                              "device_ms_last_update": tot_ms, "device_ms_wait_for_peers_and_sum": red_ms,
+                              "bit_exact_vs_nccl_reduce": bool(parity.get("nccl_reduce_bit_exact")) and
+                              bool(np.array_equal(hm.view(np.int64), reduced.cpu().numpy())),
+                              "what": "fs_multi_trace + fs_build_ir on %d devices from ONE process (wall clock around enqueue + synchronise)" % N}
+            except Exception as e:                                          # never lose the headline line over the extra measurement
+                cabi_multi = {"error": str(e)[:300]}
+        dist.barrier(group=host_group)
     if rank == 0:
         ext_ms_all, trc_ms = st["extend_ms"], st["trace_ms"]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": K, "warmup": W,
                 "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
                 "dtype": "f32 + u64 Q32.32", "data": "synthetic", "config": config_dict(args, N),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_1thread": cpu1, "parity": parity, "north_star": north,
+                "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_1thread": cpu1, "parity": parity, "north_star": north, "cabi_multi": cabi_multi,
                 "mrays_per_s": st["rays"] * N / (dev_ms / K * 1e-3) / 1e6,
                 "ms_per_ir_update": dev_ms / K,
                 "stage_ms": {"trace_closest": trc_ms, "shade_gen": ext_ms_all - trc_ms, "connect": st["connect_ms"], "eval_splat": st["eval_ms"]},

@@ -136,6 +136,8 @@ typedef struct fs_stats {
     float    eval_ms;          /*   "   k_eval (evaluate + splat) */
     uint32_t extend_launches;  /* closest-hit traversal launches (k_trace_closest / k_extend) in the last trace */
     float    trace_ms;         /* only with FS_FLAG_TIME_KERNELS: sum over the k_trace_closest launches alone */
+    uint32_t persistent_launches; /* of those, launches of the persistent per-batch kernel (k_path_q: every bounce of a batch -- traversal
+                                  and shading -- in one launch); 0 = the per-bounce pipeline ran (small jobs, trivial scenes) */
     float    last_conv_ms;     /* device time of the k_conv_blocks launch(es) of the last fs_conv_process* call (CUDA events on the
                                   convolver's stream) */
 } fs_stats;
