@@ -96,7 +96,7 @@ int fs_create(const fs_config* cfg, fs_ctx** out)
     if (ctx->cfg.max_batch_paths == 0) ctx->cfg.max_batch_paths = 1u << 21;
     ctx->device = dev;
     ctx->ir_window = ir_window;
-    ctx->launches.store(0);
+    ctx->launches.store(0); ctx->conv_active.store(0);
     ctx->tune_refill = 4; ctx->tune_leaf_max = FS_LEAF_MAX; ctx->tune_tex = 2; ctx->tune_builder = 1; ctx->tune_wide = 1; ctx->tune_node_min = 14; ctx->tune_tri_min = 4; ctx->tune_collapse = 1; ctx->tune_l2pin_mb = 0; ctx->tune_streams = 2;
     if (const char* e14 = getenv("FS_TUNE_STREAMS")) { int v = atoi(e14); if (v >= 1 && v <= FS_MAX_LANES) ctx->tune_streams = (uint32_t)v; } ctx->tune_tq = 2;      // 0: phased kernels, 1: queue kernel for extension rays only, 2: also for connection rays
     ctx->tune_tq_node_min = 10; ctx->tune_tq_flush = 24;
@@ -501,7 +501,8 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
         const uint64_t nb1 = g_count ? (g_count + cap_cfg - 1) / cap_cfg : 1;
         const uint64_t cap1 = g_count ? (g_count + nb1 - 1) / nb1 : 1;
         const bool mega_job = !(ctx->cfg.flags & (FS_FLAG_COUNT_VISITS | FS_FLAG_CONNECT_ALL | FS_FLAG_MIS)) && max_depth >= 1 &&
-                              (ctx->tune_mega == 1u || (ctx->tune_mega == 2u && cap1 >= (1u << 18) && ctx->bvh.n_tris >= 4096u));
+                              (ctx->tune_mega == 1u || (ctx->tune_mega == 2u && cap1 >= (1u << 18) && ctx->bvh.n_tris >= 4096u &&
+                                                        ctx->conv_active.load() == 0));
         if (mega_job && n_lanes > ctx->tune_mega_lanes) n_lanes = ctx->tune_mega_lanes;
     }
     while (n_lanes > 1 && g_count / n_lanes < (1u << 17)) --n_lanes;            // small jobs: not worth a second set of launches
@@ -942,7 +943,7 @@ int fs_conv_release_source(fs_ctx* ctx, uint32_t source)
     std::lock_guard<std::mutex> lk(ctx->conv_mu);
     // Source.ClearBuffers(), REV.cpp:112-116: the history goes, the slot (and its IR, which the game thread may be
     // rebuilding right now on its own stream) stays until fs_destroy
-    if (ctx->conv[source]) ctx->conv[source]->active = false;
+    if (ctx->conv[source] && ctx->conv[source]->active) { ctx->conv[source]->active = false; ctx->conv_active.fetch_sub(1); }
     return FS_OK;
 }
 

@@ -220,7 +220,11 @@ cudaError_t fs_conv_setup(fs_ctx* ctx)
         tw[m] = make_float2((float)cos(ang), (float)sin(ang));
     }
     cudaError_t e;
-    if ((e = cudaStreamCreateWithFlags(&ctx->conv_stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    {   // the audio thread's stream: highest priority, so its CTAs are placed first whenever a trace kernel frees an SM
+        int lo = 0, hi = 0;
+        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) { lo = hi = 0; (void)cudaGetLastError(); }
+        if ((e = cudaStreamCreateWithPriority(&ctx->conv_stream, cudaStreamNonBlocking, hi)) != cudaSuccess) return e;
+    }
     if ((e = cudaMalloc(&ctx->d_twiddle, sizeof(float2) * tw.size())) != cudaSuccess) return e;
     if ((e = cudaMemcpy(ctx->d_twiddle, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
     const size_t smem = sizeof(float2) * 2 * ctx->fft_n;
@@ -275,12 +279,15 @@ cudaError_t fs_conv_source_alloc(fs_ctx* ctx, uint32_t source, bool reset_histor
         if ((e = cudaMemsetAsync(s->H[1], 0, sizeof(float2) * sp, st)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(s->ir, 0, sizeof(float) * c.n_channels * c.sample_rate, st)) != cudaSuccess) return e;
         s->pub = 0; s->pending = -1;
-        reset_history = true;
-    }
-    if (reset_history) {
         if ((e = cudaMemsetAsync(s->fdl, 0, sizeof(float2) * sp, st)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(s->prev, 0, sizeof(float) * c.n_channels * c.conv_block, st)) != cudaSuccess) return e;
         s->head = 0;
+    }
+    if (reset_history) {                  // fs_conv_init_source: the slot becomes an audio source (an IR build alone does not)
+        if ((e = cudaMemsetAsync(s->fdl, 0, sizeof(float2) * sp, st)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(s->prev, 0, sizeof(float) * c.n_channels * c.conv_block, st)) != cudaSuccess) return e;
+        s->head = 0;
+        if (!s->active) ctx->conv_active.fetch_add(1);
         s->active = true;
     }
     return cudaStreamSynchronize(st);
@@ -290,6 +297,7 @@ void fs_conv_source_free(fs_ctx* ctx, uint32_t source)
 {
     if (source >= ctx->conv.size() || !ctx->conv[source]) return;
     fs_conv_source* s = ctx->conv[source];
+    if (s->active) ctx->conv_active.fetch_sub(1);
     cudaFree(s->fdl); cudaFree(s->H[0]); cudaFree(s->H[1]); cudaFree(s->prev); cudaFree(s->ir);
     for (int i = 0; i < 2; ++i) if (s->h_ready[i]) cudaEventDestroy(s->h_ready[i]);
     delete s;

@@ -142,6 +142,7 @@ struct fs_ctx {
     fs_path_dbg* d_dbg; uint64_t dbg_cap;
     fs_stats stats;                      // game-thread fields only; kernel launches are counted in `launches`
     std::atomic<uint64_t> launches;
+    std::atomic<int> conv_active;        // initialised convolver sources: while > 0 the tracer keeps to short per-bounce kernels
     cudaEvent_t ev0, ev1, ev_ir0, ev_ir1; bool timed, ir_timed;
     std::vector<cudaEvent_t> kev; size_t kev_used;   // FS_FLAG_TIME_KERNELS: 4 events per batch
     std::vector<cudaEvent_t> tev; size_t tev_used;   //   + one (begin, end) pair per k_trace_closest launch

@@ -2150,7 +2150,10 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, fs_lane* lane, const fs_trace
         // FS_TUNE_MEGA: 0 = never, 1 = always, 2 (default) = when it pays: large batches on scenes where traversal dominates
         // (measured, profiles/r2_experiments.md: room 2^20 pairs -5.7 %, hall -2.2 %; 2^16-pair jobs and the 12-triangle
         // shoebox +16 ... +32 %: one long persistent launch has a longer tail than it saves, in-kernel shading at partial warps)
-        const bool mega_ok = ctx->tune_mega == 1u || (ctx->tune_mega == 2u && tp.batch >= (1u << 18) && tp.bv.n_tris >= 4096u);
+        // ... and only while no convolver source is active: a persistent grid holds every SM for the whole batch (4-5 ms), an
+        // audio callback issued meanwhile would wait for it (measured p99 3.6 ms); between per-bounce kernels it waits 0.3 ms
+        const bool mega_ok = ctx->tune_mega == 1u || (ctx->tune_mega == 2u && tp.batch >= (1u << 18) && tp.bv.n_tris >= 4096u &&
+                                                      ctx->conv_active.load() == 0);
         const bool mega = !COUNT && use_tq && wb.log_o && mega_ok && (uint64_t)n_sub * D <= wb.log_cap;
         const uint32_t k0 = mega ? (ctx->tune_mega_from < D ? ctx->tune_mega_from : D) : D;
         for (uint32_t k = 0; k <= D; ++k) {

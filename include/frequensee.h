@@ -28,7 +28,11 @@
  * computed, it keeps the previous IR (the reference shares ImpulseBuffer with no
  * synchronisation, COMP.cpp:378 vs REV.cpp:136).  An update is guaranteed to be in effect for
  * callbacks issued after a host-synchronising call of the game thread has returned
- * (fs_build_ir* with ir_out, fs_set_ir, fs_synchronize).
+ * (fs_build_ir* with ir_out, fs_set_ir, fs_synchronize).  While at least one convolver source
+ * is initialised, fs_trace* keeps to short kernels (one per bounce) so that a callback is
+ * placed between two of them (measured p99 0.3 ms beside 5 ms updates); with no source
+ * active, a large update runs as one persistent kernel per batch (5 % faster, but it holds
+ * every SM for milliseconds).
  *
  * Ownership: the caller owns every host buffer passed in or out; the library copies at call
  * time and retains nothing.  Device memory is owned by the context.
