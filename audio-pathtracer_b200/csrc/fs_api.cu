@@ -2,6 +2,7 @@
 // entry point either runs the CUDA path or returns an error.
 #include "fs_internal.h"
 
+#include <nvtx3/nvToolsExt.h>          // header-only NVTX 3: named ranges per stage for nsys / ncu --nvtx
 #include <stdio.h>
 #include <utility>
 #include <stdlib.h>
@@ -32,6 +33,11 @@ static int fail_cuda(fs_ctx* ctx, cudaError_t e, const char* what)
     (void)cudaGetLastError();
     return e == cudaErrorMemoryAllocation ? FS_ERR_NOMEM : FS_ERR_CUDA;
 }
+
+struct nvtx_range {                    // RAII range on the calling thread
+    explicit nvtx_range(const char* name) { nvtxRangePushA(name); }
+    ~nvtx_range() { nvtxRangePop(); }
+};
 
 struct dev_guard {
     int prev; bool ok;
@@ -368,6 +374,7 @@ int fs_scene_commit(fs_ctx* ctx)
 {
     if (!ctx) return FS_ERR_INVALID;
     if (!ctx->tris_set || !ctx->mats_set) return fail(ctx, FS_ERR_STATE, "fs_scene_commit: set triangles and materials first");
+    nvtx_range nv("fs_scene_commit (BVH build)");
     dev_guard g(ctx->device);
     if (ctx->n_tris) {
         // validate material ids on the host copy-back of the id array (one-time, commit only)
@@ -449,6 +456,7 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
                         uint64_t n_paths, uint64_t g_first, uint64_t g_count, uint32_t max_depth, uint64_t seed,
                         unsigned long long* d_hist, fs_path_dbg* d_dbg)
 {
+    nvtx_range nv("fs_trace");
     if (!ctx->committed) return fail(ctx, FS_ERR_STATE, "fs_trace: call fs_scene_commit first");
     if (!src_pos || !lis_pos || n_sources == 0) return fail(ctx, FS_ERR_INVALID, "fs_trace: null positions / no source");
     if (n_paths == 0) return fail(ctx, FS_ERR_INVALID, "fs_trace: n_paths must be > 0");
@@ -805,6 +813,7 @@ static int ensure_pin_ir(fs_ctx* ctx, size_t n_floats)
 static int ir_common(fs_ctx* ctx, uint32_t hist_source, uint32_t source, const float* energy, float* ir_out,
                      bool per_band = false, uint64_t noise_seed = 0)
 {
+    nvtx_range nv("fs_build_ir");
     const fs_config& c = ctx->cfg;
     int rc = check_overflow(ctx, false);            // never build an IR from a histogram known to be incomplete
     if (rc) return rc;
@@ -954,6 +963,7 @@ static int conv_process(fs_ctx* ctx, const uint32_t* sources, uint32_t n_src, co
     if (!in || !out || !sources) return fail(ctx, FS_ERR_INVALID, "fs_conv_process: null buffer");
     if (frames != ctx->cfg.conv_block) return fail(ctx, FS_ERR_INVALID, "fs_conv_process: frames must equal conv_block");
     if (n_blocks == 0 || n_src == 0) return FS_OK;
+    nvtx_range nv("fs_conv_process");
     dev_guard g(ctx->device);
     std::lock_guard<std::mutex> lk(ctx->conv_mu);
     for (uint32_t i = 0; i < n_src; ++i) {

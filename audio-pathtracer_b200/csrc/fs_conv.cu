@@ -226,7 +226,8 @@ cudaError_t fs_conv_setup(fs_ctx* ctx)
         if ((e = cudaStreamCreateWithPriority(&ctx->conv_stream, cudaStreamNonBlocking, hi)) != cudaSuccess) return e;
     }
     if ((e = cudaMalloc(&ctx->d_twiddle, sizeof(float2) * tw.size())) != cudaSuccess) return e;
-    if ((e = cudaMemcpy(ctx->d_twiddle, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(ctx->d_twiddle, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice, ctx->conv_stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(ctx->conv_stream)) != cudaSuccess) return e;
     const size_t smem = sizeof(float2) * 2 * ctx->fft_n;
     if (smem > 48 * 1024) {
         if ((e = cudaFuncSetAttribute(k_ir_spectra, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;

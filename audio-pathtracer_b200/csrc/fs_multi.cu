@@ -253,7 +253,7 @@ int fs_multi_trace(fs_multi* m, const float* src_pos, uint32_t n_sources, const 
             cudaDeviceSynchronize();
             cudaFree(m->d_local[i]); m->d_local[i] = nullptr;
             if (cudaMalloc(&m->d_local[i], 8 * cap) != cudaSuccess) return mfail(FS_ERR_NOMEM, "fs_multi_trace: shard histogram");
-            if (cudaMemset(m->d_local[i], 0, 8 * cap) != cudaSuccess) return mfail(FS_ERR_CUDA, "cudaMemset");
+            // (every update clears it on the device's own stream before tracing: zero_first below)
         }
         m->cap = cap;
     }
