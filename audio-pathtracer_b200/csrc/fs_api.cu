@@ -103,7 +103,7 @@ int fs_create(const fs_config* cfg, fs_ctx** out)
     ctx->device = dev;
     ctx->ir_window = ir_window;
     ctx->launches.store(0); ctx->conv_active.store(0);
-    ctx->tune_refill = 4; ctx->tune_leaf_max = FS_LEAF_MAX; ctx->tune_tex = 2; ctx->tune_builder = 1; ctx->tune_wide = 1; ctx->tune_node_min = 14; ctx->tune_tri_min = 4; ctx->tune_collapse = 1; ctx->tune_l2pin_mb = 0; ctx->tune_streams = 2;
+    ctx->tune_refill = 4; ctx->tune_leaf_max = FS_LEAF_MAX; ctx->tune_tex = 2; ctx->tune_builder = 1; ctx->tune_wide = 1; ctx->tune_node_min = 14; ctx->tune_tri_min = 4; ctx->tune_collapse = 1; ctx->tune_l2pin_mb = 0xffffffffu /* automatic */; ctx->tune_streams = 2;
     if (const char* e14 = getenv("FS_TUNE_STREAMS")) { int v = atoi(e14); if (v >= 1 && v <= FS_MAX_LANES) ctx->tune_streams = (uint32_t)v; } ctx->tune_tq = 2;      // 0: phased kernels, 1: queue kernel for extension rays only, 2: also for connection rays
     ctx->tune_tq_node_min = 10; ctx->tune_tq_flush = 24;
     if (const char* e11 = getenv("FS_TUNE_TQ")) ctx->tune_tq = (uint32_t)atoi(e11);
@@ -282,7 +282,16 @@ int fs_scene_set_materials(fs_ctx* ctx, const float* absorption, uint32_t n_mate
 // hundreds of MB) cannot evict the nodes every ray visits.  FS_TUNE_L2PIN = MB to pin (0 = off).
 static void apply_l2_policy(fs_ctx* ctx)
 {
-    if (!ctx->bvh.wnodes || !ctx->tune_l2pin_mb) return;
+    if (!ctx->bvh.wnodes) return;
+    if (ctx->tune_l2pin_mb == 0xffffffffu) {
+        // automatic (default): only for scenes whose nodes + triangles do not fit the L2 anyway -- there a 48 MB window over
+        // the top of the tree is worth 2 % (concert hall, profiles/r2_experiments.md); scenes that fit need no help
+        int l2 = 0;
+        cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, ctx->device);
+        const size_t bvh_bytes = (size_t)ctx->bvh.n_wide * 64u + (size_t)ctx->bvh.n_tris * 64u;
+        ctx->tune_l2pin_mb = (l2 > 0 && bvh_bytes > (size_t)l2) ? 48u : 0u;
+    }
+    if (!ctx->tune_l2pin_mb) return;
     int max_persist = 0, max_window = 0;
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
     cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);

@@ -24,6 +24,24 @@ namespace {
 
 constexpr int WF_THREADS = 256;
 
+// Per-step streaming state (ray queues / ray log, hit records, node records, end points: hundreds of MB per update) is written
+// once and read once.  With FS_STREAM_HINTS the accesses carry the evict-first hint (st.global.cs / ld.global.cs) so that they
+// do not push the BVH out of L2 -- it matters for scenes whose nodes + triangles do not fit the 126 MB L2 anyway.
+#ifndef FS_STREAM_HINTS
+#define FS_STREAM_HINTS 0      // measured (r2j): no effect on the room or the hall, left off
+#endif
+#if FS_STREAM_HINTS
+#define FS_ST4(ptr, v) __stcs((ptr), (v))
+#define FS_ST2(ptr, v) __stcs((ptr), (v))
+#define FS_LD4(ptr) __ldcs(ptr)
+#define FS_LD2(ptr) __ldcs(ptr)
+#else
+#define FS_ST4(ptr, v) (*(ptr) = (v))
+#define FS_ST2(ptr, v) (*(ptr) = (v))
+#define FS_LD4(ptr) (*(ptr))
+#define FS_LD2(ptr) (*(ptr))
+#endif
+
 enum { MODE_BVH = 0, MODE_TOP = 1, MODE_BRUTE = 2 };
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
@@ -362,7 +380,7 @@ k_eval(const fs_trace_params tp, const fs_wave_buffers wb, unsigned long long* _
             for (uint32_t i0 = 1; i0 < nf; i0 += 4) {     // segments F_{i-1} -> F_i
                 float4 r[4];
 #pragma unroll
-                for (uint32_t u = 0; u < 4; ++u) r[u] = (i0 + u < nf) ? rf[(size_t)(i0 + u) * stride] : make_float4(0.f, 0.f, 1.f, 1.f);
+                for (uint32_t u = 0; u < 4; ++u) r[u] = (i0 + u < nf) ? FS_LD4(rf + (size_t)(i0 + u) * stride) : make_float4(0.f, 0.f, 1.f, 1.f);
 #pragma unroll
                 for (uint32_t u = 0; u < 4; ++u) {
                     if (i0 + u < nf) {
@@ -382,7 +400,7 @@ k_eval(const fs_trace_params tp, const fs_wave_buffers wb, unsigned long long* _
             for (int i0 = (int)nb - 1; i0 >= 1; i0 -= 4) { // B_i -> B_{i-1}
                 float4 r[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) r[u] = (i0 - u >= 1) ? rb[(size_t)(i0 - u) * stride] : make_float4(0.f, 0.f, 1.f, 1.f);
+                for (int u = 0; u < 4; ++u) r[u] = (i0 - u >= 1) ? FS_LD4(rb + (size_t)(i0 - u) * stride) : make_float4(0.f, 0.f, 1.f, 1.f);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (i0 - u >= 1) {
@@ -663,8 +681,8 @@ k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_d
                     pos = fs_mk(__ldg(tp.src_pos + 3 * s), __ldg(tp.src_pos + 3 * s + 1), __ldg(tp.src_pos + 3 * s + 2));
                 }
             } else {
-                const float4 a = in_o[j], b = in_d[j];
-                const float2 h = wb.hit[j];
+                const float4 a = FS_LD4(in_o + j), b = FS_LD4(in_d + j);
+                const float2 h = FS_LD2(wb.hit + j);
                 sp_id = __float_as_uint(a.w);
                 const fs_vec3 o = fs_mk(a.x, a.y, a.z), d = fs_mk(b.x, b.y, b.z);
                 const int tri = __float_as_int(h.y);
@@ -707,10 +725,10 @@ k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_d
                 emit = choose_direction(tp, k, g, sp_id & 1u, nrm, din, mat, pos, dir, prob, ev, org);
             }
             // node record of node k: the lobe the walk takes here rides in the top byte of the material word
-            if (hit) wb.rec[(size_t)k * stride + sp_id] = make_float4(seg, __uint_as_float(mat | (ev << 24)), pdf_in, fs_pow(pdf_in, tp.ep.pdf_exponent));
+            if (hit) FS_ST4(wb.rec + (size_t)k * stride + sp_id, make_float4(seg, __uint_as_float(mat | (ev << 24)), pdf_in, fs_pow(pdf_in, tp.ep.pdf_exponent)));
             // the walk ends at this node -- or, with the material model, may end here if the ray just emitted misses
             const bool at_node = (k == 0) ? !(tp.lis_mode && (sp_id & 1u) == tp.lis_mode - 1u) : hit;
-            if (at_node && (!emit || tp.lobes)) wb.end_pos[sp_id] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(nodes));
+            if (at_node && (!emit || tp.lobes)) FS_ST4(wb.end_pos + sp_id, make_float4(pos.x, pos.y, pos.z, __uint_as_float(nodes)));
             pos = org;                            // the ray starts at the node, or beyond its surface after a pass-through
         }
         const uint32_t m = __ballot_sync(FULLM, emit);
@@ -725,8 +743,8 @@ k_shade_gen(const fs_trace_params tp, const fs_wave_buffers wb, uint32_t k, fs_d
         __syncthreads();
         if (emit) {
             const uint32_t o = s_base + s_cnt[warp] + __popc(m & ((1u << lane) - 1u));
-            out_o[o] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(sp_id));
-            out_d[o] = make_float4(dir.x, dir.y, dir.z, prob);
+            FS_ST4(out_o + o, make_float4(pos.x, pos.y, pos.z, __uint_as_float(sp_id)));
+            FS_ST4(out_d + o, make_float4(dir.x, dir.y, dir.z, prob));
         }
         __syncthreads();                                   // s_cnt / s_base are rewritten by the next tile
     }
@@ -1167,7 +1185,7 @@ k_trace_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* 
             if (!running) {
                 const uint32_t jj = base + (uint32_t)__popc(m_idle & ((1u << lane) - 1u));
                 if (jj < count) {
-                    const float4 a = ray_o[jj], b = ray_d[jj];
+                    const float4 a = FS_LD4(ray_o + jj), b = FS_LD4(ray_d + jj);
                     tr_init<true>(s, bv, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z));
                     bt = ANY ? a.w : __int_as_float(0x7f800000); *mykey = KEY_NONE;
                     j = ANY ? __float_as_uint(b.w) : jj; running = true;
@@ -1300,7 +1318,7 @@ k_trace_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* 
                 }
                 if (retire) running = false;
             } else if (retire) {
-                hits[j] = make_float2(bt, __int_as_float((int)(uint32_t)kk));
+                FS_ST2(hits + j, make_float2(bt, __int_as_float((int)(uint32_t)kk)));
                 running = false;
                 if (COUNT) { atomicMax(&dc->max_steps, ray_steps); atomicAdd(&dc->steps_hist[ray_steps / 8u < 15u ? ray_steps / 8u : 15u], 1u); }
             }
@@ -1614,8 +1632,8 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
                         spk_out = sp_id | (k << 22);
                     }
                     if (hit) {
-                        wb.rec[(size_t)k * stride + sp_id] = make_float4(seg, __uint_as_float(mat | (ev << 24)), pdf_in, fs_pow(pdf_in, tp.ep.pdf_exponent));
-                        if (!emit || tp.lobes) wb.end_pos[sp_id] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(nodes));
+                        FS_ST4(wb.rec + (size_t)k * stride + sp_id, make_float4(seg, __uint_as_float(mat | (ev << 24)), pdf_in, fs_pow(pdf_in, tp.ep.pdf_exponent)));
+                        if (!emit || tp.lobes) FS_ST4(wb.end_pos + sp_id, make_float4(pos.x, pos.y, pos.z, __uint_as_float(nodes)));
                     }
                     pos = org;
                 }
@@ -1970,6 +1988,8 @@ int resident_ctas(K kernel, int threads, size_t smem)
 {
     int n = 0;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // experiment knob: shared-memory carve-out in percent of the 228 KB (the rest is L1); default = the driver's choice
+    if (const char* e = getenv("FS_TUNE_CARVEOUT")) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) n = 1;
     return n;
 }
