@@ -1,4 +1,6 @@
-"""Small workload that touches every kernel family once, for compute-sanitizer (tools/sanitize.sh): per-bounce pipeline,
+"""Small workload that touches every kernel family once (written for compute-sanitizer, which this GPU pool refuses to run --
+profiles/r2l_sanitizer_unavailable.log; usable as `compute-sanitizer --tool memcheck|racecheck python tools/sanitize_workload.py`
+elsewhere, and run plainly by tests/test_gpu_workload.py): per-bounce pipeline,
 persistent per-batch kernel, all-prefix connections, MIS, material model, shared listener, IR build (single / multi / per band),
 convolver (single / multi), the multi-context reduce, the BVH build (PLOC) on a small furnished room."""
 import os, sys
