@@ -121,6 +121,8 @@ int fs_create(const fs_config* cfg, fs_ctx** out)
     if (const char* e7 = getenv("FS_TUNE_TRI_MIN")) ctx->tune_tri_min = (uint32_t)atoi(e7);
     if (const char* e6 = getenv("FS_TUNE_NODE_MIN")) ctx->tune_node_min = (uint32_t)atoi(e6);
     if (const char* e5 = getenv("FS_TUNE_WIDE")) ctx->tune_wide = (uint32_t)atoi(e5);
+    ctx->tune_w8 = 0;            // 1: 8-wide compressed nodes (experimental: measured 5-10 % slower than the 4-wide nodes, profiles/r2_experiments.md)
+    if (const char* e18 = getenv("FS_TUNE_W8")) ctx->tune_w8 = (uint32_t)atoi(e18);
     if (const char* e4 = getenv("FS_TUNE_BUILDER")) ctx->tune_builder = (uint32_t)atoi(e4);
     if (const char* e3 = getenv("FS_TUNE_TEX")) ctx->tune_tex = (uint32_t)atoi(e3);
     if (const char* e1 = getenv("FS_TUNE_REFILL")) { int v = atoi(e1); if (v >= 1 && v <= 32) ctx->tune_refill = (uint32_t)v; }
@@ -399,12 +401,13 @@ int fs_scene_commit(fs_ctx* ctx)
     }
     uint64_t bvh_launches = 0;
     CK(fs_bvh_build(ctx->stream, ctx->d_verts, ctx->d_tri_mat, ctx->n_tris, &ctx->bvh, &bvh_launches,
-                    ctx->tune_leaf_max, ctx->tune_builder, ctx->tune_collapse));
+                    ctx->tune_leaf_max, ctx->tune_builder, ctx->tune_collapse | (ctx->tune_w8 ? 4u : 0u)));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->launches.fetch_add(bvh_launches);
     ctx->stats.bvh_nodes = ctx->bvh.n_inner;
     if (getenv("FS_VERBOSE")) fprintf(stderr, "[frequensee] BVH: %u triangles, %u BVH2 nodes, %u reachable 4-wide nodes (%.1f MB)\n",
                                       ctx->bvh.n_tris, ctx->bvh.n_inner, ctx->bvh.n_wide, ctx->bvh.n_wide * 64.0 / 1e6);
+    if (getenv("FS_VERBOSE") && ctx->bvh.w8nodes) fprintf(stderr, "[frequensee] BVH: %u 8-wide compressed nodes (%.1f MB)\n", ctx->bvh.n_w8, ctx->bvh.n_w8 * 80.0 / 1e6);
     ctx->stats.bvh_max_leaf = ctx->bvh.max_leaf;
     apply_l2_policy(ctx);
     ctx->committed = true;
@@ -421,6 +424,9 @@ static void fill_params(fs_ctx* ctx, fs_trace_params* tp, const float lis[3], ui
     tp->bv.tris_tex = (ctx->tune_tex && ctx->bvh.tris_tex) ? (unsigned long long)ctx->bvh.tris_tex : 0ull;
     tp->bv.wnodes = ctx->tune_wide ? ctx->bvh.wnodes : nullptr;
     tp->bv.wnodes_tex = (ctx->tune_tex && ctx->bvh.wnodes_tex) ? (unsigned long long)ctx->bvh.wnodes_tex : 0ull;
+    const bool w8 = ctx->tune_w8 && ctx->tune_wide && ctx->bvh.w8nodes;
+    tp->bv.w8nodes = w8 ? ctx->bvh.w8nodes : nullptr; tp->bv.tris8 = w8 ? ctx->bvh.tris8 : nullptr; tp->bv.tri8_map = w8 ? ctx->bvh.tri8_map : nullptr;
+    tp->bv.w8_magic = 0x47000000u;
     for (int a = 0; a < 3; ++a) { tp->bv.qbase[a] = ctx->bvh.qbase[a]; tp->bv.qscale[a] = ctx->bvh.qscale[a]; }
     tp->bv.nodes = ctx->bvh.nodes; tp->bv.tris = ctx->bvh.tris; tp->bv.tri_orig = ctx->bvh.tri_orig;
     tp->bv.tri_mat = ctx->bvh.tri_mat; tp->bv.tri_nm = ctx->bvh.tri_nm; tp->bv.n_tris = ctx->bvh.n_tris; tp->bv.n_inner = ctx->bvh.n_inner;

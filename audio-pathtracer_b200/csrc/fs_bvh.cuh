@@ -27,6 +27,21 @@
 //             empty slot: inverted box (lo = 65535, hi = 0).  Dequantisation is folded into the slab FMA:
 //             t = fma(2^23 + q, s, b'), s = qscale * idir, b' = (qbase - o) * idir - 2^23 s (one PRMT per
 //             plane, chosen by the ray octant so there is no per-axis min/max).
+//   w8nodes : uint4[n_w8][5]     80 B per 8-WIDE compressed node (production traversal format, after Ylitie, Karras,
+//             Laine 2017).  Child boxes are quantised to 8 bits on a grid local to the node: origin p (the node's low
+//             corner, float3), one power-of-two quantum per axis, outward rounding.
+//               u0 = (p.x, p.y, p.z, 2^ex as float bits | imask | lmask << 8)   (masks in the mantissa bits)
+//               u1 = (2^ey, 2^ez, child_base, tri_base)
+//               u2 = (lo.x[0..3], lo.x[4..7], lo.y[0..3], lo.y[4..7])           one byte per child slot
+//               u3 = (lo.z[0..3], lo.z[4..7], hi.x[0..3], hi.x[4..7])
+//               u4 = (hi.y[0..3], hi.y[4..7], hi.z[0..3], hi.z[4..7])
+//             imask / lmask: slots holding an inner node / a leaf (one triangle); empty slot: inverted box (lo 255, hi 0).
+//             Inner child in slot s = node child_base + popc(imask below s); leaf child = triangle tri_base + popc(lmask
+//             below s) of tris8 (the triangle records in W8 order; tri8_map gives the index into tris / tri_nm that hit
+//             records carry).  Children sit in the slots by direction from the node centre, so visiting the hit slots in
+//             the order of (slot XOR ray octant), highest first, is near-to-far without a sort.  Slab test:
+//             t = fma(2^15 + q, A, B), A = 2^e / d, B = (p - o) / d - 2^15 A; the byte goes into bits 8..15 of a float
+//             with exponent 2^15 by one PRMT, so the cancellation error is 2^-9 of a quantum (no spare quantum needed).
 // Boxes are padded at build time so that the slab test (FMA form, not bit-reproducible against
 // the oracle and not required to be) is conservative: any triangle whose exact-arithmetic
 // fs_intersect_tri() succeeds is reached.  The hit itself comes from fs_intersect_tri() only.
@@ -53,6 +68,11 @@ struct fs_bvh_view {
     unsigned long long tris_tex;    // same over `tris`
     unsigned long long wnodes_tex;  // cudaTextureObject_t over `wnodes` (uint4 texels)
     const uint4* wnodes;            // 4-wide quantised nodes (below), indexed like `nodes`
+    const uint4* w8nodes;           // 8-wide compressed nodes, 5 x uint4 each; null = not built / switched off
+    const float4* tris8;            // triangle records in W8 order
+    const uint32_t* tri8_map;       // W8 triangle position -> index into tris / tri_nm
+    uint32_t w8_magic;              // 0x47000000 (2^15 as float bits), kept out of the compiler's sight as a kernel parameter: a literal
+                                    // takes PRMT's only immediate slot and pushes the byte selector into a register (+1 MOV per plane)
     float qbase[3], qscale[3];      // world = qbase + q * qscale, q in [0, 65535]
     const float4* nodes;
     const float4* tris;

@@ -592,6 +592,221 @@ __global__ void k_wide_place(const uint4* __restrict__ src, uint4* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// 8-wide compressed nodes (fs_bvh.cuh: w8nodes) from the finished BVH2.
+//
+// k_emit8 (one thread per BVH2 node): open the inner child with the largest box until there are eight slots (greedy by
+// surface area, as for the 4-wide nodes), quantise the child boxes to 8 bits on a grid LOCAL to the node (origin = the
+// node's low corner, a power-of-two quantum per axis, outward rounding), and place the children in the slots so that
+// slot s holds the child lying farthest in the direction (s&1 ? +x : -x, s&2 ? +y : -y, s&4 ? +z : -z): the traversal
+// then visits the hit children in the order of (slot XOR ray octant), near to far, without sorting by distance
+// (Ylitie, Karras, Laine 2017).  Greedy assignment on cost(c, s) = <centre(c) - centre(node), sigma_s>.
+// k_w8_count / k_w8_place: dense breadth-first relayout of the reachable nodes, as for the 4-wide nodes.  The inner
+// children of a node get CONSECUTIVE node slots in slot order and its leaf children consecutive slots of a triangle
+// array in W8 order (tris8), so a child is addressed by base + popc(mask below its slot): no per-child reference.
+// ---------------------------------------------------------------------------------------------
+#define W8_EMPTY 0x7fffffff
+__device__ __forceinline__ uint32_t q8_lo(float v, float p, float inv)
+{
+    const float q = floorf((v - p) * inv - 0.001953125f);
+    return (uint32_t)fminf(fmaxf(q, 0.0f), 255.0f);
+}
+__device__ __forceinline__ uint32_t q8_hi(float v, float p, float inv)
+{
+    const float q = ceilf((v - p) * inv + 0.001953125f);
+    return (uint32_t)fminf(fmaxf(q, 0.0f), 255.0f);
+}
+// biased exponent eb of the quantum 2^(eb-127) for an axis of extent ext: 254 quanta cover the extent
+__device__ __forceinline__ int q8_exponent(float ext)
+{
+    int k = -60;
+    if (ext > 1e-18f) { (void)frexpf(ext / 254.0f, &k); }      // ext / 254 = m 2^k, m in [0.5, 1): 2^k > ext / 254
+    k = k < -60 ? -60 : (k > 60 ? 60 : k);
+    return k + 127;
+}
+
+// Which BVH2 nodes become 8-wide nodes: minimise the summed surface area of the 8-wide nodes (= the expected number of
+// node steps of a random line) under the eight-slot limit, by dynamic programming over the BVH2 (the optimal collapse of
+// Ylitie et al. 2017, with unit node cost).  T[n][j-1] = least cost of the subtree of n when it may occupy at most j slots
+// of its parent's node: T[n][1] = area(n) + min_a T[l][a] + T[r][8-a] (n is a node of its own), T[n][j] = min(T[n][j-1],
+// min_a T[l][a] + T[r][j-a]) (n is dissolved into the parent); leaves cost nothing.  Bottom-up with one arrival counter
+// per node (as k_refit); k_emit8 then walks the choices down from each node.
+__global__ void k_w8_parents(uint32_t n_inner, const float4* __restrict__ nodes, int* __restrict__ parent, uint32_t* __restrict__ need)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_inner) return;
+    const float4 n3 = nodes[(size_t)i * 4 + 3];
+    const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+    need[i] = (c0 >= 0 ? 1u : 0u) + (c1 >= 0 ? 1u : 0u);
+    if (c0 >= 0) parent[c0] = (int)i;
+    if (c1 >= 0) parent[c1] = (int)i;
+    if (i == 0) parent[0] = -1;
+}
+__device__ __forceinline__ float w8_t(const float* T, int ref, int j) { return ref >= 0 ? __ldcg(T + (size_t)ref * 8 + (j - 1)) : 0.0f; }
+__global__ void k_w8_dp(uint32_t n_inner, const float4* __restrict__ nodes, const int* __restrict__ parent,
+                        const uint32_t* __restrict__ need, uint32_t* __restrict__ arrive, float* T)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_inner || need[i] != 0u) return;
+    int n = (int)i;
+    for (;;) {
+        cbox a, b;
+        load_children(nodes, n, a, b);
+        float ta[8], tb[8], t[8];
+        for (int j = 1; j <= 8; ++j) { ta[j - 1] = w8_t(T, a.ref, j); tb[j - 1] = w8_t(T, b.ref, j); }
+        cbox u;
+        u.lx = fminf(a.lx, b.lx); u.hx = fmaxf(a.hx, b.hx); u.ly = fminf(a.ly, b.ly); u.hy = fmaxf(a.hy, b.hy);
+        u.lz = fminf(a.lz, b.lz); u.hz = fmaxf(a.hz, b.hz);
+        float best = 3.0e38f;
+        for (int x = 1; x <= 7; ++x) best = fminf(best, ta[x - 1] + tb[7 - x]);
+        t[0] = cbox_area(u) + best;
+        for (int j = 2; j <= 8; ++j) {
+            float m = t[j - 2];
+            for (int x = 1; x < j; ++x) m = fminf(m, ta[x - 1] + tb[j - x - 1]);
+            t[j - 1] = m;
+        }
+        for (int j = 0; j < 8; ++j) T[(size_t)n * 8 + j] = t[j];
+        __threadfence();
+        const int p = parent[n];
+        if (p < 0) break;
+        if (atomicAdd(arrive + p, 1u) + 1u < need[p]) break;
+        n = p;
+    }
+}
+
+// T = null: greedy collapse (open the inner child with the largest box until there are eight slots)
+__global__ void k_emit8(uint32_t n_inner, const float4* __restrict__ nodes, const float* __restrict__ T, uint4* __restrict__ w8tmp,
+                        int* __restrict__ w8ref)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_inner) return;
+    cbox c[8];
+    int k = 2;
+    if (T) {
+        cbox st[8]; int sb[8]; int sp = 0;
+        k = 0;
+        {
+            cbox l, r;
+            load_children(nodes, (int)i, l, r);
+            float best = 3.0e38f; int ba = 1;
+            for (int x = 1; x <= 7; ++x) { const float v = w8_t(T, l.ref, x) + w8_t(T, r.ref, 8 - x); if (v < best) { best = v; ba = x; } }
+            st[0] = l; sb[0] = ba; st[1] = r; sb[1] = 8 - ba; sp = 2;
+        }
+        while (sp) {
+            --sp;
+            const cbox m = st[sp]; const int j = sb[sp];
+            if (m.ref < 0 || j == 1) { c[k++] = m; continue; }
+            cbox x, y;
+            load_children(nodes, m.ref, x, y);
+            float best = w8_t(T, m.ref, 1); int ba = 0;                      // stay a node of its own ...
+            for (int q = 1; q < j; ++q) { const float v = w8_t(T, x.ref, q) + w8_t(T, y.ref, j - q); if (v < best) { best = v; ba = q; } }
+            if (!ba) { c[k++] = m; continue; }
+            st[sp] = x; sb[sp] = ba; st[sp + 1] = y; sb[sp + 1] = j - ba; sp += 2;      // ... or dissolve into this one
+        }
+    } else {
+        load_children(nodes, (int)i, c[0], c[1]);
+        while (k < 8) {
+            int pick = -1; float best = -1.0f;
+            for (int j = 0; j < k; ++j)
+                if (c[j].ref >= 0) { const float a = cbox_area(c[j]); if (a > best) { best = a; pick = j; } }
+            if (pick < 0) break;
+            const int r = c[pick].ref;
+            load_children(nodes, r, c[pick], c[k]);
+            ++k;
+        }
+    }
+    float lx = c[0].lx, hx = c[0].hx, ly = c[0].ly, hy = c[0].hy, lz = c[0].lz, hz = c[0].hz;
+    for (int j = 1; j < k; ++j) {
+        lx = fminf(lx, c[j].lx); hx = fmaxf(hx, c[j].hx); ly = fminf(ly, c[j].ly); hy = fmaxf(hy, c[j].hy);
+        lz = fminf(lz, c[j].lz); hz = fmaxf(hz, c[j].hz);
+    }
+    if (!(hx < 1e29f) || !(lx > -1e29f) || !(hy < 1e29f) || !(hz < 1e29f)) {       // single-triangle dummy child: never here (n >= 3)
+        hx = fminf(hx, 1e29f); hy = fminf(hy, 1e29f); hz = fminf(hz, 1e29f);
+    }
+    // slot assignment: greedy on <centre(c) - centre(node), sigma_s>
+    const float mx = 0.5f * (lx + hx), my = 0.5f * (ly + hy), mz = 0.5f * (lz + hz);
+    int slot_of[8], child_in[8];
+    for (int j = 0; j < 8; ++j) { slot_of[j] = -1; child_in[j] = -1; }
+    for (int it = 0; it < k; ++it) {
+        float best = -3.0e38f; int bc = -1, bs = -1;
+        for (int j = 0; j < k; ++j) {
+            if (slot_of[j] >= 0) continue;
+            const float dx = 0.5f * (c[j].lx + c[j].hx) - mx, dy = 0.5f * (c[j].ly + c[j].hy) - my, dz = 0.5f * (c[j].lz + c[j].hz) - mz;
+            for (int s = 0; s < 8; ++s) {
+                if (child_in[s] >= 0) continue;
+                const float cost = ((s & 1) ? dx : -dx) + ((s & 2) ? dy : -dy) + ((s & 4) ? dz : -dz);
+                if (cost > best) { best = cost; bc = j; bs = s; }
+            }
+        }
+        slot_of[bc] = bs; child_in[bs] = bc;
+    }
+    const int ebx = q8_exponent(hx - lx), eby = q8_exponent(hy - ly), ebz = q8_exponent(hz - lz);
+    const float ix = __uint_as_float((uint32_t)(254 - ebx) << 23), iy = __uint_as_float((uint32_t)(254 - eby) << 23),
+                iz = __uint_as_float((uint32_t)(254 - ebz) << 23);            // 2^-(eb-127)
+    uint32_t q[12];                                 // lox[2] loy[2] loz[2] hix[2] hiy[2] hiz[2], one byte per slot
+    for (int w = 0; w < 12; ++w) q[w] = 0u;
+    uint32_t imask = 0, lmask = 0;
+    int refs[8];
+    for (int s = 0; s < 8; ++s) {
+        const int j = child_in[s];
+        uint32_t b[6];
+        if (j < 0) { b[0] = b[1] = b[2] = 255u; b[3] = b[4] = b[5] = 0u; refs[s] = W8_EMPTY; }      // inverted box: never entered
+        else {
+            b[0] = q8_lo(c[j].lx, lx, ix); b[1] = q8_lo(c[j].ly, ly, iy); b[2] = q8_lo(c[j].lz, lz, iz);
+            b[3] = q8_hi(c[j].hx, lx, ix); b[4] = q8_hi(c[j].hy, ly, iy); b[5] = q8_hi(c[j].hz, lz, iz);
+            refs[s] = c[j].ref;
+            if (c[j].ref >= 0) imask |= 1u << s; else lmask |= 1u << s;
+        }
+        for (int a = 0; a < 6; ++a) q[a * 2 + (s >> 2)] |= b[a] << (8 * (s & 3));
+    }
+    uint4* o = w8tmp + (size_t)i * 5;
+    o[0] = make_uint4(__float_as_uint(lx), __float_as_uint(ly), __float_as_uint(lz), ((uint32_t)ebx << 23) | imask | (lmask << 8));
+    o[1] = make_uint4((uint32_t)eby << 23, (uint32_t)ebz << 23, 0u, 0u);
+    o[2] = make_uint4(q[0], q[1], q[2], q[3]);
+    o[3] = make_uint4(q[4], q[5], q[6], q[7]);
+    o[4] = make_uint4(q[8], q[9], q[10], q[11]);
+    for (int s = 0; s < 8; ++s) w8ref[(size_t)i * 8 + s] = refs[s];
+}
+
+__global__ void k_w8_count(const uint4* __restrict__ w8tmp, const int* __restrict__ frontier, uint32_t nf,
+                           uint32_t* __restrict__ cnt_in, uint32_t* __restrict__ cnt_leaf)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nf) return;
+    const uint32_t w = w8tmp[(size_t)frontier[t] * 5].w;
+    cnt_in[t] = (uint32_t)__popc(w & 0xffu);
+    cnt_leaf[t] = (uint32_t)__popc((w >> 8) & 0xffu);
+}
+
+__global__ void k_w8_place(const uint4* __restrict__ w8tmp, const int* __restrict__ w8ref, uint4* __restrict__ dst,
+                           const int* __restrict__ frontier, uint32_t nf, const uint32_t* __restrict__ off_in,
+                           const uint32_t* __restrict__ off_leaf, uint32_t level_base, uint32_t tri_level_base,
+                           int* __restrict__ next_frontier, const float4* __restrict__ tris, float4* __restrict__ tris8,
+                           uint32_t* __restrict__ tri8_map)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nf) return;
+    const int src = frontier[t];
+    const uint4* p = w8tmp + (size_t)src * 5;
+    uint4* q = dst + (size_t)(level_base + t) * 5;
+    uint4 u1 = p[1];
+    uint32_t oi = off_in[t], ol = tri_level_base + off_leaf[t];
+    u1.z = level_base + nf + oi;
+    u1.w = ol;
+    q[0] = p[0]; q[1] = u1; q[2] = p[2]; q[3] = p[3]; q[4] = p[4];
+    for (int s = 0; s < 8; ++s) {
+        const int r = w8ref[(size_t)src * 8 + s];
+        if (r == W8_EMPTY) continue;
+        if (r >= 0) next_frontier[oi++] = r;
+        else {
+            const uint32_t first = (uint32_t)(~r) >> 3;          // single-triangle leaves (PLOC)
+            for (int a = 0; a < 4; ++a) tris8[(size_t)ol * 4 + a] = tris[(size_t)first * 4 + a];
+            tri8_map[ol] = first;
+            ++ol;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Tree rotations (Kensler 2008) on the finished BVH2: for a node N with children L, R, swapping L with a child of
 // R (or R with a child of L) changes only the box of R (or L); take the swap that shrinks it most.  Nodes of one
 // depth own disjoint subtrees, so a whole level is processed in parallel, levels bottom-up (a rotation only changes
@@ -882,6 +1097,67 @@ fail:
     return err;
 }
 
+// 8-wide compressed nodes + the triangle array in their order; single-triangle leaves only (PLOC trees)
+static cudaError_t w8_build(cudaStream_t st, uint32_t n, uint32_t n_inner, const float4* nodes, const float4* tris,
+                            fs_bvh_device* out, uint64_t* launches, bool dp)
+{
+    cudaError_t err = cudaSuccess;
+    float* T = nullptr; int* parent = nullptr; uint32_t *need = nullptr, *arrive = nullptr;
+    uint4 *tmp = nullptr, *dense = nullptr, *fit = nullptr;
+    int *ref = nullptr, *fr[2] = {nullptr, nullptr};
+    uint32_t *cnt_in = nullptr, *cnt_leaf = nullptr, *off_in = nullptr, *off_leaf = nullptr, *tile_sums = nullptr, *total = nullptr;
+    float4* tris8 = nullptr; uint32_t* map = nullptr;
+    const int TPB = 256;
+    uint32_t nf = 1, base = 0, tri_base = 0;
+    int pp = 0;
+    const int zero = 0;
+    BCHECK(cudaMalloc(&tmp, sizeof(uint4) * 5ull * n_inner));
+    BCHECK(cudaMalloc(&ref, 4ull * 8 * n_inner));
+    BCHECK(cudaMalloc(&dense, sizeof(uint4) * 5ull * n_inner));
+    BCHECK(cudaMalloc(&fr[0], 4ull * n_inner)); BCHECK(cudaMalloc(&fr[1], 4ull * n_inner));
+    BCHECK(cudaMalloc(&cnt_in, 4ull * n_inner)); BCHECK(cudaMalloc(&cnt_leaf, 4ull * n_inner));
+    BCHECK(cudaMalloc(&off_in, 4ull * n_inner)); BCHECK(cudaMalloc(&off_leaf, 4ull * n_inner));
+    BCHECK(cudaMalloc(&tile_sums, 4ull * ((n_inner + SCAN_TILE - 1) / SCAN_TILE + 2)));
+    BCHECK(cudaMalloc(&total, 8));
+    BCHECK(cudaMalloc(&tris8, sizeof(float4) * 4ull * n));
+    BCHECK(cudaMalloc(&map, 4ull * n));
+    if (dp) {
+        BCHECK(cudaMalloc(&T, sizeof(float) * 8ull * n_inner));
+        BCHECK(cudaMalloc(&parent, 4ull * n_inner)); BCHECK(cudaMalloc(&need, 4ull * n_inner)); BCHECK(cudaMalloc(&arrive, 4ull * n_inner));
+        BCHECK(cudaMemsetAsync(arrive, 0, 4ull * n_inner, st));
+        k_w8_parents<<<(n_inner + TPB - 1) / TPB, TPB, 0, st>>>(n_inner, nodes, parent, need);
+        k_w8_dp<<<(n_inner + TPB - 1) / TPB, TPB, 0, st>>>(n_inner, nodes, parent, need, arrive, T);
+        *launches += 2;
+    }
+    k_emit8<<<(n_inner + TPB - 1) / TPB, TPB, 0, st>>>(n_inner, nodes, T, tmp, ref); ++*launches;
+    BCHECK(cudaMemcpyAsync(fr[0], &zero, 4, cudaMemcpyHostToDevice, st));
+    while (nf) {
+        const uint32_t g = (nf + TPB - 1) / TPB;
+        uint32_t next[2] = {0, 0};
+        k_w8_count<<<g, TPB, 0, st>>>(tmp, fr[pp], nf, cnt_in, cnt_leaf); ++*launches;
+        scan_u32(st, cnt_in, off_in, nf, tile_sums, total, launches);
+        scan_u32(st, cnt_leaf, off_leaf, nf, tile_sums, total + 1, launches);
+        k_w8_place<<<g, TPB, 0, st>>>(tmp, ref, dense, fr[pp], nf, off_in, off_leaf, base, tri_base, fr[pp ^ 1], tris, tris8, map);
+        ++*launches;
+        BCHECK(cudaMemcpyAsync(next, total, 8, cudaMemcpyDeviceToHost, st));
+        BCHECK(cudaStreamSynchronize(st));
+        base += nf; nf = next[0]; tri_base += next[1]; pp ^= 1;
+        if ((uint64_t)base + nf > n_inner || tri_base > n) { err = cudaErrorUnknown; goto fail; }     // cannot happen for a tree
+    }
+    BCHECK(cudaGetLastError());
+    if (tri_base != n) { err = cudaErrorUnknown; goto fail; }
+    BCHECK(cudaMalloc(&fit, sizeof(uint4) * 5ull * base));                  // right-sized copy (the bound was one node per BVH2 node)
+    BCHECK(cudaMemcpyAsync(fit, dense, sizeof(uint4) * 5ull * base, cudaMemcpyDeviceToDevice, st));
+    BCHECK(cudaStreamSynchronize(st));
+    out->w8nodes = fit; fit = nullptr; out->n_w8 = base;
+    out->tris8 = tris8; tris8 = nullptr; out->tri8_map = map; map = nullptr;
+fail:
+    cudaFree(T); cudaFree(parent); cudaFree(need); cudaFree(arrive);
+    cudaFree(tmp); cudaFree(ref); cudaFree(dense); cudaFree(fit); cudaFree(fr[0]); cudaFree(fr[1]); cudaFree(cnt_in); cudaFree(cnt_leaf);
+    cudaFree(off_in); cudaFree(off_leaf); cudaFree(tile_sums); cudaFree(total); cudaFree(tris8); cudaFree(map);
+    return err;
+}
+
 cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* d_mats, uint64_t T64,
                          fs_bvh_device* out, uint64_t* launches, uint32_t leaf_max_u, uint32_t builder, uint32_t collapse_u)
 {
@@ -1032,6 +1308,8 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
     }
     k_top_treelet<<<1, 32, 0, st>>>(out->nodes, n_inner, FS_TOP_CAP, out->top_nodes, misc + 7, queue); ++*launches;
     BCHECK(cudaGetLastError());
+    // 8-wide compressed nodes (FS_TUNE_W8=1 -> collapse bit 2): optional traversal format, see profiles/r2_experiments.md
+    if (builder == 1 && n >= 3 && out->max_leaf == 1 && (collapse & 4)) BCHECK(w8_build(st, n, n_inner, out->nodes, out->tris, out, launches, !(collapse & 8)));   // bit 3: greedy instead of the optimal collapse
     {
         uint32_t h[16];   // misc[0..15]
         BCHECK(cudaMemcpyAsync(h, misc, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -1056,6 +1334,7 @@ void fs_bvh_free(fs_bvh_device* b)
     if (b->nodes_tex) cudaDestroyTextureObject(b->nodes_tex);
     if (b->tris_tex) cudaDestroyTextureObject(b->tris_tex);
     if (b->wnodes_tex) cudaDestroyTextureObject(b->wnodes_tex);
+    cudaFree(b->w8nodes); cudaFree(b->tris8); cudaFree(b->tri8_map);
     cudaFree(b->nodes); cudaFree(b->wnodes); cudaFree(b->tris); cudaFree(b->tri_orig); cudaFree(b->tri_mat); cudaFree(b->tri_nm); cudaFree(b->top_nodes);
     memset(b, 0, sizeof(*b));
 }

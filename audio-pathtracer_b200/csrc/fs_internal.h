@@ -27,12 +27,17 @@ struct fs_bvh_device {
     float qbase[3], qscale[3];
     uint32_t n_tris, n_inner, n_top, max_leaf;
     uint32_t n_wide;             // wide nodes reachable from the root (dense breadth-first array)
+    uint4* w8nodes;              // 8-wide compressed nodes (80 B each), dense breadth-first; null if not built
+    float4* tris8;               // triangle records in the order the 8-wide nodes address them
+    uint32_t* tri8_map;          // position in tris8 -> position in tris (the index hit records carry)
+    uint32_t n_w8;
     float extent;
 };
 
 cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* d_mats, uint64_t n_tris,
                          fs_bvh_device* out, uint64_t* launches, uint32_t leaf_max, uint32_t builder /*0 LBVH, 1 PLOC*/,
-                         uint32_t collapse /*wide nodes: bit 0 greedy by surface area (else grandchildren), bit 1 keep the sparse layout*/);
+                         uint32_t collapse /*wide nodes: bit 0 greedy by surface area (else grandchildren), bit 1 keep the sparse layout,
+                                                    bit 2 also build the 8-wide compressed nodes, bit 3 greedy instead of optimal 8-wide collapse*/);
 void fs_bvh_free(fs_bvh_device* b);
 
 // device-side counters of one trace call
@@ -148,7 +153,7 @@ struct fs_ctx {
     std::vector<cudaEvent_t> tev; size_t tev_used;   //   + one (begin, end) pair per k_trace_closest launch
     int sm_count;
     int occ[16];                         // resident CTAs per SM of the persistent kernels (per context = per device)
-    uint32_t tune_refill, tune_leaf_max, tune_tex, tune_builder, tune_wide, tune_node_min, tune_tri_min, tune_collapse, tune_l2pin_mb, tune_tq, tune_tq_node_min, tune_tq_flush, tune_mega, tune_mega_from, tune_mega_lanes, cur_lanes;      // experiment knobs (env FS_TUNE_REFILL / FS_TUNE_LEAF_MAX)
+    uint32_t tune_refill, tune_leaf_max, tune_tex, tune_builder, tune_wide, tune_node_min, tune_tri_min, tune_collapse, tune_l2pin_mb, tune_tq, tune_tq_node_min, tune_tq_flush, tune_mega, tune_mega_from, tune_mega_lanes, cur_lanes, tune_w8;      // experiment knobs (env FS_TUNE_REFILL / FS_TUNE_LEAF_MAX)
     // IR / conv
     float* d_energy;            // [K] scratch
     float* d_amp;               // [K]

@@ -758,6 +758,7 @@ struct tr_state {
     float idx, idy, idz, oodx, oody, oodz;
     int node, leaf, sp;
     uint32_t tc, te;
+    uint32_t oct;        // 8-wide nodes: bit a set = direction component a is >= 0 (near plane = low plane)
 };
 
 __device__ __forceinline__ float fs_rcp_fast(float x)
@@ -1093,6 +1094,94 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
     if (COUNT) flush_counters(dc, vc);
 }
 
+
+// =============================================================================================
+// 8-wide compressed nodes (fs_bvh.cuh: w8nodes).  One step = one 80 B node: eight child boxes against the ray
+// (near / far byte planes picked per axis by the ray octant, one PRMT + one FMA per plane), a hit mask instead of
+// entry distances, no sorting network: the children sit in their slots by direction, the hit slots are visited in the
+// order of (slot XOR octant).  The stack holds GROUPS -- (first child node, hits << 8 | inner mask), at most one entry per
+// tree level -- so a step pushes one 8-byte entry instead of up to three, and an 8-wide tree is half as deep.
+// =============================================================================================
+#ifndef FS_W8_SSTACK
+#define FS_W8_SSTACK 6                 // group-stack entries per thread in shared memory (8 B each); deeper ones in local memory
+#endif
+#define FS_W8_STACK_SIZE 40
+struct w8_stack {
+    uint2* sh;        // &smem[threadIdx.x], stride TR_THREADS
+    uint2* loc;
+    __device__ __forceinline__ void put(int i, uint2 e) const { if (i < FS_W8_SSTACK) sh[i * TR_THREADS] = e; else loc[i - FS_W8_SSTACK] = e; }
+    __device__ __forceinline__ uint2 get(int i) const { return (i < FS_W8_SSTACK) ? sh[i * TR_THREADS] : loc[i - FS_W8_SSTACK]; }
+};
+
+__device__ __forceinline__ void tr_init8(tr_state& s, const fs_bvh_view& bv, fs_vec3 o, fs_vec3 d)
+{
+    s.o = o; s.d = d;
+    const float dx = (fabsf(d.x) > 1e-30f) ? d.x : ((d.x < 0.0f) ? -1e-30f : 1e-30f);
+    const float dy = (fabsf(d.y) > 1e-30f) ? d.y : ((d.y < 0.0f) ? -1e-30f : 1e-30f);
+    const float dz = (fabsf(d.z) > 1e-30f) ? d.z : ((d.z < 0.0f) ? -1e-30f : 1e-30f);
+    s.idx = fs_rcp_fast(dx); s.idy = fs_rcp_fast(dy); s.idz = fs_rcp_fast(dz);     // conservative boxes: 1 ulp is inside the padding
+    s.oodx = s.oody = s.oodz = 0.0f;
+    s.oct = ((~__float_as_uint(s.idx)) >> 31) | (((~__float_as_uint(s.idy)) >> 31) << 1) | (((~__float_as_uint(s.idz)) >> 31) << 2);
+    s.node = bv.n_tris ? 0 : TR_SENT; s.leaf = 0; s.sp = 0; s.tc = 0; s.te = 0;
+}
+
+// 2^15 + (byte B of w) as a float: the byte goes to bits 8..15 of 0x47000000
+#define FS_Q8(w, B) __uint_as_float(__byte_perm((w), magic, 0x7504u | ((B) << 4)))
+
+// One step of lane state `s` through its node.  Returns the leaf slots the ray enters (hleaf, with the node's leaf mask
+// and first triangle: triangle of slot b = tri_base + popc(lmask below b)) and moves s.node on to the next inner node
+// (nearest hit child, else the next one of the newest group on the stack, else TR_SENT).
+__device__ __forceinline__ void w8_step(const fs_bvh_view& bv, tr_state& s, const w8_stack& stack, const float tlimit,
+                                        uint32_t& hleaf, uint32_t& lmask, uint32_t& tri_base, uint32_t* overflow)
+{
+    const uint32_t magic = bv.w8_magic;
+    const uint4* p = bv.w8nodes + (size_t)s.node * 5;
+    const uint4 u0 = ldg_u4(p), u1 = ldg_u4(p + 1), u2 = ldg_u4(p + 2), u3 = ldg_u4(p + 3), u4 = ldg_u4(p + 4);
+    const float ax = __uint_as_float(u0.w & 0x7f800000u) * s.idx, ay = __uint_as_float(u1.x) * s.idy, az = __uint_as_float(u1.y) * s.idz;
+    const float bx = fmaf(-32768.0f, ax, (__uint_as_float(u0.x) - s.o.x) * s.idx);
+    const float by = fmaf(-32768.0f, ay, (__uint_as_float(u0.y) - s.o.y) * s.idy);
+    const float bz = fmaf(-32768.0f, az, (__uint_as_float(u0.z) - s.o.z) * s.idz);
+    const bool px = (s.oct & 1u) != 0u, py = (s.oct & 2u) != 0u, pz = (s.oct & 4u) != 0u;
+    const uint32_t nx0 = px ? u2.x : u3.z, nx1 = px ? u2.y : u3.w, fx0 = px ? u3.z : u2.x, fx1 = px ? u3.w : u2.y;
+    const uint32_t ny0 = py ? u2.z : u4.x, ny1 = py ? u2.w : u4.y, fy0 = py ? u4.x : u2.z, fy1 = py ? u4.y : u2.w;
+    const uint32_t nz0 = pz ? u3.x : u4.z, nz1 = pz ? u3.y : u4.w, fz0 = pz ? u4.z : u3.x, fz1 = pz ? u4.w : u3.y;
+    uint32_t H = 0u;
+#define FS_W8_CHILD(J, W, B)                                                                                          \
+    {                                                                                                                 \
+        const float tn = fmaxf(fmaxf(fmaf(FS_Q8(nx##W, B), ax, bx), fmaf(FS_Q8(ny##W, B), ay, by)),                   \
+                               fmaxf(fmaf(FS_Q8(nz##W, B), az, bz), 0.0f));                                           \
+        const float tf = fminf(fminf(fmaf(FS_Q8(fx##W, B), ax, bx), fmaf(FS_Q8(fy##W, B), ay, by)),                   \
+                               fminf(fmaf(FS_Q8(fz##W, B), az, bz), tlimit));                                         \
+        if (tn <= tf) H |= 1u << (J);                                                                                 \
+    }
+    FS_W8_CHILD(0, 0, 0u) FS_W8_CHILD(1, 0, 1u) FS_W8_CHILD(2, 0, 2u) FS_W8_CHILD(3, 0, 3u)
+    FS_W8_CHILD(4, 1, 0u) FS_W8_CHILD(5, 1, 1u) FS_W8_CHILD(6, 1, 2u) FS_W8_CHILD(7, 1, 3u)
+#undef FS_W8_CHILD
+    const uint32_t imask = u0.w & 0xffu;
+    lmask = (u0.w >> 8) & 0xffu;
+    hleaf = H & lmask;
+    tri_base = u1.w;
+    // inner hits, moved to traversal positions: position = slot XOR octant, highest first
+    uint32_t P = H & imask;
+    if (s.oct & 4u) P = ((P & 0x0fu) << 4) | (P >> 4);
+    if (s.oct & 2u) P = ((P & 0x33u) << 2) | ((P >> 2) & 0x33u);
+    if (s.oct & 1u) P = ((P & 0x55u) << 1) | ((P >> 1) & 0x55u);
+    uint32_t gb = u1.z, gm = (P << 8) | imask;
+    if (P == 0u) {                                   // nothing entered here: next child of the newest group on the stack
+        if (s.sp == 0) { s.node = TR_SENT; return; }
+        --s.sp;
+        const uint2 e = stack.get(s.sp);
+        gb = e.x; gm = e.y;
+    }
+    const uint32_t pbit = 31u - (uint32_t)__clz((int)gm);       // in 8..15
+    gm ^= 1u << pbit;
+    const uint32_t slot = (pbit - 8u) ^ s.oct;
+    s.node = (int)(gb + (uint32_t)__popc(gm & ((1u << slot) - 1u)));        // slot <= 7: the mask only covers the inner-mask bits
+    if (gm >> 8) {
+        if (s.sp < FS_W8_STACK_SIZE) { stack.put(s.sp, make_uint2(gb, gm)); ++s.sp; } else *overflow = 1u;
+    }
+}
+
 // =============================================================================================
 // k_trace_q: traversal with a WARP-SHARED TRIANGLE QUEUE (closest hit of extension rays; any hit of connection rays).
 //
@@ -1134,7 +1223,12 @@ k_trace_closest(const fs_bvh_view bv, const float4* __restrict__ ray_o, const fl
 // ANY = true : connection rays (F.xyz, tmax) (dir.xyz, path id): any triangle closer than tmax occludes; the paths that
 //              stay visible are appended to conn_queue.  Same node phase and queue; the "best key" of a lane degenerates
 //              to an occluded flag (any store wins), and bt is the constant tmax.
-template <bool COUNT, int TEX, bool ANY>
+// at most FLUSH_MIN - 1 (<= 31) entries wait when a node-phase iteration starts; an 8-wide step adds at most 8 x 32
+#define FS_TQ8_CAP 288
+#define TR_SMEM_TQ8 (FS_W8_SSTACK * TR_THREADS * sizeof(uint2) + TR_THREADS * sizeof(unsigned long long) + \
+                     TQ_WARPS * FS_TQ8_CAP * sizeof(uint32_t) + TQ_WARPS * sizeof(uint32_t) + TR_THREADS * sizeof(uint32_t))
+// W8 = true: 8-wide compressed nodes (w8_step), group stack, triangles in W8 order; false: 4-wide nodes (wide_children)
+template <bool COUNT, int TEX, bool ANY, bool W8>
 __global__ void __launch_bounds__(TR_THREADS, FS_TR_MINBLOCKS)
 k_trace_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
           const uint32_t* __restrict__ count_ptr, uint32_t* __restrict__ cursor,
@@ -1143,21 +1237,27 @@ k_trace_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* 
           const uint32_t NODE_MIN, const uint32_t FLUSH_MIN)
 {
     constexpr bool DRAIN_SPLIT = FS_DRAIN_SPLIT != 0;
+    constexpr uint32_t QCAP = W8 ? FS_TQ8_CAP : FS_TQ_CAP;
+    constexpr int SST = W8 ? FS_W8_SSTACK : FS_SSTACK;         // stack entries per thread in shared memory
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t count = *count_ptr;
     extern __shared__ __align__(8) unsigned char smem_raw[];
     int* const sstack = reinterpret_cast<int*>(smem_raw);
-    unsigned long long* const skey = reinterpret_cast<unsigned long long*>(sstack + FS_SSTACK * TR_THREADS);
-    uint32_t* const squeue = reinterpret_cast<uint32_t*>(skey + TR_THREADS) + warp * FS_TQ_CAP;
-    uint32_t* const sqcount = reinterpret_cast<uint32_t*>(skey + TR_THREADS) + TQ_WARPS * FS_TQ_CAP + warp;
+    uint2* const gstack = reinterpret_cast<uint2*>(smem_raw);
+    unsigned long long* const skey = reinterpret_cast<unsigned long long*>(smem_raw + (W8 ? FS_W8_SSTACK * sizeof(uint2) : FS_SSTACK * sizeof(int)) * TR_THREADS);
+    uint32_t* const squeue = reinterpret_cast<uint32_t*>(skey + TR_THREADS) + warp * QCAP;
+    uint32_t* const sqcount = reinterpret_cast<uint32_t*>(skey + TR_THREADS) + TQ_WARPS * QCAP + warp;
     // helpers working for each lane's ray (drain splitting, below)
-    uint32_t* const whelp = reinterpret_cast<uint32_t*>(skey + TR_THREADS) + TQ_WARPS * FS_TQ_CAP + TQ_WARPS + (threadIdx.x & ~31u);
+    uint32_t* const whelp = reinterpret_cast<uint32_t*>(skey + TR_THREADS) + TQ_WARPS * QCAP + TQ_WARPS + (threadIdx.x & ~31u);
     unsigned long long* const mykey = skey + threadIdx.x;
     unsigned long long* const wkey = skey + (threadIdx.x & ~31u);
-    int lstack[FS_STACK_SIZE - FS_SSTACK];
+    int lstack[W8 ? 1 : FS_STACK_SIZE - FS_SSTACK];
+    uint2 lstack8[W8 ? FS_W8_STACK_SIZE - FS_W8_SSTACK : 1];
     tr_stack<false> stack; stack.sh = sstack + threadIdx.x; stack.loc = lstack;
+    w8_stack stack8; stack8.sh = gstack + threadIdx.x; stack8.loc = lstack8;
+    const float4* const tris = W8 ? bv.tris8 : bv.tris;
     const unsigned long long KEY_NONE = ((unsigned long long)0x7f800000u << 32) | 0xffffffffull;
-    for (uint32_t i = lane; i < (uint32_t)FS_TQ_CAP; i += 32) squeue[i] = TQ_INVALID;
+    for (uint32_t i = lane; i < QCAP; i += 32) squeue[i] = TQ_INVALID;
     if (lane == 0) *sqcount = 0u;
     *mykey = KEY_NONE;
     whelp[lane] = 0u;
@@ -1186,7 +1286,8 @@ k_trace_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* 
                 const uint32_t jj = base + (uint32_t)__popc(m_idle & ((1u << lane) - 1u));
                 if (jj < count) {
                     const float4 a = FS_LD4(ray_o + jj), b = FS_LD4(ray_d + jj);
-                    tr_init<true>(s, bv, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z));
+                    if (W8) tr_init8(s, bv, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z));
+                    else tr_init<true>(s, bv, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z));
                     bt = ANY ? a.w : __int_as_float(0x7f800000); *mykey = KEY_NONE;
                     j = ANY ? __float_as_uint(b.w) : jj; running = true;
                     if (COUNT) ray_steps = 0;
@@ -1204,41 +1305,56 @@ k_trace_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* 
                 uint32_t nl = 0;
                 if (can) {
                     if (COUNT) { vc.nodes++; ray_steps++; }
-                    const float INF = __int_as_float(0x7f800000);
-                    float k0, k1, k2, k3; int v0, v1, v2, v3;
-                    wide_children<2, TEX>(bv, s, bt, k0, k1, k2, k3, v0, v1, v2, v3);
-                    // every leaf child the ray enters goes to the queue right away (single-triangle leaves), so the
-                    // stack only ever holds inner nodes and the step is straight-line code.
-                    // leaf code v = ~(first << 3): entry = first << 5 | lane = -4 v + (lane - 4)
-                    const bool l0 = k0 != INF && v0 < 0, l1 = k1 != INF && v1 < 0, l2 = k2 != INF && v2 < 0, l3 = k3 != INF && v3 < 0;
-                    nl = (uint32_t)l0 + (uint32_t)l1 + (uint32_t)l2 + (uint32_t)l3;
-                    if (nl) {
-                        uint32_t* q = squeue + atomicAdd(sqcount, nl);
-                        const uint32_t lm4 = owner - 4u;
+                    if (W8) {
+                        uint32_t hleaf, lmask, tri_base;
+                        w8_step(bv, s, stack8, bt, hleaf, lmask, tri_base, ovf_p);
+                        nl = (uint32_t)__popc(hleaf);
+                        if (nl) {                     // entry = triangle << 5 | owner lane; triangle of slot b = tri_base + leaves below b
+                            uint32_t* q = squeue + atomicAdd(sqcount, nl);
+                            const uint32_t e0 = (tri_base << 5) | owner;
+                            do {
+                                const uint32_t bit = hleaf & (0u - hleaf);
+                                *q++ = e0 + ((uint32_t)__popc(lmask & (bit - 1u)) << 5);
+                                hleaf ^= bit;
+                            } while (hleaf);
+                        }
+                    } else {
+                        const float INF = __int_as_float(0x7f800000);
+                        float k0, k1, k2, k3; int v0, v1, v2, v3;
+                        wide_children<2, TEX>(bv, s, bt, k0, k1, k2, k3, v0, v1, v2, v3);
+                        // every leaf child the ray enters goes to the queue right away (single-triangle leaves), so the
+                        // stack only ever holds inner nodes and the step is straight-line code.
+                        // leaf code v = ~(first << 3): entry = first << 5 | lane = -4 v + (lane - 4)
+                        const bool l0 = k0 != INF && v0 < 0, l1 = k1 != INF && v1 < 0, l2 = k2 != INF && v2 < 0, l3 = k3 != INF && v3 < 0;
+                        nl = (uint32_t)l0 + (uint32_t)l1 + (uint32_t)l2 + (uint32_t)l3;
+                        if (nl) {
+                            uint32_t* q = squeue + atomicAdd(sqcount, nl);
+                            const uint32_t lm4 = owner - 4u;
 #if FS_PREFETCH_TRIS
 #define FS_PF_TRI(v) asm volatile("prefetch.global.L2 [%0];" :: "l"(bv.tris + (size_t)((uint32_t)(~(v)) >> 3) * 4))
 #else
 #define FS_PF_TRI(v)
 #endif
-                        if (l0) { *q = (uint32_t)v0 * 0xfffffffcu + lm4; FS_PF_TRI(v0); }
-                        q += l0;
-                        if (l1) { *q = (uint32_t)v1 * 0xfffffffcu + lm4; FS_PF_TRI(v1); }
-                        q += l1;
-                        if (l2) { *q = (uint32_t)v2 * 0xfffffffcu + lm4; FS_PF_TRI(v2); }
-                        q += l2;
-                        if (l3) { *q = (uint32_t)v3 * 0xfffffffcu + lm4; FS_PF_TRI(v3); }
+                            if (l0) { *q = (uint32_t)v0 * 0xfffffffcu + lm4; FS_PF_TRI(v0); }
+                            q += l0;
+                            if (l1) { *q = (uint32_t)v1 * 0xfffffffcu + lm4; FS_PF_TRI(v1); }
+                            q += l1;
+                            if (l2) { *q = (uint32_t)v2 * 0xfffffffcu + lm4; FS_PF_TRI(v2); }
+                            q += l2;
+                            if (l3) { *q = (uint32_t)v3 * 0xfffffffcu + lm4; FS_PF_TRI(v3); }
 #undef FS_PF_TRI
-                    }
-                    k0 = l0 ? INF : k0; k1 = l1 ? INF : k1; k2 = l2 ? INF : k2; k3 = l3 ? INF : k3;
-                    FS_CSWAP(k0, v0, k1, v1) FS_CSWAP(k2, v2, k3, v3) FS_CSWAP(k0, v0, k2, v2) FS_CSWAP(k1, v1, k3, v3) FS_CSWAP(k1, v1, k2, v2)
-                    if (k1 != INF) {
-                        stack.push3(s.sp, k2 != INF, k3 != INF, v1, k1, v2, k2, v3, k3, ovf_p);
+                        }
+                        k0 = l0 ? INF : k0; k1 = l1 ? INF : k1; k2 = l2 ? INF : k2; k3 = l3 ? INF : k3;
+                        FS_CSWAP(k0, v0, k1, v1) FS_CSWAP(k2, v2, k3, v3) FS_CSWAP(k0, v0, k2, v2) FS_CSWAP(k1, v1, k3, v3) FS_CSWAP(k1, v1, k2, v2)
+                        if (k1 != INF) {
+                            stack.push3(s.sp, k2 != INF, k3 != INF, v1, k1, v2, k2, v3, k3, ovf_p);
 #if FS_PREFETCH_PUSHED
-                        // the nearest pushed sibling is the next node this lane pops: pull its 64 B towards the SM now
-                        asm volatile("prefetch.global.L2 [%0];" :: "l"(bv.wnodes + (size_t)v1 * 4));
+                            // the nearest pushed sibling is the next node this lane pops: pull its 64 B towards the SM now
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(bv.wnodes + (size_t)v1 * 4));
 #endif
+                        }
+                        s.node = (k0 != INF) ? v0 : stack.pop(s.sp, 0.f);
                     }
-                    s.node = (k0 != INF) ? v0 : stack.pop(s.sp, 0.f);
                 }
                 qn += __reduce_add_sync(FULLM, nl);         // the queue length, tracked in a (uniform) register
             }
@@ -1254,7 +1370,7 @@ k_trace_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* 
                 const float bto = __shfl_sync(FULLM, bt, eo);
                 if (e != TQ_INVALID) {
                     const uint32_t tri = e >> 5;
-                    const float4* tq = bv.tris + (size_t)tri * 4;
+                    const float4* tq = tris + (size_t)tri * 4;
 #if FS_TRI_TEX
                     // one of the three triangle quarters through the texture data pipe (as for the nodes)
                     const bool ttex = TEX >= 2 && bv.tris_tex;
@@ -1281,7 +1397,7 @@ k_trace_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* 
                             if (t == told) {
                                 const uint32_t otri = (uint32_t)old;
                                 better = otri == 0xffffffffu ||
-                                         __float_as_uint(fs_ldg4(tq + 3).x) < __float_as_uint(fs_ldg4(bv.tris + (size_t)otri * 4 + 3).x);
+                                         __float_as_uint(fs_ldg4(tq + 3).x) < __float_as_uint(fs_ldg4(tris + (size_t)otri * 4 + 3).x);
                             }
                             if (!better) break;
                             const unsigned long long prev = atomicCAS(wkey + eo, old, mine);
@@ -1318,7 +1434,9 @@ k_trace_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* 
                 }
                 if (retire) running = false;
             } else if (retire) {
-                FS_ST2(hits + j, make_float2(bt, __int_as_float((int)(uint32_t)kk)));
+                uint32_t ht = (uint32_t)kk;                      // 8-wide nodes: position in tris8 -> the index hit records carry
+                if (W8 && ht != 0xffffffffu) ht = bv.tri8_map[ht];
+                FS_ST2(hits + j, make_float2(bt, __int_as_float((int)ht)));
                 running = false;
                 if (COUNT) { atomicMax(&dc->max_steps, ray_steps); atomicAdd(&dc->steps_hist[ray_steps / 8u < 15u ? ray_steps / 8u : 15u], 1u); }
             }
@@ -1328,7 +1446,7 @@ k_trace_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* 
             // of a busy lane's stack and walks it as a helper of the same ray.  The result is the same set of candidates.
             if (DRAIN_SPLIT && exhausted) {
                 const uint32_t m_free = __ballot_sync(FULLM, !running);
-                const bool give = running && s.node != TR_SENT && s.sp >= 1 && s.sp <= FS_SSTACK;
+                const bool give = running && s.node != TR_SENT && s.sp >= 1 && s.sp <= SST;
                 const uint32_t m_give = __ballot_sync(FULLM, give);
                 const uint32_t nf = (uint32_t)__popc(m_free), ng = (uint32_t)__popc(m_give);
                 const uint32_t n = nf < ng ? nf : ng;
@@ -1346,12 +1464,28 @@ k_trace_q(const fs_bvh_view bv, const float4* __restrict__ ray_o, const float4* 
                     const uint32_t down = __shfl_sync(FULLM, owner, donor);
                     if (take) {
                         const int h = (dsp + 1) >> 1;
-                        const int* src = sstack + (threadIdx.x & ~31u) + donor;
-                        for (int i = 0; i < h; ++i) stack.sh[i * TR_THREADS] = src[(dsp - h + i) * TR_THREADS];
                         s.o = fs_mk(ox, oy, oz); s.d = fs_mk(dx, dy, dz);
                         s.idx = ix; s.idy = iy; s.idz = iz; s.oodx = px; s.oody = py; s.oodz = pz;
-                        s.sp = h; bt = dbt; owner = down;
-                        s.node = stack.pop(s.sp, 0.f);
+                        bt = dbt; owner = down;
+                        if (W8) {
+                            const uint2* src = gstack + (threadIdx.x & ~31u) + donor;
+                            for (int i = 0; i < h; ++i) stack8.sh[i * TR_THREADS] = src[(dsp - h + i) * TR_THREADS];
+                            s.oct = ((~__float_as_uint(ix)) >> 31) | (((~__float_as_uint(iy)) >> 31) << 1) | (((~__float_as_uint(iz)) >> 31) << 2);
+                            // next child of the newest group taken over (as the pop of w8_step)
+                            s.sp = h - 1;
+                            const uint2 e = stack8.sh[s.sp * TR_THREADS];
+                            uint32_t gm = e.y;
+                            const uint32_t pbit = 31u - (uint32_t)__clz((int)gm);
+                            gm ^= 1u << pbit;
+                            const uint32_t slot = (pbit - 8u) ^ s.oct;
+                            s.node = (int)(e.x + (uint32_t)__popc(gm & ((1u << slot) - 1u)));
+                            if (gm >> 8) { stack8.sh[s.sp * TR_THREADS] = make_uint2(e.x, gm); ++s.sp; }
+                        } else {
+                            const int* src = sstack + (threadIdx.x & ~31u) + donor;
+                            for (int i = 0; i < h; ++i) stack.sh[i * TR_THREADS] = src[(dsp - h + i) * TR_THREADS];
+                            s.sp = h;
+                            s.node = stack.pop(s.sp, 0.f);
+                        }
                         running = true;
                         atomicAdd(whelp + down, 1u);
                     }
@@ -1393,6 +1527,7 @@ struct pq_globals { uint32_t tail, head, done, error; };
                  TQ_WARPS * FS_TQ_CAP * sizeof(uint32_t) + TQ_WARPS * sizeof(uint32_t) + \
                  TQ_WARPS * PQ_SQ_CAP * 3 * sizeof(uint32_t))
 
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 __device__ __forceinline__ float4 ld_cg_f4(const float4* p)
 {
@@ -1429,27 +1564,35 @@ __global__ void k_pq_finish(const fs_wave_buffers wb, const pq_globals* __restri
 #ifndef FS_PQ_MINBLOCKS
 #define FS_PQ_MINBLOCKS 4      // 62 registers, 32 warps/SM (3: 72 registers is slower, 5: spills and no L1 left)
 #endif
-template <int TEX>
+#define PQ_SMEM8 (FS_W8_SSTACK * TR_THREADS * sizeof(uint2) + TR_THREADS * sizeof(unsigned long long) + \
+                  TQ_WARPS * FS_TQ8_CAP * sizeof(uint32_t) + TQ_WARPS * sizeof(uint32_t) + \
+                  TQ_WARPS * PQ_SQ_CAP * 3 * sizeof(uint32_t))
+template <int TEX, bool W8>
 __global__ void __launch_bounds__(TR_THREADS, FS_PQ_MINBLOCKS)
 k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict__ log_o, float4* __restrict__ log_d,
          uint32_t* __restrict__ log_flag, const uint32_t epoch, const uint32_t log_cap, pq_globals* __restrict__ g,
          const uint32_t REFILL_MIN, const uint32_t NODE_MIN, const uint32_t FLUSH_MIN)
 {
     const fs_bvh_view& bv = tp.bv;
+    constexpr uint32_t QCAP = W8 ? FS_TQ8_CAP : FS_TQ_CAP;
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     extern __shared__ __align__(8) unsigned char smem_raw[];
     int* const sstack = reinterpret_cast<int*>(smem_raw);
-    unsigned long long* const skey = reinterpret_cast<unsigned long long*>(sstack + FS_SSTACK * TR_THREADS);
+    uint2* const gstack = reinterpret_cast<uint2*>(smem_raw);
+    unsigned long long* const skey = reinterpret_cast<unsigned long long*>(smem_raw + (W8 ? FS_W8_SSTACK * sizeof(uint2) : FS_SSTACK * sizeof(int)) * TR_THREADS);
     uint32_t* const w32 = reinterpret_cast<uint32_t*>(skey + TR_THREADS);
-    uint32_t* const squeue = w32 + warp * FS_TQ_CAP;
-    uint32_t* const sqcount = w32 + TQ_WARPS * FS_TQ_CAP + warp;
-    uint32_t* const shq = w32 + TQ_WARPS * FS_TQ_CAP + TQ_WARPS + warp * (PQ_SQ_CAP * 3);   // shade queue, 3 planes
+    uint32_t* const squeue = w32 + warp * QCAP;
+    uint32_t* const sqcount = w32 + TQ_WARPS * QCAP + warp;
+    uint32_t* const shq = w32 + TQ_WARPS * QCAP + TQ_WARPS + warp * (PQ_SQ_CAP * 3);   // shade queue, 3 planes
     uint32_t my_ray = 0;                                                              // ray-log index of the ray this lane walks
     unsigned long long* const mykey = skey + threadIdx.x;
     unsigned long long* const wkey = skey + (threadIdx.x & ~31u);
-    int lstack[FS_STACK_SIZE - FS_SSTACK];
+    int lstack[W8 ? 1 : FS_STACK_SIZE - FS_SSTACK];
+    uint2 lstack8[W8 ? FS_W8_STACK_SIZE - FS_W8_SSTACK : 1];
     tr_stack<false> stack; stack.sh = sstack + threadIdx.x; stack.loc = lstack;
+    w8_stack stack8; stack8.sh = gstack + threadIdx.x; stack8.loc = lstack8;
+    const float4* const tris = W8 ? bv.tris8 : bv.tris;
     const unsigned long long KEY_NONE = ((unsigned long long)0x7f800000u << 32) | 0xffffffffull;
     if (lane == 0) *sqcount = 0u;
     *mykey = KEY_NONE;
@@ -1476,9 +1619,12 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
         }
         // ---- a ticket becomes a ray once its log entry is published
         if (!running && ticket != PQ_NO_TICKET && ticket < log_cap && ld_cg_u32(log_flag + ticket) == epoch) {
-            __threadfence();
+            // no fence on this side: the flag and the entry are both read at the L2 (ld.cg), the entry only after the flag's
+            // value has come back (the branch needs it), and the writer released the flag after the entry.  __threadfence()
+            // here was MEMBAR.SC + CCTL.IVALL -- an L1 flush of the BVH nodes at every ray start (6 % of the stall samples)
             const float4 a = ld_cg_f4(log_o + ticket), b = ld_cg_f4(log_d + ticket);
-            tr_init<true>(s, bv, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z));
+            if (W8) tr_init8(s, bv, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z));
+            else tr_init<true>(s, bv, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z));
             bt = __int_as_float(0x7f800000); *mykey = KEY_NONE;
             my_ray = ticket;
             running = true; ticket = PQ_NO_TICKET;
@@ -1501,26 +1647,41 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
                 if (NODE_MIN && qn && (uint32_t)__popc(m_can) < NODE_MIN) break;
                 uint32_t nl = 0;
                 if (can) {
-                    const float INF = __int_as_float(0x7f800000);
-                    float k0, k1, k2, k3; int v0, v1, v2, v3;
-                    wide_children<2, TEX>(bv, s, bt, k0, k1, k2, k3, v0, v1, v2, v3);
-                    const bool l0 = k0 != INF && v0 < 0, l1 = k1 != INF && v1 < 0, l2 = k2 != INF && v2 < 0, l3 = k3 != INF && v3 < 0;
-                    nl = (uint32_t)l0 + (uint32_t)l1 + (uint32_t)l2 + (uint32_t)l3;
-                    if (nl) {
-                        uint32_t* q = squeue + atomicAdd(sqcount, nl);
-                        const uint32_t lm4 = lane - 4u;
-                        if (l0) *q = (uint32_t)v0 * 0xfffffffcu + lm4;
-                        q += l0;
-                        if (l1) *q = (uint32_t)v1 * 0xfffffffcu + lm4;
-                        q += l1;
-                        if (l2) *q = (uint32_t)v2 * 0xfffffffcu + lm4;
-                        q += l2;
-                        if (l3) *q = (uint32_t)v3 * 0xfffffffcu + lm4;
+                    if (W8) {
+                        uint32_t hleaf, lmask, tri_base;
+                        w8_step(bv, s, stack8, bt, hleaf, lmask, tri_base, ovf_p);
+                        nl = (uint32_t)__popc(hleaf);
+                        if (nl) {
+                            uint32_t* q = squeue + atomicAdd(sqcount, nl);
+                            const uint32_t e0 = (tri_base << 5) | lane;
+                            do {
+                                const uint32_t bit = hleaf & (0u - hleaf);
+                                *q++ = e0 + ((uint32_t)__popc(lmask & (bit - 1u)) << 5);
+                                hleaf ^= bit;
+                            } while (hleaf);
+                        }
+                    } else {
+                        const float INF = __int_as_float(0x7f800000);
+                        float k0, k1, k2, k3; int v0, v1, v2, v3;
+                        wide_children<2, TEX>(bv, s, bt, k0, k1, k2, k3, v0, v1, v2, v3);
+                        const bool l0 = k0 != INF && v0 < 0, l1 = k1 != INF && v1 < 0, l2 = k2 != INF && v2 < 0, l3 = k3 != INF && v3 < 0;
+                        nl = (uint32_t)l0 + (uint32_t)l1 + (uint32_t)l2 + (uint32_t)l3;
+                        if (nl) {
+                            uint32_t* q = squeue + atomicAdd(sqcount, nl);
+                            const uint32_t lm4 = lane - 4u;
+                            if (l0) *q = (uint32_t)v0 * 0xfffffffcu + lm4;
+                            q += l0;
+                            if (l1) *q = (uint32_t)v1 * 0xfffffffcu + lm4;
+                            q += l1;
+                            if (l2) *q = (uint32_t)v2 * 0xfffffffcu + lm4;
+                            q += l2;
+                            if (l3) *q = (uint32_t)v3 * 0xfffffffcu + lm4;
+                        }
+                        k0 = l0 ? INF : k0; k1 = l1 ? INF : k1; k2 = l2 ? INF : k2; k3 = l3 ? INF : k3;
+                        FS_CSWAP(k0, v0, k1, v1) FS_CSWAP(k2, v2, k3, v3) FS_CSWAP(k0, v0, k2, v2) FS_CSWAP(k1, v1, k3, v3) FS_CSWAP(k1, v1, k2, v2)
+                        if (k1 != INF) stack.push3(s.sp, k2 != INF, k3 != INF, v1, k1, v2, k2, v3, k3, ovf_p);
+                        s.node = (k0 != INF) ? v0 : stack.pop(s.sp, 0.f);
                     }
-                    k0 = l0 ? INF : k0; k1 = l1 ? INF : k1; k2 = l2 ? INF : k2; k3 = l3 ? INF : k3;
-                    FS_CSWAP(k0, v0, k1, v1) FS_CSWAP(k2, v2, k3, v3) FS_CSWAP(k0, v0, k2, v2) FS_CSWAP(k1, v1, k3, v3) FS_CSWAP(k1, v1, k2, v2)
-                    if (k1 != INF) stack.push3(s.sp, k2 != INF, k3 != INF, v1, k1, v2, k2, v3, k3, ovf_p);
-                    s.node = (k0 != INF) ? v0 : stack.pop(s.sp, 0.f);
                 }
                 qn += __reduce_add_sync(FULLM, nl);
             }
@@ -1536,7 +1697,7 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
                 const float bto = __shfl_sync(FULLM, bt, eo);
                 if (e != TQ_INVALID) {
                     const uint32_t tri = e >> 5;
-                    const float4* tq = bv.tris + (size_t)tri * 4;
+                    const float4* tq = tris + (size_t)tri * 4;
                     const float4 a = fs_ldg4(tq), b = fs_ldg4(tq + 1), c = fs_ldg4(tq + 2);
                     float t;
                     if (fs_intersect_tri(fs_mk(ox, oy, oz), fs_mk(dx, dy, dz), fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z), fs_mk(c.x, c.y, c.z), t)
@@ -1549,7 +1710,7 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
                             if (t == told) {
                                 const uint32_t otri = (uint32_t)old;
                                 better = otri == 0xffffffffu ||
-                                         __float_as_uint(fs_ldg4(tq + 3).x) < __float_as_uint(fs_ldg4(bv.tris + (size_t)otri * 4 + 3).x);
+                                         __float_as_uint(fs_ldg4(tq + 3).x) < __float_as_uint(fs_ldg4(tris + (size_t)otri * 4 + 3).x);
                             }
                             if (!better) break;
                             const unsigned long long prev = atomicCAS(wkey + eo, old, mine);
@@ -1572,7 +1733,9 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
                 const uint32_t q = sn + (uint32_t)__popc(m_fin & lt);
                 shq[0 * PQ_SQ_CAP + q] = my_ray;
                 shq[1 * PQ_SQ_CAP + q] = __float_as_uint(bt);
-                shq[2 * PQ_SQ_CAP + q] = (uint32_t)kk;
+                uint32_t ht = (uint32_t)kk;                      // 8-wide nodes: position in tris8 -> index into tri_nm
+                if (W8 && ht != 0xffffffffu) ht = bv.tri8_map[ht];
+                shq[2 * PQ_SQ_CAP + q] = ht;
                 running = false;
             }
             sn += (uint32_t)__popc(m_fin);
@@ -1647,14 +1810,13 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
                         if (w < log_cap) {
                             log_d[w] = make_float4(dir.x, dir.y, dir.z, prob);
                             log_o[w] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(spk_out));
-                            __threadfence();
-                            *(volatile uint32_t*)(log_flag + w) = epoch;
+                            st_release_u32(log_flag + w, epoch);      // MEMBAR.ALL.GPU + ST.STRONG: no L1 invalidation
                         } else atomicMax(&g->error, 2u);        // the log is sized for the worst case: cannot happen
                     }
                 }
             }
             __syncwarp();
-            __threadfence();
+            // lane 0 made every tail increment of this batch itself and used the returned slots: they are performed before this
             if (lane == 0) atomicAdd(&g->done, sn);            // after the successors were appended
             sn = 0u;
         }
@@ -2133,9 +2295,11 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, fs_lane* lane, const fs_trace
     // resident CTAs per SM of the persistent kernels: cached per context (= per device) and per instantiation
     int* occ = ctx->occ + (COUNT ? 4 : 0);
     if (!occ[0]) occ[0] = resident_ctas(k_trace_closest<COUNT, 2, true>, TR_THREADS, TR_SMEM_CLOSEST);
-    if (!occ[1]) occ[1] = resident_ctas(k_trace_q<COUNT, 2, false>, TR_THREADS, TR_SMEM_TQ);
+    if (!occ[1]) occ[1] = resident_ctas(k_trace_q<COUNT, 2, false, false>, TR_THREADS, TR_SMEM_TQ);
+    if (!occ[3]) occ[3] = resident_ctas(k_trace_q<COUNT, 0, false, true>, TR_THREADS, TR_SMEM_TQ8);
     if (!occ[2]) occ[2] = resident_ctas(k_trace_any<COUNT, 2, true>, TR_THREADS, TR_SMEM_ANY);
-    const int occ_tr = occ[0], occ_tq = occ[1], occ_any = occ[2];
+    const bool use_w8 = ctx->tune_tq && tp.bv.w8nodes != nullptr;               // 8-wide compressed nodes (single-triangle leaves by construction)
+    const int occ_tr = occ[0], occ_tq = use_w8 ? occ[3] : occ[1], occ_any = occ[2];
     const bool timing = (tp.flags & FS_FLAG_TIME_KERNELS) != 0;
     cudaEvent_t* ev = nullptr;
     if (timing) {
@@ -2154,7 +2318,7 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, fs_lane* lane, const fs_trace
     const uint32_t n_sub = 2u * tp.batch;
     uint32_t grid_sh = (n_sub + FS_SG_THREADS - 1) / FS_SG_THREADS;
     if (grid_sh > (uint32_t)ctx->sm_count * (2048u / FS_SG_THREADS)) grid_sh = (uint32_t)ctx->sm_count * (2048u / FS_SG_THREADS);
-    const bool use_tq = ctx->tune_tq && tp.bv.wnodes != nullptr && ctx->bvh.max_leaf == 1;    // queue entries are single triangles
+    const bool use_tq = (ctx->tune_tq && tp.bv.wnodes != nullptr && ctx->bvh.max_leaf == 1) || use_w8;    // queue entries are single triangles
     uint32_t grid_tr = (uint32_t)(ctx->sm_count * (use_tq ? occ_tq : occ_tr));
     const uint32_t ctas_needed = (n_sub + TR_THREADS - 1) / TR_THREADS;
     if (grid_tr > ctas_needed) grid_tr = ctas_needed ? ctas_needed : 1;
@@ -2184,8 +2348,9 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, fs_lane* lane, const fs_trace
                 // the flag / ticket protocol does not need the whole grid resident (any resident warp can take any ray);
                 // with several batch lanes each lane's persistent grid gets its share of the SMs
                 const bool texq = tp.bv.wnodes_tex && ctx->tune_tex >= 2;
-                int& occ_pq = ctx->occ[texq ? 8 : 9];
-                if (!occ_pq) occ_pq = texq ? resident_ctas(k_path_q<2>, TR_THREADS, PQ_SMEM) : resident_ctas(k_path_q<0>, TR_THREADS, PQ_SMEM);
+                int& occ_pq = ctx->occ[use_w8 ? 10 : (texq ? 8 : 9)];
+                if (!occ_pq) occ_pq = use_w8 ? resident_ctas(k_path_q<0, true>, TR_THREADS, PQ_SMEM8)
+                                             : (texq ? resident_ctas(k_path_q<2, false>, TR_THREADS, PQ_SMEM) : resident_ctas(k_path_q<0, false>, TR_THREADS, PQ_SMEM));
                 const uint32_t epoch = ++wb.pq_epoch;
                 pq_globals* g = (pq_globals*)wb.pq;
                 k_pq_seed<<<ctx->sm_count * 4, 256, 0, st>>>(wb, wb.log_o, wb.log_d, wb.log_flag, epoch, g, k0);
@@ -2202,9 +2367,11 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, fs_lane* lane, const fs_trace
                     ctx->tev_used += 2;
                     cudaEventRecord(te[0], st);
                 }
-                if (texq) k_path_q<2><<<grid_pq, TR_THREADS, PQ_SMEM, st>>>(tp, wb, wb.log_o, wb.log_d, wb.log_flag, epoch, wb.log_cap, g,
+                if (use_w8) k_path_q<0, true><<<grid_pq, TR_THREADS, PQ_SMEM8, st>>>(tp, wb, wb.log_o, wb.log_d, wb.log_flag, epoch, wb.log_cap, g,
+                                                                                   ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush);
+                else if (texq) k_path_q<2, false><<<grid_pq, TR_THREADS, PQ_SMEM, st>>>(tp, wb, wb.log_o, wb.log_d, wb.log_flag, epoch, wb.log_cap, g,
                                                                           ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush);
-                else k_path_q<0><<<grid_pq, TR_THREADS, PQ_SMEM, st>>>(tp, wb, wb.log_o, wb.log_d, wb.log_flag, epoch, wb.log_cap, g,
+                else k_path_q<0, false><<<grid_pq, TR_THREADS, PQ_SMEM, st>>>(tp, wb, wb.log_o, wb.log_d, wb.log_flag, epoch, wb.log_cap, g,
                                                                      ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush);
                 if (timing) cudaEventRecord(te[1], st);
                 ctx->stats.persistent_launches += 1;
@@ -2229,11 +2396,12 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, fs_lane* lane, const fs_trace
 #define FS_LAUNCH_TRACE(TEXV, WIDEV)                                                                                   \
             k_trace_closest<COUNT, TEXV, WIDEV><<<grid_tr, TR_THREADS, TR_SMEM_CLOSEST, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u], \
                 wb.q_count + k, wb.q_cursor + k, wb.hit, ctx->d_counters, ctx->tune_refill, ctx->tune_node_min, ctx->tune_tri_min)
-#define FS_LAUNCH_TQ(TEXV)                                                                                             \
-            k_trace_q<COUNT, TEXV, false><<<grid_tr, TR_THREADS, TR_SMEM_TQ, st>>>(tp.bv, wb.st_pos[k & 1u], wb.st_nrm[k & 1u],   \
-                wb.q_count + k, wb.q_cursor + k, wb.hit, nullptr, nullptr, nullptr, ctx->d_counters, ctx->tune_refill,           \
+#define FS_LAUNCH_TQ(TEXV, W8V)                                                                                        \
+            k_trace_q<COUNT, TEXV, false, W8V><<<grid_tr, TR_THREADS, W8V ? TR_SMEM_TQ8 : TR_SMEM_TQ, st>>>(tp.bv, wb.st_pos[k & 1u], \
+                wb.st_nrm[k & 1u], wb.q_count + k, wb.q_cursor + k, wb.hit, nullptr, nullptr, nullptr, ctx->d_counters, ctx->tune_refill, \
                 ctx->tune_tq_node_min, ctx->tune_tq_flush)
-            if (use_tq) { if (texm >= 2) FS_LAUNCH_TQ(2); else FS_LAUNCH_TQ(0); }
+            if (use_w8) FS_LAUNCH_TQ(0, true);
+            else if (use_tq) { if (texm >= 2) FS_LAUNCH_TQ(2, false); else FS_LAUNCH_TQ(0, false); }
             else if (wide) { if (texm >= 2) FS_LAUNCH_TRACE(2, true); else FS_LAUNCH_TRACE(0, true); }
             else { if (texm >= 2) FS_LAUNCH_TRACE(2, false); else FS_LAUNCH_TRACE(0, false); }
 #undef FS_LAUNCH_TQ
@@ -2273,11 +2441,12 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, fs_lane* lane, const fs_trace
 #define FS_LAUNCH_ANY(TEXV, WIDEV)                                                                                     \
         k_trace_any<COUNT, TEXV, WIDEV><<<grid_any, TR_THREADS, TR_SMEM_ANY, st>>>(tp.bv, any_o, any_d, wb.q_count + (D + 2), \
             wb.q_cursor + (D + 2), any_conn, wb.q_count + (D + 1), ctx->d_counters, all ? nullptr : d_dbg, ctx->tune_refill, ctx->tune_node_min)
-#define FS_LAUNCH_ANYQ(TEXV)                                                                                           \
-        k_trace_q<COUNT, TEXV, true><<<grid_any, TR_THREADS, TR_SMEM_TQ, st>>>(tp.bv, any_o, any_d, wb.q_count + (D + 2),     \
-            wb.q_cursor + (D + 2), nullptr, any_conn, wb.q_count + (D + 1), all ? nullptr : d_dbg, ctx->d_counters,               \
+#define FS_LAUNCH_ANYQ(TEXV, W8V)                                                                                      \
+        k_trace_q<COUNT, TEXV, true, W8V><<<grid_any, TR_THREADS, W8V ? TR_SMEM_TQ8 : TR_SMEM_TQ, st>>>(tp.bv, any_o, any_d,       \
+            wb.q_count + (D + 2), wb.q_cursor + (D + 2), nullptr, any_conn, wb.q_count + (D + 1), all ? nullptr : d_dbg, ctx->d_counters, \
             ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush)
-        if (use_tq && ctx->tune_tq >= 2) { if (tex) FS_LAUNCH_ANYQ(2); else FS_LAUNCH_ANYQ(0); }
+        if (use_w8 && ctx->tune_tq >= 2) FS_LAUNCH_ANYQ(0, true);
+        else if (use_tq && ctx->tune_tq >= 2) { if (tex) FS_LAUNCH_ANYQ(2, false); else FS_LAUNCH_ANYQ(0, false); }
         else if (wide) { if (tex) FS_LAUNCH_ANY(2, true); else FS_LAUNCH_ANY(0, true); }
         else { if (tex) FS_LAUNCH_ANY(2, false); else FS_LAUNCH_ANY(0, false); }
 #undef FS_LAUNCH_ANYQ
@@ -2344,16 +2513,18 @@ cudaError_t fs_wave_debug_rays(fs_ctx* ctx, const fs_trace_params& tp, const flo
         if (grid > (uint32_t)ctx->sm_count * 5u) grid = (uint32_t)ctx->sm_count * 5u;
         if (d_hit) {
 #define FS_DBG_ANY(TEXV, WIDEV) k_trace_any<false, TEXV, WIDEV><<<grid, TR_THREADS, TR_SMEM_ANY, st>>>(tp.bv, ro, rd, misc, misc + 1, conn, misc + 2, ctx->d_counters, nullptr, ctx->tune_refill, ctx->tune_node_min)
-#define FS_DBG_ANYQ(TEXV) k_trace_q<false, TEXV, true><<<grid, TR_THREADS, TR_SMEM_TQ, st>>>(tp.bv, ro, rd, misc, misc + 1, nullptr, conn, misc + 2, nullptr, ctx->d_counters, ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush)
-            if (wide && ctx->tune_tq >= 2 && ctx->bvh.max_leaf == 1) { if (tex) FS_DBG_ANYQ(2); else FS_DBG_ANYQ(0); }
+#define FS_DBG_ANYQ(TEXV, W8V) k_trace_q<false, TEXV, true, W8V><<<grid, TR_THREADS, W8V ? TR_SMEM_TQ8 : TR_SMEM_TQ, st>>>(tp.bv, ro, rd, misc, misc + 1, nullptr, conn, misc + 2, nullptr, ctx->d_counters, ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush)
+            if (tp.bv.w8nodes && ctx->tune_tq >= 2) FS_DBG_ANYQ(0, true);
+            else if (wide && ctx->tune_tq >= 2 && ctx->bvh.max_leaf == 1) { if (tex) FS_DBG_ANYQ(2, false); else FS_DBG_ANYQ(0, false); }
             else if (wide) { if (tex) FS_DBG_ANY(2, true); else FS_DBG_ANY(0, true); } else { if (tex) FS_DBG_ANY(2, false); else FS_DBG_ANY(0, false); }
 #undef FS_DBG_ANYQ
 #undef FS_DBG_ANY
             k_dbg_unpack_any<<<g, 256, 0, st>>>(conn, misc + 2, d_hit);
         } else {
 #define FS_DBG_CL(TEXV, WIDEV) k_trace_closest<false, TEXV, WIDEV><<<grid, TR_THREADS, TR_SMEM_CLOSEST, st>>>(tp.bv, ro, rd, misc, misc + 1, hits, ctx->d_counters, ctx->tune_refill, ctx->tune_node_min, ctx->tune_tri_min)
-#define FS_DBG_TQ(TEXV) k_trace_q<false, TEXV, false><<<grid, TR_THREADS, TR_SMEM_TQ, st>>>(tp.bv, ro, rd, misc, misc + 1, hits, nullptr, nullptr, nullptr, ctx->d_counters, ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush)
-            if (wide && ctx->tune_tq && ctx->bvh.max_leaf == 1) { if (tex) FS_DBG_TQ(2); else FS_DBG_TQ(0); }
+#define FS_DBG_TQ(TEXV, W8V) k_trace_q<false, TEXV, false, W8V><<<grid, TR_THREADS, W8V ? TR_SMEM_TQ8 : TR_SMEM_TQ, st>>>(tp.bv, ro, rd, misc, misc + 1, hits, nullptr, nullptr, nullptr, ctx->d_counters, ctx->tune_refill, ctx->tune_tq_node_min, ctx->tune_tq_flush)
+            if (tp.bv.w8nodes && ctx->tune_tq) FS_DBG_TQ(0, true);
+            else if (wide && ctx->tune_tq && ctx->bvh.max_leaf == 1) { if (tex) FS_DBG_TQ(2, false); else FS_DBG_TQ(0, false); }
             else if (wide) { if (tex) FS_DBG_CL(2, true); else FS_DBG_CL(0, true); } else { if (tex) FS_DBG_CL(2, false); else FS_DBG_CL(0, false); }
 #undef FS_DBG_TQ
 #undef FS_DBG_CL

@@ -31,20 +31,29 @@ def test_bvh_equals_brute_force_and_oracle(fs, oracle, scene_name, kw, lo, hi):
     else:
         rays = _rays(rng, lo, hi, n)
     rays[:64, 3:] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 64)] * rng.choice([-1, 1], (64, 1))  # axis-parallel
-    with fs.Context() as a, fs.Context(flags=capi.FLAG_BRUTE_FORCE) as b, fs.Context(flags=capi.FLAG_FUSED_EXTEND) as c:
-        for ctx in (a, b, c):
+    import os
+    os.environ["FS_TUNE_W8"] = "1"               # FS_TUNE_* are read by fs_create: the 8-wide compressed nodes (optional format)
+    try:
+        w8 = fs.Context()
+    finally:
+        os.environ.pop("FS_TUNE_W8", None)
+    with fs.Context() as a, fs.Context(flags=capi.FLAG_BRUTE_FORCE) as b, fs.Context(flags=capi.FLAG_FUSED_EXTEND) as c, w8:
+        for ctx in (a, b, c, w8):
             ctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
+        t8, i8 = w8.closest_hits(rays)
         ta, ia = a.closest_hits(rays)            # production kernels: 4-wide quantised nodes, smem stack, ray replacement
         tc, ic = c.closest_hits(rays)            # per-thread traversal of the BVH2 float nodes
         nb = 6000
         tb, ib = b.closest_hits(rays[:nb])
         assert np.array_equal(ta, tc) and np.array_equal(ia, ic)
+        assert np.array_equal(ta, t8) and np.array_equal(ia, i8)
         assert np.array_equal(ta[:nb], tb) and np.array_equal(ia[:nb], ib)
         assert (ia != 0xffffffff).mean() > 0.5
         tmax = (ta * rng.uniform(0.5, 1.5, n)).astype(np.float32)
         tmax[~np.isfinite(tmax)] = 10.0
         ha = a.any_hits(rays, tmax)
         assert np.array_equal(ha, c.any_hits(rays, tmax))
+        assert np.array_equal(ha, w8.any_hits(rays, tmax))
         hb = b.any_hits(rays[:nb], tmax[:nb])
         assert np.array_equal(ha[:nb], hb)
     S = oracle.Scene(sc.verts, sc.tri_mat, sc.absorption, use_bvh=True)

@@ -241,7 +241,8 @@ def test_every_traversal_kernel_and_bvh_layout_gives_the_same_histogram(fs, orac
     for env in ({}, {"FS_TUNE_TQ": 0}, {"FS_TUNE_TQ": 1}, {"FS_TUNE_COLLAPSE": 0}, {"FS_TUNE_PLOC_R": 3}, {"FS_TUNE_ROTATE": 3}, {"FS_TUNE_MEGA": 1}, {"FS_TUNE_MEGA": 1, "FS_TUNE_TEX": 0}, {"FS_TUNE_COLLAPSE": 3}, {"FS_TUNE_TQ": 0, "FS_TUNE_COLLAPSE": 2},
                 {"FS_TUNE_WIDE": 0}, {"FS_TUNE_BUILDER": 0}, {"FS_TUNE_BUILDER": 0, "FS_TUNE_LEAF_MAX": 1},
                 {"FS_TUNE_TQ_FLUSH": 1}, {"FS_TUNE_TQ_FLUSH": 32, "FS_TUNE_TQ_NODE_MIN": 0}, {"FS_TUNE_REFILL": 1},
-                {"FS_TUNE_L2PIN": 8}):
+                {"FS_TUNE_L2PIN": 8}, {"FS_TUNE_W8": 1}, {"FS_TUNE_W8": 1, "FS_TUNE_MEGA": 1}, {"FS_TUNE_W8": 1, "FS_TUNE_COLLAPSE": 9},
+                {"FS_TUNE_W8": 1, "FS_TUNE_TQ_FLUSH": 1}):
         with _env(**env):
             ctx = _ctx(fs, room)
         with ctx:
