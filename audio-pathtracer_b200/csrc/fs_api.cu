@@ -109,7 +109,8 @@ int fs_create(const fs_config* cfg, fs_ctx** out)
     if (const char* e11 = getenv("FS_TUNE_TQ")) ctx->tune_tq = (uint32_t)atoi(e11);
     ctx->tune_mega = 2;          // one persistent launch per batch for the extension stage (k_path_q): 0 never, 1 always, 2 when it pays
     if (const char* e15 = getenv("FS_TUNE_MEGA")) ctx->tune_mega = (uint32_t)atoi(e15);
-    ctx->tune_mega_from = 0; ctx->tune_mega_lanes = 1;   // first bounce inside the persistent kernel; batch lanes with it
+    ctx->tune_mega_from = 0; ctx->tune_mega_lanes = 2;   // first bounce inside the persistent kernel; batch lanes with it (2: each lane's
+                                                         // persistent grid on half of the SMs -- one batch's connect / evaluate stage and tail overlap the other's walk: room -2.5 %)
     if (const char* e16 = getenv("FS_TUNE_MEGA_FROM")) ctx->tune_mega_from = (uint32_t)atoi(e16);
     if (const char* e17 = getenv("FS_TUNE_MEGA_LANES")) { int v = atoi(e17); if (v >= 1 && v <= FS_MAX_LANES) ctx->tune_mega_lanes = (uint32_t)v; }
     if (const char* e12 = getenv("FS_TUNE_TQ_NODE_MIN")) ctx->tune_tq_node_min = (uint32_t)atoi(e12);
@@ -518,7 +519,7 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
         if (cap_cfg > lim) cap_cfg = lim;
         n_lanes = 1;
     }
-    // one persistent kernel per batch fills the GPU by itself: a job that will use it runs on one lane (same rule as in
+    // a job that will use the persistent per-batch kernel runs on at most tune_mega_lanes lanes (same rule as in
     // launch_batch_split: batches of >= 2^18 pairs on a scene of >= 4096 triangles, or FS_TUNE_MEGA=1)
     {
         const uint64_t nb1 = g_count ? (g_count + cap_cfg - 1) / cap_cfg : 1;

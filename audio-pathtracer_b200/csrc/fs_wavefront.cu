@@ -1561,6 +1561,9 @@ __global__ void k_pq_finish(const fs_wave_buffers wb, const pq_globals* __restri
     if (g->error) dc->overflow = 0x100u | g->error;
 }
 
+#ifndef PQ_AHEAD
+#define PQ_AHEAD 0      // measured: no gain (room 4.42 vs 4.40 ms, hall 10.78 vs 10.72), profiles/r2_experiments.md
+#endif
 #ifndef FS_PQ_MINBLOCKS
 #define FS_PQ_MINBLOCKS 4      // 62 registers, 32 warps/SM (3: 72 registers is slower, 5: spills and no L1 left)
 #endif
@@ -1600,15 +1603,17 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
     tr_state s;
     s.node = TR_SENT; s.leaf = 0; s.sp = 0; s.tc = 0; s.te = 0;
     s.o = fs_mk(0.f, 0.f, 0.f); s.d = s.o; s.idx = s.idy = s.idz = s.oodx = s.oody = s.oodz = 0.f;
-    bool running = false;
+    bool running = false, ready = false;              // ready: the entry of `ticket` is published
     uint32_t ticket = PQ_NO_TICKET;
     uint32_t* const ovf_p = &g->error;                 // stack overflow lands in the same word (value 1)
     float bt = __int_as_float(0x7f800000);
     uint32_t qn = 0, sn = 0, polls = 0;
     const uint32_t stride = 2u * wb.cap;
     for (;;) {
-        // ---- idle lanes take tickets for the next entries of the ray log (one atomic per warp)
-        const bool need = !running && ticket == PQ_NO_TICKET;
+        // ---- lanes without a ticket take one for the next entries of the ray log (one atomic per warp).  PQ_AHEAD: also while
+        // they still walk a ray, and the ticket's flag is polled meanwhile, so that a ray start costs ONE round trip to the L2
+        // (the entry) instead of three in a row (ticket, flag, entry) during which the lane sat out the warp's node steps
+        const bool need = (PQ_AHEAD || !running) && ticket == PQ_NO_TICKET;
         const uint32_t m_need = __ballot_sync(FULLM, need);
         const uint32_t m_run0 = __ballot_sync(FULLM, running);
         if ((uint32_t)__popc(m_need) >= REFILL_MIN || (m_need && m_run0 == 0u)) {
@@ -1618,16 +1623,17 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
             if (need) ticket = base + (uint32_t)__popc(m_need & lt);
         }
         // ---- a ticket becomes a ray once its log entry is published
-        if (!running && ticket != PQ_NO_TICKET && ticket < log_cap && ld_cg_u32(log_flag + ticket) == epoch) {
-            // no fence on this side: the flag and the entry are both read at the L2 (ld.cg), the entry only after the flag's
-            // value has come back (the branch needs it), and the writer released the flag after the entry.  __threadfence()
-            // here was MEMBAR.SC + CCTL.IVALL -- an L1 flush of the BVH nodes at every ray start (6 % of the stall samples)
+        // no fence on this side: the flag and the entry are both read at the L2 (ld.cg), the entry only after the flag's
+        // value has come back (the branch needs it), and the writer released the flag after the entry.  __threadfence()
+        // here was MEMBAR.SC + CCTL.IVALL -- an L1 flush of the BVH nodes at every ray start (6 % of the stall samples)
+        if ((PQ_AHEAD || !running) && !ready && ticket != PQ_NO_TICKET && ticket < log_cap && ld_cg_u32(log_flag + ticket) == epoch) ready = true;
+        if (!running && ready) {
             const float4 a = ld_cg_f4(log_o + ticket), b = ld_cg_f4(log_d + ticket);
             if (W8) tr_init8(s, bv, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z));
             else tr_init<true>(s, bv, fs_mk(a.x, a.y, a.z), fs_mk(b.x, b.y, b.z));
             bt = __int_as_float(0x7f800000); *mykey = KEY_NONE;
             my_ray = ticket;
-            running = true; ticket = PQ_NO_TICKET;
+            running = true; ticket = PQ_NO_TICKET; ready = false;
         }
         const uint32_t m_run = __ballot_sync(FULLM, running);
         if (m_run == 0u && sn == 0u) {                // nothing to walk, nothing to shade: finished, or wait for rays
