@@ -826,6 +826,24 @@ static int ensure_pin_ir(fs_ctx* ctx, size_t n_floats)
     return FS_OK;
 }
 
+// page-locked destination (fs_host_alloc, or registered by the caller): the DMA engine can write it directly
+static bool host_is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int fs_host_alloc(size_t bytes, void** out)
+{
+    if (!out || !bytes) return FS_ERR_INVALID;
+    *out = nullptr;
+    if (cudaMallocHost(out, bytes) != cudaSuccess) { (void)cudaGetLastError(); g_err = "fs_host_alloc: cudaMallocHost failed"; return FS_ERR_NOMEM; }
+    return FS_OK;
+}
+
+void fs_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 static int ir_common(fs_ctx* ctx, uint32_t hist_source, uint32_t source, const float* energy, float* ir_out,
                      bool per_band = false, uint64_t noise_seed = 0)
 {
@@ -849,10 +867,11 @@ static int ir_common(fs_ctx* ctx, uint32_t hist_source, uint32_t source, const f
     ctx->ir_timed = true;
     if (ir_out) {
         const size_t n = (size_t)c.n_channels * c.sample_rate;
-        if ((rc = ensure_pin_ir(ctx, n)) != FS_OK) return rc;
-        CK(cudaMemcpyAsync(ctx->h_pin_ir, s->ir, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        const bool direct = host_is_pinned(ir_out);
+        if (!direct && (rc = ensure_pin_ir(ctx, n)) != FS_OK) return rc;
+        CK(cudaMemcpyAsync(direct ? ir_out : ctx->h_pin_ir, s->ir, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        memcpy(ir_out, ctx->h_pin_ir, sizeof(float) * n);
+        if (!direct) memcpy(ir_out, ctx->h_pin_ir, sizeof(float) * n);
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->ev_ir0, ctx->ev_ir1) == cudaSuccess) ctx->stats.last_ir_ms = ms;
         return check_overflow(ctx, true);
@@ -903,13 +922,16 @@ int fs_build_ir_all(fs_ctx* ctx, uint32_t n_sources, float* ir_out)
     CK(cudaEventRecord(ctx->ev_ir1, ctx->stream));
     ctx->ir_timed = true;
     if (ir_out) {
-        // all IRs leave through one pinned staging buffer (a pageable destination would be staged 64 KB at a time)
+        // straight into the caller's buffer when it is page-locked (fs_host_alloc); otherwise through one pinned staging
+        // buffer (a pageable destination would be staged 64 KB at a time by the driver)
         const size_t per = (size_t)c.n_channels * c.sample_rate;
-        if ((rc = ensure_pin_ir(ctx, per * n_sources)) != FS_OK) return rc;
+        const bool direct = host_is_pinned(ir_out);
+        if (!direct && (rc = ensure_pin_ir(ctx, per * n_sources)) != FS_OK) return rc;
+        float* dst = direct ? ir_out : ctx->h_pin_ir;
         for (uint32_t s = 0; s < n_sources; ++s)
-            CK(cudaMemcpyAsync(ctx->h_pin_ir + s * per, ctx->conv[s]->ir, sizeof(float) * per, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(dst + s * per, ctx->conv[s]->ir, sizeof(float) * per, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        memcpy(ir_out, ctx->h_pin_ir, sizeof(float) * per * n_sources);
+        if (!direct) memcpy(ir_out, ctx->h_pin_ir, sizeof(float) * per * n_sources);
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->ev_ir0, ctx->ev_ir1) == cudaSuccess) ctx->stats.last_ir_ms = ms;
         return check_overflow(ctx, true);

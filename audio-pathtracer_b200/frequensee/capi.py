@@ -29,12 +29,51 @@ ABI_SYMBOLS = [
     "fs_debug_closest_hits", "fs_debug_any_hits",
     "fs_build_ir", "fs_build_ir_to", "fs_build_ir_all", "fs_build_ir_bands", "fs_build_ir_from_energy", "fs_set_histogram", "fs_set_histogram_device",
     "fs_get_histogram", "fs_get_histogram_sources", "fs_set_ir", "fs_load_float_array", "fs_save_float_array",
+    "fs_host_alloc", "fs_host_free",
     "fs_conv_init_source", "fs_conv_release_source", "fs_conv_process", "fs_conv_process_many", "fs_conv_process_multi",
     "fs_debug_rfft", "fs_get_stats",
     "fs_multi_create", "fs_multi_destroy", "fs_multi_last_error", "fs_multi_device_count", "fs_multi_context",
     "fs_multi_scene_set_triangles", "fs_multi_scene_set_materials", "fs_multi_scene_set_materials_ex", "fs_multi_scene_commit",
     "fs_multi_trace", "fs_multi_last_ms", "fs_multi_synchronize",
 ]
+
+
+class _Pinned:
+    """owner of one fs_host_alloc() block; numpy views keep it alive through their .base chain"""
+
+    def __init__(self, nbytes):
+        self.p = C.c_void_p()
+        rc = load().fs_host_alloc(nbytes, C.byref(self.p))
+        if rc != 0 or not self.p.value:
+            raise MemoryError("fs_host_alloc(%d) failed" % nbytes)
+        self.buf = (C.c_char * nbytes).from_address(self.p.value)
+
+    def __del__(self):
+        try:
+            if self.p.value:
+                load().fs_host_free(self.p)
+                self.p = C.c_void_p()
+        except Exception:
+            pass
+
+
+def host_alloc(shape, dtype=np.float32):
+    """page-locked numpy array (fs_host_alloc): IR / histogram destinations the copy engine writes directly"""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    own = _Pinned(max(n, 1))
+    a = np.frombuffer(own.buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    return _PinnedArray(a, own)
+
+
+class _PinnedArray(np.ndarray):
+    def __new__(cls, arr, owner):
+        obj = arr.view(cls)
+        obj._fs_owner = owner
+        return obj
+
+    def __array_finalize__(self, obj):
+        self._fs_owner = getattr(obj, "_fs_owner", None)
 
 
 class Config(C.Structure):
@@ -125,6 +164,9 @@ def load():
     L.fs_build_ir_all.argtypes = [vp, u32, vp]
     L.fs_load_float_array.argtypes = [C.c_char_p, vp, u64, C.POINTER(u64)]
     L.fs_save_float_array.argtypes = [C.c_char_p, vp, u64]
+    L.fs_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.fs_host_free.argtypes = [vp]
+    L.fs_host_free.restype = None
     L.fs_conv_init_source.argtypes = [vp, u32]
     L.fs_conv_release_source.argtypes = [vp, u32]
     L.fs_conv_process.argtypes = [vp, u32, vp, vp, u32]
@@ -315,10 +357,15 @@ class Context:
         self._ck(self.L.fs_build_ir_to(self.h, hist_source, conv_source, ir.ctypes.data if want_ir else None))
         return ir
 
-    def build_ir_all(self, n_sources, want_ir=True):
-        """all sources of a multi-emitter update, IR kernels launched once per 64 sources"""
-        out = np.zeros((n_sources, self.cfg.n_channels, self.cfg.sample_rate), dtype=np.float32) if want_ir else None
-        self._ck(self.L.fs_build_ir_all(self.h, n_sources, out.ctypes.data if want_ir else None))
+    def build_ir_all(self, n_sources, want_ir=True, out=None):
+        """all sources of a multi-emitter update, IR kernels launched once per 64 sources.  `out`: a caller-owned float32
+        [n_sources][C][fs] array (page-locked if it came from host_alloc(): written by the copy engine directly)"""
+        shape = (n_sources, self.cfg.n_channels, self.cfg.sample_rate)
+        if out is None:
+            out = np.zeros(shape, dtype=np.float32) if want_ir else None
+        elif out.shape != shape or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float32 array of shape %r" % (shape,))
+        self._ck(self.L.fs_build_ir_all(self.h, n_sources, out.ctypes.data if out is not None else None))
         return out
 
     def build_ir_bands(self, noise_seed, hist_source=0, conv_source=0, want_ir=True):

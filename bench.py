@@ -405,10 +405,12 @@ def run_b200(args):
     g_first, g_count, n_global = wl.g_first, wl.g_count, wl.n_global
     d_hist = wl.d_hist
     if rank == 0 or N > 1:
+        # multi-emitter updates: the host keeps ONE page-locked IR buffer (fs_host_alloc) and reuses it every update
+        ir_buf = wl.capi.host_alloc((NS_, ctx.cfg.n_channels, ctx.cfg.sample_rate)) if (NS_ > 1 and rank == 0) else None
         def step_host(seed):
             if N == 1:
                 h = ctx.trace(sc.sources, sc.listener, n_global, D, seed)    # positions H2D, histogram D2H
-                ir = ctx.build_ir(0) if NS_ == 1 else ctx.build_ir_all(NS_)  # IR D2H
+                ir = ctx.build_ir(0) if NS_ == 1 else ctx.build_ir_all(NS_, out=ir_buf)  # IR D2H
                 return h, ir
             h = ctx.trace_range(sc.sources, sc.listener, n_global, g_first, g_count, D, seed)
             return h, None
@@ -422,7 +424,7 @@ def run_b200(args):
                 dist.reduce(d_hist, dst=0, op=dist.ReduceOp.SUM)
                 if rank == 0:
                     ctx.set_histogram(d_hist.cpu().numpy().view(np.uint64), n_global)
-                    ir = ctx.build_ir(0) if NS_ == 1 else ctx.build_ir_all(NS_)
+                    ir = ctx.build_ir(0) if NS_ == 1 else ctx.build_ir_all(NS_, out=ir_buf)
         barrier()
         wall = time.perf_counter() - t0
         tw = torch.tensor([wall], dtype=torch.float64, device="cuda")

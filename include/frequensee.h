@@ -40,6 +40,7 @@
 #ifndef FREQUENSEE_H
 #define FREQUENSEE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -253,6 +254,15 @@ int fs_set_ir(fs_ctx* ctx, uint32_t source, const float* ir);
  * (call with out = NULL, cap = 0 to size the buffer).  Returns FS_ERR_INVALID if the file cannot be read.
  * fs_save_float_array writes the shortest decimal form that reads back to the same float ("%.9g"). */
 int fs_load_float_array(const char* path, float* out, uint64_t cap, uint64_t* n_out);
+
+/* ---- page-locked host buffers ---------------------------------------------------------------
+ * no reference counterpart (the reference's ImpulseBuffer is a TArray in the component, COMP.h:93).  An IR / histogram
+ * destination that is page-locked -- allocated here, or registered by the caller with the CUDA runtime -- is written by
+ * the copy engine directly; any other destination goes through the context's pinned staging buffer and one memcpy.
+ * 64 emitters x 2 x 48 000 floats = 24.6 MB per update: the difference is the memcpy and the page faults of a fresh
+ * buffer.  Usable before fs_create; free with fs_host_free. */
+int  fs_host_alloc(size_t bytes, void** out);
+void fs_host_free(void* p);
 int fs_save_float_array(const char* path, const float* data, uint64_t n);
 
 /* ---- convolution ----------------------------------------------------------------------------

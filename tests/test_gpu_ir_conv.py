@@ -168,10 +168,16 @@ def test_build_ir_all_equals_per_source_builds(fs, oracle):
         ctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
         ctx.trace(srcs, sc.listener, 4096, 8, 31)
         allir = ctx.build_ir_all(len(srcs))
+        # a page-locked destination (fs_host_alloc) is written by the copy engine directly: same floats
+        pinned = fs.capi.host_alloc((len(srcs), 2, 48000))
+        pinned[:] = -1.0
+        assert ctx.build_ir_all(len(srcs), out=pinned) is pinned
         for s in range(len(srcs)):
             ctx.conv_init_source(s)
         y_all = np.stack([ctx.conv_process_many(x, s) for s in range(len(srcs))])
     assert np.array_equal(one, allir) and np.array_equal(y_one, y_all)
+    assert np.array_equal(np.asarray(pinned), allir)
+    del pinned
     cfg = oracle.default_config()
     for s in range(len(srcs)):
         assert _rel(allir[s], oracle.build_ir(cfg, h[s], 4096)) < 1e-5
