@@ -528,6 +528,8 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
                               (ctx->tune_mega == 1u || (ctx->tune_mega == 2u && cap1 >= (1u << 18) && ctx->bvh.n_tris >= 4096u &&
                                                         ctx->conv_active.load() == 0));
         if (mega_job && n_lanes > ctx->tune_mega_lanes) n_lanes = ctx->tune_mega_lanes;
+        // ... and on one lane when half of it would fall below the size from which the persistent kernel pays
+        while (mega_job && ctx->tune_mega == 2u && n_lanes > 1 && g_count / n_lanes < (1u << 18)) --n_lanes;
     }
     while (n_lanes > 1 && g_count / n_lanes < (1u << 17)) --n_lanes;            // small jobs: not worth a second set of launches
     uint64_t n_batches = g_count ? (g_count + cap_cfg - 1) / cap_cfg : 1;
