@@ -1772,7 +1772,9 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
                         if (!tp.lobes) wb.end_pos[sp_id] = make_float4(o.x, o.y, o.z, __uint_as_float(k));
                         else if (k >= 2u) {           // material model: see k_shade_gen
                             float4* rp = wb.rec + (size_t)(k - 1u) * stride + sp_id;
-                            float4 rv = *rp;
+                            // written earlier in THIS launch, possibly by another SM, and its 32-byte sector also holds the
+                            // record of the pair's other subpath: read at the L2, never through a (possibly stale) L1 line
+                            float4 rv = ld_cg_f4(rp);
                             rv.y = __uint_as_float(__float_as_uint(rv.y) & 0x00ffffffu);
                             *rp = rv;
                         }
