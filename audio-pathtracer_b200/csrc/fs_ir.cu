@@ -130,6 +130,34 @@ k_ir_multi(const float* __restrict__ amp, uint32_t n_bins, uint32_t spb, uint32_
     ir_tile(amp + (size_t)src * n_bins, n_bins, spb, n_samples, n_channels, a, (float*)tab.p[src], sraw, win);
 }
 
+// FS_FLAG_IR_NORMALIZE (NormalizeImpulseResponse, COMP.cpp:382-406): one CTA per (channel, source); sum of squares in double
+// over a fixed tree, then every sample divided by the float norm; a channel below 1e-4 is left alone
+__global__ void __launch_bounds__(1024)
+k_ir_normalize(fs_ptr_table tab, float* single, uint32_t n_samples)
+{
+    __shared__ double red[1024];
+    float* ir = (single ? single : (float*)tab.p[blockIdx.y]) + (size_t)blockIdx.x * n_samples;
+    double s = 0.0;
+    for (uint32_t i = threadIdx.x; i < n_samples; i += 1024) { const double v = (double)ir[i]; s += v * v; }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (uint32_t w = 512; w; w >>= 1) {
+        if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    const float norm = (float)sqrt(red[0]);
+    if (norm < 1e-4f) return;
+    for (uint32_t i = threadIdx.x; i < n_samples; i += 1024) ir[i] = ir[i] / norm;
+}
+
+static void ir_normalize(fs_ctx* ctx, const fs_ptr_table* tab, uint32_t n, float* single)
+{
+    if (!(ctx->cfg.flags & FS_FLAG_IR_NORMALIZE)) return;
+    fs_ptr_table t0; memset(&t0, 0, sizeof(t0));
+    k_ir_normalize<<<dim3(ctx->cfg.n_channels, n), 1024, 0, ctx->stream>>>(tab ? *tab : t0, single, ctx->cfg.sample_rate);
+    ctx->launches.fetch_add(1);
+}
+
 }  // namespace
 
 // same arithmetic as fs_ir_build, for sources [s0, s0 + n) (n <= FS_PTR_TABLE): d_ir[i] = device IR of source s0 + i
@@ -150,6 +178,7 @@ cudaError_t fs_ir_build_multi(fs_ctx* ctx, const unsigned long long* d_hist, uin
     k_ir_multi<<<dim3((c.sample_rate + IR_TILE - 1) / IR_TILE, n), IR_TILE, sizeof(float) * (IR_TILE + ctx->ir_window), ctx->stream>>>(
         ctx->d_amp_all, c.n_bins, spb, c.sample_rate, c.n_channels, c.ir_lowpass, d_ir, ctx->ir_window);
     ctx->launches.fetch_add(2);
+    ir_normalize(ctx, &d_ir, n, nullptr);
     return cudaGetLastError();
 }
 
@@ -210,6 +239,7 @@ cudaError_t fs_ir_build_bands(fs_ctx* ctx, const unsigned long long* d_hist_src,
     k_ir_bands<<<(c.sample_rate + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_amp_bands, ctx->d_carriers, c.n_bands, c.n_bins, spb,
                                                                       c.sample_rate, c.n_channels, d_ir_out);
     ctx->launches.fetch_add(2);
+    ir_normalize(ctx, nullptr, 1, d_ir_out);
     return cudaGetLastError();
 }
 
@@ -224,5 +254,6 @@ cudaError_t fs_ir_build(fs_ctx* ctx, const unsigned long long* d_hist_src, uint6
     k_ir<<<(c.sample_rate + IR_TILE - 1) / IR_TILE, IR_TILE, sizeof(float) * (IR_TILE + ctx->ir_window), ctx->stream>>>(
         ctx->d_amp, c.n_bins, spb, c.sample_rate, c.n_channels, c.ir_lowpass, d_ir_out, ctx->ir_window);
     ctx->launches.fetch_add(2);
+    ir_normalize(ctx, nullptr, 1, d_ir_out);
     return cudaGetLastError();
 }

@@ -89,6 +89,11 @@ typedef enum fs_status {
                                        the cosine lobe, with the authors' own energy split (MaterialAcousticProcessor.cpp:50-66:
                                        Refl = 1 - alpha, tau <= 1 - Refl, specular Refl (1 - sigma), diffuse Refl sigma, transmitted
                                        tau ^ (ThicknessCm / 2.5)).  Off by default: the reference's tracers read Absorption only */
+#define FS_FLAG_IR_NORMALIZE 1024u  /* every IR that is built is scaled to unit L2 norm per channel before it is published to the
+                                       convolver / returned: the normalisation the reference computes in NormalizeImpulseResponse
+                                       (COMP.cpp:382-406) and then discards (":404 FIXME", :377-378).  A channel whose norm is below
+                                       KINDA_SMALL_NUMBER (1e-4) is left alone (:394-397).  Off by default = the reference's effective
+                                       behaviour */
 #define FS_FLAG_FUSED_EXTEND  32u   /* A/B: fused RR+sample+traverse+shade kernel per bounce instead of the
                                        split shade/trace wavefront with per-lane ray replacement */
 

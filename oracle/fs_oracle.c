@@ -1000,6 +1000,22 @@ int fso_trace(const fso_scene* sc, const fso_config* cfg, const float* src_pos, 
 /* ------------------------------------------------------------------------------------------
  * IR: ReconstructImpulseResponse, COMP.cpp:320-380
  * ---------------------------------------------------------------------------------------- */
+/* NormalizeImpulseResponse, COMP.cpp:382-406 -- the L2 normalisation the reference computes (and then zeroes, ":404 FIXME",
+ * on a copy it throws away, :377-378): optional here (FSO_FLAG_IR_NORMALIZE), applied per channel to the IR that is output;
+ * a channel whose norm is below KINDA_SMALL_NUMBER (1e-4) is left alone (:394-397).  Sum of squares in double. */
+void fso_ir_normalize(const fso_config* cfg, float* ir)
+{
+    const uint32_t NS = cfg->sample_rate;
+    for (uint32_t c = 0; c < cfg->n_channels; ++c) {
+        float* x = ir + (uint64_t)c * NS;
+        double ss = 0.0;
+        for (uint32_t i = 0; i < NS; ++i) ss += (double)x[i] * (double)x[i];
+        const float norm = (float)sqrt(ss);
+        if (norm < 1e-4f) continue;
+        for (uint32_t i = 0; i < NS; ++i) x[i] = x[i] / norm;
+    }
+}
+
 int fso_build_ir_from_energy(const fso_config* cfg, const float* energy, float* ir_out)
 {
     const uint32_t K = cfg->n_bins;
@@ -1031,6 +1047,7 @@ int fso_build_ir_from_energy(const fso_config* cfg, const float* energy, float* 
     for (uint32_t c = 1; c < cfg->n_channels; ++c)               /* both channels read the same mono histogram, :327-330 */
         memcpy(ir_out + (uint64_t)c * NS, out0, (size_t)NS * 4);
     free(raw);
+    if (cfg->reserved[1] & FSO_FLAG_IR_NORMALIZE) fso_ir_normalize(cfg, ir_out);
     return 0;
 }
 
@@ -1122,6 +1139,7 @@ int fso_build_ir_bands(const fso_config* cfg, const uint64_t* hist, uint64_t n_p
             ir_out[(uint64_t)c * NS + t] = acc;
         }
     free(car); free(amp);
+    if (cfg->reserved[1] & FSO_FLAG_IR_NORMALIZE) fso_ir_normalize(cfg, ir_out);
     return 0;
 }
 

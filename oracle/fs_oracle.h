@@ -66,6 +66,7 @@ typedef struct fso_config {
 } fso_config;
 #define FSO_FLAG_SHARE_LISTENER 128u /* listener subpath keyed by the path index only: shared by all sources */
 #define FSO_FLAG_MATERIAL_MODEL 256u /* transmission / scattering / thickness of the material asset drive the walk */
+#define FSO_FLAG_IR_NORMALIZE 1024u  /* every IR that is built is scaled to unit L2 norm per channel (NormalizeImpulseResponse, COMP.cpp:382-406) */
 #define FSO_FLAG_MIS 512u             /* all prefix connections weighted by the balance heuristic over a physically based contribution */
 #define FSO_FLAG_MIS_T1 (1u << 20)    /* oracle only (tests): only the strategies t = 1, weight 1 -- an independent estimator of the same integral */
 #define FSO_FLAG_MIS_S1 (1u << 21)    /* oracle only (tests): only the strategies s = 1 */
@@ -144,6 +145,7 @@ int32_t fso_bin_index(const fso_config* cfg, float delay_s);
 /* hist: [B][K] for one source; ir_out: [C][sample_rate] */
 int fso_build_ir(const fso_config* cfg, const uint64_t* hist, uint64_t n_paths, float* ir_out);
 /* float-histogram variant: the reference's own signature, EnergyBuffer float[K] -> IR */
+void fso_ir_normalize(const fso_config* cfg, float* ir /* [C][sample_rate], in place */);
 int fso_build_ir_from_energy(const fso_config* cfg, const float* energy, float* ir_out);
 /* per-band synthesis: band envelopes x band-limited noise carriers; carriers [C][B][sample_rate] */
 void fso_band_carriers(const fso_config* cfg, uint64_t seed, float* out);

@@ -150,6 +150,7 @@ FLAG_CONNECT_ALL = 64
 FLAG_SHARE_LISTENER = 128
 FLAG_MATERIAL_MODEL = 256
 FLAG_MIS = 512
+FLAG_IR_NORMALIZE = 1024
 FLAG_MIS_T1 = 1 << 20
 FLAG_MIS_S1 = 1 << 21
 

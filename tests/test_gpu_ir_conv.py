@@ -47,6 +47,36 @@ def test_ir_from_energy_seam_and_edge_histograms(fs, oracle):
         assert np.array_equal(ctx.get_histogram(), h)
 
 
+def test_ir_l2_normalisation_flag(fs, oracle):
+    """FS_FLAG_IR_NORMALIZE (NormalizeImpulseResponse, COMP.cpp:382-406): every build path gives the oracle's unit-norm IR,
+    and the convolver runs on it"""
+    from frequensee import scenes, capi
+    sc = scenes.shoebox()
+    cfg = oracle.default_config(flags=oracle.FLAG_IR_NORMALIZE)
+    srcs = np.array([[1.5, 1.2, 1.0], [3.0, 2.0, 1.5], [5.5, 4.0, 2.0]], np.float32)
+    x = np.zeros((2, 1024, 2), np.float32); x[0, 0] = 1.0; x[1, 7] = -0.25
+    with fs.Context(flags=capi.FLAG_IR_NORMALIZE) as ctx:
+        ctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
+        h = ctx.trace(srcs, sc.listener, 8192, 8, 77)
+        one = ctx.build_ir(1)
+        allir = ctx.build_ir_all(3)
+        bands = ctx.build_ir_bands(9, hist_source=2, conv_source=2)
+        e = np.where((np.arange(1000) > 30) & (np.arange(1000) < 200), 0.01, 0).astype(np.float32)
+        from_e = ctx.build_ir_from_energy(e, source=0)
+        ctx.build_ir(1)
+        ctx.conv_init_source(1)
+        y = ctx.conv_process_many(x, 1)
+    assert np.allclose(np.linalg.norm(one.astype(np.float64), axis=1), 1.0, rtol=1e-5)
+    assert _rel(one, oracle.build_ir(cfg, h[1], 8192)) < TOL and np.array_equal(one, allir[1])
+    for s in range(3):
+        assert _rel(allir[s], oracle.build_ir(cfg, h[s], 8192)) < TOL
+    assert _rel(bands, oracle.build_ir_bands(cfg, h[2], 8192, 9)) < TOL
+    assert _rel(from_e, oracle.build_ir_from_energy(cfg, e)) < TOL
+    cv = oracle.Conv(cfg); cv.set_ir(oracle.build_ir(cfg, h[1], 8192))
+    yo = np.stack([cv.process(b) for b in x])
+    assert _rel(y, yo) < TOL
+
+
 def test_device_fft_vs_reference_kissfft_and_numpy(fs, oracle):
     rng = np.random.default_rng(0)
     with fs.Context() as ctx:

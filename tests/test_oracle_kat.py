@@ -147,6 +147,27 @@ def test_ir_single_bin_kat(oracle):
     assert oracle.build_ir_from_energy(cfg, e3)[0, 999 * 48 + 1:].any()
 
 
+def test_ir_l2_normalisation_flag(oracle):
+    """NormalizeImpulseResponse (COMP.cpp:382-406) as an option: unit L2 norm per channel, silence and near-silence untouched"""
+    rng = np.random.default_rng(7)
+    e = (rng.uniform(0, 0.05, 1000) * (rng.uniform(size=1000) < 0.3)).astype(np.float32)
+    plain = oracle.build_ir_from_energy(oracle.default_config(), e)
+    cfg = oracle.default_config(flags=oracle.FLAG_IR_NORMALIZE)
+    ir = oracle.build_ir_from_energy(cfg, e)
+    n = np.linalg.norm(plain[0].astype(np.float64))
+    assert np.allclose(np.linalg.norm(ir.astype(np.float64), axis=1), 1.0, rtol=1e-6)
+    assert np.allclose(ir, plain / np.float32(n), rtol=2e-7, atol=0)
+    assert not oracle.build_ir_from_energy(cfg, np.zeros(1000, np.float32)).any()
+    tiny = np.zeros(1000, np.float32); tiny[3] = 1e-10                       # norm below KINDA_SMALL_NUMBER: left alone (:394-397)
+    lo = dict(ir_threshold=1e-12)
+    quiet = oracle.build_ir_from_energy(oracle.default_config(**lo), tiny)
+    assert quiet.any() and np.linalg.norm(quiet[0]) < 1e-4
+    assert np.array_equal(oracle.build_ir_from_energy(oracle.default_config(flags=oracle.FLAG_IR_NORMALIZE, **lo), tiny), quiet)
+    h = np.zeros((8, 1000), np.uint64); h[:, 20:60] = rng.integers(1, 2 ** 28, size=(8, 40)).astype(np.uint64)
+    assert np.allclose(np.linalg.norm(oracle.build_ir(cfg, h, 100).astype(np.float64), axis=1), 1.0, rtol=1e-6)
+    assert np.allclose(np.linalg.norm(oracle.build_ir_bands(cfg, h, 100, 5).astype(np.float64), axis=1), 1.0, rtol=1e-6)
+
+
 def test_ir_from_histogram_normalisation(oracle):
     """1/N applied after the integer reduction (SUB.cpp:164), bands summed"""
     cfg = oracle.default_config()
