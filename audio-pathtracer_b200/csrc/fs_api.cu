@@ -520,16 +520,16 @@ static int trace_common(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, c
         n_lanes = 1;
     }
     // a job that will use the persistent per-batch kernel runs on at most tune_mega_lanes lanes (same rule as in
-    // launch_batch_split: batches of >= 2^18 pairs on a scene of >= 4096 triangles, or FS_TUNE_MEGA=1)
+    // launch_batch_split: batches of >= FS_MEGA_MIN_BATCH = 2^17 pairs on a scene of >= 4096 triangles, or FS_TUNE_MEGA=1)
     {
         const uint64_t nb1 = g_count ? (g_count + cap_cfg - 1) / cap_cfg : 1;
         const uint64_t cap1 = g_count ? (g_count + nb1 - 1) / nb1 : 1;
         const bool mega_job = !(ctx->cfg.flags & (FS_FLAG_COUNT_VISITS | FS_FLAG_CONNECT_ALL | FS_FLAG_MIS)) && max_depth >= 1 &&
-                              (ctx->tune_mega == 1u || (ctx->tune_mega == 2u && cap1 >= (1u << 18) && ctx->bvh.n_tris >= 4096u &&
+                              (ctx->tune_mega == 1u || (ctx->tune_mega == 2u && cap1 >= FS_MEGA_MIN_BATCH && ctx->bvh.n_tris >= 4096u &&
                                                         ctx->conv_active.load() == 0));
         if (mega_job && n_lanes > ctx->tune_mega_lanes) n_lanes = ctx->tune_mega_lanes;
         // ... and on one lane when half of it would fall below the size from which the persistent kernel pays
-        while (mega_job && ctx->tune_mega == 2u && n_lanes > 1 && g_count / n_lanes < (1u << 18)) --n_lanes;
+        while (mega_job && ctx->tune_mega == 2u && n_lanes > 1 && g_count / n_lanes < FS_MEGA_MIN_BATCH) --n_lanes;
     }
     while (n_lanes > 1 && g_count / n_lanes < (1u << 17)) --n_lanes;            // small jobs: not worth a second set of launches
     uint64_t n_batches = g_count ? (g_count + cap_cfg - 1) / cap_cfg : 1;

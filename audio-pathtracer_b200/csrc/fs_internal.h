@@ -110,6 +110,9 @@ struct fs_conv_source {
     uint32_t head;              // FDL head slot
 };
 
+// smallest batch (path pairs) the persistent per-batch kernel is chosen for automatically (FS_TUNE_MEGA=2): measured break-even
+// in the furnished room (2^17 pairs: 1.47 vs 1.49 ms; 2^16: 1.35 vs 1.23 ms), -14 % already at 164 k pairs in the concert hall
+#define FS_MEGA_MIN_BATCH (1u << 17)
 #define FS_MAX_LANES 4
 #define FS_MAX_SOURCES 4096
 #define FS_PTR_TABLE 64

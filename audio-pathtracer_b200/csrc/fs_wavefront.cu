@@ -2202,7 +2202,7 @@ cudaError_t fs_wave_alloc(fs_ctx* ctx, fs_lane* lane, uint32_t cap, uint32_t max
         if ((e = cudaMalloc(&wb->all_d, sizeof(float4) * wb->all_cap)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&wb->all_conn, 4ull * wb->all_cap)) != cudaSuccess) return e;
     }
-    const bool mega_alloc = ctx->tune_mega == 1u || (ctx->tune_mega == 2u && cap >= (1u << 18) && ctx->bvh.n_tris >= 4096u);
+    const bool mega_alloc = ctx->tune_mega == 1u || (ctx->tune_mega == 2u && cap >= FS_MEGA_MIN_BATCH && ctx->bvh.n_tris >= 4096u);
     if (mega_alloc && max_depth >= 1 && cap <= (1u << 21) && !(ctx->cfg.flags & (FS_FLAG_CONNECT_ALL | FS_FLAG_MIS | FS_FLAG_COUNT_VISITS))) {
         const uint64_t lc = (uint64_t)n2 * max_depth;                  // every subpath traces at most max_depth rays
         if (lc < 0xffffffffull) {
@@ -2344,7 +2344,7 @@ static cudaError_t launch_batch_split(fs_ctx* ctx, fs_lane* lane, const fs_trace
         // shoebox +16 ... +32 %: one long persistent launch has a longer tail than it saves, in-kernel shading at partial warps)
         // ... and only while no convolver source is active: a persistent grid holds every SM for the whole batch (4-5 ms), an
         // audio callback issued meanwhile would wait for it (measured p99 3.6 ms); between per-bounce kernels it waits 0.3 ms
-        const bool mega_ok = ctx->tune_mega == 1u || (ctx->tune_mega == 2u && tp.batch >= (1u << 18) && tp.bv.n_tris >= 4096u &&
+        const bool mega_ok = ctx->tune_mega == 1u || (ctx->tune_mega == 2u && tp.batch >= FS_MEGA_MIN_BATCH && tp.bv.n_tris >= 4096u &&
                                                       ctx->conv_active.load() == 0);
         const bool mega = !COUNT && use_tq && wb.log_o && mega_ok && (uint64_t)n_sub * D <= wb.log_cap;
         const uint32_t k0 = mega ? (ctx->tune_mega_from < D ? ctx->tune_mega_from : D) : D;

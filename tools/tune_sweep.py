@@ -16,6 +16,10 @@ if which in ("room", "both"):
     jobs.append(("room", scenes.furnished_room(), 1 << 20, 16))
 if which in ("hall", "both"):
     jobs.append(("hall", scenes.concert_hall(), 1310720, 32))
+if which == "mid":
+    jobs.append(("room128k", scenes.furnished_room(), 1 << 17, 16))
+    jobs.append(("room256k", scenes.furnished_room(), 1 << 18, 16))
+    jobs.append(("hall164k", scenes.concert_hall(), 163840, 32))
 if which == "small":
     jobs.append(("room64k", scenes.furnished_room(), 1 << 16, 16))
     jobs.append(("shoebox1M", scenes.shoebox(), 1 << 20, 8))
