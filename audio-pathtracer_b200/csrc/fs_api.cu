@@ -312,6 +312,9 @@ static void apply_l2_policy(fs_ctx* ctx)
     v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
     if (cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) (void)cudaGetLastError();
+    for (int l = 1; l < FS_MAX_LANES; ++l)                 // the other batch lanes walk the same tree on streams of their own
+        if (ctx->lanes[l].stream && cudaStreamSetAttribute(ctx->lanes[l].stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess)
+            (void)cudaGetLastError();
     if (getenv("FS_VERBOSE")) fprintf(stderr, "[frequensee] L2 persisting window: %.1f MB of wide nodes (device max %d MB)\n", want / 1048576.0, max_persist >> 20);
 }
 
