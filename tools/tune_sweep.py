@@ -25,10 +25,12 @@ if which == "small":
     jobs.append(("shoebox1M", scenes.shoebox(), 1 << 20, 8))
 for name, sc, n, depth in jobs:
     for env in settings:
+        kw = {k[4:]: int(v) for k, v in env.items() if k.startswith("cfg.")}      # cfg.max_batch_paths=262144 -> fs_config field
+        env = {k: v for k, v in env.items() if not k.startswith("cfg.")}
         old = {k: os.environ.get(k) for k in env}
         os.environ.update(env)
         try:
-            ctx = fs.Context()
+            ctx = fs.Context(**kw)
         finally:
             for k, v in old.items():
                 if v is None:
@@ -46,4 +48,4 @@ for name, sc, n, depth in jobs:
             if i == 0:
                 crc = zlib.crc32(h.tobytes())
         ctx.close()
-        print(json.dumps({"scene": name, "env": env, "trace_ms_median": float(np.median(ms[2:])), "min": float(min(ms[2:])), "crc": crc}), flush=True)
+        print(json.dumps({"scene": name, "env": dict(env, **{"cfg." + k: v for k, v in kw.items()}), "trace_ms_median": float(np.median(ms[2:])), "min": float(min(ms[2:])), "crc": crc}), flush=True)
