@@ -11,9 +11,14 @@ IR -> convolver partition spectra).  N GPUs: weak scaling, every rank traces 2^2
 global N * 2^20 work range against a replicated BVH, one NCCL integer reduce per step.
 
 One JSON line on stdout (rank 0).  `value` = path pairs/s with everything resident in HBM;
-`e2e` = the same through the C-ABI with host buffers (positions in, histogram + IR out);
-`roofline` = k_trace_closest_q (BVH traversal) algorithmic bytes / its CUDA-event time vs the measured HBM
-peak; `cpu_baseline` = the CPU oracle (a port of the reference's loop) on a bounded sample.
+`e2e` = the same through the C-ABI with host buffers (positions in, histogram + IR out; at N > 1 the shard
+histograms stay on the devices, rank 0 reads the reduced histogram and the IR back);
+`roofline` = the traversal kernel that ran (k_path_q for this workload: every bounce of a batch in one persistent
+launch; k_trace_q per bounce for small jobs): algorithmic bytes / its CUDA-event time vs the measured HBM peak, with
+the binding resource, the L2-relative figure and an instruction roofline; `cpu_baseline` = the CPU oracle (a port of the
+reference's loop) on a bounded sample; `parity` = GPU histogram == oracle on that sample (and NCCL-reduced shards == one
+GPU at N > 1); `north_star` (N = 8) = the 10.5 M-pair / 5 M-triangle hall update; `cabi_multi` = all N GPUs from one
+process through fs_multi_*.
 """
 import argparse
 import json
@@ -399,11 +404,15 @@ def run_b200(args):
             parity["nccl_reduce_check"] = "%d path pairs x %d sources, %d shards reduced over NCCL vs one GPU" % (n_chk, NS_, N)
         barrier()
 
-    # e2e: the public C-ABI call with host buffers in and out, copies inside the timed region
-    ctx.set_stream(None)
+    # e2e: the public C-ABI calls with host buffers in (positions) and out (histogram, impulse responses), copies inside the
+    # timed region.  N = 1: fs_trace + fs_build_ir*.  N > 1: every rank traces its shard into device memory
+    # (fs_trace_range_device, positions from the host), one NCCL reduce, rank 0 adopts the sum (fs_set_histogram_device) and
+    # reads the results back (fs_get_histogram + fs_build_ir*) -- the shard histograms never visit the host
     e2e = None
     g_first, g_count, n_global = wl.g_first, wl.g_count, wl.n_global
     d_hist = wl.d_hist
+    if N == 1:
+        ctx.set_stream(None)
     if rank == 0 or N > 1:
         # multi-emitter updates: the host keeps ONE page-locked IR buffer (fs_host_alloc) and reuses it every update
         ir_buf = wl.capi.host_alloc((NS_, ctx.cfg.n_channels, ctx.cfg.sample_rate)) if (NS_ > 1 and rank == 0) else None
@@ -412,19 +421,19 @@ def run_b200(args):
                 h = ctx.trace(sc.sources, sc.listener, n_global, D, seed)    # positions H2D, histogram D2H
                 ir = ctx.build_ir(0) if NS_ == 1 else ctx.build_ir_all(NS_, out=ir_buf)  # IR D2H
                 return h, ir
-            h = ctx.trace_range(sc.sources, sc.listener, n_global, g_first, g_count, D, seed)
-            return h, None
+            ctx.trace_range_device(sc.sources, sc.listener, n_global, g_first, g_count, D, seed, d_hist.data_ptr(), True)
+            dist.reduce(d_hist, dst=0, op=dist.ReduceOp.SUM)
+            if rank != 0:
+                return None, None
+            ctx.set_histogram_device(d_hist.data_ptr(), NS_, n_global)
+            h = ctx.get_histogram()                                          # reduced histogram D2H
+            ir = ctx.build_ir(0) if NS_ == 1 else ctx.build_ir_all(NS_, out=ir_buf)      # IR D2H
+            return h, ir
         step_host(SEED0 - 1)
         barrier()
         t0 = time.perf_counter()
         for k in range(K):
             h, ir = step_host(SEED0 + k)
-            if N > 1:                                                         # host-buffer API: reduce through the device tensor
-                d_hist.copy_(torch.from_numpy(h.view(np.int64)))
-                dist.reduce(d_hist, dst=0, op=dist.ReduceOp.SUM)
-                if rank == 0:
-                    ctx.set_histogram(d_hist.cpu().numpy().view(np.uint64), n_global)
-                    ir = ctx.build_ir(0) if NS_ == 1 else ctx.build_ir_all(NS_, out=ir_buf)
         barrier()
         wall = time.perf_counter() - t0
         tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
