@@ -1547,7 +1547,7 @@ struct pq_globals { uint32_t tail, head, done, error; };
 // when the entry is shaded -- 3 instead of 10 words per entry keeps a CTA at 25 KB of shared memory
 #define PQ_SMEM (FS_SSTACK * TR_THREADS * sizeof(int) + TR_THREADS * sizeof(unsigned long long) + \
                  TQ_WARPS * FS_TQ_CAP * sizeof(uint32_t) + TQ_WARPS * sizeof(uint32_t) + \
-                 TQ_WARPS * PQ_SQ_CAP * 3 * sizeof(uint32_t))
+                 TQ_WARPS * PQ_SQ_CAP * 3 * sizeof(uint32_t) + TR_THREADS * sizeof(uint32_t))
 
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
@@ -1583,6 +1583,12 @@ __global__ void k_pq_finish(const fs_wave_buffers wb, const pq_globals* __restri
     if (g->error) dc->overflow = 0x100u | g->error;
 }
 
+#ifndef PQ_DRAIN_SPLIT
+#define PQ_DRAIN_SPLIT 0      // measured: hall +5 %, room -0.6 % (profiles/r2_experiments.md #67)
+#endif
+#ifndef PQ_TAIL_LANES
+#define PQ_TAIL_LANES 16u    // measured: hall -1.7 %, room unchanged; 24: room +4 % (#66)
+#endif
 #ifndef PQ_AHEAD
 #define PQ_AHEAD 0      // measured: no gain (room 4.42 vs 4.40 ms, hall 10.78 vs 10.72), profiles/r2_experiments.md
 #endif
@@ -1591,7 +1597,7 @@ __global__ void k_pq_finish(const fs_wave_buffers wb, const pq_globals* __restri
 #endif
 #define PQ_SMEM8 (FS_W8_SSTACK * TR_THREADS * sizeof(uint2) + TR_THREADS * sizeof(unsigned long long) + \
                   TQ_WARPS * FS_TQ8_CAP * sizeof(uint32_t) + TQ_WARPS * sizeof(uint32_t) + \
-                  TQ_WARPS * PQ_SQ_CAP * 3 * sizeof(uint32_t))
+                  TQ_WARPS * PQ_SQ_CAP * 3 * sizeof(uint32_t) + TR_THREADS * sizeof(uint32_t))
 template <int TEX, bool W8>
 __global__ void __launch_bounds__(TR_THREADS, FS_PQ_MINBLOCKS)
 k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict__ log_o, float4* __restrict__ log_d,
@@ -1610,6 +1616,9 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
     uint32_t* const squeue = w32 + warp * QCAP;
     uint32_t* const sqcount = w32 + TQ_WARPS * QCAP + warp;
     uint32_t* const shq = w32 + TQ_WARPS * QCAP + TQ_WARPS + warp * (PQ_SQ_CAP * 3);   // shade queue, 3 planes
+    // helpers working for each lane's ray (drain splitting, below)
+    uint32_t* const whelp = w32 + TQ_WARPS * QCAP + TQ_WARPS + TQ_WARPS * (PQ_SQ_CAP * 3) + (threadIdx.x & ~31u);
+    constexpr bool SPLIT = PQ_DRAIN_SPLIT != 0 && !W8;
     uint32_t my_ray = 0;                                                              // ray-log index of the ray this lane walks
     unsigned long long* const mykey = skey + threadIdx.x;
     unsigned long long* const wkey = skey + (threadIdx.x & ~31u);
@@ -1621,6 +1630,8 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
     const unsigned long long KEY_NONE = ((unsigned long long)0x7f800000u << 32) | 0xffffffffull;
     if (lane == 0) *sqcount = 0u;
     *mykey = KEY_NONE;
+    whelp[lane] = 0u;
+    uint32_t owner = lane;                            // lane whose ray this lane walks (itself, except for drain helpers)
     __syncwarp();
     tr_state s;
     s.node = TR_SENT; s.leaf = 0; s.sp = 0; s.tc = 0; s.te = 0;
@@ -1696,7 +1707,7 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
                         nl = (uint32_t)l0 + (uint32_t)l1 + (uint32_t)l2 + (uint32_t)l3;
                         if (nl) {
                             uint32_t* q = squeue + atomicAdd(sqcount, nl);
-                            const uint32_t lm4 = lane - 4u;
+                            const uint32_t lm4 = owner - 4u;
                             if (l0) *q = (uint32_t)v0 * 0xfffffffcu + lm4;
                             q += l0;
                             if (l1) *q = (uint32_t)v1 * 0xfffffffcu + lm4;
@@ -1750,11 +1761,16 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
             __syncwarp();
             if (lane == 0) *sqcount = 0u;
             qn = 0u;
-            const unsigned long long kk = *(volatile unsigned long long*)mykey;
+            const unsigned long long kk = *(volatile unsigned long long*)(wkey + owner);
             bt = __uint_as_float((uint32_t)(kk >> 32));
             __syncwarp();
-            // ---- retire: the finished ray goes to the warp's shade queue
-            const bool fin = running && s.node == TR_SENT;
+            // ---- retire: helpers first, then the owners whose helpers are all done: the finished ray goes to the warp's shade queue
+            bool fin = running && s.node == TR_SENT;
+            if (SPLIT) {
+                if (fin && owner != lane) { atomicSub(whelp + owner, 1u); running = false; owner = lane; fin = false; }
+                __syncwarp();
+                fin = fin && *(volatile uint32_t*)(whelp + lane) == 0u;
+            }
             const uint32_t m_fin = __ballot_sync(FULLM, fin);
             if (fin) {
                 const uint32_t q = sn + (uint32_t)__popc(m_fin & lt);
@@ -1766,9 +1782,50 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
                 running = false;
             }
             sn += (uint32_t)__popc(m_fin);
+            // ---- drain (as in k_trace_q): a lane that has no ray and whose ticket is not published yet takes the top half of a
+            // busy lane's stack and walks it as a helper of the same ray.  At the end of a batch the surviving paths are chains
+            // of dependent rays on an almost empty GPU: the batch ends with its slowest chain, and a long ray (up to 435 node
+            // steps in the hall against 27 on average) is walked by up to 32 lanes instead of one
+            if (SPLIT) {
+                // only a lane that HOLDS a ticket whose entry does not exist yet is out of work (a lane without a ticket is merely
+                // waiting for the warp's next ticket request: splitting then fragments rays in the steady state, +25 %)
+                const bool idle = !running && !ready && ticket != PQ_NO_TICKET;
+                const uint32_t m_free = __ballot_sync(FULLM, idle);
+                const bool give = running && owner == lane && s.node != TR_SENT && s.sp >= 1 && s.sp <= FS_SSTACK;
+                const uint32_t m_give = __ballot_sync(FULLM, give);
+                const uint32_t nf = (uint32_t)__popc(m_free), ng = (uint32_t)__popc(m_give);
+                const uint32_t n = nf < ng ? nf : ng;
+                if (n) {
+                    const uint32_t rf = (uint32_t)__popc(m_free & lt), rg = (uint32_t)__popc(m_give & lt);
+                    const bool take = idle && rf < n;
+                    const uint32_t donor = take ? __fns(m_give, 0u, (int)rf + 1) : lane;      // k-th free lane <- k-th giver
+                    const int dsp = __shfl_sync(FULLM, s.sp, donor);
+                    const float ox = __shfl_sync(FULLM, s.o.x, donor), oy = __shfl_sync(FULLM, s.o.y, donor), oz = __shfl_sync(FULLM, s.o.z, donor);
+                    const float dx = __shfl_sync(FULLM, s.d.x, donor), dy = __shfl_sync(FULLM, s.d.y, donor), dz = __shfl_sync(FULLM, s.d.z, donor);
+                    const float ix = __shfl_sync(FULLM, s.idx, donor), iy = __shfl_sync(FULLM, s.idy, donor), iz = __shfl_sync(FULLM, s.idz, donor);
+                    const float px = __shfl_sync(FULLM, s.oodx, donor), py = __shfl_sync(FULLM, s.oody, donor), pz = __shfl_sync(FULLM, s.oodz, donor);
+                    const float dbt = __shfl_sync(FULLM, bt, donor);
+                    if (take) {
+                        const int h = (dsp + 1) >> 1;
+                        const int* src = sstack + (threadIdx.x & ~31u) + donor;
+                        for (int i = 0; i < h; ++i) stack.sh[i * TR_THREADS] = src[(dsp - h + i) * TR_THREADS];
+                        s.o = fs_mk(ox, oy, oz); s.d = fs_mk(dx, dy, dz);
+                        s.idx = ix; s.idy = iy; s.idz = iz; s.oodx = px; s.oody = py; s.oodz = pz;
+                        s.sp = h; bt = dbt; owner = donor;
+                        s.node = stack.pop(s.sp, 0.f);
+                        running = true;
+                        atomicAdd(whelp + donor, 1u);
+                    }
+                    __syncwarp();
+                    if (give && rg < n) s.sp -= (s.sp + 1) >> 1;
+                }
+            }
         }
         // ---- shading phase: converged, lane i shades entry i (the arithmetic of k_shade_gen for node k = bounce + 1)
-        if (sn >= PQ_SHADE_MIN || (sn && !__any_sync(FULLM, running))) {
+        // ... or, with PQ_TAIL_LANES, as soon as fewer than that many lanes of the warp still walk: at the end of a batch the few
+        // surviving paths are chains of dependent rays, and a finished ray that waits for the slowest ray of its warp before it is
+        // shaded lengthens every link of the chain
+        if (sn >= PQ_SHADE_MIN || (sn && (uint32_t)__popc(__ballot_sync(FULLM, running)) < (PQ_TAIL_LANES ? PQ_TAIL_LANES : 1u))) {
             __syncwarp();
             for (uint32_t base = 0; base < sn; base += 32) {
                 const uint32_t qi = base + lane;

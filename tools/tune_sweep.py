@@ -20,6 +20,11 @@ if which == "mid":
     jobs.append(("room128k", scenes.furnished_room(), 1 << 17, 16))
     jobs.append(("room256k", scenes.furnished_room(), 1 << 18, 16))
     jobs.append(("hall164k", scenes.concert_hall(), 163840, 32))
+if which == "big":
+    jobs.append(("room2M", scenes.furnished_room(), 1 << 21, 16))
+    jobs.append(("room512k", scenes.furnished_room(), 1 << 19, 16))
+    jobs.append(("hall2.6M", scenes.concert_hall(), 2621440, 32))
+    jobs.append(("hall655k", scenes.concert_hall(), 655360, 32))
 if which == "small":
     jobs.append(("room64k", scenes.furnished_room(), 1 << 16, 16))
     jobs.append(("shoebox1M", scenes.shoebox(), 1 << 20, 8))
