@@ -955,11 +955,15 @@ __device__ __forceinline__ void tr_node_step(const fs_bvh_view& bv, tr_state& s,
 // entry distances k (INF = miss) and references v; ORDER 1: sorted near-to-far, 0: hits moved to the front, 2: slot order
 template <int ORDER, int TEX>
 __device__ __forceinline__ void wide_children(const fs_bvh_view& bv, const tr_state& s, float tlimit,
-                                              float& k0, float& k1, float& k2, float& k3, int& v0, int& v1, int& v2, int& v3)
+                                              float& k0, float& k1, float& k2, float& k3, int& v0, int& v1, int& v2, int& v3,
+                                              const uint4* top = nullptr, int n_top = 0)
 {
     const uint4* p = bv.wnodes + (size_t)s.node * 4;
     uint4 u0, u1, u2, u3;
-    if (TEX >= 2) {                      // two quarters through the texture data pipe, two through LSU
+    if (n_top && s.node < n_top) {       // FS_PQ_TOP: the top of the (breadth-first) node array staged in shared memory
+        const uint4* q = top + s.node * 4;
+        u0 = q[0]; u1 = q[1]; u2 = q[2]; u3 = q[3];
+    } else if (TEX >= 2) {                      // two quarters through the texture data pipe, two through LSU
         const int b = s.node * 4;
         u0 = tex1Dfetch<uint4>((cudaTextureObject_t)bv.wnodes_tex, b);
         u1 = tex1Dfetch<uint4>((cudaTextureObject_t)bv.wnodes_tex, b + 1);
@@ -1547,7 +1551,7 @@ struct pq_globals { uint32_t tail, head, done, error; };
 // when the entry is shaded -- 3 instead of 10 words per entry keeps a CTA at 25 KB of shared memory
 #define PQ_SMEM (FS_SSTACK * TR_THREADS * sizeof(int) + TR_THREADS * sizeof(unsigned long long) + \
                  TQ_WARPS * FS_TQ_CAP * sizeof(uint32_t) + TQ_WARPS * sizeof(uint32_t) + \
-                 TQ_WARPS * PQ_SQ_CAP * 3 * sizeof(uint32_t) + TR_THREADS * sizeof(uint32_t))
+                 TQ_WARPS * PQ_SQ_CAP * 3 * sizeof(uint32_t) + TR_THREADS * sizeof(uint32_t) + (size_t)FS_PQ_TOP * 64)
 
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
@@ -1583,6 +1587,9 @@ __global__ void k_pq_finish(const fs_wave_buffers wb, const pq_globals* __restri
     if (g->error) dc->overflow = 0x100u | g->error;
 }
 
+#ifndef FS_PQ_TOP
+#define FS_PQ_TOP 0             // nodes of the top of the tree staged in shared memory by k_path_q (experiment #68: no gain)
+#endif
 #ifndef PQ_DRAIN_SPLIT
 #define PQ_DRAIN_SPLIT 0      // measured: hall +5 %, room -0.6 % (profiles/r2_experiments.md #67)
 #endif
@@ -1597,7 +1604,7 @@ __global__ void k_pq_finish(const fs_wave_buffers wb, const pq_globals* __restri
 #endif
 #define PQ_SMEM8 (FS_W8_SSTACK * TR_THREADS * sizeof(uint2) + TR_THREADS * sizeof(unsigned long long) + \
                   TQ_WARPS * FS_TQ8_CAP * sizeof(uint32_t) + TQ_WARPS * sizeof(uint32_t) + \
-                  TQ_WARPS * PQ_SQ_CAP * 3 * sizeof(uint32_t) + TR_THREADS * sizeof(uint32_t))
+                  TQ_WARPS * PQ_SQ_CAP * 3 * sizeof(uint32_t) + TR_THREADS * sizeof(uint32_t) + (size_t)FS_PQ_TOP * 64)
 template <int TEX, bool W8>
 __global__ void __launch_bounds__(TR_THREADS, FS_PQ_MINBLOCKS)
 k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict__ log_o, float4* __restrict__ log_d,
@@ -1608,7 +1615,17 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
     constexpr uint32_t QCAP = W8 ? FS_TQ8_CAP : FS_TQ_CAP;
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
-    extern __shared__ __align__(8) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    // FS_PQ_TOP > 0 (experiment): the first FS_PQ_TOP nodes of the breadth-first array = the top of the tree, in shared memory
+    constexpr int NTOP = W8 ? 0 : FS_PQ_TOP;
+    const uint4* const stop = reinterpret_cast<const uint4*>(smem_all);
+    unsigned char* const smem_raw = smem_all + (size_t)FS_PQ_TOP * 64;
+    if (NTOP) {
+        uint4* w = reinterpret_cast<uint4*>(smem_all);
+        const uint32_t nn = (uint32_t)NTOP * 4u;
+        for (uint32_t i = threadIdx.x; i < nn; i += TR_THREADS) w[i] = (i / 4u < bv.n_inner) ? bv.wnodes[i] : make_uint4(0x0000ffffu, 0x0000ffffu, 0x0000ffffu, 0x7fffffffu);
+        __syncthreads();
+    }
     int* const sstack = reinterpret_cast<int*>(smem_raw);
     uint2* const gstack = reinterpret_cast<uint2*>(smem_raw);
     unsigned long long* const skey = reinterpret_cast<unsigned long long*>(smem_raw + (W8 ? FS_W8_SSTACK * sizeof(uint2) : FS_SSTACK * sizeof(int)) * TR_THREADS);
@@ -1702,7 +1719,7 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
                     } else {
                         const float INF = __int_as_float(0x7f800000);
                         float k0, k1, k2, k3; int v0, v1, v2, v3;
-                        wide_children<2, TEX>(bv, s, bt, k0, k1, k2, k3, v0, v1, v2, v3);
+                        wide_children<2, TEX>(bv, s, bt, k0, k1, k2, k3, v0, v1, v2, v3, stop, NTOP);
                         const bool l0 = k0 != INF && v0 < 0, l1 = k1 != INF && v1 < 0, l2 = k2 != INF && v2 < 0, l3 = k3 != INF && v3 < 0;
                         nl = (uint32_t)l0 + (uint32_t)l1 + (uint32_t)l2 + (uint32_t)l3;
                         if (nl) {
