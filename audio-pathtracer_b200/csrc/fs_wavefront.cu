@@ -1587,6 +1587,9 @@ __global__ void k_pq_finish(const fs_wave_buffers wb, const pq_globals* __restri
     if (g->error) dc->overflow = 0x100u | g->error;
 }
 
+#ifndef PQ_IDLE_NS
+#define PQ_IDLE_NS 256
+#endif
 #ifndef FS_PQ_TOP
 #define FS_PQ_TOP 0             // nodes of the top of the tree staged in shared memory by k_path_q (experiment #68: no gain)
 #endif
@@ -1691,7 +1694,7 @@ k_path_q(const fs_trace_params tp, const fs_wave_buffers wb, float4* __restrict_
             const uint32_t tl = ld_cg_u32(&g->tail);
             if (dn == tl || ld_cg_u32(&g->error)) break;
             if (++polls > (1u << 21)) { if (lane == 0) atomicMax(&g->error, 3u); break; }
-            __nanosleep(256);
+            __nanosleep(PQ_IDLE_NS);
             continue;
         }
         if (m_run) {
