@@ -641,8 +641,12 @@ __global__ void k_w8_parents(uint32_t n_inner, const float4* __restrict__ nodes,
     if (c1 >= 0) parent[c1] = (int)i;
     if (i == 0) parent[0] = -1;
 }
-__device__ __forceinline__ float w8_t(const float* T, int ref, int j) { return ref >= 0 ? __ldcg(T + (size_t)ref * 8 + (j - 1)) : 0.0f; }
-__global__ void k_w8_dp(uint32_t n_inner, const float4* __restrict__ nodes, const int* __restrict__ parent,
+template <int W>
+__device__ __forceinline__ float wide_t(const float* T, int ref, int j) { return ref >= 0 ? __ldcg(T + (size_t)ref * W + (j - 1)) : 0.0f; }
+__device__ __forceinline__ float w8_t(const float* T, int ref, int j) { return wide_t<8>(T, ref, j); }
+// W = node width (8: compressed nodes, 4: the quantised 4-wide nodes)
+template <int W>
+__global__ void k_wide_dp(uint32_t n_inner, const float4* __restrict__ nodes, const int* __restrict__ parent,
                         const uint32_t* __restrict__ need, uint32_t* __restrict__ arrive, float* T)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -651,26 +655,65 @@ __global__ void k_w8_dp(uint32_t n_inner, const float4* __restrict__ nodes, cons
     for (;;) {
         cbox a, b;
         load_children(nodes, n, a, b);
-        float ta[8], tb[8], t[8];
-        for (int j = 1; j <= 8; ++j) { ta[j - 1] = w8_t(T, a.ref, j); tb[j - 1] = w8_t(T, b.ref, j); }
+        float ta[W], tb[W], t[W];
+        for (int j = 1; j <= W; ++j) { ta[j - 1] = wide_t<W>(T, a.ref, j); tb[j - 1] = wide_t<W>(T, b.ref, j); }
         cbox u;
         u.lx = fminf(a.lx, b.lx); u.hx = fmaxf(a.hx, b.hx); u.ly = fminf(a.ly, b.ly); u.hy = fmaxf(a.hy, b.hy);
         u.lz = fminf(a.lz, b.lz); u.hz = fmaxf(a.hz, b.hz);
         float best = 3.0e38f;
-        for (int x = 1; x <= 7; ++x) best = fminf(best, ta[x - 1] + tb[7 - x]);
+        for (int x = 1; x <= W - 1; ++x) best = fminf(best, ta[x - 1] + tb[W - 1 - x]);
         t[0] = cbox_area(u) + best;
-        for (int j = 2; j <= 8; ++j) {
+        for (int j = 2; j <= W; ++j) {
             float m = t[j - 2];
             for (int x = 1; x < j; ++x) m = fminf(m, ta[x - 1] + tb[j - x - 1]);
             t[j - 1] = m;
         }
-        for (int j = 0; j < 8; ++j) T[(size_t)n * 8 + j] = t[j];
+        for (int j = 0; j < W; ++j) T[(size_t)n * W + j] = t[j];
         __threadfence();
         const int p = parent[n];
         if (p < 0) break;
         if (atomicAdd(arrive + p, 1u) + 1u < need[p]) break;
         n = p;
     }
+}
+
+// the children of wide node i chosen by the table: walks the choices of k_wide_dp down from BVH2 node i; returns their number
+template <int W>
+__device__ __forceinline__ int dp_cut(const float4* __restrict__ nodes, const float* __restrict__ T, int i, cbox* c)
+{
+    cbox st[W]; int sb[W]; int sp = 0, k = 0;
+    {
+        cbox l, r;
+        load_children(nodes, i, l, r);
+        float best = 3.0e38f; int ba = 1;
+        for (int x = 1; x <= W - 1; ++x) { const float v = wide_t<W>(T, l.ref, x) + wide_t<W>(T, r.ref, W - x); if (v < best) { best = v; ba = x; } }
+        st[0] = l; sb[0] = ba; st[1] = r; sb[1] = W - ba; sp = 2;
+    }
+    while (sp) {
+        --sp;
+        const cbox m = st[sp]; const int j = sb[sp];
+        if (m.ref < 0 || j == 1) { c[k++] = m; continue; }
+        cbox x, y;
+        load_children(nodes, m.ref, x, y);
+        float best = wide_t<W>(T, m.ref, 1); int ba = 0;                     // stay a node of its own ...
+        for (int q = 1; q < j; ++q) { const float v = wide_t<W>(T, x.ref, q) + wide_t<W>(T, y.ref, j - q); if (v < best) { best = v; ba = q; } }
+        if (!ba) { c[k++] = m; continue; }
+        st[sp] = x; sb[sp] = ba; st[sp + 1] = y; sb[sp + 1] = j - ba; sp += 2;      // ... or dissolve into this one
+    }
+    return k;
+}
+
+// the 4-wide nodes with the children chosen by the table instead of greedily (FS_TUNE_COLLAPSE bit 4)
+__global__ void k_emit4_dp(uint32_t n_inner, const float4* __restrict__ nodes, const float* __restrict__ T, const float* __restrict__ grid,
+                           uint4* __restrict__ wnodes)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_inner) return;
+    const uint4 EMPTY = make_uint4(0x0000ffffu, 0x0000ffffu, 0x0000ffffu, 0x7fffffffu);
+    cbox c[4];
+    const int k = dp_cut<4>(nodes, T, (int)i, c);
+    for (int j = 0; j < 4; ++j)
+        wnodes[(size_t)i * 4 + j] = (j < k) ? quant_box(c[j].lx, c[j].hx, c[j].ly, c[j].hy, c[j].lz, c[j].hz, c[j].ref, grid) : EMPTY;
 }
 
 // T = null: greedy collapse (open the inner child with the largest box until there are eight slots)
@@ -682,26 +725,7 @@ __global__ void k_emit8(uint32_t n_inner, const float4* __restrict__ nodes, cons
     cbox c[8];
     int k = 2;
     if (T) {
-        cbox st[8]; int sb[8]; int sp = 0;
-        k = 0;
-        {
-            cbox l, r;
-            load_children(nodes, (int)i, l, r);
-            float best = 3.0e38f; int ba = 1;
-            for (int x = 1; x <= 7; ++x) { const float v = w8_t(T, l.ref, x) + w8_t(T, r.ref, 8 - x); if (v < best) { best = v; ba = x; } }
-            st[0] = l; sb[0] = ba; st[1] = r; sb[1] = 8 - ba; sp = 2;
-        }
-        while (sp) {
-            --sp;
-            const cbox m = st[sp]; const int j = sb[sp];
-            if (m.ref < 0 || j == 1) { c[k++] = m; continue; }
-            cbox x, y;
-            load_children(nodes, m.ref, x, y);
-            float best = w8_t(T, m.ref, 1); int ba = 0;                      // stay a node of its own ...
-            for (int q = 1; q < j; ++q) { const float v = w8_t(T, x.ref, q) + w8_t(T, y.ref, j - q); if (v < best) { best = v; ba = q; } }
-            if (!ba) { c[k++] = m; continue; }
-            st[sp] = x; sb[sp] = ba; st[sp + 1] = y; sb[sp + 1] = j - ba; sp += 2;      // ... or dissolve into this one
-        }
+        k = dp_cut<8>(nodes, T, (int)i, c);
     } else {
         load_children(nodes, (int)i, c[0], c[1]);
         while (k < 8) {
@@ -1126,7 +1150,7 @@ static cudaError_t w8_build(cudaStream_t st, uint32_t n, uint32_t n_inner, const
         BCHECK(cudaMalloc(&parent, 4ull * n_inner)); BCHECK(cudaMalloc(&need, 4ull * n_inner)); BCHECK(cudaMalloc(&arrive, 4ull * n_inner));
         BCHECK(cudaMemsetAsync(arrive, 0, 4ull * n_inner, st));
         k_w8_parents<<<(n_inner + TPB - 1) / TPB, TPB, 0, st>>>(n_inner, nodes, parent, need);
-        k_w8_dp<<<(n_inner + TPB - 1) / TPB, TPB, 0, st>>>(n_inner, nodes, parent, need, arrive, T);
+        k_wide_dp<8><<<(n_inner + TPB - 1) / TPB, TPB, 0, st>>>(n_inner, nodes, parent, need, arrive, T);
         *launches += 2;
     }
     k_emit8<<<(n_inner + TPB - 1) / TPB, TPB, 0, st>>>(n_inner, nodes, T, tmp, ref); ++*launches;
@@ -1282,7 +1306,24 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
         k_leaf_stats<<<gb, TPB, 0, st>>>((int)n, ranges, misc + 8, leaf_max); ++*launches;
     }
     k_quant_grid<<<1, 32, 0, st>>>(out->nodes, grid); ++*launches;
-    k_emit4<<<(n_inner + TPB - 1) / TPB, TPB, 0, st>>>(n_inner, out->nodes, grid, out->wnodes, collapse & 1); ++*launches;
+    if ((collapse & 16) && n >= 3) {
+        // optimal collapse (dynamic programme over the BVH2, as for the 8-wide nodes) instead of the greedy one
+        float* T4 = nullptr; int* par = nullptr; uint32_t *need = nullptr, *arr = nullptr;
+        cudaError_t e4 = cudaSuccess;
+        if ((e4 = cudaMalloc(&T4, sizeof(float) * 4ull * n_inner)) == cudaSuccess && (e4 = cudaMalloc(&par, 4ull * n_inner)) == cudaSuccess &&
+            (e4 = cudaMalloc(&need, 4ull * n_inner)) == cudaSuccess && (e4 = cudaMalloc(&arr, 4ull * n_inner)) == cudaSuccess &&
+            (e4 = cudaMemsetAsync(arr, 0, 4ull * n_inner, st)) == cudaSuccess) {
+            k_w8_parents<<<(n_inner + TPB - 1) / TPB, TPB, 0, st>>>(n_inner, out->nodes, par, need);
+            k_wide_dp<4><<<(n_inner + TPB - 1) / TPB, TPB, 0, st>>>(n_inner, out->nodes, par, need, arr, T4);
+            k_emit4_dp<<<(n_inner + TPB - 1) / TPB, TPB, 0, st>>>(n_inner, out->nodes, T4, grid, out->wnodes);
+            *launches += 3;
+            e4 = cudaStreamSynchronize(st);
+        }
+        cudaFree(T4); cudaFree(par); cudaFree(need); cudaFree(arr);
+        BCHECK(e4);
+    } else {
+        k_emit4<<<(n_inner + TPB - 1) / TPB, TPB, 0, st>>>(n_inner, out->nodes, grid, out->wnodes, collapse & 1); ++*launches;
+    }
     out->n_wide = n_inner;
     if (!(collapse & 2)) {                          // FS_TUNE_COLLAPSE bit 1 keeps the sparse layout (A/B)
         uint4* dense = nullptr; uint32_t n_wide = 0;

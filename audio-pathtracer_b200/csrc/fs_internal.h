@@ -37,7 +37,8 @@ struct fs_bvh_device {
 cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* d_mats, uint64_t n_tris,
                          fs_bvh_device* out, uint64_t* launches, uint32_t leaf_max, uint32_t builder /*0 LBVH, 1 PLOC*/,
                          uint32_t collapse /*wide nodes: bit 0 greedy by surface area (else grandchildren), bit 1 keep the sparse layout,
-                                                    bit 2 also build the 8-wide compressed nodes, bit 3 greedy instead of optimal 8-wide collapse*/);
+                                                    bit 2 also build the 8-wide compressed nodes, bit 3 greedy instead of optimal 8-wide collapse,
+                                                    bit 4 optimal (dynamic programme) instead of greedy 4-wide collapse*/);
 void fs_bvh_free(fs_bvh_device* b);
 
 // device-side counters of one trace call

@@ -238,7 +238,7 @@ def test_every_traversal_kernel_and_bvh_layout_gives_the_same_histogram(fs, orac
     BVH2 float nodes, LBVH with multi-triangle leaves: the closest hit does not depend on the structure"""
     S = oracle.Scene(room.verts, room.tri_mat, room.absorption, use_bvh=True)
     ho, so = S.trace(oracle.default_config(), room.sources, room.listener, 8192, 16, 1, n_threads=16)
-    for env in ({}, {"FS_TUNE_TQ": 0}, {"FS_TUNE_TQ": 1}, {"FS_TUNE_COLLAPSE": 0}, {"FS_TUNE_PLOC_R": 3}, {"FS_TUNE_ROTATE": 3}, {"FS_TUNE_MEGA": 1}, {"FS_TUNE_MEGA": 1, "FS_TUNE_TEX": 0}, {"FS_TUNE_COLLAPSE": 3}, {"FS_TUNE_TQ": 0, "FS_TUNE_COLLAPSE": 2},
+    for env in ({}, {"FS_TUNE_TQ": 0}, {"FS_TUNE_TQ": 1}, {"FS_TUNE_COLLAPSE": 0}, {"FS_TUNE_COLLAPSE": 1}, {"FS_TUNE_COLLAPSE": 16}, {"FS_TUNE_PLOC_R": 3}, {"FS_TUNE_ROTATE": 3}, {"FS_TUNE_MEGA": 1}, {"FS_TUNE_MEGA": 1, "FS_TUNE_TEX": 0}, {"FS_TUNE_COLLAPSE": 3}, {"FS_TUNE_TQ": 0, "FS_TUNE_COLLAPSE": 2},
                 {"FS_TUNE_WIDE": 0}, {"FS_TUNE_BUILDER": 0}, {"FS_TUNE_BUILDER": 0, "FS_TUNE_LEAF_MAX": 1},
                 {"FS_TUNE_TQ_FLUSH": 1}, {"FS_TUNE_TQ_FLUSH": 32, "FS_TUNE_TQ_NODE_MIN": 0}, {"FS_TUNE_REFILL": 1},
                 {"FS_TUNE_L2PIN": 8}, {"FS_TUNE_W8": 1}, {"FS_TUNE_W8": 1, "FS_TUNE_MEGA": 1}, {"FS_TUNE_W8": 1, "FS_TUNE_COLLAPSE": 9},
