@@ -1264,6 +1264,7 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
         if (n < 4096) n_cand = 1;                         // tiny scenes: nothing to gain
         double best_cost = 0.0; int best = -1;
         float4* alt = nullptr; double* d_cost = nullptr;
+        float* cT4 = nullptr; int* cpar = nullptr; uint32_t *cneed = nullptr, *carr = nullptr;
         if (n_cand > 1) { BCHECK(cudaMalloc(&alt, sizeof(float4) * 4ull * n_inner)); BCHECK(cudaMalloc(&d_cost, 8)); }
         for (int ci = 0; ci < n_cand; ++ci) {
             float4* dst = (n_cand > 1) ? alt : out->nodes;
@@ -1275,12 +1276,30 @@ cudaError_t fs_bvh_build(cudaStream_t st, const float* d_verts, const uint32_t* 
             BCHECK(cudaMemcpyAsync(&h_cost, d_cost, 8, cudaMemcpyDeviceToHost, st));
             BCHECK(cudaStreamSynchronize(st));
             if (getenv("FS_VERBOSE")) fprintf(stderr, "[frequensee] PLOC radius %d: surface-area cost %.6g\n", cand[ci], h_cost);
+            if (collapse & 16) {
+                // rank the candidates by what the traversal will walk: the summed area of the 4-wide nodes after the optimal
+                // collapse (= the root's entry of the dynamic programme's table; the leaf boxes are the same in every tree)
+                if (!cT4) {
+                    BCHECK(cudaMalloc(&cT4, sizeof(float) * 4ull * n_inner)); BCHECK(cudaMalloc(&cpar, 4ull * n_inner));
+                    BCHECK(cudaMalloc(&cneed, 4ull * n_inner)); BCHECK(cudaMalloc(&carr, 4ull * n_inner));
+                }
+                float root_cost = 0.f;
+                BCHECK(cudaMemsetAsync(carr, 0, 4ull * n_inner, st));
+                k_w8_parents<<<(n_inner + TPB - 1) / TPB, TPB, 0, st>>>(n_inner, dst, cpar, cneed);
+                k_wide_dp<4><<<(n_inner + TPB - 1) / TPB, TPB, 0, st>>>(n_inner, dst, cpar, cneed, carr, cT4);
+                *launches += 2;
+                BCHECK(cudaMemcpyAsync(&root_cost, cT4, 4, cudaMemcpyDeviceToHost, st));
+                BCHECK(cudaStreamSynchronize(st));
+                if (getenv("FS_VERBOSE")) fprintf(stderr, "[frequensee] PLOC radius %d: summed area of the 4-wide nodes %.6g\n", cand[ci], (double)root_cost);
+                h_cost = (double)root_cost;
+            }
             if (best < 0 || h_cost < best_cost) {
                 best = ci; best_cost = h_cost;
                 BCHECK(cudaMemcpyAsync(out->nodes, alt, sizeof(float4) * 4ull * n_inner, cudaMemcpyDeviceToDevice, st));
             }
         }
         if (alt) { cudaStreamSynchronize(st); cudaFree(alt); cudaFree(d_cost); }
+        cudaFree(cT4); cudaFree(cpar); cudaFree(cneed); cudaFree(carr);
         out->max_leaf = 1;
         {
             int sweeps = 0;      // measured: PLOC trees gain 0.3-0.5 % of surface-area cost and < 1 % of node visits; off by default
