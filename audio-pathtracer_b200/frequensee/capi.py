@@ -281,13 +281,21 @@ class Context:
         lis = np.ascontiguousarray(lis_pos, dtype=np.float32).reshape(3)
         return src, lis
 
-    def trace(self, src_pos, lis_pos, n_paths, max_depth, seed, want_hist=True):
+    def trace(self, src_pos, lis_pos, n_paths, max_depth, seed, want_hist=True, out=None):
+        """`out`: a caller-owned uint64 [S][B][K] array that receives the histogram (page-locked if it came from host_alloc():
+        written by the copy engine directly, and no fresh allocation per update)"""
         src, lis = self._pos(src_pos, lis_pos)
         S = len(src)
         self.n_sources = S
-        hist = np.zeros((S, self.cfg.n_bands, self.cfg.n_bins), dtype=np.uint64) if want_hist else None
+        shape = (S, self.cfg.n_bands, self.cfg.n_bins)
+        if out is not None:
+            if out.shape != shape or out.dtype != np.uint64 or not out.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous uint64 array of shape %r" % (shape,))
+            hist = out
+        else:
+            hist = np.zeros(shape, dtype=np.uint64) if want_hist else None
         self._ck(self.L.fs_trace(self.h, src.ctypes.data, S, lis.ctypes.data, n_paths, max_depth, seed,
-                                 hist.ctypes.data if want_hist else None))
+                                 hist.ctypes.data if hist is not None else None))
         return hist
 
     def trace_range(self, src_pos, lis_pos, n_paths, g_first, g_count, max_depth, seed, hist=None):
@@ -348,9 +356,15 @@ class Context:
         self._ck(self.L.fs_get_histogram(self.h, hist.ctypes.data))
         return hist
 
-    def build_ir(self, source=0, want_ir=True):
-        ir = np.zeros((self.cfg.n_channels, self.cfg.sample_rate), dtype=np.float32) if want_ir else None
-        self._ck(self.L.fs_build_ir(self.h, source, ir.ctypes.data if want_ir else None))
+    def build_ir(self, source=0, want_ir=True, out=None):
+        shape = (self.cfg.n_channels, self.cfg.sample_rate)
+        if out is not None:
+            if out.shape != shape or out.dtype != np.float32 or not out.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous float32 array of shape %r" % (shape,))
+            ir = out
+        else:
+            ir = np.zeros(shape, dtype=np.float32) if want_ir else None
+        self._ck(self.L.fs_build_ir(self.h, source, ir.ctypes.data if ir is not None else None))
         return ir
 
     def build_ir_to(self, hist_source, conv_source, want_ir=True):

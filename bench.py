@@ -414,12 +414,14 @@ def run_b200(args):
     if N == 1:
         ctx.set_stream(None)
     if rank == 0 or N > 1:
-        # multi-emitter updates: the host keeps ONE page-locked IR buffer (fs_host_alloc) and reuses it every update
-        ir_buf = wl.capi.host_alloc((NS_, ctx.cfg.n_channels, ctx.cfg.sample_rate)) if (NS_ > 1 and rank == 0) else None
+        # the host keeps ONE set of page-locked result buffers (fs_host_alloc) and reuses it every update, as a plugin would:
+        # the copy engine writes them directly and no update pays for a fresh allocation
+        ir_buf = wl.capi.host_alloc((NS_, ctx.cfg.n_channels, ctx.cfg.sample_rate)) if rank == 0 else None
+        h_buf = wl.capi.host_alloc((NS_, B, Kb), np.uint64) if (rank == 0 and N == 1) else None
         def step_host(seed):
             if N == 1:
-                h = ctx.trace(sc.sources, sc.listener, n_global, D, seed)    # positions H2D, histogram D2H
-                ir = ctx.build_ir(0) if NS_ == 1 else ctx.build_ir_all(NS_, out=ir_buf)  # IR D2H
+                h = ctx.trace(sc.sources, sc.listener, n_global, D, seed, out=h_buf)    # positions H2D, histogram D2H
+                ir = ctx.build_ir(0, out=ir_buf[0]) if NS_ == 1 else ctx.build_ir_all(NS_, out=ir_buf)  # IR D2H
                 return h, ir
             ctx.trace_range_device(sc.sources, sc.listener, n_global, g_first, g_count, D, seed, d_hist.data_ptr(), True)
             dist.reduce(d_hist, dst=0, op=dist.ReduceOp.SUM)
@@ -427,7 +429,7 @@ def run_b200(args):
                 return None, None
             ctx.set_histogram_device(d_hist.data_ptr(), NS_, n_global)
             h = ctx.get_histogram()                                          # reduced histogram D2H
-            ir = ctx.build_ir(0) if NS_ == 1 else ctx.build_ir_all(NS_, out=ir_buf)      # IR D2H
+            ir = ctx.build_ir(0, out=ir_buf[0]) if NS_ == 1 else ctx.build_ir_all(NS_, out=ir_buf)      # IR D2H
             return h, ir
         step_host(SEED0 - 1)
         barrier()

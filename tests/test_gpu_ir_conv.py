@@ -19,6 +19,14 @@ def test_ir_from_trace_matches_oracle(fs, oracle):
         ctx.set_scene(sc.verts, sc.tri_mat, sc.absorption)
         h = ctx.trace(sc.sources, sc.listener, 16384, 8, 0x5EED)
         ir = ctx.build_ir(0)
+        # caller-owned, page-locked result buffers (fs_host_alloc), reused across updates: the same integers and floats
+        hb = fs.capi.host_alloc(h.shape, np.uint64); ib = fs.capi.host_alloc(ir.shape)
+        for _ in range(2):
+            hb[:] = 7; ib[:] = -1.0
+            assert ctx.trace(sc.sources, sc.listener, 16384, 8, 0x5EED, out=hb) is hb and ctx.build_ir(0, out=ib) is ib
+            assert np.array_equal(np.asarray(hb), h) and np.array_equal(np.asarray(ib), ir)
+        with pytest.raises(ValueError):
+            ctx.build_ir(0, out=np.zeros((2, 100), np.float32))
     iro = oracle.build_ir(oracle.default_config(), h[0], 16384)
     assert ir.shape == (2, 48000) and np.array_equal(ir[0], ir[1])
     assert np.abs(iro).max() > 0 and _rel(ir, iro) < TOL
