@@ -944,6 +944,24 @@ int fs_build_ir_all(fs_ctx* ctx, uint32_t n_sources, float* ir_out)
     return FS_OK;
 }
 
+int fs_update(fs_ctx* ctx, const float* src_pos, uint32_t n_sources, const float lis_pos[3], uint64_t n_paths,
+              uint32_t max_depth, uint64_t seed, uint64_t* hist_out, float* ir_out)
+{
+    if (!ctx) return FS_ERR_INVALID;
+    nvtx_range nv("fs_update");
+    int rc = fs_trace(ctx, src_pos, n_sources, lis_pos, n_paths, max_depth, seed, nullptr);      // enqueued, not synchronised
+    if (rc) return rc;
+    dev_guard g(ctx->device);
+    if (hist_out) {
+        const size_t hn = (size_t)n_sources * ctx->cfg.n_bands * ctx->cfg.n_bins;
+        CK(cudaMemcpyAsync(hist_out, ctx->d_hist, 8 * hn, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    rc = (n_sources == 1) ? ir_common(ctx, 0, 0, nullptr, ir_out) : fs_build_ir_all(ctx, n_sources, ir_out);
+    if (rc) return rc;
+    if (!ir_out) return hist_out ? finish_stats(ctx) : FS_OK;      // with ir_out the IR read-back has synchronised already
+    return FS_OK;
+}
+
 int fs_build_ir_bands(fs_ctx* ctx, uint32_t hist_source, uint32_t conv_source, uint64_t noise_seed, float* ir_out)
 {
     if (!ctx) return FS_ERR_INVALID;

@@ -26,7 +26,7 @@ FLAG_IR_NORMALIZE = 1024
 ABI_SYMBOLS = [
     "fs_default_config", "fs_create", "fs_destroy", "fs_last_error", "fs_set_stream", "fs_synchronize",
     "fs_scene_set_triangles", "fs_scene_set_materials", "fs_scene_set_materials_ex", "fs_scene_commit",
-    "fs_trace", "fs_trace_range_device", "fs_trace_range", "fs_trace_debug",
+    "fs_trace", "fs_update", "fs_trace_range_device", "fs_trace_range", "fs_trace_debug",
     "fs_debug_closest_hits", "fs_debug_any_hits",
     "fs_build_ir", "fs_build_ir_to", "fs_build_ir_all", "fs_build_ir_bands", "fs_build_ir_from_energy", "fs_set_histogram", "fs_set_histogram_device",
     "fs_get_histogram", "fs_get_histogram_sources", "fs_set_ir", "fs_load_float_array", "fs_save_float_array",
@@ -148,6 +148,7 @@ def load():
     L.fs_scene_set_materials_ex.argtypes = [vp, vp, vp, vp, vp, u32, u32]
     L.fs_scene_commit.argtypes = [vp]
     L.fs_trace.argtypes = [vp, vp, u32, vp, u64, u32, u64, vp]
+    L.fs_update.argtypes = [vp, vp, u32, vp, u64, u32, u64, vp, vp]
     L.fs_trace_range_device.argtypes = [vp, vp, u32, vp, u64, u64, u64, u32, u64, vp, i32]
     L.fs_trace_range.argtypes = [vp, vp, u32, vp, u64, u64, u64, u32, u64, vp]
     L.fs_trace_debug.argtypes = [vp, vp, u32, vp, u64, u64, u64, u32, u64, vp]
@@ -297,6 +298,21 @@ class Context:
         self._ck(self.L.fs_trace(self.h, src.ctypes.data, S, lis.ctypes.data, n_paths, max_depth, seed,
                                  hist.ctypes.data if hist is not None else None))
         return hist
+
+    def update(self, src_pos, lis_pos, n_paths, max_depth, seed, hist_out=None, ir_out=None):
+        """fs_update: trace + IR rebuild of every source in one call with one synchronisation (UpdateSource, SUB.cpp:128-195).
+        hist_out: uint64 [S][B][K] or None; ir_out: float32 [S][C][fs] or None (caller-owned, ideally from host_alloc())"""
+        src, lis = self._pos(src_pos, lis_pos)
+        S = len(src)
+        self.n_sources = S
+        for a, shape, dt in ((hist_out, (S, self.cfg.n_bands, self.cfg.n_bins), np.uint64),
+                             (ir_out, (S, self.cfg.n_channels, self.cfg.sample_rate), np.float32)):
+            if a is not None and (a.shape != shape or a.dtype != dt or not a.flags.c_contiguous):
+                raise ValueError("buffer must be C-contiguous %s of shape %r" % (np.dtype(dt).name, shape))
+        self._ck(self.L.fs_update(self.h, src.ctypes.data, S, lis.ctypes.data, n_paths, max_depth, seed,
+                                  hist_out.ctypes.data if hist_out is not None else None,
+                                  ir_out.ctypes.data if ir_out is not None else None))
+        return hist_out, ir_out
 
     def trace_range(self, src_pos, lis_pos, n_paths, g_first, g_count, max_depth, seed, hist=None):
         src, lis = self._pos(src_pos, lis_pos)

@@ -420,9 +420,8 @@ def run_b200(args):
         h_buf = wl.capi.host_alloc((NS_, B, Kb), np.uint64) if (rank == 0 and N == 1) else None
         def step_host(seed):
             if N == 1:
-                h = ctx.trace(sc.sources, sc.listener, n_global, D, seed, out=h_buf)    # positions H2D, histogram D2H
-                ir = ctx.build_ir(0, out=ir_buf[0]) if NS_ == 1 else ctx.build_ir_all(NS_, out=ir_buf)  # IR D2H
-                return h, ir
+                # one call = one update (UpdateSource): positions H2D, trace, IR rebuild, histogram + IR D2H, one synchronisation
+                return ctx.update(sc.sources, sc.listener, n_global, D, seed, hist_out=h_buf, ir_out=ir_buf)
             ctx.trace_range_device(sc.sources, sc.listener, n_global, g_first, g_count, D, seed, d_hist.data_ptr(), True)
             dist.reduce(d_hist, dst=0, op=dist.ReduceOp.SUM)
             if rank != 0:

@@ -204,6 +204,15 @@ int fs_scene_commit(fs_ctx* ctx);
 int fs_trace(fs_ctx* ctx, const float* src_pos /*[S][3]*/, uint32_t n_sources, const float lis_pos[3],
              uint64_t n_paths, uint32_t max_depth, uint64_t seed, uint64_t* hist_out);
 
+/* One whole update in one call, as the reference does it: UpdateSource (SUB.cpp:128-195) flushes, traces, splats AND calls
+ * ReconstructImpulseResponse (:192).  = fs_trace (all sources) followed by fs_build_ir (one source) / fs_build_ir_all (several),
+ * enqueued back to back with ONE synchronisation at the end.  hist_out ([S][B][K] uint64) and ir_out ([S][C][sample_rate]
+ * float) are host buffers and may be NULL; page-locked ones (fs_host_alloc) are written by the copy engine directly.
+ * If the traversal stack overflowed the call returns FS_ERR_OVERFLOW and the impulse responses it published are invalid until
+ * the next successful update. */
+int fs_update(fs_ctx* ctx, const float* src_pos /*[S][3]*/, uint32_t n_sources, const float lis_pos[3], uint64_t n_paths,
+              uint32_t max_depth, uint64_t seed, uint64_t* hist_out, float* ir_out);
+
 /* Shard form for multi-GPU: traces only g in [g_first, g_first + g_count) and ACCUMULATES into
  * a caller-provided DEVICE histogram d_hist [S][B][K] (uint64; e.g. a torch int64 tensor that
  * is then summed over ranks with one NCCL reduce).  zero_first != 0 clears it before. */

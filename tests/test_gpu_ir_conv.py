@@ -27,6 +27,14 @@ def test_ir_from_trace_matches_oracle(fs, oracle):
             assert np.array_equal(np.asarray(hb), h) and np.array_equal(np.asarray(ib), ir)
         with pytest.raises(ValueError):
             ctx.build_ir(0, out=np.zeros((2, 100), np.float32))
+        # fs_update = UpdateSource in one call (trace + IR rebuild, one synchronisation): same results, pageable or page-locked
+        ib3 = fs.capi.host_alloc((1,) + ir.shape)
+        hb[:] = 7; ib3[:] = -1.0
+        ctx.update(sc.sources, sc.listener, 16384, 8, 0x5EED, hist_out=hb, ir_out=ib3)
+        assert np.array_equal(np.asarray(hb), h) and np.array_equal(np.asarray(ib3)[0], ir)
+        h2, ir2 = ctx.update(sc.sources, sc.listener, 16384, 8, 0x5EED, hist_out=np.zeros_like(h), ir_out=np.zeros((1,) + ir.shape, np.float32))
+        assert np.array_equal(h2, h) and np.array_equal(ir2[0], ir)
+        assert ctx.update(sc.sources, sc.listener, 16384, 8, 0x5EED) == (None, None) and np.array_equal(ctx.get_histogram(), h)
     iro = oracle.build_ir(oracle.default_config(), h[0], 16384)
     assert ir.shape == (2, 48000) and np.array_equal(ir[0], ir[1])
     assert np.abs(iro).max() > 0 and _rel(ir, iro) < TOL
