@@ -315,16 +315,23 @@ __device__ __forceinline__ int encode_child(int c, int n, const int2* __restrict
     return c;
 }
 
-// Conservative padding of a child box: 2^-15 of its largest |coordinate| (~512 float ulps at
-// that magnitude) + 1e-5 m.  It must cover (a) the rounding of the FMA slab test (~3 ulps of
-// max(|o|, |plane|)), (b) v0+e1 / v0+e2 differing from v1 / v2 by an ulp, (c) the rounding of
-// fs_intersect_tri's barycentrics, so that every triangle the exact-sequence test accepts is
-// reached.  tests/test_gpu_intersect.py checks BVH == brute force on the device.
+// Conservative padding of a child box: 2^-17 of its largest |coordinate| (~128 float ulps at that magnitude) + 1e-5 m.
+// It must cover (a) the rounding of the FMA slab test (~3 ulps of max(|o|, |plane|), as a displacement of the plane),
+// (b) v0+e1 / v0+e2 differing from v1 / v2 by an ulp, (c) the rounding of fs_intersect_tri's barycentrics (tvec = o - v0
+// carries 2^-24 of max(|o|, |v0|): a hit can be accepted ~1e-5 m outside the triangle at 50 m coordinates), so that every
+// triangle the exact-sequence test accepts is reached: together ~2e-5 m at 50 m, i.e. 2^-21 relative; 2^-17 leaves a factor
+// of 16.  The first version used 2^-15: at the concert hall's coordinates that is 1.5 mm on every side of 6 cm triangles,
+// and the looser leaf boxes cost 3.4 % of the update (hall 10.29 -> 9.94 ms; room unchanged).  The quantised 4-wide boxes add
+// their own outward rounding + one spare quantum on top.  tests/test_gpu_intersect.py checks BVH == brute force on the
+// device, the full-size parity tests compare 16 M + 4.5 M rays with the CPU oracle.
+#ifndef FS_BOX_PAD_REL
+#define FS_BOX_PAD_REL (1.0f / 131072.0f)
+#endif
 __device__ __forceinline__ float box_pad(float4 lo, float4 hi)
 {
     float m = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))),
                     fmaxf(fabsf(lo.z), fabsf(hi.z)));
-    return fmaf(m, 1.0f / 32768.0f, 1e-5f);
+    return fmaf(m, FS_BOX_PAD_REL, 1e-5f);
 }
 
 __global__ void k_emit(int n, const int2* __restrict__ children, const int2* __restrict__ ranges,
